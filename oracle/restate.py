@@ -1,0 +1,424 @@
+"""TEST INFRASTRUCTURE ONLY - CPU restatement of the reference's Monte-Carlo EC trial.
+
+This is the parity oracle for the CUDA path.  Only ``tests/``,
+``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference`` legs
+of ``bench.py`` may import it; the product package never does (it fails loudly
+when the CUDA library is missing instead of falling back to this).
+
+Pinned against the live reference (XanaduAI/flamingpy v0.10.1b1.dev3, imported
+from ``/root/reference`` through ``oracle/ref_shim.py``) by
+``tests/test_oracle_vs_reference.py`` on shared seeded noise, and against the
+committed vectors in ``tests/golden/`` (generated from the reference by
+``oracle/gen_golden.py``).  Each function cites the reference lines it follows
+(paths relative to the reference root).
+
+All arrays are per trial; a "complex" is one error complex (primal / dual) with
+the static tables of ``flamingpy_b200.lattice.ComplexTables``.
+"""
+
+from __future__ import annotations
+
+import heapq
+import math
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import numpy as np
+
+ALPHA = float(np.sqrt(np.pi))  # bin width, cv/gkp.py:53
+FLOAT_MIN = 2.2250738585072014e-308  # sys.float_info.min, decoders/decoder.py:27
+P_COUNT_ERR = {2: 1 / 4, 3: 1 / 3, 4: 2 / 5}  # decoders/decoder.py:86
+
+
+# --------------------------------------------------------------------------------------
+# a2: state labels with the carry-over of a reused CVLayer
+# --------------------------------------------------------------------------------------
+class LabelChain:
+    """``CVLayer.populate_states`` for one reused layer (= one reference rank).
+
+    Follows ``noise/cv.py:121-140,306-321``: if ``p_swap`` is truthy draw
+    ``num_p = rng.binomial(N, p_swap)`` then ``rng.choice(range(N), num_p,
+    replace=False)`` (``p_swap == 1`` takes all nodes without touching the
+    RNG); the GKP set is everything not in ANY entry of ``self.states`` - and the
+    previous trial's ``states["GKP"]`` is still one of those entries, so
+    ``GKP_t = V \\ (p_t U GKP_{t-1})`` (SURVEY.md finding 0.3).  Nodes in neither
+    set keep standard deviation 0 in ``_covs_sampler``.
+    """
+
+    def __init__(self, N: int, p_swap, fresh: bool = False):
+        self.N = N
+        self.p_swap = p_swap
+        self.fresh = fresh
+        self.prev_gkp = np.zeros(N, bool)
+
+    def next(self, rng) -> np.ndarray:
+        """Return uint8[N] state codes: 0 silent, 1 noisy GKP, 2 p-squeezed."""
+        N = self.N
+        p_mask = np.zeros(N, bool)
+        if self.p_swap:
+            if self.p_swap == 1:
+                p_mask[:] = True
+            else:
+                num_p = rng.binomial(N, self.p_swap)
+                inds = rng.choice(range(N), size=int(np.floor(num_p)), replace=False)
+                p_mask[inds] = True
+        prev = np.zeros(N, bool) if self.fresh else self.prev_gkp
+        gkp = ~p_mask & ~prev
+        self.prev_gkp = gkp
+        state = np.zeros(N, np.uint8)
+        state[gkp] = 1
+        state[p_mask] = 2
+        return state
+
+
+def sigma_from_state(state: np.ndarray, delta: float) -> np.ndarray:
+    """float32[2N] standard deviations, ``noise/cv.py:277-290`` ("initial"
+    sampling order): q block then p block."""
+    N = state.shape[0]
+    covs = np.zeros(2 * N, dtype=np.float32)
+    noise_q = {2: 1 / (2 * delta) ** 0.5, 1: (delta / 2) ** 0.5}
+    noise_p = {2: (delta / 2) ** 0.5, 1: (delta / 2) ** 0.5}
+    for code in (2, 1):
+        idx = np.nonzero(state == code)[0]
+        if len(idx):
+            covs[idx] = noise_q[code]
+            covs[idx + N] = noise_p[code]
+    return covs
+
+
+def draw_quadratures(rng, sigma: np.ndarray) -> np.ndarray:
+    """``outcomes = rng.normal(means, covs)`` with float32 zero means,
+    ``noise/cv.py:205,323-326``."""
+    means = np.zeros(sigma.shape[0], dtype=np.float32)
+    return rng.normal(means, sigma)
+
+
+# --------------------------------------------------------------------------------------
+# a4: CZ entangling  p'_i = sum_j A_ij q_j + p_i
+# --------------------------------------------------------------------------------------
+def entangle(lat, x: np.ndarray) -> np.ndarray:
+    """p-homodyne value of every node after ``SCZ_apply`` (``cv/ops.py:65,84``):
+    the sparse product with ``[[I, 0], [A, I]]`` accumulates, for row N+i,
+    ``0 + A_ij1 x_j1 + A_ij2 x_j2 + ... + x_{N+i}`` with neighbours in ascending
+    index order.  Returns float64[N]; the caller keeps the syndrome entries
+    (``noise/cv.py:213``)."""
+    N = lat.N
+    q, p = x[:N], x[N:]
+    out = np.zeros(N, np.float64)
+    deg = np.diff(lat.adj_indptr)
+    for k in range(int(deg.max())):
+        has = deg > k
+        pos = lat.adj_indptr[:-1][has] + k
+        out[has] = out[has] + lat.adj_vals[pos].astype(np.float64) * q[lat.adj_indices[pos]]
+    return out + p
+
+
+# --------------------------------------------------------------------------------------
+# a5: GKP binning (np.divmod semantics spelled out)
+# --------------------------------------------------------------------------------------
+def integer_fractional(x, alpha: float = ALPHA):
+    """``cv/gkp.py:19-34``.  ``np.divmod`` is NumPy's ``npy_divmod``:
+    ``mod = fmod(x, a)``; ``div = (x - mod) / a``; if ``mod != 0`` and its sign
+    differs from ``a``'s, ``mod += a; div -= 1``; then ``floordiv = floor(div)``,
+    bumped by one when ``div - floordiv > 0.5``.  Afterwards a remainder above
+    ``alpha / 2`` moves to the next bin."""
+    x = np.asarray(x, np.float64)
+    mod = np.fmod(x, alpha)
+    div = (x - mod) / alpha
+    fix = (mod != 0) & (mod < 0)
+    mod = np.where(fix, mod + alpha, mod)
+    div = np.where(fix, div - 1.0, div)
+    mod = np.where(mod == 0, np.copysign(0.0, alpha), mod)
+    floordiv = np.floor(div)
+    floordiv = np.where(div - floordiv > 0.5, floordiv + 1.0, floordiv)
+    floordiv = np.where(div == 0, np.copysign(0.0, x / alpha), floordiv)
+    large = (mod > alpha / 2).astype(int)
+    f = mod - alpha * large
+    n = floordiv.astype(int) + large
+    return n, f
+
+
+def gkp_binner(x):
+    """``GKP_binner`` (``cv/gkp.py:37-62``): bit = n mod 2 (Python modulo, 0/1);
+    also returns the fractional part."""
+    n, f = integer_fractional(x, ALPHA)
+    return (n % 2).astype(np.uint8), f
+
+
+# --------------------------------------------------------------------------------------
+# a7: conditional phase-error probability
+# --------------------------------------------------------------------------------------
+def z_err_cond(var, frac):
+    """Scalar branch of ``Z_err_cond`` (``cv/gkp.py:91-133``) with the default
+    ``var_num=10, use_hom_val=False``, vectorised over qubits: numerator sums
+    ``exp(-(f - (2n+1) sqrt(pi))^2 / var)`` and denominator
+    ``exp(-(f - n sqrt(pi))^2 / var)`` over ``n = -10 .. 9`` (``np.arange(-n_max,
+    n_max)`` - the asymmetric range is the reference's); 0 where the denominator
+    underflows to 0."""
+    var = np.asarray(var, np.float64)
+    frac = np.asarray(frac, np.float64)
+    n = np.arange(-10, 10)
+    sq = np.sqrt(np.pi)
+    num = np.zeros_like(frac)
+    den = np.zeros_like(frac)
+    for k in n:
+        num = num + np.exp(-((frac - (2 * k + 1) * sq) ** 2) / var)
+        den = den + np.exp(-((frac - k * sq) ** 2) / var)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        out = np.where(den != 0, num / den, 0.0)
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# a6: weights
+# --------------------------------------------------------------------------------------
+def p_neighbour_count(lat, state: np.ndarray) -> np.ndarray:
+    """Number of neighbours labelled "p" for every node (``decoder.py:64-65``)."""
+    is_p = (state == 2).astype(np.int32)
+    csum = np.concatenate([[0], np.cumsum(is_p[lat.adj_indices])])
+    return (csum[lat.adj_indptr[1:]] - csum[lat.adj_indptr[:-1]]).astype(np.int32)
+
+
+def assign_weights(
+    lat,
+    nodes: np.ndarray,
+    hom: np.ndarray,
+    state: np.ndarray,
+    delta: float,
+    method: str = "blueprint",
+    integer: bool = False,
+    multiplier=1,
+):
+    """``assign_weights`` for the MWPM decoder (``decoders/decoder.py:31-116``)
+    for the syndrome qubits ``nodes`` with homodyne values ``hom``."""
+    nq = len(nodes)
+    if method == "uniform":
+        return np.ones(nq, np.float64)
+    if method != "blueprint":
+        raise ValueError(method)
+    deg = lat.degree[nodes]
+    pc = p_neighbour_count(lat, state)[nodes]
+    _, frac = gkp_binner(hom)
+    err = z_err_cond((deg + 1) * delta, frac)
+    err = np.minimum(err, 0.5)
+    err = np.where(err == 0, FLOAT_MIN, err)
+    for c, e in P_COUNT_ERR.items():
+        err = np.where(pc == c, e, err)
+    if integer:
+        # Python round() = round-half-even on the float product
+        return np.array([float(round(-multiplier * math.log(e))) for e in err], np.float64)
+    return -np.log(err)
+
+
+# --------------------------------------------------------------------------------------
+# a9: stabilizer parity
+# --------------------------------------------------------------------------------------
+def stabilizer_parity(ct, bits_local: np.ndarray) -> np.ndarray:
+    """``Stabilizer.parity`` (``codes/stabilizer.py:43-55``) for every cube of a
+    complex; ``bits_local`` is indexed by the complex's local qubit id."""
+    b = np.where(ct.cube_qubit >= 0, bits_local[np.maximum(ct.cube_qubit, 0)], 0)
+    return (b.sum(axis=1) % 2).astype(np.uint8)
+
+
+# --------------------------------------------------------------------------------------
+# a10 / a11: matching graph
+# --------------------------------------------------------------------------------------
+def _dijkstra(ct, w_local: np.ndarray, sources, use_connectors: bool):
+    """Label-setting shortest paths on the stabilizer graph
+    (``codes/graphs/stabilizer_graph.py:392-410`` -> networkx
+    ``single_source_dijkstra``).  ``sources`` is a list of (cube, start_distance,
+    predecessor_qubit).  Boundary points are leaves, so with
+    ``use_connectors=False`` (``shortest_paths_without_high_low``) the search
+    never leaves the cube grid."""
+    S = ct.S
+    dist = np.full(S, np.inf)
+    pred = np.full(S, -1, np.int64)  # previous cube (-1 for a seed)
+    pred_q = np.full(S, -1, np.int64)  # qubit crossed to get here
+    done = np.zeros(S, bool)
+    heap = []
+    for c, d0, q0 in sources:
+        if d0 < dist[c]:
+            dist[c] = d0
+            pred_q[c] = q0
+            heapq.heappush(heap, (d0, c))
+    while heap:
+        d, u = heapq.heappop(heap)
+        if done[u]:
+            continue
+        done[u] = True
+        for k in range(6):
+            v = ct.nbr[u, k]
+            if v < 0 or v >= S:
+                continue
+            nd = d + w_local[ct.cube_qubit[u, k]]
+            if nd < dist[v]:
+                dist[v] = nd
+                pred[v] = u
+                pred_q[v] = ct.cube_qubit[u, k]
+                heapq.heappush(heap, (nd, v))
+    return dist, pred, pred_q
+
+
+@dataclass
+class MatchingData:
+    odd: np.ndarray  # int32[K] odd cubes in stabilizer order
+    pair_len: np.ndarray  # float64[K(K-1)/2] packed upper triangle, row-major (a < b)
+    bnd_len: np.ndarray  # float64[K] (empty without boundary points)
+    bnd_side: np.ndarray  # uint8[K] 0 low, 1 high
+    pair_paths: Optional[Dict] = None  # (a, b) -> list of local qubit ids along the path
+    bnd_paths: Optional[List] = None
+
+
+def matching_graph(ct, w_local: np.ndarray, parity: np.ndarray, want_paths: bool = False) -> MatchingData:
+    """``MatchingGraph.with_edges_from`` (``decoders/mwpm/matching.py:97-173``):
+    complete graph on the odd cubes with shortest-path lengths computed without
+    the LOW/HIGH connectors; with boundary points, one virtual partner per odd
+    cube at the nearer connector (ties -> low, ``np.argmin``)."""
+    odd = np.nonzero(parity)[0].astype(np.int32)
+    K = len(odd)
+    pair_len = np.empty(K * (K - 1) // 2, np.float64)
+    pair_paths = {} if want_paths else None
+    pos = 0
+    for a in range(K - 1):
+        dist, pred, pred_q = _dijkstra(ct, w_local, [(int(odd[a]), 0.0, -1)], False)
+        pair_len[pos : pos + K - 1 - a] = dist[odd[a + 1 :]]
+        if want_paths:
+            for b in range(a + 1, K):
+                pair_paths[(a, b)] = _walk(pred, pred_q, int(odd[b]))
+        pos += K - 1 - a
+    bnd_len = np.empty(0, np.float64)
+    bnd_side = np.empty(0, np.uint8)
+    bnd_paths = None
+    if ct.has_boundary and K > 0:
+        seeds_lo = [(int(c), float(w_local[ct.slot_qubit[s]]), int(ct.slot_qubit[s]))
+                    for c, s in zip(ct.low_seed_cube, ct.low_seed_slot)]
+        seeds_hi = [(int(c), float(w_local[ct.slot_qubit[s]]), int(ct.slot_qubit[s]))
+                    for c, s in zip(ct.high_seed_cube, ct.high_seed_slot)]
+        dlo, plo, qlo = _dijkstra(ct, w_local, seeds_lo, True)
+        dhi, phi, qhi = _dijkstra(ct, w_local, seeds_hi, True)
+        lo, hi = dlo[odd], dhi[odd]
+        bnd_side = (hi < lo).astype(np.uint8)  # argmin((low, high)): tie -> low
+        bnd_len = np.where(bnd_side == 1, hi, lo)
+        if want_paths:
+            bnd_paths = [
+                _walk(phi, qhi, int(c)) if s else _walk(plo, qlo, int(c)) for c, s in zip(odd, bnd_side)
+            ]
+    return MatchingData(odd, pair_len, bnd_len, bnd_side, pair_paths, bnd_paths)
+
+
+def _walk(pred, pred_q, target: int):
+    """Qubits crossed on the tree path ending at ``target`` (any order)."""
+    out = []
+    c = target
+    while c >= 0 and pred_q[c] >= 0:
+        out.append(int(pred_q[c]))
+        c = int(pred[c])
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# a12 / a13: decode, recover, check
+# --------------------------------------------------------------------------------------
+def mwpm_pairs(md: MatchingData, has_boundary: bool):
+    """Min-weight perfect matching of the matching graph with networkx
+    (``decoders/mwpm/matching.py:209-210``).  Nodes 0..K-1 are odd cubes,
+    K..2K-1 their virtual partners.  Returns a list of (u, v)."""
+    import networkx as nx
+
+    K = len(md.odd)
+    if K == 0:
+        return []
+    G = nx.Graph()
+    pos = 0
+    for a in range(K - 1):
+        for b in range(a + 1, K):
+            G.add_edge(a, b, inverse_weight=-md.pair_len[pos])
+            pos += 1
+    if has_boundary:
+        for a in range(K):
+            G.add_edge(a, K + a, inverse_weight=-md.bnd_len[a])
+        for a in range(K - 1):
+            for b in range(a + 1, K):
+                G.add_edge(K + a, K + b, inverse_weight=-0.0)
+    return list(nx.max_weight_matching(G, maxcardinality=True, weight="inverse_weight"))
+
+
+def decode_complex(ct, w_local, bits_local, md: Optional[MatchingData] = None):
+    """One complex of ``correct`` (``decoders/decoder.py:282-285``):
+    ``mwpm_decoder`` (``mwpm/algos.py:50-96``) + ``recovery``
+    (``decoder.py:140-141``) + the plane check of ``check_correction``
+    (``decoder.py:186-214``).  Returns (success, corrected bits)."""
+    parity = stabilizer_parity(ct, bits_local)
+    if md is None or md.pair_paths is None:
+        md = matching_graph(ct, w_local, parity, want_paths=True)
+    K = len(md.odd)
+    bits = bits_local.copy()
+    for u, v in mwpm_pairs(md, ct.has_boundary):
+        u, v = (u, v) if u < v else (v, u)
+        if u >= K:
+            continue  # virtual - virtual
+        path = md.pair_paths[(u, v)] if v < K else md.bnd_paths[u]
+        for q in path:
+            bits[q] ^= 1
+    ok = True
+    for plane in ct.planes:
+        ok = ok and (int(bits[plane].sum()) % 2 == 0)
+    return ok, bits
+
+
+# --------------------------------------------------------------------------------------
+# whole trial
+# --------------------------------------------------------------------------------------
+@dataclass
+class TrialResult:
+    state: np.ndarray  # uint8[N]
+    x: np.ndarray  # float64[2N] raw draws
+    hom_all: np.ndarray  # float64[N] entangled p-homodyne of every node
+    per_complex: Dict[str, dict]
+
+
+def trial_from_draws(lat, state, x, delta, weight_opts=None, want_graph=True, want_paths=False) -> TrialResult:
+    """noise -> bits -> weights -> parity -> matching graph for injected draws."""
+    wo = {"method": "uniform", "integer": False, "multiplier": 1}
+    wo.update(weight_opts or {})
+    hom_all = entangle(lat, x)
+    out = {}
+    for ec in lat.ec:
+        ct = lat.complexes[ec]
+        hom = hom_all[ct.qubits]
+        bits, frac = gkp_binner(hom)
+        w = assign_weights(lat, ct.qubits, hom, state, wo.get("delta", delta), wo["method"],
+                           wo["integer"], wo["multiplier"])
+        par = stabilizer_parity(ct, bits)
+        rec = {"hom": hom, "bits": bits, "frac": frac, "weights": w, "parity": par}
+        if want_graph:
+            rec["graph"] = matching_graph(ct, w, par, want_paths=want_paths)
+        out[ec] = rec
+    return TrialResult(state, x, hom_all, out)
+
+
+class TrialChain:
+    """A reused ``CVLayer`` + the body of ``ec_mc_trial`` (``simulations.py:46-59``):
+    same NumPy RNG call order as the reference, so with the same seed it sees
+    the same labels and draws."""
+
+    def __init__(self, lat, delta, p_swap, weight_opts=None, fresh=False):
+        self.lat = lat
+        self.delta = delta
+        self.weight_opts = weight_opts
+        self.labels = LabelChain(lat.N, p_swap, fresh=fresh)
+
+    def next(self, rng, want_graph=True, want_paths=False) -> TrialResult:
+        state = self.labels.next(rng)
+        sig = sigma_from_state(state, self.delta)
+        x = draw_quadratures(rng, sig)
+        return trial_from_draws(self.lat, state, x, self.delta, self.weight_opts, want_graph, want_paths)
+
+    def correct(self, res: TrialResult) -> bool:
+        ok = True
+        for ec in self.lat.ec:
+            ct = self.lat.complexes[ec]
+            rec = res.per_complex[ec]
+            good, _ = decode_complex(ct, rec["weights"], rec["bits"], rec.get("graph"))
+            ok = ok and good
+        return ok

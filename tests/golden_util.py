@@ -1,0 +1,36 @@
+"""Helpers to read tests/golden/*.npz (see oracle/gen_golden.py)."""
+
+import glob
+import os
+
+import numpy as np
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def golden_files():
+    return sorted(glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+
+
+def load(path):
+    z = np.load(path)
+    g = {k: z[k] for k in z.files}
+    dims = tuple(int(v) for v in g["dims"])
+    g["dims"] = dims
+    g["distance"] = dims[0] if len(set(dims)) == 1 else dims
+    for k in ("ec", "boundaries", "method"):
+        g[k] = str(g[k])
+    g["delta"] = float(g["delta"])
+    ps = float(g["p_swap"])
+    g["p_swap"] = int(ps) if ps in (0.0, 1.0) else ps
+    g["trials"] = int(g["trials"])
+    g["integer"] = bool(g["integer"])
+    g["multiplier"] = int(g["multiplier"])
+    g["weight_opts"] = {"method": g["method"], "delta": g["delta"], "integer": g["integer"],
+                        "multiplier": g["multiplier"]}
+    return g
+
+
+def ragged(g, key, t):
+    off = g[key + "_off"]
+    return g[key][off[t]:off[t + 1]]
