@@ -1,0 +1,602 @@
+// C ABI of the B200 Monte-Carlo EC trial backend (see include/fpb.h).
+//
+// Host side only: owns the device tables and result buffers of a handle, launches the
+// kernels of fpb_kernels.cuh on the handle's stream and times every stage with CUDA events.
+// There is no CPU fallback anywhere in this file: without a usable device fpb_create fails.
+#include "../../include/fpb.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "fpb_kernels.cuh"
+
+using namespace fpb;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess) {                                                                  \
+      char buf_[512];                                                                         \
+      snprintf(buf_, sizeof buf_, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,        \
+               cudaGetErrorString(e_));                                                       \
+      return fail(e_ == cudaErrorMemoryAllocation ? FPB_ERR_NOMEM : FPB_ERR_CUDA, buf_);      \
+    }                                                                                         \
+  } while (0)
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;  // elements
+  int ensure(size_t n) {
+    if (n <= cap) return FPB_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = n + n / 8 + 64;
+    CK(cudaMalloc(&p, want * sizeof(T)));
+    cap = want;
+    return FPB_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+template <typename T>
+int upload(const T* host, size_t n, T** dev) {
+  *dev = nullptr;
+  if (n == 0) return FPB_OK;
+  CK(cudaMalloc(dev, n * sizeof(T)));
+  CK(cudaMemcpy(*dev, host, n * sizeof(T), cudaMemcpyHostToDevice));
+  return FPB_OK;
+}
+
+struct ComplexHost {
+  int S = 0, Q = 0, qoff = 0, par_words = 0, n_slots = 0, n_low = 0, n_high = 0;
+  int* cube_qubit = nullptr;
+  uint16_t* ninfo = nullptr;
+  uint16_t* sbase = nullptr;
+  int* slot_qubit = nullptr;
+  int *low_cube = nullptr, *low_slot = nullptr, *high_cube = nullptr, *high_slot = nullptr;
+  int d_off[12], s_off[12];
+  DevBuf<uint32_t> parity;
+  DevBuf<int> odd_count, odd_fixed, odd_ids;
+  DevBuf<long long> odd_off, pair_off;
+  DevBuf<double> pair_len, bnd_len;
+  DevBuf<uint8_t> bnd_side;
+  long long total_odd = 0, total_pairs = 0;
+};
+
+}  // namespace
+
+struct fpb_handle {
+  int device = 0;
+  int sm_count = 0;
+  int N = 0, Qtot = 0, bit_words = 0, ncx = 0;
+  int S_max = 0, slots_max = 0;
+  double delta = 0, p_swap = 0, weight_delta = 0, weight_multiplier = 1, step_factor = 1;
+  int weight_method = 0, weight_integer = 0, label_mode = 0;
+  long long chain_len = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int *adj_indptr = nullptr, *adj_indices = nullptr, *qubit_node = nullptr;
+  int8_t* adj_vals = nullptr;
+  ComplexHost cx[FPB_MAX_COMPLEX];
+  DevBuf<double> x, hom, weights;
+  DevBuf<uint8_t> state;
+  DevBuf<uint32_t> bits, flips;
+  DevBuf<int> item_off, counter, q_trial, q_cx, q_src, q_dst;
+  DevBuf<long long> totals;
+  long long* totals_host = nullptr;  // pinned
+  long long T = 0;
+  int last_stage = 0;
+  bool have_rng = false;
+  fpb_timings tm;
+  // shortest-path launch configuration
+  int warps = 0, ctas_per_sm = 0, tasks_per_item = 0;
+  size_t paths_smem = 0;
+};
+
+namespace {
+
+ComplexDev make_dev(const ComplexHost& c) {
+  ComplexDev d;
+  memset(&d, 0, sizeof d);
+  d.S = c.S; d.Q = c.Q; d.qoff = c.qoff; d.par_words = c.par_words; d.n_slots = c.n_slots;
+  d.n_low = c.n_low; d.n_high = c.n_high;
+  d.cube_qubit = c.cube_qubit; d.ninfo = c.ninfo; d.sbase = c.sbase; d.slot_qubit = c.slot_qubit;
+  d.low_cube = c.low_cube; d.low_slot = c.low_slot; d.high_cube = c.high_cube; d.high_slot = c.high_slot;
+  memcpy(d.d_off, c.d_off, sizeof d.d_off);
+  memcpy(d.s_off, c.s_off, sizeof d.s_off);
+  d.parity = c.parity.p; d.odd_count = c.odd_count.p; d.odd_fixed = c.odd_fixed.p;
+  d.odd_off = c.odd_off.p; d.pair_off = c.pair_off.p; d.odd_ids = c.odd_ids.p;
+  d.pair_len = c.pair_len.p; d.bnd_len = c.bnd_len.p; d.bnd_side = c.bnd_side.p;
+  return d;
+}
+
+int configure_paths(fpb_handle* h) {
+  // shared-memory budget: one CTA-wide copy of the trial's weights and the face tables, plus a
+  // distance array, open list and flag array per warp (= per concurrent search)
+  int max_optin = 0;
+  CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+  int smem_per_sm = 0;
+  CK(cudaDeviceGetAttribute(&smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, h->device));
+  const size_t cta_b = paths_cta_bytes(h->S_max, h->slots_max);
+  const size_t warp_b = paths_warp_bytes(h->S_max);
+  h->warps = 0;
+  for (int ctas = 1; ctas <= 4; ++ctas) {
+    // per-CTA budget when `ctas` CTAs share an SM (1 KB reserved per CTA by the runtime)
+    size_t budget = (size_t)smem_per_sm / ctas - 1024;
+    if (budget > (size_t)max_optin) budget = max_optin;
+    if (budget < cta_b + warp_b) break;
+    int w = (int)((budget - cta_b) / warp_b);
+    if (w > 16) w = 16;
+    if (w * ctas > h->warps * h->ctas_per_sm || h->warps == 0) {
+      h->warps = w;
+      h->ctas_per_sm = ctas;
+    }
+    if (w * ctas >= 32) break;
+  }
+  if (h->warps == 0)
+    return fail(FPB_ERR_UNSUPPORTED,
+                "lattice too large for the shared-memory shortest-path kernel (needs " +
+                    std::to_string(cta_b + warp_b) + " bytes per CTA)");
+  h->paths_smem = cta_b + (size_t)h->warps * warp_b;
+  h->tasks_per_item = h->warps * 4;
+  CK(cudaFuncSetAttribute(k_paths, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->paths_smem));
+  return FPB_OK;
+}
+
+int ensure_batch(fpb_handle* h, long long T) {
+  int rc;
+  if ((rc = h->x.ensure((size_t)T * 2 * h->N))) return rc;
+  if ((rc = h->state.ensure((size_t)T * h->N))) return rc;
+  if ((rc = h->hom.ensure((size_t)T * h->Qtot))) return rc;
+  if ((rc = h->weights.ensure((size_t)T * h->Qtot))) return rc;
+  if ((rc = h->bits.ensure((size_t)T * h->bit_words))) return rc;
+  if ((rc = h->item_off.ensure((size_t)T * h->ncx + 1))) return rc;
+  if ((rc = h->counter.ensure(1))) return rc;
+  if ((rc = h->totals.ensure(2 * MAXC + 1))) return rc;
+  for (int c = 0; c < h->ncx; ++c) {
+    ComplexHost& cx = h->cx[c];
+    if ((rc = cx.parity.ensure((size_t)T * cx.par_words))) return rc;
+    if ((rc = cx.odd_count.ensure((size_t)T))) return rc;
+    if ((rc = cx.odd_fixed.ensure((size_t)T * cx.S))) return rc;
+    if ((rc = cx.odd_off.ensure((size_t)T + 1))) return rc;
+    if ((rc = cx.pair_off.ensure((size_t)T + 1))) return rc;
+  }
+  return FPB_OK;
+}
+
+int run_pipeline(fpb_handle* h, long long T, int stage, bool gen, uint64_t seed, long long first_trial) {
+  if (T <= 0) return fail(FPB_ERR_ARG, "n_trials must be positive");
+  if (T > 0x7fffffffll / (h->ncx > 0 ? h->ncx : 1) / 2) return fail(FPB_ERR_ARG, "n_trials too large for one batch");
+  if (stage < FPB_STAGE_NOISE || stage > FPB_STAGE_GRAPH) return fail(FPB_ERR_ARG, "bad stage");
+  cudaStream_t st = h->stream;
+  memset(&h->tm, 0, sizeof h->tm);
+  h->T = T;
+  h->last_stage = stage;
+  for (int c = 0; c < h->ncx; ++c) h->cx[c].total_odd = h->cx[c].total_pairs = 0;
+  int launches = 0;
+
+  CK(cudaEventRecord(h->ev[0], st));
+  if (gen) {
+    GenParams g;
+    g.N = h->N;
+    g.seed_lo = (uint32_t)seed;
+    g.seed_hi = (uint32_t)(seed >> 32);
+    g.first_trial = first_trial;
+    g.chain_len = h->chain_len;
+    g.fresh = h->label_mode == FPB_MODE_FRESH;
+    g.p_swap = h->p_swap;
+    double th = h->p_swap * 4294967296.0;
+    g.p_thresh = th >= 4294967295.0 ? 0xffffffffu : (uint32_t)th;
+    // float32-rounded standard deviations, noise/cv.py:280-289
+    g.sigma_q_p = (double)(float)(1.0 / pow(2.0 * h->delta, 0.5));
+    g.sigma_q_gkp = (double)(float)pow(h->delta / 2.0, 0.5);
+    g.sigma_p = (double)(float)pow(h->delta / 2.0, 0.5);
+    g.x = h->x.p;
+    g.state = h->state.p;
+    long long total = T * (long long)h->N;
+    long long blocks = (total + 255) / 256;
+    long long cap = (long long)h->sm_count * 32;
+    k_gen<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(g, T);
+    ++launches;
+  }
+  CK(cudaEventRecord(h->ev[1], st));
+  {
+    NoiseParams p;
+    p.N = h->N; p.Qtot = h->Qtot; p.bit_words = h->bit_words;
+    p.adj_indptr = h->adj_indptr; p.adj_indices = h->adj_indices; p.adj_vals = h->adj_vals;
+    p.qubit_node = h->qubit_node;
+    p.delta_w = h->weight_delta; p.method = h->weight_method; p.integer = h->weight_integer;
+    p.multiplier = h->weight_multiplier;
+    p.x = h->x.p; p.state = h->state.p; p.hom = h->hom.p; p.weights = h->weights.p; p.bits = h->bits.p;
+    long long bpt = (h->Qtot + 255) / 256;
+    k_noise<<<(unsigned)(bpt * T), 256, 0, st>>>(p);
+    ++launches;
+  }
+  CK(cudaEventRecord(h->ev[2], st));
+  if (stage >= FPB_STAGE_SYNDROME) {
+    SyndromeParams sp;
+    sp.n_complex = h->ncx; sp.bit_words = h->bit_words; sp.bits = h->bits.p;
+    for (int c = 0; c < h->ncx; ++c) sp.cx[c] = make_dev(h->cx[c]);
+    k_syndrome<<<dim3((unsigned)T, h->ncx), 256, 0, st>>>(sp);
+    ++launches;
+    ScanParams sc;
+    sc.n_complex = h->ncx;
+    sc.tasks_per_item = h->tasks_per_item > 0 ? h->tasks_per_item : 1;
+    for (int c = 0; c < h->ncx; ++c) {
+      sc.cx[c] = sp.cx[c];
+      sc.has_boundary[c] = h->cx[c].n_low > 0;
+    }
+    sc.item_off = h->item_off.p;
+    sc.totals = h->totals.p;
+    k_scan<<<1, 1024, 0, st>>>(sc, (int)T);
+    ++launches;
+    CK(cudaMemcpyAsync(h->totals_host, h->totals.p, (2 * MAXC + 1) * sizeof(long long),
+                       cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    int rc;
+    for (int c = 0; c < h->ncx; ++c) {
+      ComplexHost& cx = h->cx[c];
+      cx.total_odd = h->totals_host[c];
+      cx.total_pairs = h->totals_host[MAXC + c];
+      if ((rc = cx.odd_ids.ensure((size_t)cx.total_odd + 1))) return rc;
+      if ((rc = cx.bnd_len.ensure((size_t)cx.total_odd + 1))) return rc;
+      if ((rc = cx.bnd_side.ensure((size_t)cx.total_odd + 1))) return rc;
+      if (stage >= FPB_STAGE_GRAPH)
+        if ((rc = cx.pair_len.ensure((size_t)cx.total_pairs + 1))) return rc;
+      k_compact_odd<<<(unsigned)T, 256, 0, st>>>(make_dev(cx), (int)T);
+      ++launches;
+    }
+  }
+  CK(cudaEventRecord(h->ev[3], st));
+  if (stage >= FPB_STAGE_GRAPH) {
+    if (h->warps == 0) return fail(FPB_ERR_UNSUPPORTED, "shortest-path kernel not configured for this lattice");
+    const long long total_items = h->totals_host[2 * MAXC];
+    if (total_items > 0) {
+      PathsParams pp;
+      memset(&pp, 0, sizeof pp);
+      pp.n_complex = h->ncx; pp.T = (int)T; pp.Qtot = h->Qtot;
+      pp.tasks_per_item = h->tasks_per_item;
+      pp.S_max = h->S_max; pp.slots_max = h->slots_max; pp.warps = h->warps;
+      pp.step_factor = h->step_factor;
+      pp.weights = h->weights.p;
+      pp.item_off = h->item_off.p;
+      pp.total_items = (int)total_items;
+      pp.counter = h->counter.p;
+      for (int c = 0; c < h->ncx; ++c) pp.cx[c] = make_dev(h->cx[c]);
+      CK(cudaMemsetAsync(h->counter.p, 0, sizeof(int), st));
+      long long grid = (long long)h->sm_count * h->ctas_per_sm;
+      if (grid > total_items) grid = total_items;
+      k_paths<<<(unsigned)grid, h->warps * 32, h->paths_smem, st>>>(pp);
+      ++launches;
+      h->tm.graph_ctas = (int)grid;
+    }
+  }
+  CK(cudaEventRecord(h->ev[4], st));
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(st));
+  CK(cudaEventElapsedTime(&h->tm.gen_ms, h->ev[0], h->ev[1]));
+  CK(cudaEventElapsedTime(&h->tm.noise_ms, h->ev[1], h->ev[2]));
+  CK(cudaEventElapsedTime(&h->tm.syndrome_ms, h->ev[2], h->ev[3]));
+  CK(cudaEventElapsedTime(&h->tm.graph_ms, h->ev[3], h->ev[4]));
+  CK(cudaEventElapsedTime(&h->tm.total_ms, h->ev[0], h->ev[4]));
+  h->tm.launches = launches;
+  h->tm.graph_warps_per_cta = h->warps;
+  h->tm.graph_smem_bytes = (int)h->paths_smem;
+  return FPB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* fpb_last_error(void) { return g_err.c_str(); }
+int fpb_abi_version(void) { return FPB_ABI_VERSION; }
+
+int fpb_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) return fail(FPB_ERR_CUDA, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+  return n;
+}
+
+int fpb_create(const fpb_config* cfg, fpb_handle** out) {
+  if (!cfg || !out) return fail(FPB_ERR_ARG, "null argument");
+  *out = nullptr;
+  if (cfg->abi_version != FPB_ABI_VERSION) return fail(FPB_ERR_ARG, "ABI version mismatch");
+  if (cfg->n_complex < 1 || cfg->n_complex > FPB_MAX_COMPLEX) return fail(FPB_ERR_ARG, "n_complex must be 1 or 2");
+  if (cfg->n_nodes <= 0 || !cfg->adj_indptr || !cfg->adj_indices || !cfg->adj_vals)
+    return fail(FPB_ERR_ARG, "missing lattice adjacency");
+  if (!(cfg->delta > 0)) return fail(FPB_ERR_ARG, "delta must be positive");
+  if (cfg->p_swap < 0 || cfg->p_swap > 1) return fail(FPB_ERR_ARG, "p_swap must be in [0, 1]");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(FPB_ERR_CUDA, std::string("no usable CUDA device (no CPU fallback exists): ") +
+                                  (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(FPB_ERR_ARG, "device ordinal out of range");
+  CK(cudaSetDevice(cfg->device));
+  fpb_handle* h = new fpb_handle();
+  h->device = cfg->device;
+  int rc = FPB_OK;
+  auto bail = [&](int code) {
+    fpb_destroy(h);
+    return code;
+  };
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) return bail(fail(FPB_ERR_CUDA, "cudaGetDeviceProperties failed"));
+  h->sm_count = prop.multiProcessorCount;
+  h->N = cfg->n_nodes;
+  h->ncx = cfg->n_complex;
+  h->delta = cfg->delta;
+  h->p_swap = cfg->p_swap;
+  h->weight_method = cfg->weight_method;
+  h->weight_delta = cfg->weight_delta > 0 ? cfg->weight_delta : cfg->delta;
+  h->weight_integer = cfg->weight_integer;
+  h->weight_multiplier = cfg->weight_multiplier != 0 ? cfg->weight_multiplier : 1.0;
+  h->label_mode = cfg->label_mode;
+  h->chain_len = cfg->chain_len;
+  h->step_factor = cfg->delta_step > 0 ? cfg->delta_step : 2.0;
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(FPB_ERR_CUDA, "stream creation failed"));
+  for (auto& ev : h->ev)
+    if (cudaEventCreate(&ev) != cudaSuccess) return bail(fail(FPB_ERR_CUDA, "event creation failed"));
+  if (cudaMallocHost(&h->totals_host, (2 * MAXC + 1) * sizeof(long long)) != cudaSuccess) return bail(fail(FPB_ERR_CUDA, "pinned allocation failed"));
+  memset(h->totals_host, 0, (2 * MAXC + 1) * sizeof(long long));
+
+  const int N = h->N;
+  const int nnz = cfg->adj_indptr[N];
+  if ((rc = upload(cfg->adj_indptr, (size_t)N + 1, &h->adj_indptr))) return bail(rc);
+  if ((rc = upload(cfg->adj_indices, (size_t)nnz, &h->adj_indices))) return bail(rc);
+  if ((rc = upload(cfg->adj_vals, (size_t)nnz, &h->adj_vals))) return bail(rc);
+
+  std::vector<int> qnode;
+  int qoff = 0;
+  for (int c = 0; c < h->ncx; ++c) {
+    const fpb_complex_desc& d = cfg->complex_[c];
+    ComplexHost& cx = h->cx[c];
+    if (d.n_cubes <= 0 || d.n_qubits <= 0 || !d.qubit_node || !d.cube_qubit || !d.ninfo || !d.sbase || !d.slot_qubit)
+      return bail(fail(FPB_ERR_ARG, "incomplete complex description"));
+    if (d.n_cubes > 65535 || d.n_slots > 65535)
+      return bail(fail(FPB_ERR_UNSUPPORTED, "complex exceeds the 16-bit cube / slot index range"));
+    cx.S = d.n_cubes; cx.Q = d.n_qubits; cx.qoff = qoff; cx.par_words = (d.n_cubes + 31) / 32;
+    cx.n_slots = d.n_slots; cx.n_low = d.n_low; cx.n_high = d.n_high;
+    if ((cx.n_low > 0) != (cx.n_high > 0)) return bail(fail(FPB_ERR_ARG, "LOW and HIGH connectors must come together"));
+    memcpy(cx.d_off, d.d_off, sizeof cx.d_off);
+    memcpy(cx.s_off, d.s_off, sizeof cx.s_off);
+    for (int q = 0; q < d.n_qubits; ++q) {
+      if (d.qubit_node[q] < 0 || d.qubit_node[q] >= N) return bail(fail(FPB_ERR_ARG, "qubit node index out of range"));
+      qnode.push_back(d.qubit_node[q]);
+    }
+    std::vector<uint16_t> sb16(d.n_cubes);
+    for (int s = 0; s < d.n_cubes; ++s) {
+      if (d.sbase[s] < 0 || d.sbase[s] > 65535) return bail(fail(FPB_ERR_ARG, "sbase out of range"));
+      sb16[s] = (uint16_t)d.sbase[s];
+    }
+    if ((rc = upload(d.cube_qubit, (size_t)d.n_cubes * 6, &cx.cube_qubit))) return bail(rc);
+    if ((rc = upload(d.ninfo, (size_t)d.n_cubes, &cx.ninfo))) return bail(rc);
+    if ((rc = upload(sb16.data(), (size_t)d.n_cubes, &cx.sbase))) return bail(rc);
+    if ((rc = upload(d.slot_qubit, (size_t)d.n_slots, &cx.slot_qubit))) return bail(rc);
+    if ((rc = upload(d.low_cube, (size_t)d.n_low, &cx.low_cube))) return bail(rc);
+    if ((rc = upload(d.low_slot, (size_t)d.n_low, &cx.low_slot))) return bail(rc);
+    if ((rc = upload(d.high_cube, (size_t)d.n_high, &cx.high_cube))) return bail(rc);
+    if ((rc = upload(d.high_slot, (size_t)d.n_high, &cx.high_slot))) return bail(rc);
+    qoff += d.n_qubits;
+    if (d.n_cubes > h->S_max) h->S_max = d.n_cubes;
+    if (d.n_slots > h->slots_max) h->slots_max = d.n_slots;
+  }
+  h->Qtot = qoff;
+  h->bit_words = (qoff + 31) / 32;
+  if ((rc = upload(qnode.data(), qnode.size(), &h->qubit_node))) return bail(rc);
+  rc = configure_paths(h);
+  if (rc != FPB_OK && rc != FPB_ERR_UNSUPPORTED) return bail(rc);
+  // FPB_ERR_UNSUPPORTED: the handle still serves the noise / syndrome stages
+  *out = h;
+  return FPB_OK;
+}
+
+int fpb_destroy(fpb_handle* h) {
+  if (!h) return FPB_OK;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  cudaFree(h->adj_indptr); cudaFree(h->adj_indices); cudaFree(h->adj_vals); cudaFree(h->qubit_node);
+  for (auto& cx : h->cx) {
+    cudaFree(cx.cube_qubit); cudaFree(cx.ninfo); cudaFree(cx.sbase); cudaFree(cx.slot_qubit);
+    cudaFree(cx.low_cube); cudaFree(cx.low_slot); cudaFree(cx.high_cube); cudaFree(cx.high_slot);
+    cx.parity.release(); cx.odd_count.release(); cx.odd_fixed.release(); cx.odd_ids.release();
+    cx.odd_off.release(); cx.pair_off.release(); cx.pair_len.release(); cx.bnd_len.release();
+    cx.bnd_side.release();
+  }
+  h->x.release(); h->hom.release(); h->weights.release(); h->state.release(); h->bits.release();
+  h->flips.release(); h->item_off.release(); h->counter.release(); h->totals.release();
+  h->q_trial.release(); h->q_cx.release(); h->q_src.release(); h->q_dst.release();
+  if (h->totals_host) cudaFreeHost(h->totals_host);
+  for (auto& ev : h->ev)
+    if (ev) cudaEventDestroy(ev);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return FPB_OK;
+}
+
+int fpb_run_injected(fpb_handle* h, int64_t n_trials, const double* x, const uint8_t* state, int on_device,
+                     int stage) {
+  if (!h || !x || !state) return fail(FPB_ERR_ARG, "null argument");
+  CK(cudaSetDevice(h->device));
+  int rc = ensure_batch(h, n_trials);
+  if (rc) return rc;
+  const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  CK(cudaMemcpyAsync(h->x.p, x, (size_t)n_trials * 2 * h->N * sizeof(double), kind, h->stream));
+  CK(cudaMemcpyAsync(h->state.p, state, (size_t)n_trials * h->N, kind, h->stream));
+  h->have_rng = false;
+  return run_pipeline(h, n_trials, stage, false, 0, 0);
+}
+
+int fpb_run_rng(fpb_handle* h, uint64_t seed, int64_t first_trial, int64_t n_trials, int stage) {
+  if (!h) return fail(FPB_ERR_ARG, "null handle");
+  if (first_trial < 0) return fail(FPB_ERR_ARG, "first_trial must be >= 0");
+  CK(cudaSetDevice(h->device));
+  int rc = ensure_batch(h, n_trials);
+  if (rc) return rc;
+  h->have_rng = true;
+  return run_pipeline(h, n_trials, stage, true, seed, first_trial);
+}
+
+int fpb_get_sizes(fpb_handle* h, fpb_sizes* out) {
+  if (!h || !out) return fail(FPB_ERR_ARG, "null argument");
+  memset(out, 0, sizeof *out);
+  out->n_trials = h->T;
+  out->n_complex = h->ncx;
+  out->total_qubits = h->Qtot;
+  for (int c = 0; c < h->ncx; ++c) {
+    out->total_odd[c] = h->cx[c].total_odd;
+    out->total_pairs[c] = h->last_stage >= FPB_STAGE_GRAPH ? h->cx[c].total_pairs : 0;
+  }
+  return FPB_OK;
+}
+
+int fpb_device_outputs(fpb_handle* h, fpb_outputs* out) {
+  if (!h || !out) return fail(FPB_ERR_ARG, "null argument");
+  if (h->T <= 0) return fail(FPB_ERR_STATE, "no run yet");
+  memset(out, 0, sizeof *out);
+  out->hom = h->hom.p; out->bits = h->bits.p; out->weights = h->weights.p;
+  out->state = h->state.p; out->x = h->x.p;
+  for (int c = 0; c < h->ncx; ++c) {
+    ComplexHost& cx = h->cx[c];
+    if (h->last_stage >= FPB_STAGE_SYNDROME) {
+      out->parity[c] = cx.parity.p; out->odd_count[c] = cx.odd_count.p; out->odd_ids[c] = cx.odd_ids.p;
+    }
+    if (h->last_stage >= FPB_STAGE_GRAPH) {
+      out->pair_len[c] = cx.pair_len.p;
+      if (cx.n_low > 0) { out->bnd_len[c] = cx.bnd_len.p; out->bnd_side[c] = cx.bnd_side.p; }
+    }
+  }
+  return FPB_OK;
+}
+
+int fpb_fetch(fpb_handle* h, const fpb_outputs* dst, int on_device) {
+  if (!h || !dst) return fail(FPB_ERR_ARG, "null argument");
+  if (h->T <= 0) return fail(FPB_ERR_STATE, "no run yet");
+  CK(cudaSetDevice(h->device));
+  const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  cudaStream_t st = h->stream;
+  const size_t T = (size_t)h->T;
+#define COPY(dstp, srcp, count, type)                                                             \
+  if ((dstp) && (count) > 0) CK(cudaMemcpyAsync((dstp), (srcp), (size_t)(count) * sizeof(type), kind, st))
+  COPY(dst->hom, h->hom.p, T * h->Qtot, double);
+  COPY(dst->bits, h->bits.p, T * h->bit_words, uint32_t);
+  COPY(dst->weights, h->weights.p, T * h->Qtot, double);
+  COPY(dst->state, h->state.p, T * h->N, uint8_t);
+  COPY(dst->x, h->x.p, T * 2 * h->N, double);
+  for (int c = 0; c < h->ncx; ++c) {
+    ComplexHost& cx = h->cx[c];
+    const bool syn = h->last_stage >= FPB_STAGE_SYNDROME, gr = h->last_stage >= FPB_STAGE_GRAPH;
+    if ((dst->parity[c] || dst->odd_count[c] || dst->odd_ids[c]) && !syn)
+      return fail(FPB_ERR_STATE, "syndrome outputs requested but the last run stopped before that stage");
+    if ((dst->pair_len[c] || dst->bnd_len[c] || dst->bnd_side[c]) && !gr)
+      return fail(FPB_ERR_STATE, "graph outputs requested but the last run stopped before that stage");
+    COPY(dst->parity[c], cx.parity.p, T * cx.par_words, uint32_t);
+    COPY(dst->odd_count[c], cx.odd_count.p, T, int32_t);
+    COPY(dst->odd_ids[c], cx.odd_ids.p, cx.total_odd, int32_t);
+    COPY(dst->pair_len[c], cx.pair_len.p, cx.total_pairs, double);
+    if (cx.n_low > 0) {
+      COPY(dst->bnd_len[c], cx.bnd_len.p, cx.total_odd, double);
+      COPY(dst->bnd_side[c], cx.bnd_side.p, cx.total_odd, uint8_t);
+    }
+  }
+#undef COPY
+  CK(cudaStreamSynchronize(st));
+  return FPB_OK;
+}
+
+int fpb_get_timings(fpb_handle* h, fpb_timings* out) {
+  if (!h || !out) return fail(FPB_ERR_ARG, "null argument");
+  *out = h->tm;
+  return FPB_OK;
+}
+
+int fpb_synchronize(fpb_handle* h) {
+  if (!h) return fail(FPB_ERR_ARG, "null handle");
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  return FPB_OK;
+}
+
+int fpb_paths_toggle(fpb_handle* h, int64_t n_queries, const int32_t* trial, const int32_t* cx_id,
+                     const int32_t* src, const int32_t* dst, uint32_t* flips_host) {
+  if (!h || !flips_host) return fail(FPB_ERR_ARG, "null argument");
+  if (h->last_stage < FPB_STAGE_GRAPH) return fail(FPB_ERR_STATE, "fpb_paths_toggle needs a completed graph-stage run");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  int rc;
+  const size_t nflip = (size_t)h->T * h->bit_words;
+  if ((rc = h->flips.ensure(nflip))) return rc;
+  CK(cudaMemsetAsync(h->flips.p, 0, nflip * sizeof(uint32_t), st));
+  if (n_queries > 0) {
+    if (!trial || !cx_id || !src || !dst) return fail(FPB_ERR_ARG, "null query array");
+    // validate on the host: indices must address odd cubes of the last run
+    std::vector<int> counts[FPB_MAX_COMPLEX];
+    for (int c = 0; c < h->ncx; ++c) {
+      counts[c].resize((size_t)h->T);
+      CK(cudaMemcpyAsync(counts[c].data(), h->cx[c].odd_count.p, (size_t)h->T * sizeof(int), cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    for (int64_t i = 0; i < n_queries; ++i) {
+      if (trial[i] < 0 || trial[i] >= h->T || cx_id[i] < 0 || cx_id[i] >= h->ncx) return fail(FPB_ERR_ARG, "query trial / complex out of range");
+      const int K = counts[cx_id[i]][trial[i]];
+      if (src[i] < 0 || src[i] >= K || dst[i] >= K || dst[i] < -1 || dst[i] == src[i]) return fail(FPB_ERR_ARG, "query endpoint out of range");
+      if (dst[i] == -1 && h->cx[cx_id[i]].n_low == 0) return fail(FPB_ERR_ARG, "connector query on a complex without boundary points");
+    }
+    if ((rc = h->q_trial.ensure((size_t)n_queries))) return rc;
+    if ((rc = h->q_cx.ensure((size_t)n_queries))) return rc;
+    if ((rc = h->q_src.ensure((size_t)n_queries))) return rc;
+    if ((rc = h->q_dst.ensure((size_t)n_queries))) return rc;
+    CK(cudaMemcpyAsync(h->q_trial.p, trial, (size_t)n_queries * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->q_cx.p, cx_id, (size_t)n_queries * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->q_src.p, src, (size_t)n_queries * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->q_dst.p, dst, (size_t)n_queries * sizeof(int), cudaMemcpyHostToDevice, st));
+    PathsParams pp;
+    memset(&pp, 0, sizeof pp);
+    pp.n_complex = h->ncx; pp.T = (int)h->T; pp.Qtot = h->Qtot;
+    pp.S_max = h->S_max; pp.slots_max = h->slots_max;
+    pp.step_factor = h->step_factor;
+    pp.weights = h->weights.p;
+    for (int c = 0; c < h->ncx; ++c) pp.cx[c] = make_dev(h->cx[c]);
+    pp.n_queries = (int)n_queries;
+    pp.q_trial = h->q_trial.p; pp.q_cx = h->q_cx.p; pp.q_src = h->q_src.p; pp.q_dst = h->q_dst.p;
+    pp.flips = h->flips.p; pp.bit_words = h->bit_words;
+    int max_optin = 0;
+    CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+    const size_t per_warp = (size_t)h->slots_max * 8 + paths_warp_bytes(h->S_max);
+    int warps = (int)(((size_t)max_optin - 1024) / per_warp);
+    if (warps < 1) return fail(FPB_ERR_UNSUPPORTED, "lattice too large for the path-toggle kernel");
+    if (warps > 8) warps = 8;
+    const size_t smem = (size_t)warps * per_warp;
+    CK(cudaFuncSetAttribute(k_path_toggle, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long long grid = (n_queries + warps - 1) / warps;
+    const long long cap = (long long)h->sm_count * 4;
+    if (grid > cap) grid = cap;
+    k_path_toggle<<<(unsigned)grid, warps * 32, smem, st>>>(pp);
+    CK(cudaGetLastError());
+  }
+  CK(cudaMemcpyAsync(flips_host, h->flips.p, nflip * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return FPB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,282 @@
+"""Batched trial engine: the Python face of the C ABI (``include/fpb.h``).
+
+One ``TrialEngine`` = one code instance + noise parameters + weight options on
+one GPU.  It runs batches of independent Monte-Carlo trials through
+noise -> bits -> weights -> syndrome -> matching graph on the device and hands
+back NumPy arrays.  The reference-compatible classes in ``codes.py``,
+``noise.py``, ``decoder.py`` and ``simulations.py`` are thin layers over this.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import numpy as np
+
+from . import _lib
+from .lattice import LatticeTables
+
+
+def _ptr(a: np.ndarray, typ):
+    return a.ctypes.data_as(typ)
+
+
+@dataclass
+class ComplexBatch:
+    """Per-complex results of a batch (ragged arrays are concatenated over
+    trials with ``*_off`` offsets)."""
+
+    parity: Optional[np.ndarray] = None  # uint8[T, S]
+    odd_count: Optional[np.ndarray] = None  # int32[T]
+    odd_off: Optional[np.ndarray] = None  # int64[T + 1]
+    odd_ids: Optional[np.ndarray] = None  # int32[sum K]
+    pair_off: Optional[np.ndarray] = None  # int64[T + 1]
+    pair_len: Optional[np.ndarray] = None  # float64[sum K(K-1)/2]
+    bnd_len: Optional[np.ndarray] = None  # float64[sum K]
+    bnd_side: Optional[np.ndarray] = None  # uint8[sum K]
+
+    def odd(self, t: int) -> np.ndarray:
+        return self.odd_ids[self.odd_off[t] : self.odd_off[t + 1]]
+
+    def pairs(self, t: int) -> np.ndarray:
+        return self.pair_len[self.pair_off[t] : self.pair_off[t + 1]]
+
+    def boundary(self, t: int):
+        sl = slice(self.odd_off[t], self.odd_off[t + 1])
+        return self.bnd_len[sl], self.bnd_side[sl]
+
+
+@dataclass
+class TrialBatch:
+    n_trials: int
+    stage: int
+    hom: Optional[np.ndarray] = None  # float64[T, Qtot]
+    bits: Optional[np.ndarray] = None  # uint8[T, Qtot]
+    weights: Optional[np.ndarray] = None  # float64[T, Qtot]
+    state: Optional[np.ndarray] = None  # uint8[T, N]
+    x: Optional[np.ndarray] = None  # float64[T, 2N]
+    complexes: Optional[Dict[str, ComplexBatch]] = None
+    timings: Optional[dict] = None
+
+
+class TrialEngine:
+    """Owns an ``fpb_handle``.  ``weight_opts`` follows the reference's
+    ``weight_options`` dict (``decoders/decoder.py:31-56``): ``method``
+    ("uniform" | "blueprint"), ``integer``, ``multiplier``, ``delta``."""
+
+    def __init__(
+        self,
+        lat: LatticeTables,
+        delta: float,
+        p_swap=None,
+        weight_opts: Optional[dict] = None,
+        mode: str = "compat",
+        chain_len: int = 0,
+        device: int = 0,
+        delta_step: float = 0.0,
+    ):
+        lib = _lib.load()
+        self._lib = lib
+        self.lat = lat
+        self.delta = float(delta)
+        self.p_swap = float(p_swap or 0.0)
+        wo = {"method": "uniform", "integer": False, "multiplier": 1}
+        wo.update(weight_opts or {})
+        if wo["method"] not in ("uniform", "blueprint"):
+            raise ValueError(f"unknown weight method {wo['method']!r}")
+        if mode not in ("compat", "fresh"):
+            raise ValueError("mode must be 'compat' or 'fresh'")
+        self.weight_opts = wo
+        self.mode = mode
+        self.device = device
+        self.ec = list(lat.ec)
+        self._keep = []  # arrays referenced by the config while fpb_create runs
+
+        cfg = _lib.Config()
+        cfg.abi_version = _lib.FPB_ABI_VERSION
+        cfg.device = device
+        cfg.n_nodes = lat.N
+
+        def keep(a, dtype):
+            a = np.ascontiguousarray(a, dtype=dtype)
+            self._keep.append(a)
+            return a
+
+        cfg.adj_indptr = _ptr(keep(lat.adj_indptr, np.int32), _lib._i32p)
+        cfg.adj_indices = _ptr(keep(lat.adj_indices, np.int32), _lib._i32p)
+        cfg.adj_vals = _ptr(keep(lat.adj_vals, np.int8), _lib._i8p)
+        cfg.n_complex = len(lat.ec)
+        self.q_off = {}
+        off = 0
+        for i, ec in enumerate(lat.ec):
+            ct = lat.complexes[ec]
+            d = cfg.complex_[i]
+            d.n_cubes = ct.S
+            d.n_qubits = ct.Q
+            d.qubit_node = _ptr(keep(ct.qubits, np.int32), _lib._i32p)
+            d.cube_qubit = _ptr(keep(ct.cube_qubit, np.int32), _lib._i32p)
+            d.ninfo = _ptr(keep(ct.ninfo, np.uint16), _lib._u16p)
+            d.sbase = _ptr(keep(ct.sbase, np.int32), _lib._i32p)
+            for j, v in enumerate(np.asarray(ct.d_off, np.int32).ravel()):
+                d.d_off[j] = int(v)
+            for j, v in enumerate(np.asarray(ct.s_off, np.int32).ravel()):
+                d.s_off[j] = int(v)
+            d.n_slots = ct.n_slots
+            d.slot_qubit = _ptr(keep(ct.slot_qubit, np.int32), _lib._i32p)
+            d.n_low = len(ct.low_seed_cube)
+            d.low_cube = _ptr(keep(ct.low_seed_cube, np.int32), _lib._i32p)
+            d.low_slot = _ptr(keep(ct.low_seed_slot, np.int32), _lib._i32p)
+            d.n_high = len(ct.high_seed_cube)
+            d.high_cube = _ptr(keep(ct.high_seed_cube, np.int32), _lib._i32p)
+            d.high_slot = _ptr(keep(ct.high_seed_slot, np.int32), _lib._i32p)
+            self.q_off[ec] = off
+            off += ct.Q
+        self.Qtot = off
+        self.bit_words = (off + 31) // 32
+        cfg.delta = self.delta
+        cfg.p_swap = self.p_swap
+        cfg.weight_method = _lib.WEIGHT_BLUEPRINT if wo["method"] == "blueprint" else _lib.WEIGHT_UNIFORM
+        cfg.weight_delta = float(wo.get("delta") or self.delta)
+        cfg.weight_integer = int(bool(wo["integer"]))
+        cfg.weight_multiplier = float(wo["multiplier"])
+        cfg.label_mode = _lib.MODE_FRESH if mode == "fresh" else _lib.MODE_COMPAT
+        cfg.chain_len = int(chain_len)
+        cfg.delta_step = float(delta_step)
+        handle = C.c_void_p()
+        _lib.check(lib.fpb_create(C.byref(cfg), C.byref(handle)))
+        self._h = handle
+        self._keep = []
+
+    # ------------------------------------------------------------------ lifecycle
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.fpb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ runs
+    def run_injected(self, x: np.ndarray, state: np.ndarray, stage: int = _lib.STAGE_GRAPH,
+                     fetch: bool = True) -> TrialBatch:
+        """Run trials on injected draws ``x`` [T, 2N] and labels ``state`` [T, N]."""
+        x = np.ascontiguousarray(x, np.float64)
+        state = np.ascontiguousarray(state, np.uint8)
+        if x.ndim != 2 or x.shape[1] != 2 * self.lat.N:
+            raise ValueError(f"x must have shape [T, {2 * self.lat.N}]")
+        if state.shape != (x.shape[0], self.lat.N):
+            raise ValueError(f"state must have shape [T, {self.lat.N}]")
+        T = x.shape[0]
+        _lib.check(self._lib.fpb_run_injected(self._h, T, x.ctypes.data, state.ctypes.data, 0, stage))
+        return self.fetch(stage) if fetch else TrialBatch(T, stage, timings=self.timings())
+
+    def run_rng(self, seed: int, first_trial: int, n_trials: int, stage: int = _lib.STAGE_GRAPH,
+                fetch: bool = True, want_draws: bool = False) -> TrialBatch:
+        """Run trials ``[first_trial, first_trial + n_trials)`` of the Philox stream ``seed``."""
+        _lib.check(self._lib.fpb_run_rng(self._h, seed & (2**64 - 1), first_trial, n_trials, stage))
+        return self.fetch(stage, want_draws=want_draws) if fetch else TrialBatch(
+            n_trials, stage, timings=self.timings())
+
+    def sizes(self) -> _lib.Sizes:
+        s = _lib.Sizes()
+        _lib.check(self._lib.fpb_get_sizes(self._h, C.byref(s)))
+        return s
+
+    def timings(self) -> dict:
+        t = _lib.Timings()
+        _lib.check(self._lib.fpb_get_timings(self._h, C.byref(t)))
+        return {name: getattr(t, name) for name, _ in _lib.Timings._fields_}
+
+    def device_outputs(self) -> _lib.Outputs:
+        o = _lib.Outputs()
+        _lib.check(self._lib.fpb_device_outputs(self._h, C.byref(o)))
+        return o
+
+    def fetch(self, stage: int = _lib.STAGE_GRAPH, want_draws: bool = False, want_noise: bool = True) -> TrialBatch:
+        """Copy the last run's results to host arrays."""
+        s = self.sizes()
+        T = int(s.n_trials)
+        N, Q = self.lat.N, self.Qtot
+        out = _lib.Outputs()
+        batch = TrialBatch(T, stage)
+        packed_bits = None
+        if want_noise:
+            batch.hom = np.empty((T, Q), np.float64)
+            batch.weights = np.empty((T, Q), np.float64)
+            packed_bits = np.empty((T, self.bit_words), np.uint32)
+            out.hom = _ptr(batch.hom, _lib._f64p)
+            out.weights = _ptr(batch.weights, _lib._f64p)
+            out.bits = _ptr(packed_bits, _lib._u32p)
+        if want_draws:
+            batch.state = np.empty((T, N), np.uint8)
+            batch.x = np.empty((T, 2 * N), np.float64)
+            out.state = _ptr(batch.state, _lib._u8p)
+            out.x = _ptr(batch.x, _lib._f64p)
+        packed_par: List[Optional[np.ndarray]] = []
+        batch.complexes = {}
+        for i, ec in enumerate(self.ec):
+            ct = self.lat.complexes[ec]
+            cb = ComplexBatch()
+            pp = None
+            if stage >= _lib.STAGE_SYNDROME:
+                pw = (ct.S + 31) // 32
+                pp = np.empty((T, pw), np.uint32)
+                cb.odd_count = np.empty(T, np.int32)
+                cb.odd_ids = np.empty(int(s.total_odd[i]), np.int32)
+                out.parity[i] = _ptr(pp, _lib._u32p)
+                out.odd_count[i] = _ptr(cb.odd_count, _lib._i32p)
+                out.odd_ids[i] = _ptr(cb.odd_ids, _lib._i32p)
+            if stage >= _lib.STAGE_GRAPH:
+                cb.pair_len = np.empty(int(s.total_pairs[i]), np.float64)
+                out.pair_len[i] = _ptr(cb.pair_len, _lib._f64p)
+                if ct.has_boundary:
+                    cb.bnd_len = np.empty(int(s.total_odd[i]), np.float64)
+                    cb.bnd_side = np.empty(int(s.total_odd[i]), np.uint8)
+                    out.bnd_len[i] = _ptr(cb.bnd_len, _lib._f64p)
+                    out.bnd_side[i] = _ptr(cb.bnd_side, _lib._u8p)
+                else:
+                    cb.bnd_len = np.empty(0, np.float64)
+                    cb.bnd_side = np.empty(0, np.uint8)
+            packed_par.append(pp)
+            batch.complexes[ec] = cb
+        _lib.check(self._lib.fpb_fetch(self._h, C.byref(out), 0))
+        if packed_bits is not None:
+            batch.bits = unpack_bits(packed_bits, Q)
+        for i, ec in enumerate(self.ec):
+            cb = batch.complexes[ec]
+            if packed_par[i] is not None:
+                cb.parity = unpack_bits(packed_par[i], self.lat.complexes[ec].S)
+                K = cb.odd_count.astype(np.int64)
+                cb.odd_off = np.concatenate([[0], np.cumsum(K)]).astype(np.int64)
+                cb.pair_off = np.concatenate([[0], np.cumsum(K * (K - 1) // 2)]).astype(np.int64)
+        batch.timings = self.timings()
+        return batch
+
+    def paths_toggle(self, trial, cx, src, dst) -> np.ndarray:
+        """XOR-toggle the qubits on the shortest paths of the given (trial,
+        complex, odd-index src, odd-index dst | -1) queries of the last run.
+        Returns uint8[T, Qtot] flips."""
+        s = self.sizes()
+        T = int(s.n_trials)
+        trial = np.ascontiguousarray(trial, np.int32)
+        cx = np.ascontiguousarray(cx, np.int32)
+        src = np.ascontiguousarray(src, np.int32)
+        dst = np.ascontiguousarray(dst, np.int32)
+        n = len(trial)
+        flips = np.zeros((T, self.bit_words), np.uint32)
+        _lib.check(self._lib.fpb_paths_toggle(
+            self._h, n, _ptr(trial, _lib._i32p), _ptr(cx, _lib._i32p), _ptr(src, _lib._i32p),
+            _ptr(dst, _lib._i32p), _ptr(flips, _lib._u32p)))
+        return unpack_bits(flips, self.Qtot)
+
+
+def unpack_bits(words: np.ndarray, n: int) -> np.ndarray:
+    """uint32[T, W] (LSB-first) -> uint8[T, n]."""
+    T = words.shape[0]
+    b = np.unpackbits(words.view(np.uint8).reshape(T, -1), axis=1, bitorder="little")
+    return np.ascontiguousarray(b[:, :n])

@@ -1,0 +1,190 @@
+/*
+ * fpb.h - C ABI of the B200 Monte-Carlo error-correction trial backend.
+ *
+ * The reference (XanaduAI/flamingpy) has no C ABI for this path: its plug-in
+ * surface is Python (`CVLayer.apply_noise`, `assign_weights`,
+ * `MatchingGraph.with_edges_from`) plus one pybind11 pattern
+ * (`flamingpy/cpp/lemonpy.cpp:50-84`: C-contiguous arrays in, freshly owned
+ * arrays out, errors as exceptions).  This header is the boundary a maintainer
+ * binds instead (INTEGRATION.md shows the ctypes / pybind11 stubs).  Each entry
+ * point names the reference interface it replaces; paths are relative to the
+ * reference root.
+ *
+ * Conventions: plain pointers and sizes, caller-owned buffers, every function
+ * returns 0 on success or a negative error code with the message available
+ * from fpb_last_error().  A handle owns one CUDA device, one stream and its
+ * device buffers; it is thread-compatible (one thread at a time per handle).
+ * There is no CPU fallback: fpb_create fails if no CUDA device is usable.
+ */
+#ifndef FPB_H
+#define FPB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FPB_ABI_VERSION 1
+#define FPB_MAX_COMPLEX 2
+
+/* error codes */
+#define FPB_OK 0
+#define FPB_ERR_ARG (-1)
+#define FPB_ERR_CUDA (-2)
+#define FPB_ERR_NOMEM (-3)
+#define FPB_ERR_STATE (-4)
+#define FPB_ERR_UNSUPPORTED (-5)
+
+/* weight methods: assign_weights(method=...) flamingpy/decoders/decoder.py:58-116 */
+#define FPB_WEIGHT_UNIFORM 0
+#define FPB_WEIGHT_BLUEPRINT 1
+
+/* label modes for the device RNG (SURVEY.md finding 0.3) */
+#define FPB_MODE_COMPAT 0 /* one reused CVLayer per chain: GKP_t = V \ (p_t U GKP_{t-1}) */
+#define FPB_MODE_FRESH 1  /* a new CVLayer per trial: every non-p node is a noisy GKP state */
+
+/* node states in `state` arrays */
+#define FPB_STATE_SILENT 0
+#define FPB_STATE_GKP 1
+#define FPB_STATE_P 2
+
+/* stages to run */
+#define FPB_STAGE_NOISE 1    /* homodyne values, bits, weights */
+#define FPB_STAGE_SYNDROME 2 /* + stabilizer parities and odd-cube lists */
+#define FPB_STAGE_GRAPH 3    /* + matching-graph lengths */
+
+/* One error complex = one stabilizer graph: a 3-D box of cubes in the order of
+ * `SurfaceCode.{ec}_stabilizers` (flamingpy/codes/surface_code.py:396-428), each
+ * with six face slots (-x,+x,-y,+y,-z,+z).  Replaces StabilizerGraph.__init__ /
+ * connect_nodes (codes/graphs/stabilizer_graph.py:72-88,289-302). */
+typedef struct fpb_complex_desc {
+  int32_t n_cubes;           /* S */
+  int32_t n_qubits;          /* Q: syndrome qubits of this complex */
+  const int32_t* qubit_node; /* [Q] lattice node index of each syndrome qubit, ascending */
+  const int32_t* cube_qubit; /* [S*6] local qubit id on each face, -1 if absent */
+  const uint16_t* ninfo;     /* [S] six 2-bit face kinds: 0 regular, 1 periodic wrap, 2 none, 3 LOW/HIGH */
+  const int32_t* sbase;      /* [S] weight-slot base of each cube */
+  int32_t d_off[12];         /* [6][2] cube-index offset per direction for kind 0 / 1 */
+  int32_t s_off[12];         /* [6][2] weight-slot offset per direction for kind 0 / 1 */
+  int32_t n_slots;
+  const int32_t* slot_qubit; /* [n_slots] local qubit id held by each weight slot, -1 unused */
+  int32_t n_low;             /* cubes adjacent to the LOW connector (0 without boundary points) */
+  const int32_t* low_cube;   /* [n_low] */
+  const int32_t* low_slot;   /* [n_low] weight slot of the boundary qubit */
+  int32_t n_high;
+  const int32_t* high_cube;
+  const int32_t* high_slot;
+} fpb_complex_desc;
+
+/* Static description of SurfaceCode + CVLayer + weight options.
+ * Replaces SurfaceCode.__init__ tables (codes/surface_code.py:309-371),
+ * CVLayer.__init__ (noise/cv.py:70-105) and the weight_options dict of
+ * correct() (decoders/decoder.py:227-273). */
+typedef struct fpb_config {
+  int32_t abi_version; /* FPB_ABI_VERSION */
+  int32_t device;      /* CUDA device ordinal */
+  int32_t n_nodes;     /* N */
+  const int32_t* adj_indptr;  /* [N+1] CSR of EGraph.adj_generator (codes/graphs/egraph.py:157-178) */
+  const int32_t* adj_indices; /* ascending within a row */
+  const int8_t* adj_vals;     /* edge weight (+-1 polarity) */
+  int32_t n_complex;          /* 1, or 2 for ec="both" */
+  fpb_complex_desc complex_[FPB_MAX_COMPLEX];
+  double delta;         /* CVLayer(delta=...) */
+  double p_swap;        /* CVLayer(p_swap=...); 0 = none */
+  int32_t weight_method; /* FPB_WEIGHT_* */
+  double weight_delta;  /* weight_options["delta"] */
+  int32_t weight_integer;   /* weight_options["integer"] */
+  double weight_multiplier; /* weight_options["multiplier"] */
+  int32_t label_mode;   /* FPB_MODE_* (device RNG only) */
+  int64_t chain_len;    /* trials per reused-layer chain in compat mode; <=0: one chain */
+  double delta_step;    /* shortest-path bucket width in units of the trial's minimum weight; <=0: default */
+} fpb_config;
+
+typedef struct fpb_handle fpb_handle;
+
+/* Result sizes of the last run (per complex c). */
+typedef struct fpb_sizes {
+  int64_t n_trials;
+  int32_t n_complex;
+  int64_t total_qubits;            /* sum of Q over complexes = row length of hom / weights */
+  int64_t total_odd[FPB_MAX_COMPLEX];   /* sum over trials of K */
+  int64_t total_pairs[FPB_MAX_COMPLEX]; /* sum over trials of K(K-1)/2 */
+} fpb_sizes;
+
+/* Host (or device) destinations for fpb_fetch; any pointer may be NULL to skip it.
+ * Row-major, trial-major.  Qubit columns are complex 0's qubits then complex 1's. */
+typedef struct fpb_outputs {
+  double* hom;        /* [T][Qtot]  CVLayer.measure_hom hom_val_p (noise/cv.py:161-217) */
+  uint32_t* bits;     /* [T][ceil(Qtot/32)] bit-packed bit_val, LSB first (noise/cv.py:147-158) */
+  double* weights;    /* [T][Qtot]  node attribute "weight" (decoders/decoder.py:58-116) */
+  uint8_t* state;     /* [T][N]     FPB_STATE_* labels used (noise/cv.py:121-140) */
+  double* x;          /* [T][2N]    raw quadrature draws (noise/cv.py:205) */
+  uint32_t* parity[FPB_MAX_COMPLEX];  /* [T][ceil(S/32)] Stabilizer.parity (codes/stabilizer.py:43-55) */
+  int32_t* odd_count[FPB_MAX_COMPLEX]; /* [T] K */
+  int32_t* odd_ids[FPB_MAX_COMPLEX];   /* [total_odd] odd cubes, stabilizer order, trials concatenated */
+  double* pair_len[FPB_MAX_COMPLEX];   /* [total_pairs] per trial the packed upper triangle (a<b, row-major)
+                                          of shortest-path lengths (decoders/mwpm/matching.py:125-142) */
+  double* bnd_len[FPB_MAX_COMPLEX];    /* [total_odd] length to the nearer connector (matching.py:144-173) */
+  uint8_t* bnd_side[FPB_MAX_COMPLEX];  /* [total_odd] 0 low, 1 high */
+} fpb_outputs;
+
+/* Per-stage device times of the last run, CUDA events on the handle's stream. */
+typedef struct fpb_timings {
+  float gen_ms;      /* Philox label + quadrature generation (device RNG runs only) */
+  float noise_ms;    /* entangle + bin + weights */
+  float syndrome_ms; /* parity + odd-list compaction + offsets */
+  float graph_ms;    /* shortest paths + matching-graph assembly */
+  float total_ms;
+  int32_t launches;  /* kernels launched by the last run */
+  int32_t graph_ctas;
+  int32_t graph_warps_per_cta;
+  int32_t graph_smem_bytes;
+} fpb_timings;
+
+const char* fpb_last_error(void);
+int fpb_abi_version(void);
+/* number of visible CUDA devices, or a negative error code */
+int fpb_device_count(void);
+
+/* Build a handle: uploads the static tables.  Replaces constructing
+ * SurfaceCode + CVLayer (codes/surface_code.py:309, noise/cv.py:70). */
+int fpb_create(const fpb_config* cfg, fpb_handle** out);
+int fpb_destroy(fpb_handle* h);
+
+/* Injected-noise trials: `x` [T][2N] are the draws rng.normal(0, sigma) would
+ * return (q block then p block) and `state` [T][N] the FPB_STATE_* labels.
+ * Replaces CVLayer.apply_noise after sampling + assign_weights + MatchingGraph
+ * construction (noise/cv.py:205-217,147-158; decoders/decoder.py:31-119;
+ * decoders/mwpm/matching.py:97-173).  `on_device` != 0: pointers are device
+ * pointers on the handle's device.  `stage` = FPB_STAGE_*. */
+int fpb_run_injected(fpb_handle* h, int64_t n_trials, const double* x, const uint8_t* state,
+                     int on_device, int stage);
+
+/* Device-RNG trials [first_trial, first_trial + n_trials): Philox4x32-10 keyed by
+ * `seed` with counter (trial, node, slot), so results do not depend on batching
+ * or on the number of GPUs.  Replaces the body of ec_mc_trial up to the
+ * matching graph (flamingpy/simulations.py:46-59). */
+int fpb_run_rng(fpb_handle* h, uint64_t seed, int64_t first_trial, int64_t n_trials, int stage);
+
+int fpb_get_sizes(fpb_handle* h, fpb_sizes* out);
+/* Copy results of the last run into caller buffers (host if on_device == 0). */
+int fpb_fetch(fpb_handle* h, const fpb_outputs* dst, int on_device);
+/* Raw device pointers of the last run's result buffers (valid until the next run). */
+int fpb_device_outputs(fpb_handle* h, fpb_outputs* out);
+int fpb_get_timings(fpb_handle* h, fpb_timings* out);
+int fpb_synchronize(fpb_handle* h);
+
+/* Correction paths for matched pairs of the last run.  Query i asks, in trial
+ * trial[i] and complex cx[i], for the shortest path from odd cube src[i] to
+ * odd cube dst[i] (dst >= 0), or to its nearer connector (dst == -1).  The local
+ * qubit ids crossed are XOR-toggled into flips [T][ceil(Qtot/32)] (bit-packed,
+ * same layout as bits).  Replaces edge_path + the common_vertex loop of
+ * mwpm_decoder (decoders/mwpm/algos.py:88-95). */
+int fpb_paths_toggle(fpb_handle* h, int64_t n_queries, const int32_t* trial, const int32_t* cx,
+                     const int32_t* src, const int32_t* dst, uint32_t* flips_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FPB_H */
