@@ -1,0 +1,392 @@
+#!/usr/bin/env python
+"""Benchmark of the Monte-Carlo EC trial path (noise -> weights -> syndrome -> matching graph).
+
+    python bench.py --gpus N --steps K --warmup W            # B200 arm
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm (oracle port on host cores)
+
+One step = one batch of `--batch` independent trials per GPU pushed through the whole hot path.
+Prints one JSON line (rank 0).  See DESIGN.md "Measurement" for what every field means.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SEED = 20261019
+
+WORKLOADS = {
+    # BASELINE.json configs[2]: the d=13 configuration the metric is quoted on
+    "d13_periodic_both": dict(distance=13, ec="both", boundaries="periodic", delta=0.09, p_swap=0.0,
+                              weight_opts={"method": "blueprint", "delta": 0.09}),
+    # BASELINE.json configs[1]
+    "d9_open_primal": dict(distance=9, ec="primal", boundaries="open", delta=0.08, p_swap=0.5,
+                           weight_opts={"method": "blueprint", "delta": 0.08}),
+    "d13_open_primal": dict(distance=13, ec="primal", boundaries="open", delta=0.09, p_swap=0.0,
+                            weight_opts={"method": "blueprint", "delta": 0.09}),
+    "d3_open_primal": dict(distance=3, ec="primal", boundaries="open", delta=0.09, p_swap=0.25,
+                           weight_opts={"method": "blueprint", "delta": 0.09}),
+}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            with open(p) as f:
+                return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.idx = device_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [s.strip() for s in line.split(",")]
+                if len(f) < 8:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                     f[4:8]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
+                       samples=len(sm))
+        return out
+
+
+def algorithmic_bytes(lat, n_trials, total_odd, total_pairs):
+    """B_trial = 32 Q + (2N + 2Q + 2S)/8 + 4 K + 8 [K(K-1)/2 + K_b],
+    summed exactly over the trials of a run (Q, S, K over both complexes, N once)."""
+    Q = sum(lat.complexes[e].Q for e in lat.ec)
+    S = sum(lat.complexes[e].S for e in lat.ec)
+    static = n_trials * (32 * Q + (2 * lat.N + 2 * Q + 2 * S) / 8.0)
+    dyn = 0.0
+    for i, e in enumerate(lat.ec):
+        kb = total_odd[i] if lat.complexes[e].has_boundary else 0
+        dyn += 4 * total_odd[i] + 8 * (total_pairs[i] + kb)
+    return static + dyn
+
+
+def paths_kernel_bytes(lat, n_trials, total_odd, total_pairs):
+    """Algorithmic bytes of the matching-graph kernel alone: it reads each trial's weights
+    (8 Q) and odd list (4 K) once and writes the lengths 8 [K(K-1)/2 + K_b] once."""
+    Q = sum(lat.complexes[e].Q for e in lat.ec)
+    b = n_trials * 8.0 * Q
+    for i, e in enumerate(lat.ec):
+        kb = total_odd[i] if lat.complexes[e].has_boundary else 0
+        b += 4 * total_odd[i] + 8 * (total_pairs[i] + kb)
+    return b
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# --------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on host cores
+# --------------------------------------------------------------------------------------------
+def host_inputs(lat, cfg, n_trials, seed, fresh):
+    from flamingpy_b200.noise import sample_batch
+
+    rng = np.random.default_rng(seed)
+    return sample_batch(rng, lat.N, cfg["delta"], cfg["p_swap"], n_trials, fresh=fresh)
+
+
+def time_cpu_port(lat, cfg, n_trials, fresh, threads=0, seed=SEED):
+    """Time oracle/fpb_oracle.c (the CPU restatement of the reference path) on `n_trials`
+    host-sampled trials, sampling included.  Returns (seconds, threads used)."""
+    from oracle import c_oracle  # checker / baseline leg only
+
+    c_oracle.load()
+    t0 = time.perf_counter()
+    x, st = host_inputs(lat, cfg, n_trials, seed, fresh)
+    c_oracle.run(lat, cfg["delta"], cfg["p_swap"], cfg["weight_opts"], x, st, n_threads=threads, copy_out=False)
+    dt = time.perf_counter() - t0
+    return dt, (threads if threads > 0 else c_oracle.max_threads())
+
+
+def run_reference_arm(args, cfg, lat):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    fresh = args.mode == "fresh"
+    cores = os.cpu_count() or 1
+    per_step = args.cpu_trials if args.cpu_trials > 0 else max(8, 2 * cores)
+    for _ in range(args.warmup):
+        time_cpu_port(lat, cfg, max(2, per_step // 4), fresh)
+    t_tot = 0.0
+    threads = cores
+    for s in range(args.steps):
+        dt, threads = time_cpu_port(lat, cfg, per_step, fresh, seed=SEED + s)
+        t_tot += dt
+    value = per_step * args.steps / t_tot
+    line = {
+        "impl": "reference", "metric": "EC Monte Carlo trials/sec at d=%d" % lat.dims[0], "value": value,
+        "unit": "trials/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t_tot / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, **{k: v for k, v in cfg.items() if k != "weight_opts"},
+                   "weights": cfg["weight_opts"]["method"], "mode": args.mode,
+                   "span": "noise->weights->syndrome->matching graph (MWPM excluded)"},
+        "cpu_baseline": {"value": value, "unit": "trials/s", "cores": threads, "kind": "port",
+                         "sample": f"{per_step} trials/step x {args.steps} steps, oracle/fpb_oracle.c (C + OpenMP "
+                                   f"restatement of the reference path; the Python reference itself cannot run on "
+                                   f"this box), host NumPy sampling included"},
+        "e2e": {"value": value, "unit": "trials/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+# B200 arm
+# --------------------------------------------------------------------------------------------
+def run_gpu_arm(args, cfg, lat):
+    import torch
+
+    from flamingpy_b200 import _lib
+    from flamingpy_b200.engine import TrialEngine
+
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback")
+    torch.cuda.set_device(local)
+    use_dist = world > 1
+    if use_dist:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    fresh = args.mode == "fresh"
+    B = args.batch
+    eng = TrialEngine(lat, cfg["delta"], cfg["p_swap"], cfg["weight_opts"], mode=args.mode, device=local,
+                      delta_step=args.delta_step)
+
+    def barrier():
+        if use_dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+        eng._lib.fpb_synchronize(eng._h)
+
+    def first_trial(step):  # contiguous block per (step, rank): independent of the GPU count
+        return (step * world + rank) * B
+
+    # ---------------- device-resident throughput (`value`) ----------------
+    for s in range(args.warmup):
+        eng.run_rng(SEED, first_trial(s), B, fetch=False)
+    clocks = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        clocks.start()
+    dev_ms = graph_ms = 0.0
+    launches = 0
+    tot_odd = [0, 0]
+    tot_pairs = [0, 0]
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        eng.mark(0)
+        eng.run_rng(SEED, first_trial(args.warmup + s), B, fetch=False)
+        eng.mark(1)
+        dev_ms += eng.elapsed_ms()
+        tm = eng.timings()
+        graph_ms += tm["graph_ms"]
+        launches += tm["launches"]
+        sz = eng.sizes()
+        for i in range(sz.n_complex):
+            tot_odd[i] += int(sz.total_odd[i])
+            tot_pairs[i] += int(sz.total_pairs[i])
+    barrier()
+    wall = time.perf_counter() - t0
+    clk = clocks.stop() if rank == 0 else None
+    tmax = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64, device="cuda")
+    counts = torch.tensor([B * args.steps, sum(tot_odd)], dtype=torch.int64, device="cuda")
+    if use_dist:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM)  # the path's one collective (simulations.py:110)
+    dev_ms_max, wall_ms_max = (float(v) for v in tmax.tolist())
+    total_trials = int(counts[0].item())
+    value = total_trials / (dev_ms_max * 1e-3)
+
+    # ---------------- end to end through the public API with host buffers (`e2e`) ----------------
+    Be = args.e2e_batch
+    n_sets = min(args.steps + args.warmup, 3)
+    N, Q = lat.N, eng.Qtot
+    pin = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True).numpy()  # noqa: E731
+    xs = [pin((Be, 2 * N), torch.float64) for _ in range(n_sets)]
+    sts = [pin((Be, N), torch.uint8) for _ in range(n_sets)]
+    from flamingpy_b200.noise import LabelSampler, sample_batch
+
+    sampler = LabelSampler(N, cfg["p_swap"], fresh)
+    rng = np.random.default_rng(SEED + 1000 * rank)
+    for i in range(n_sets):
+        sample_batch(rng, N, cfg["delta"], cfg["p_swap"], Be, sampler=sampler, out_x=xs[i], out_state=sts[i])
+    # host result buffers sized from a probe run
+    eng.run_injected(xs[0], sts[0], fetch=False)
+    sz = eng.sizes()
+    bufs = {"hom": pin((Be * Q,), torch.float64), "weights": pin((Be * Q,), torch.float64),
+            "bits": pin((Be * eng.bit_words,), torch.int32).view(np.uint32)}
+    for i, e in enumerate(lat.ec):
+        ct = lat.complexes[e]
+        mo = int(sz.total_odd[i] * 1.25) + 1024
+        mp = int(sz.total_pairs[i] * 1.25) + 1024
+        bufs[f"parity{i}"] = pin((Be * ((ct.S + 31) // 32),), torch.int32).view(np.uint32)
+        bufs[f"odd_count{i}"] = pin((Be,), torch.int32)
+        bufs[f"odd_ids{i}"] = pin((mo,), torch.int32)
+        bufs[f"pair_len{i}"] = pin((mp,), torch.float64)
+        if ct.has_boundary:
+            bufs[f"bnd_len{i}"] = pin((mo,), torch.float64)
+            bufs[f"bnd_side{i}"] = pin((mo,), torch.uint8)
+
+    def e2e_step(i):
+        eng.run_injected(xs[i % n_sets], sts[i % n_sets], fetch=False)  # H2D inside
+        s_ = eng.fetch_into(bufs)  # D2H inside
+        d2h = Be * (16 * Q + 4 * eng.bit_words) + sum(
+            Be * (4 * ((lat.complexes[e].S + 31) // 32) + 4) + 4 * int(s_.total_odd[j]) + 8 * int(s_.total_pairs[j])
+            + (9 * int(s_.total_odd[j]) if lat.complexes[e].has_boundary else 0) for j, e in enumerate(lat.ec))
+        return d2h
+
+    for s in range(max(1, args.warmup)):
+        e2e_step(s)
+    barrier()
+    t0 = time.perf_counter()
+    d2h_bytes = 0
+    for s in range(args.steps):
+        d2h_bytes += e2e_step(s)
+    barrier()
+    e2e_wall = time.perf_counter() - t0
+    e2e_t = torch.tensor([e2e_wall], dtype=torch.float64, device="cuda")
+    if use_dist:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = Be * args.steps * world / float(e2e_t.item())
+    h2d_per_step = Be * (2 * N * 8 + N)
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        kb = paths_kernel_bytes(lat, B * args.steps, tot_odd, tot_pairs)
+        achieved = kb / (graph_ms * 1e-3) / 1e9 if graph_ms > 0 else 0.0
+        pipe_b = algorithmic_bytes(lat, B * args.steps, tot_odd, tot_pairs)
+        line = {
+            "metric": "EC Monte Carlo trials/sec at d=%d" % lat.dims[0], "value": value, "unit": "trials/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, **{k: v for k, v in cfg.items() if k != "weight_opts"},
+                       "weights": cfg["weight_opts"]["method"], "mode": args.mode,
+                       "trials_per_gpu_per_step": B, "rng": "Philox4x32-10 keyed by (seed, global trial, node)",
+                       "span": "noise->weights->syndrome->matching graph (MWPM excluded)",
+                       "l2": "per-step inputs and outputs exceed L2 (%.0f MB written per step)" % (
+                           pipe_b / args.steps / 1e6),
+                       "odd_cubes_per_trial": sum(tot_odd) / max(1, B * args.steps)},
+            "wall_ms_per_step": wall_ms_max / args.steps,
+            "e2e": {"value": e2e_value, "unit": "trials/s", "h2d_bytes_per_step": h2d_per_step,
+                    "d2h_bytes_per_step": d2h_bytes // max(1, args.steps), "trials_per_gpu_per_step": Be,
+                    "api": "TrialEngine.run_injected(host x, host labels) + fetch_into(pinned host buffers)"},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": "k_paths", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "share_of_step": graph_ms / dev_ms if dev_ms else None,
+                         "note": "k_paths is bound by shared-memory latency/issue, not HBM (DESIGN.md)",
+                         "pipeline_achieved": pipe_b / (dev_ms * 1e-3) / 1e9,
+                         "pipeline_frac": pipe_b / (dev_ms * 1e-3) / 1e9 / peak},
+            "clocks": clk,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            cores = os.cpu_count() or 1
+            n_cpu = args.cpu_trials if args.cpu_trials > 0 else max(8, 2 * cores)
+            dt, threads = time_cpu_port(lat, cfg, n_cpu, fresh)
+            line["cpu_baseline"] = {
+                "value": n_cpu / dt, "unit": "trials/s", "cores": threads, "kind": "port",
+                "sample": f"{n_cpu} trials of the same workload, oracle/fpb_oracle.c (C + OpenMP restatement of "
+                          f"the reference path), host NumPy sampling included, {dt:.1f} s"}
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if use_dist:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="d13_periodic_both", choices=sorted(WORKLOADS))
+    ap.add_argument("--mode", default="compat", choices=["compat", "fresh"],
+                    help="compat = one reused CVLayer per chain like simulations.ec_monte_carlo; fresh = new layer per trial")
+    ap.add_argument("--batch", type=int, default=2048, help="trials per GPU per step (device-resident arm)")
+    ap.add_argument("--e2e-batch", type=int, default=512, help="trials per GPU per step (end-to-end arm)")
+    ap.add_argument("--delta-step", type=float, default=0.0)
+    ap.add_argument("--cpu-trials", type=int, default=0, help="CPU sample size (0: 2 x cores)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        print("bench.py: note: fewer than 3 warm-up steps requested", file=sys.stderr)
+
+    from flamingpy_b200.lattice import build_lattice
+
+    cfg = WORKLOADS[args.workload]
+    lat = build_lattice(cfg["distance"], cfg["ec"], cfg["boundaries"])
+    if args.impl == "reference":
+        run_reference_arm(args, cfg, lat)
+    else:
+        run_gpu_arm(args, cfg, lat)
+
+
+if __name__ == "__main__":
+    main()

@@ -93,6 +93,7 @@ struct fpb_handle {
   long long chain_len = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t mark[2] = {nullptr, nullptr};
   int *adj_indptr = nullptr, *adj_indices = nullptr, *qubit_node = nullptr;
   int8_t* adj_vals = nullptr;
   ComplexHost cx[FPB_MAX_COMPLEX];
@@ -357,6 +358,8 @@ int fpb_create(const fpb_config* cfg, fpb_handle** out) {
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(FPB_ERR_CUDA, "stream creation failed"));
   for (auto& ev : h->ev)
     if (cudaEventCreate(&ev) != cudaSuccess) return bail(fail(FPB_ERR_CUDA, "event creation failed"));
+  for (auto& ev : h->mark)
+    if (cudaEventCreate(&ev) != cudaSuccess) return bail(fail(FPB_ERR_CUDA, "event creation failed"));
   if (cudaMallocHost(&h->totals_host, (2 * MAXC + 1) * sizeof(long long)) != cudaSuccess) return bail(fail(FPB_ERR_CUDA, "pinned allocation failed"));
   memset(h->totals_host, 0, (2 * MAXC + 1) * sizeof(long long));
 
@@ -428,6 +431,8 @@ int fpb_destroy(fpb_handle* h) {
   h->q_trial.release(); h->q_cx.release(); h->q_src.release(); h->q_dst.release();
   if (h->totals_host) cudaFreeHost(h->totals_host);
   for (auto& ev : h->ev)
+    if (ev) cudaEventDestroy(ev);
+  for (auto& ev : h->mark)
     if (ev) cudaEventDestroy(ev);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -534,6 +539,21 @@ int fpb_synchronize(fpb_handle* h) {
   if (!h) return fail(FPB_ERR_ARG, "null handle");
   CK(cudaSetDevice(h->device));
   CK(cudaStreamSynchronize(h->stream));
+  return FPB_OK;
+}
+
+int fpb_mark(fpb_handle* h, int which) {
+  if (!h || which < 0 || which > 1) return fail(FPB_ERR_ARG, "bad mark");
+  CK(cudaSetDevice(h->device));
+  CK(cudaEventRecord(h->mark[which], h->stream));
+  return FPB_OK;
+}
+
+int fpb_elapsed_ms(fpb_handle* h, float* ms) {
+  if (!h || !ms) return fail(FPB_ERR_ARG, "null argument");
+  CK(cudaSetDevice(h->device));
+  CK(cudaEventSynchronize(h->mark[1]));
+  CK(cudaEventElapsedTime(ms, h->mark[0], h->mark[1]));
   return FPB_OK;
 }
 

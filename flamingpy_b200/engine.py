@@ -23,6 +23,62 @@ def _ptr(a: np.ndarray, typ):
     return a.ctypes.data_as(typ)
 
 
+def build_config(lat: LatticeTables, delta: float, p_swap: float, wo: dict, mode: str = "compat",
+                 chain_len: int = 0, device: int = 0, delta_step: float = 0.0):
+    """Fill an ``fpb_config`` (include/fpb.h) from lattice tables and options.
+    Returns (config, keep-alive list of arrays, qubit offsets per complex, Qtot)."""
+    keepalive = []
+
+    def keep(a, dtype):
+        a = np.ascontiguousarray(a, dtype=dtype)
+        keepalive.append(a)
+        return a
+
+    cfg = _lib.Config()
+    cfg.abi_version = _lib.FPB_ABI_VERSION
+    cfg.device = device
+    cfg.n_nodes = lat.N
+    cfg.adj_indptr = _ptr(keep(lat.adj_indptr, np.int32), _lib._i32p)
+    cfg.adj_indices = _ptr(keep(lat.adj_indices, np.int32), _lib._i32p)
+    cfg.adj_vals = _ptr(keep(lat.adj_vals, np.int8), _lib._i8p)
+    cfg.n_complex = len(lat.ec)
+    q_off = {}
+    off = 0
+    for i, ec in enumerate(lat.ec):
+        ct = lat.complexes[ec]
+        d = cfg.complex_[i]
+        d.n_cubes = ct.S
+        d.n_qubits = ct.Q
+        d.qubit_node = _ptr(keep(ct.qubits, np.int32), _lib._i32p)
+        d.cube_qubit = _ptr(keep(ct.cube_qubit, np.int32), _lib._i32p)
+        d.ninfo = _ptr(keep(ct.ninfo, np.uint16), _lib._u16p)
+        d.sbase = _ptr(keep(ct.sbase, np.int32), _lib._i32p)
+        for j, v in enumerate(np.asarray(ct.d_off, np.int32).ravel()):
+            d.d_off[j] = int(v)
+        for j, v in enumerate(np.asarray(ct.s_off, np.int32).ravel()):
+            d.s_off[j] = int(v)
+        d.n_slots = ct.n_slots
+        d.slot_qubit = _ptr(keep(ct.slot_qubit, np.int32), _lib._i32p)
+        d.n_low = len(ct.low_seed_cube)
+        d.low_cube = _ptr(keep(ct.low_seed_cube, np.int32), _lib._i32p)
+        d.low_slot = _ptr(keep(ct.low_seed_slot, np.int32), _lib._i32p)
+        d.n_high = len(ct.high_seed_cube)
+        d.high_cube = _ptr(keep(ct.high_seed_cube, np.int32), _lib._i32p)
+        d.high_slot = _ptr(keep(ct.high_seed_slot, np.int32), _lib._i32p)
+        q_off[ec] = off
+        off += ct.Q
+    cfg.delta = float(delta)
+    cfg.p_swap = float(p_swap or 0.0)
+    cfg.weight_method = _lib.WEIGHT_BLUEPRINT if wo["method"] == "blueprint" else _lib.WEIGHT_UNIFORM
+    cfg.weight_delta = float(wo.get("delta") or delta)
+    cfg.weight_integer = int(bool(wo.get("integer", False)))
+    cfg.weight_multiplier = float(wo.get("multiplier", 1))
+    cfg.label_mode = _lib.MODE_FRESH if mode == "fresh" else _lib.MODE_COMPAT
+    cfg.chain_len = int(chain_len)
+    cfg.delta_step = float(delta_step)
+    return cfg, keepalive, q_off, off
+
+
 @dataclass
 class ComplexBatch:
     """Per-complex results of a batch (ragged arrays are concatenated over
@@ -92,58 +148,9 @@ class TrialEngine:
         self.mode = mode
         self.device = device
         self.ec = list(lat.ec)
-        self._keep = []  # arrays referenced by the config while fpb_create runs
-
-        cfg = _lib.Config()
-        cfg.abi_version = _lib.FPB_ABI_VERSION
-        cfg.device = device
-        cfg.n_nodes = lat.N
-
-        def keep(a, dtype):
-            a = np.ascontiguousarray(a, dtype=dtype)
-            self._keep.append(a)
-            return a
-
-        cfg.adj_indptr = _ptr(keep(lat.adj_indptr, np.int32), _lib._i32p)
-        cfg.adj_indices = _ptr(keep(lat.adj_indices, np.int32), _lib._i32p)
-        cfg.adj_vals = _ptr(keep(lat.adj_vals, np.int8), _lib._i8p)
-        cfg.n_complex = len(lat.ec)
-        self.q_off = {}
-        off = 0
-        for i, ec in enumerate(lat.ec):
-            ct = lat.complexes[ec]
-            d = cfg.complex_[i]
-            d.n_cubes = ct.S
-            d.n_qubits = ct.Q
-            d.qubit_node = _ptr(keep(ct.qubits, np.int32), _lib._i32p)
-            d.cube_qubit = _ptr(keep(ct.cube_qubit, np.int32), _lib._i32p)
-            d.ninfo = _ptr(keep(ct.ninfo, np.uint16), _lib._u16p)
-            d.sbase = _ptr(keep(ct.sbase, np.int32), _lib._i32p)
-            for j, v in enumerate(np.asarray(ct.d_off, np.int32).ravel()):
-                d.d_off[j] = int(v)
-            for j, v in enumerate(np.asarray(ct.s_off, np.int32).ravel()):
-                d.s_off[j] = int(v)
-            d.n_slots = ct.n_slots
-            d.slot_qubit = _ptr(keep(ct.slot_qubit, np.int32), _lib._i32p)
-            d.n_low = len(ct.low_seed_cube)
-            d.low_cube = _ptr(keep(ct.low_seed_cube, np.int32), _lib._i32p)
-            d.low_slot = _ptr(keep(ct.low_seed_slot, np.int32), _lib._i32p)
-            d.n_high = len(ct.high_seed_cube)
-            d.high_cube = _ptr(keep(ct.high_seed_cube, np.int32), _lib._i32p)
-            d.high_slot = _ptr(keep(ct.high_seed_slot, np.int32), _lib._i32p)
-            self.q_off[ec] = off
-            off += ct.Q
-        self.Qtot = off
-        self.bit_words = (off + 31) // 32
-        cfg.delta = self.delta
-        cfg.p_swap = self.p_swap
-        cfg.weight_method = _lib.WEIGHT_BLUEPRINT if wo["method"] == "blueprint" else _lib.WEIGHT_UNIFORM
-        cfg.weight_delta = float(wo.get("delta") or self.delta)
-        cfg.weight_integer = int(bool(wo["integer"]))
-        cfg.weight_multiplier = float(wo["multiplier"])
-        cfg.label_mode = _lib.MODE_FRESH if mode == "fresh" else _lib.MODE_COMPAT
-        cfg.chain_len = int(chain_len)
-        cfg.delta_step = float(delta_step)
+        cfg, self._keep, self.q_off, self.Qtot = build_config(
+            lat, self.delta, self.p_swap, wo, mode, chain_len, device, delta_step)
+        self.bit_words = (self.Qtot + 31) // 32
         handle = C.c_void_p()
         _lib.check(lib.fpb_create(C.byref(cfg), C.byref(handle)))
         self._h = handle
@@ -191,6 +198,15 @@ class TrialEngine:
         t = _lib.Timings()
         _lib.check(self._lib.fpb_get_timings(self._h, C.byref(t)))
         return {name: getattr(t, name) for name, _ in _lib.Timings._fields_}
+
+    def mark(self, which: int):
+        """Record timing mark 0 / 1 on the handle's stream."""
+        _lib.check(self._lib.fpb_mark(self._h, which))
+
+    def elapsed_ms(self) -> float:
+        ms = C.c_float()
+        _lib.check(self._lib.fpb_elapsed_ms(self._h, C.byref(ms)))
+        return float(ms.value)
 
     def device_outputs(self) -> _lib.Outputs:
         o = _lib.Outputs()
@@ -256,6 +272,39 @@ class TrialEngine:
                 cb.pair_off = np.concatenate([[0], np.cumsum(K * (K - 1) // 2)]).astype(np.int64)
         batch.timings = self.timings()
         return batch
+
+    def fetch_into(self, bufs: dict) -> _lib.Sizes:
+        """Copy the last run's results into caller-owned (e.g. pinned) NumPy
+        buffers without allocating: keys ``hom``, ``weights``, ``bits`` (packed
+        uint32) and per complex index ``i``: ``parity{i}`` (packed), ``odd_count{i}``,
+        ``odd_ids{i}``, ``pair_len{i}``, ``bnd_len{i}``, ``bnd_side{i}``.  Buffers must be
+        at least as large as the sizes returned by ``sizes()``."""
+        s = self.sizes()
+        T = int(s.n_trials)
+        out = _lib.Outputs()
+
+        def need(key, n, typ):
+            a = bufs.get(key)
+            if a is None:
+                return None
+            if a.size < n:
+                raise ValueError(f"buffer {key!r} too small: {a.size} < {n}")
+            return _ptr(a, typ)
+
+        out.hom = need("hom", T * self.Qtot, _lib._f64p)
+        out.weights = need("weights", T * self.Qtot, _lib._f64p)
+        out.bits = need("bits", T * self.bit_words, _lib._u32p)
+        for i, ec in enumerate(self.ec):
+            ct = self.lat.complexes[ec]
+            out.parity[i] = need(f"parity{i}", T * ((ct.S + 31) // 32), _lib._u32p)
+            out.odd_count[i] = need(f"odd_count{i}", T, _lib._i32p)
+            out.odd_ids[i] = need(f"odd_ids{i}", int(s.total_odd[i]), _lib._i32p)
+            out.pair_len[i] = need(f"pair_len{i}", int(s.total_pairs[i]), _lib._f64p)
+            if ct.has_boundary:
+                out.bnd_len[i] = need(f"bnd_len{i}", int(s.total_odd[i]), _lib._f64p)
+                out.bnd_side[i] = need(f"bnd_side{i}", int(s.total_odd[i]), _lib._u8p)
+        _lib.check(self._lib.fpb_fetch(self._h, C.byref(out), 0))
+        return s
 
     def paths_toggle(self, trial, cx, src, dst) -> np.ndarray:
         """XOR-toggle the qubits on the shortest paths of the given (trial,

@@ -174,6 +174,11 @@ int fpb_fetch(fpb_handle* h, const fpb_outputs* dst, int on_device);
 int fpb_device_outputs(fpb_handle* h, fpb_outputs* out);
 int fpb_get_timings(fpb_handle* h, fpb_timings* out);
 int fpb_synchronize(fpb_handle* h);
+/* User timing marks on the handle's stream (the stream every kernel of the handle is
+ * launched on): fpb_mark records CUDA event `which` (0 or 1); fpb_elapsed_ms synchronises
+ * and returns the device time between mark 0 and mark 1. */
+int fpb_mark(fpb_handle* h, int which);
+int fpb_elapsed_ms(fpb_handle* h, float* ms);
 
 /* Correction paths for matched pairs of the last run.  Query i asks, in trial
  * trial[i] and complex cx[i], for the shortest path from odd cube src[i] to
