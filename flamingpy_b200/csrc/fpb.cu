@@ -137,8 +137,10 @@ int configure_paths(fpb_handle* h) {
   int smem_per_sm = 0;
   CK(cudaDeviceGetAttribute(&smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, h->device));
   const size_t cta_b = paths_cta_bytes(h->S_max, h->slots_max);
-  const size_t warp_b = paths_warp_bytes(h->S_max);
+  const size_t warp_b = paths_warp_bytes(h->S_max, false);
   h->warps = 0;
+  if (h->S_max > 16 * 32 * MAX_CHUNKS)
+    return fail(FPB_ERR_UNSUPPORTED, "lattice too large for the shortest-path kernel's bucket scan");
   for (int ctas = 1; ctas <= 4; ++ctas) {
     // per-CTA budget when `ctas` CTAs share an SM (1 KB reserved per CTA by the runtime)
     size_t budget = (size_t)smem_per_sm / ctas - 1024;
@@ -602,8 +604,8 @@ int fpb_paths_toggle(fpb_handle* h, int64_t n_queries, const int32_t* trial, con
     pp.flips = h->flips.p; pp.bit_words = h->bit_words;
     int max_optin = 0;
     CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
-    const size_t per_warp = (size_t)h->slots_max * 8 + paths_warp_bytes(h->S_max);
-    int warps = (int)(((size_t)max_optin - 1024) / per_warp);
+    const size_t per_warp = toggle_warp_bytes(h->S_max, h->slots_max);
+    int warps = (int)((size_t)max_optin / per_warp);
     if (warps < 1) return fail(FPB_ERR_UNSUPPORTED, "lattice too large for the path-toggle kernel");
     if (warps > 8) warps = 8;
     const size_t smem = (size_t)warps * per_warp;

@@ -20,7 +20,6 @@ namespace fpb {
 constexpr double SQRT_PI = 1.7724538509055159;       // np.sqrt(np.pi)
 constexpr double FLOAT_MIN = 2.2250738585072014e-308;  // sys.float_info.min (decoder.py:27)
 constexpr int MAXC = 2;
-constexpr int CURCAP = 64;  // per-warp capacity of the "current bucket" list
 
 struct ComplexDev {
   int S, Q, qoff;      // cubes, qubits, offset of this complex's qubits in the global qubit list
@@ -395,155 +394,237 @@ struct PathsParams {
   int bit_words;
 };
 
+constexpr int NRING = 32;       // ring slots: bucket index mod 32 is kept in one byte per cube
+constexpr int STAGE_CAP = 512;  // per-warp staging list of the cubes of the current bucket
+constexpr int MAX_CHUNKS = 16;  // 16-cube chunks per lane in one scan: S <= 16 * 32 * 16 = 8192
+
 struct WarpMem {
   double* dist;     // [S]
-  uint16_t* list;   // [S]
-  uint8_t* flag;    // [S]  bit0 dirty, bits1-3 incoming direction, 7<<1 = seeded from a connector
-  uint16_t* cur;    // [CURCAP]
+  uint8_t* bkt;     // [ceil16(S)] ring slot of the cube's pending entry, 0xFF none; 16-byte aligned
+  uint16_t* stage;  // [STAGE_CAP]
+  uint8_t* pred;    // [S] incoming direction (path-toggle kernel only)
 };
 
 struct CtaMem {
-  double* wslot;    // [slots_max]
-  uint16_t* ninfo;  // [S_max]
-  uint16_t* sbase;  // [S_max]
-  int* offs;        // [24] d_off then s_off
+  const double* wslot;    // [n_slots] weights of the trial in face-slot order
+  const uint16_t* ninfo;  // [S]
+  const uint16_t* sbase;  // [S]
 };
 
+// direction tables of one complex held in registers (uniform across the warp)
+struct DirTab {
+  int dreg[6], dwrap[6], sreg[6], swrap[6];
+};
+
+__host__ __device__ inline size_t align16(size_t b) { return (b + 15) / 16 * 16; }
 __host__ __device__ inline size_t paths_cta_bytes(int S_max, int slots_max) {
-  size_t b = (size_t)slots_max * 8;
-  b += ((size_t)S_max * 2 + 7) / 8 * 8;
-  b += ((size_t)S_max * 2 + 7) / 8 * 8;
-  b += 24 * 4 + 32;
-  return b;
+  return align16((size_t)slots_max * 8) + align16((size_t)S_max * 2) + align16((size_t)S_max * 2);
 }
-__host__ __device__ inline size_t paths_warp_bytes(int S_max) {
-  size_t b = (size_t)S_max * 8;
-  b += ((size_t)S_max * 2 + 7) / 8 * 8;
-  b += ((size_t)S_max + 7) / 8 * 8;
-  b += CURCAP * 2;
-  return b;
+__host__ __device__ inline size_t paths_warp_bytes(int S_max, bool pred) {
+  return align16((size_t)S_max * 8) + align16((size_t)S_max) + align16((size_t)STAGE_CAP * 2) +
+         (pred ? align16((size_t)S_max) : 0);
 }
 
 #define FPB_INF __longlong_as_double(0x7ff0000000000000ll)
 
-// One bucketed label-correcting search on the cube grid, run by one warp out of shared memory.
-// Buckets of width `step` are processed in increasing order; with step <= the minimum weight a
-// node's distance is final when its bucket is reached (label setting), with a wider bucket the
-// dirty flag re-queues nodes improved inside the bucket.  Pass A compacts the open list (drops
-// settled nodes) and collects the dirty nodes of the current bucket; pass B relaxes them, one
-// direction at a time so that the 32 targets of one instruction are distinct cubes and no
-// atomics are needed.  If `stop_at` >= 0 the search ends once that cube is settled.
-__device__ __forceinline__ void warp_search(const CtaMem& cm, const WarpMem& wm, int S, int n_seed,
-                                            double step, int lane, int stop_at) {
-  int Lc = n_seed;
-  double t_lo = 0.0, t_hi = step;
-  const uint32_t lt = (1u << lane) - 1u;
-  while (true) {
-    // ---------------- pass A ----------------
-    int out = 0, ncur = 0;
-    bool more = false;
-    double minv = FPB_INF;
-    for (int base = 0; base < Lc; base += 32) {
-      const int i = base + lane;
-      const bool valid = i < Lc;
-      const int v = valid ? wm.list[i] : 0;
-      const double dv = valid ? wm.dist[v] : FPB_INF;
-      const bool keep = valid && !(dv < t_lo);
-      const bool inb = keep && dv < t_hi;
-      const bool dirty = inb && (wm.flag[v] & 1);
-      if (keep && !inb) minv = fmin(minv, dv);
-      __syncwarp();
-      const uint32_t km = __ballot_sync(0xffffffffu, keep);
-      if (keep) wm.list[out + __popc(km & lt)] = (uint16_t)v;
-      out += __popc(km);
-      const uint32_t tm = __ballot_sync(0xffffffffu, dirty);
-      const int pos = ncur + __popc(tm & lt);
-      if (dirty) {
-        if (pos < CURCAP) {
-          wm.cur[pos] = (uint16_t)v;
-          wm.flag[v] &= 0xfe;
-        }
-      }
-      const int tot = ncur + __popc(tm);
-      if (tot > CURCAP) more = true;
-      ncur = tot < CURCAP ? tot : CURCAP;
-    }
-    Lc = out;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) minv = fmin(minv, __shfl_xor_sync(0xffffffffu, minv, o));
-    __syncwarp();
-    if (ncur == 0) {
-      if (!(minv < FPB_INF)) break;
-      if (stop_at >= 0 && wm.dist[stop_at] < t_hi) break;  // target settled
-      t_lo = t_hi;
-      t_hi = (floor(minv / step) + 1.0) * step;
-      if (!(t_hi > minv)) t_hi = minv + step;
-      continue;
-    }
-    // ---------------- pass B ----------------
-    bool again = more;
-    double min_b = FPB_INF;
-    for (int cb = 0; cb < ncur; cb += 32) {
-      const bool valid = cb + lane < ncur;
-      const int v = valid ? wm.cur[cb + lane] : 0;
-      const double dv = valid ? wm.dist[v] : 0.0;
-      const uint32_t info = valid ? cm.ninfo[v] : 0xaaau;  // all faces "none"
-      const int sb = cm.sbase[v];
-#pragma unroll
-      for (int d = 0; d < 6; ++d) {
-        const uint32_t kind = (info >> (2 * d)) & 3u;
-        const bool act = kind < 2u;
-        const int u = v + cm.offs[2 * d + (kind & 1u)];
-        const int slot = sb + cm.offs[12 + 2 * d + (kind & 1u)];
-        bool isnew = false;
-        if (act) {
-          const double nd = dv + cm.wslot[slot];
-          const double old = wm.dist[u];
-          if (nd < old) {
-            wm.dist[u] = nd;
-            wm.flag[u] = (uint8_t)(1 | (d << 1));
-            isnew = !(old < FPB_INF);
-            if (nd < t_hi) again = true;
-            else min_b = fmin(min_b, nd);
-          }
-        }
-        const uint32_t nm = __ballot_sync(0xffffffffu, isnew);
-        if (isnew) wm.list[Lc + __popc(nm & lt)] = (uint16_t)u;
-        Lc += __popc(nm);
-        __syncwarp();
-      }
-    }
-    again = __any_sync(0xffffffffu, again);
-    if (!again) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) min_b = fmin(min_b, __shfl_xor_sync(0xffffffffu, min_b, o));
-      const double mn = fmin(minv, min_b);
-      if (!(mn < FPB_INF)) break;
-      if (stop_at >= 0 && wm.dist[stop_at] < t_hi) break;
-      t_lo = t_hi;
-      t_hi = (floor(mn / step) + 1.0) * step;
-      if (!(t_hi > mn)) t_hi = mn + step;
-    }
-  }
+__device__ __forceinline__ WarpMem carve_warp(unsigned char* wp, int S_max, bool pred) {
+  WarpMem wm;
+  wm.dist = (double*)wp; wp += align16((size_t)S_max * 8);
+  wm.bkt = (uint8_t*)wp; wp += align16((size_t)S_max);
+  wm.stage = (uint16_t*)wp; wp += align16((size_t)STAGE_CAP * 2);
+  wm.pred = pred ? (uint8_t*)wp : nullptr;
+  return wm;
 }
+
+__device__ __forceinline__ DirTab load_dirtab(const ComplexDev& c) {
+  DirTab t;
+#pragma unroll
+  for (int d = 0; d < 6; ++d) {
+    t.dreg[d] = c.d_off[2 * d];
+    t.dwrap[d] = c.d_off[2 * d + 1];
+    t.sreg[d] = c.s_off[2 * d];
+    t.swrap[d] = c.s_off[2 * d + 1];
+  }
+  return t;
+}
+
+__device__ __forceinline__ int bucket_of(double x, double inv) { return __double2int_rd(x * inv); }
 
 __device__ __forceinline__ void warp_clear(const WarpMem& wm, int S, int lane) {
-  for (int v = lane; v < S; v += 32) {
-    wm.dist[v] = FPB_INF;
-    wm.flag[v] = 0;
-  }
+  for (int v = lane; v < S; v += 32) wm.dist[v] = FPB_INF;
+  const int n16 = (S + 15) >> 4;
+  uint4* b4 = reinterpret_cast<uint4*>(wm.bkt);
+  for (int i = lane; i < n16; i += 32) b4[i] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
   __syncwarp();
 }
 
-__device__ __forceinline__ void warp_seed_connector(const CtaMem& cm, const WarpMem& wm, int n,
-                                                    const int* cubes, const int* slots, int lane) {
-  for (int i = lane; i < n; i += 32) {
-    const int c = cubes[i];
-    wm.dist[c] = cm.wslot[slots[i]];
-    wm.flag[c] = (uint8_t)(1 | (7 << 1));
-    wm.list[i] = (uint16_t)c;
+// File cube c with tentative distance d0 before a search starts (bucket 0 is the ring head).
+// Returns the lane's contribution to the `present` mask.
+__device__ __forceinline__ uint32_t seed_cube(const WarpMem& wm, int c, double d0, double inv, uint8_t pred_code) {
+  wm.dist[c] = d0;
+  int bi = bucket_of(d0, inv);
+  bi = bi < NRING - 1 ? bi : NRING - 1;
+  wm.bkt[c] = (uint8_t)bi;
+  if (wm.pred) wm.pred[c] = pred_code;
+  return 1u << bi;
+}
+
+// One bucketed shortest-path search on the cube grid, run by one warp out of shared memory.
+//
+// Every cube with a pending (tentative, not yet relaxed) distance is filed under the ring slot
+// (bucket index mod 32) of that distance in one byte per cube, so a cube has exactly one entry
+// and a later improvement simply overwrites it.  Buckets of width `step` are processed in
+// increasing order: a dense 16-bytes-per-load scan stages the cubes of the current slot, then
+// they are relaxed 32 at a time.  All six neighbour distances and weights of a batch are loaded
+// up front; improvements are stored direction by direction (within one direction the 32
+// targets are distinct cubes, across directions the last store wins) and a verify round
+// re-stores any smaller value that was overwritten, so no atomics are needed.  With
+// step <= the minimum weight a cube is final when its bucket comes up (label setting); a wider
+// bucket re-files cubes improved inside it.  Cubes more than 31 buckets ahead are parked in the
+// farthest slot and moved on when that slot comes up.  If `stop_at` >= 0 the search ends as
+// soon as that cube is settled.
+template <bool PRED>
+__device__ __forceinline__ void warp_search(const CtaMem& cm, const WarpMem& wm, const DirTab& dt, int S,
+                                            double step, uint32_t present, int lane, int stop_at) {
+  const double inv = 1.0 / step;
+  const int n16 = (S + 15) >> 4;
+  const uint4* b4 = reinterpret_cast<const uint4*>(wm.bkt);
+  int cur = 0;
+  while (present) {
+    {
+      const uint32_t rot = __funnelshift_r(present, present, cur & (NRING - 1));
+      cur += __ffs(rot) - 1;
+    }
+    const int r = cur & (NRING - 1);
+    const int far = cur + NRING - 1;
+    while ((present >> r) & 1u) {
+      present &= ~(1u << r);
+      // ---------------- scan: stage the cubes filed under slot r ----------------
+      uint32_t masks[MAX_CHUNKS];
+      int cnt = 0;
+      const uint32_t r4 = (uint32_t)r * 0x01010101u;
+#pragma unroll
+      for (int j = 0; j < MAX_CHUNKS; ++j) {
+        const int ch = j * 32 + lane;
+        uint32_t m = 0;
+        if (ch < n16) {
+          const uint4 q = b4[ch];
+          const uint32_t e0 = __vcmpeq4(q.x, r4), e1 = __vcmpeq4(q.y, r4);
+          const uint32_t e2 = __vcmpeq4(q.z, r4), e3 = __vcmpeq4(q.w, r4);
+          m = (((e0 & 0x08040201u) * 0x01010101u) >> 24) | ((((e1 & 0x08040201u) * 0x01010101u) >> 24) << 4) |
+              ((((e2 & 0x08040201u) * 0x01010101u) >> 24) << 8) | ((((e3 & 0x08040201u) * 0x01010101u) >> 24) << 12);
+        }
+        masks[j] = m;
+        cnt += __popc(m);
+        if ((j + 1) * 32 >= n16) break;
+      }
+      int incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+      }
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      int pos = incl - cnt;
+#pragma unroll
+      for (int j = 0; j < MAX_CHUNKS; ++j) {
+        uint32_t m = masks[j];
+        const int base = (j * 32 + lane) << 4;
+        while (m) {
+          const int b = __ffs(m) - 1;
+          m &= m - 1;
+          if (pos < STAGE_CAP) {
+            wm.stage[pos] = (uint16_t)(base + b);
+            wm.bkt[base + b] = 0xff;
+          }
+          ++pos;
+        }
+        if ((j + 1) * 32 >= n16) break;
+      }
+      if (total > STAGE_CAP) present |= 1u << r;  // the rest stays filed; scan again afterwards
+      const int nst = total < STAGE_CAP ? total : STAGE_CAP;
+      __syncwarp();
+      // ---------------- relax the staged cubes, 32 at a time ----------------
+      uint32_t lp = 0;  // slots this lane filed cubes under
+      for (int cb = 0; cb < nst; cb += 32) {
+        const bool valid = cb + lane < nst;
+        const int v = valid ? wm.stage[cb + lane] : 0;
+        const double dv = valid ? wm.dist[v] : 0.0;
+        const int bt = bucket_of(dv, inv);
+        if (valid && bt > cur) {  // a parked cube: move it towards its real bucket
+          const int s2 = (bt < far ? bt : far) & (NRING - 1);
+          wm.bkt[v] = (uint8_t)s2;
+          lp |= 1u << s2;
+        }
+        const bool act = valid && bt <= cur;
+        const uint32_t info = act ? (uint32_t)cm.ninfo[v] : 0xaaau;  // inactive lanes: every face "none"
+        const int sb = cm.sbase[v];
+        int u[6];
+        double nd[6];
+        bool imp[6];
+#pragma unroll
+        for (int d = 0; d < 6; ++d) {
+          const uint32_t kind = (info >> (2 * d)) & 3u;
+          const bool a = kind < 2u;
+          u[d] = v + (kind ? dt.dwrap[d] : dt.dreg[d]);
+          const int slot = sb + (kind ? dt.swrap[d] : dt.sreg[d]);
+          const double w = a ? cm.wslot[slot] : 0.0;
+          const double old = a ? wm.dist[u[d]] : 0.0;
+          nd[d] = dv + w;
+          imp[d] = a && nd[d] < old;
+        }
+#pragma unroll
+        for (int d = 0; d < 6; ++d)
+          if (imp[d]) wm.dist[u[d]] = nd[d];
+        __syncwarp();
+        double fin[6];
+        bool redo;
+        do {
+          redo = false;
+#pragma unroll
+          for (int d = 0; d < 6; ++d) fin[d] = imp[d] ? wm.dist[u[d]] : 0.0;
+#pragma unroll
+          for (int d = 0; d < 6; ++d)
+            if (imp[d] && fin[d] > nd[d]) {
+              wm.dist[u[d]] = nd[d];
+              redo = true;
+            }
+          redo = __any_sync(0xffffffffu, redo);
+        } while (redo);
+#pragma unroll
+        for (int d = 0; d < 6; ++d)
+          if (imp[d]) {
+            const int bi = bucket_of(fin[d], inv);
+            const int s2 = (bi < far ? bi : far) & (NRING - 1);
+            wm.bkt[u[d]] = (uint8_t)s2;
+            lp |= 1u << s2;
+            if (PRED) {
+              if (fin[d] == nd[d]) wm.pred[u[d]] = (uint8_t)d;
+            }
+          }
+        __syncwarp();
+      }
+      present |= __reduce_or_sync(0xffffffffu, lp);
+    }
+#ifndef FPB_NO_EARLY_STOP
+    if (stop_at >= 0) {
+      if (bucket_of(wm.dist[stop_at], inv) <= cur) break;  // the target is settled
+    }
+#endif
   }
+}
+
+__device__ __forceinline__ uint32_t warp_seed_connector(const CtaMem& cm, const WarpMem& wm, int n,
+                                                        const int* cubes, const int* slots, double inv,
+                                                        int lane) {
+  uint32_t lp = 0;
+  for (int i = lane; i < n; i += 32) lp |= seed_cube(wm, cubes[i], cm.wslot[slots[i]], inv, 7);
   __syncwarp();
+  return __reduce_or_sync(0xffffffffu, lp);
+}
+
+__device__ __forceinline__ double bucket_step(double wmin, double factor) {
+  return (wmin > 0.0 && wmin < FPB_INF) ? wmin * factor : 1.0;
 }
 
 __global__ void __launch_bounds__(512) k_paths(const __grid_constant__ PathsParams p) {
@@ -553,22 +634,17 @@ __global__ void __launch_bounds__(512) k_paths(const __grid_constant__ PathsPara
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int nthreads = blockDim.x;
 
-  CtaMem cm;
   unsigned char* ptr = smem;
-  cm.wslot = (double*)ptr; ptr += (size_t)p.slots_max * 8;
-  cm.ninfo = (uint16_t*)ptr; ptr += ((size_t)p.S_max * 2 + 7) / 8 * 8;
-  cm.sbase = (uint16_t*)ptr; ptr += ((size_t)p.S_max * 2 + 7) / 8 * 8;
-  cm.offs = (int*)ptr; ptr += 24 * 4 + 32;
-  const size_t wbytes = paths_warp_bytes(p.S_max);
-  unsigned char* wp = ptr + (size_t)wid * wbytes;
-  WarpMem wm;
-  wm.dist = (double*)wp; wp += (size_t)p.S_max * 8;
-  wm.list = (uint16_t*)wp; wp += ((size_t)p.S_max * 2 + 7) / 8 * 8;
-  wm.flag = (uint8_t*)wp; wp += ((size_t)p.S_max + 7) / 8 * 8;
-  wm.cur = (uint16_t*)wp;
+  double* wslot = (double*)ptr; ptr += align16((size_t)p.slots_max * 8);
+  uint16_t* ninfo_s = (uint16_t*)ptr; ptr += align16((size_t)p.S_max * 2);
+  uint16_t* sbase_s = (uint16_t*)ptr; ptr += align16((size_t)p.S_max * 2);
+  CtaMem cm;
+  cm.wslot = wslot; cm.ninfo = ninfo_s; cm.sbase = sbase_s;
+  const WarpMem wm = carve_warp(ptr + (size_t)wid * paths_warp_bytes(p.S_max, false), p.S_max, false);
 
   int staged_tc = -1, staged_c = -1;
   double step = 1.0;
+  DirTab dt = load_dirtab(p.cx[0]);
 
   while (true) {
     if (threadIdx.x == 0) item_s = atomicAdd(p.counter, 1);
@@ -590,11 +666,10 @@ __global__ void __launch_bounds__(512) k_paths(const __grid_constant__ PathsPara
 
     if (staged_c != ci) {
       for (int v = threadIdx.x; v < S; v += nthreads) {
-        cm.ninfo[v] = c.ninfo[v];
-        cm.sbase[v] = c.sbase[v];
+        ninfo_s[v] = c.ninfo[v];
+        sbase_s[v] = c.sbase[v];
       }
-      if (threadIdx.x < 12) cm.offs[threadIdx.x] = c.d_off[threadIdx.x];
-      else if (threadIdx.x < 24) cm.offs[threadIdx.x] = c.s_off[threadIdx.x - 12];
+      dt = load_dirtab(c);
       staged_c = ci;
     }
     if (staged_tc != tc) {
@@ -603,7 +678,7 @@ __global__ void __launch_bounds__(512) k_paths(const __grid_constant__ PathsPara
       for (int s = threadIdx.x; s < c.n_slots; s += nthreads) {
         const int q = c.slot_qubit[s];
         const double ws = (q >= 0) ? w[q] : FPB_INF;
-        cm.wslot[s] = ws;
+        wslot[s] = ws;
         mn = fmin(mn, ws);
       }
 #pragma unroll
@@ -612,11 +687,12 @@ __global__ void __launch_bounds__(512) k_paths(const __grid_constant__ PathsPara
       __syncthreads();
       mn = FPB_INF;
       for (int w2 = 0; w2 < (nthreads >> 5); ++w2) mn = fmin(mn, red_s[w2]);
-      step = (mn > 0.0 && mn < FPB_INF) ? mn * p.step_factor : 1.0;
+      step = bucket_step(mn, p.step_factor);
       staged_tc = tc;
     }
     __syncthreads();
 
+    const double inv = 1.0 / step;
     const int K = c.odd_count[t];
     const int* odd = c.odd_fixed + (long long)t * S;
     const int has_bnd = c.n_low > 0;
@@ -629,24 +705,22 @@ __global__ void __launch_bounds__(512) k_paths(const __grid_constant__ PathsPara
       if (task < K - 1) {
         // single-source search from odd cube `task`; row `task` of the packed upper triangle
         const int src = odd[task];
-        if (lane == 0) {
-          wm.dist[src] = 0.0;
-          wm.flag[src] = 1;
-          wm.list[0] = (uint16_t)src;
-        }
+        uint32_t present = 0;
+        if (lane == 0) present = seed_cube(wm, src, 0.0, inv, 0);
+        present = __shfl_sync(0xffffffffu, present, 0);
         __syncwarp();
-        warp_search(cm, wm, S, 1, step, lane, -1);
+        warp_search<false>(cm, wm, dt, S, step, present, lane, -1);
         const long long row = poff + (long long)task * K - (long long)task * (task + 1) / 2;
         for (int b = task + 1 + lane; b < K; b += 32) c.pair_len[row + (b - task - 1)] = wm.dist[odd[b]];
       } else {
         // LOW then HIGH connector searches; keep the nearer one (ties -> low, matching.py:149-150)
-        warp_seed_connector(cm, wm, c.n_low, c.low_cube, c.low_slot, lane);
-        warp_search(cm, wm, S, c.n_low, step, lane, -1);
+        uint32_t present = warp_seed_connector(cm, wm, c.n_low, c.low_cube, c.low_slot, inv, lane);
+        warp_search<false>(cm, wm, dt, S, step, present, lane, -1);
         for (int b = lane; b < K; b += 32) c.bnd_len[ooff + b] = wm.dist[odd[b]];
         __syncwarp();
         warp_clear(wm, S, lane);
-        warp_seed_connector(cm, wm, c.n_high, c.high_cube, c.high_slot, lane);
-        warp_search(cm, wm, S, c.n_high, step, lane, -1);
+        present = warp_seed_connector(cm, wm, c.n_high, c.high_cube, c.high_slot, inv, lane);
+        warp_search<false>(cm, wm, dt, S, step, present, lane, -1);
         for (int b = lane; b < K; b += 32) {
           const double lo_d = c.bnd_len[ooff + b];
           const double hi_d = wm.dist[odd[b]];
@@ -665,32 +739,24 @@ __global__ void __launch_bounds__(512) k_paths(const __grid_constant__ PathsPara
 // k_path_toggle: one warp per query; search with early stop, then walk the tree back and
 // XOR-toggle the crossed qubits (mwpm/algos.py:88-95)
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(512) k_path_toggle(const __grid_constant__ PathsParams p) {
+__host__ __device__ inline size_t toggle_warp_bytes(int S_max, int slots_max) {
+  return align16((size_t)slots_max * 8) + paths_warp_bytes(S_max, true);
+}
+
+__global__ void __launch_bounds__(256) k_path_toggle(const __grid_constant__ PathsParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
-  __shared__ int item_s;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int nwarps = blockDim.x >> 5;
-  // every warp keeps its own copy of the weights here (queries of one CTA mix trials), so the
-  // layout is per warp: wslot, dist, list, flag, cur; ninfo/sbase/offs are read from global.
-  const size_t per_warp = (size_t)p.slots_max * 8 + paths_warp_bytes(p.S_max);
-  unsigned char* wp = smem + (size_t)wid * per_warp;
-  double* wslot = (double*)wp; wp += (size_t)p.slots_max * 8;
-  WarpMem wm;
-  wm.dist = (double*)wp; wp += (size_t)p.S_max * 8;
-  wm.list = (uint16_t*)wp; wp += ((size_t)p.S_max * 2 + 7) / 8 * 8;
-  wm.flag = (uint8_t*)wp; wp += ((size_t)p.S_max + 7) / 8 * 8;
-  wm.cur = (uint16_t*)wp;
-  __shared__ int offs_s[MAXC][24];
-  if (threadIdx.x < 24 * p.n_complex) {
-    const int ci = threadIdx.x / 24, j = threadIdx.x % 24;
-    offs_s[ci][j] = j < 12 ? p.cx[ci].d_off[j] : p.cx[ci].s_off[j - 12];
-  }
-  __syncthreads();
-  (void)item_s;
+  // queries of one CTA mix trials, so every warp keeps its own copy of the trial's weights;
+  // the static face tables are read from global memory (L1/L2 resident)
+  unsigned char* wp = smem + (size_t)wid * toggle_warp_bytes(p.S_max, p.slots_max);
+  double* wslot = (double*)wp; wp += align16((size_t)p.slots_max * 8);
+  const WarpMem wm = carve_warp(wp, p.S_max, true);
   for (int qi = blockIdx.x * nwarps + wid; qi < p.n_queries; qi += gridDim.x * nwarps) {
     const int t = p.q_trial[qi], ci = p.q_cx[qi];
     const ComplexDev& c = p.cx[ci];
     const int S = c.S;
+    const DirTab dt = load_dirtab(c);
     const double* w = p.weights + (long long)t * p.Qtot + c.qoff;
     double mn = FPB_INF;
     for (int s = lane; s < c.n_slots; s += 32) {
@@ -701,49 +767,40 @@ __global__ void __launch_bounds__(512) k_path_toggle(const __grid_constant__ Pat
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-    const double step = (mn > 0.0 && mn < FPB_INF) ? mn * p.step_factor : 1.0;
+    const double step = bucket_step(mn, p.step_factor);
+    const double inv = 1.0 / step;
     CtaMem cm;
-    cm.wslot = wslot;
-    cm.ninfo = const_cast<uint16_t*>(c.ninfo);
-    cm.sbase = const_cast<uint16_t*>(c.sbase);
-    cm.offs = offs_s[ci];
+    cm.wslot = wslot; cm.ninfo = c.ninfo; cm.sbase = c.sbase;
     const int* odd = c.odd_fixed + (long long)t * S;
     const int src = odd[p.q_src[qi]];
+    const bool pair_query = p.q_dst[qi] >= 0;
     uint32_t* flips = p.flips + (long long)t * p.bit_words;
     warp_clear(wm, S, lane);
-    int walk_from;
-    if (p.q_dst[qi] >= 0) {
+    int walk_from, side = 0;
+    if (pair_query) {
       const int dst = odd[p.q_dst[qi]];
-      if (lane == 0) {
-        wm.dist[src] = 0.0;
-        wm.flag[src] = 1;
-        wm.list[0] = (uint16_t)src;
-      }
+      uint32_t present = 0;
+      if (lane == 0) present = seed_cube(wm, src, 0.0, inv, 6);
+      present = __shfl_sync(0xffffffffu, present, 0);
       __syncwarp();
-      warp_search(cm, wm, S, 1, step, lane, dst);
+      warp_search<true>(cm, wm, dt, S, step, present, lane, dst);
       walk_from = dst;
     } else {
       // to the nearer connector, as recorded by the matching-graph run
-      const int side = c.bnd_side[c.odd_off[t] + p.q_src[qi]];
-      if (side == 0) {
-        warp_seed_connector(cm, wm, c.n_low, c.low_cube, c.low_slot, lane);
-        warp_search(cm, wm, S, c.n_low, step, lane, src);
-      } else {
-        warp_seed_connector(cm, wm, c.n_high, c.high_cube, c.high_slot, lane);
-        warp_search(cm, wm, S, c.n_high, step, lane, src);
-      }
+      side = c.bnd_side[c.odd_off[t] + p.q_src[qi]];
+      const uint32_t present = side ? warp_seed_connector(cm, wm, c.n_high, c.high_cube, c.high_slot, inv, lane)
+                                    : warp_seed_connector(cm, wm, c.n_low, c.low_cube, c.low_slot, inv, lane);
+      warp_search<true>(cm, wm, dt, S, step, present, lane, src);
       walk_from = src;
     }
     __syncwarp();
     if (lane == 0) {
       int u = walk_from;
-      const bool pair_query = p.q_dst[qi] >= 0;
       for (int guard = 0; guard < S + 2; ++guard) {
-        if (pair_query && u == src) break;
-        const int din = (wm.flag[u] >> 1) & 7;
+        const int din = wm.pred[u];
+        if (din == 6) break;  // reached the source cube
         if (din == 7) {
           // seeded from a connector: toggle the boundary qubit and stop
-          const int side = c.bnd_side[c.odd_off[t] + p.q_src[qi]];
           const int n = side ? c.n_high : c.n_low;
           const int* cubes = side ? c.high_cube : c.low_cube;
           const int* slots = side ? c.high_slot : c.low_slot;
@@ -758,9 +815,9 @@ __global__ void __launch_bounds__(512) k_path_toggle(const __grid_constant__ Pat
         // u was reached from v by direction din; step back along din^1
         const int back = din ^ 1;
         const uint32_t kb = (c.ninfo[u] >> (2 * back)) & 3u;
-        const int v = u + offs_s[ci][2 * back + (kb & 1u)];
+        const int v = u + (kb ? dt.dwrap[back] : dt.dreg[back]);
         const uint32_t kf = (c.ninfo[v] >> (2 * din)) & 3u;
-        const int slot = c.sbase[v] + offs_s[ci][12 + 2 * din + (kf & 1u)];
+        const int slot = c.sbase[v] + (kf ? dt.swrap[din] : dt.sreg[din]);
         const int g = c.qoff + c.slot_qubit[slot];
         atomicXor(&flips[g >> 5], 1u << (g & 31));
         u = v;

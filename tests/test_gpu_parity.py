@@ -178,16 +178,21 @@ def test_device_rng_compat_recurrence_and_statistics():
     assert not alt.x[1].any()
 
 
-def test_paths_toggle_matches_oracle_decode():
-    """Recovery through the device path walk gives the oracle's corrected bits."""
+def _toggle_case(p_swap):
     lat = build_lattice(5, "primal", "open")
     ct = lat.complexes["primal"]
-    delta, ps = 0.09, 0.25
+    delta = 0.09
     wopts = {"method": "blueprint", "delta": delta}
-    eng = _engine(lat, delta, ps, wopts, mode="fresh")
+    eng = _engine(lat, delta, p_swap, wopts, mode="fresh")
     T = 8
     batch = eng.run_rng(11, 0, T, want_draws=True)
-    cb = batch.complexes["primal"]
+    return lat, ct, delta, wopts, eng, T, batch
+
+
+def test_paths_toggle_matches_oracle_decode():
+    """Recovery through the device path walk gives the oracle's corrected bits (p_swap = 0:
+    continuous weights, so every shortest path is unique)."""
+    lat, ct, delta, wopts, eng, T, batch = _toggle_case(0)
     trial, cx, src, dst = [], [], [], []
     expect = np.zeros((T, ct.Q), np.uint8)
     for t in range(T):
@@ -203,9 +208,30 @@ def test_paths_toggle_matches_oracle_decode():
             for q in path:
                 expect[t, q] ^= 1
     flips = eng.paths_toggle(trial, cx, src, dst)
-    # a different but equally short path would also be a valid correction; with float
-    # blueprint weights the shortest path is unique
     assert np.array_equal(flips, expect)
+
+
+def test_paths_toggle_is_a_shortest_path_with_ties():
+    """With p-squeezed neighbours many weights are the constants -ln{1/4, 1/3, 2/5}
+    (decoder.py:86) and shortest paths tie; any of them is a valid correction.  Check every
+    pair and connector query: the toggled qubits flip exactly the end cubes and their weights
+    add up to the matching-graph length."""
+    lat, ct, delta, wopts, eng, T, batch = _toggle_case(0.25)
+    cb = batch.complexes["primal"]
+    w = batch.weights
+    for t in range(3):
+        K = int(cb.odd_count[t])
+        odd = cb.odd(t)
+        pl = cb.pairs(t)
+        bl, _ = cb.boundary(t)
+        qs = [(u, v) for u in range(K) for v in range(u + 1, K)] + [(u, -1) for u in range(K)]
+        for u, v in qs:
+            fl = eng.paths_toggle([t], [0], [u], [v])[t]
+            length = pl[u * K - u * (u + 1) // 2 + (v - u - 1)] if v >= 0 else bl[u]
+            np.testing.assert_allclose(w[t][fl.astype(bool)].sum(), length, rtol=1e-9)
+            par = restate.stabilizer_parity(ct, fl)
+            ends = sorted([int(odd[u])] + ([int(odd[v])] if v >= 0 else []))
+            assert np.nonzero(par)[0].tolist() == ends
 
 
 def test_d13_properties():
