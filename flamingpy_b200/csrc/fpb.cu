@@ -129,9 +129,32 @@ ComplexDev make_dev(const ComplexHost& c) {
   return d;
 }
 
+typedef void (*paths_fn)(const PathsParams);
+typedef void (*toggle_fn)(const PathsParams);
+
+// kernel variant by lattice size: NCH = 16-cube chunks each lane scans, NV = cubes relaxed per
+// lane per batch, MINB = CTAs per SM the register budget is sized for
+// (NV = 2 variants are compiled for at most 384 threads so that they get 170 registers)
+paths_fn pick_paths_kernel(int S, int* max_warps) {
+  *max_warps = 16;
+  if (S <= 1024) return k_paths<2, 1, 512, 2>;
+  if (S <= 1536) return k_paths<3, 1, 512, 1>;
+  *max_warps = 12;
+  if (S <= 2560) return k_paths<5, 2, 384, 1>;
+  if (S <= 4096) return k_paths<8, 2, 384, 1>;
+  return k_paths<16, 2, 384, 1>;
+}
+toggle_fn pick_toggle_kernel(int S) {
+  if (S <= 1024) return k_path_toggle<2>;
+  if (S <= 1536) return k_path_toggle<3>;
+  if (S <= 2560) return k_path_toggle<5>;
+  if (S <= 4096) return k_path_toggle<8>;
+  return k_path_toggle<16>;
+}
+
 int configure_paths(fpb_handle* h) {
   // shared-memory budget: one CTA-wide copy of the trial's weights and the face tables, plus a
-  // distance array, open list and flag array per warp (= per concurrent search)
+  // distance array, bucket bytes and a staging list per warp (= per concurrent search)
   int max_optin = 0;
   CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
   int smem_per_sm = 0;
@@ -139,20 +162,31 @@ int configure_paths(fpb_handle* h) {
   const size_t cta_b = paths_cta_bytes(h->S_max, h->slots_max);
   const size_t warp_b = paths_warp_bytes(h->S_max, false);
   h->warps = 0;
+  h->ctas_per_sm = 0;
   if (h->S_max > 16 * 32 * MAX_CHUNKS)
     return fail(FPB_ERR_UNSUPPORTED, "lattice too large for the shortest-path kernel's bucket scan");
+  int max_warps = 16;
+  paths_fn fn = pick_paths_kernel(h->S_max, &max_warps);
+  cudaFuncAttributes fattr;
+  CK(cudaFuncGetAttributes(&fattr, fn));
+  max_optin -= (int)fattr.sharedSizeBytes;  // static shared memory counts against the opt-in limit
+  CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
+  int best = 0;
   for (int ctas = 1; ctas <= 4; ++ctas) {
     // per-CTA budget when `ctas` CTAs share an SM (1 KB reserved per CTA by the runtime)
     size_t budget = (size_t)smem_per_sm / ctas - 1024;
     if (budget > (size_t)max_optin) budget = max_optin;
     if (budget < cta_b + warp_b) break;
     int w = (int)((budget - cta_b) / warp_b);
-    if (w > 16) w = 16;
-    if (w * ctas > h->warps * h->ctas_per_sm || h->warps == 0) {
+    if (w > max_warps) w = max_warps;
+    int resident = 0;  // what registers + shared memory really allow
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, fn, w * 32, cta_b + (size_t)w * warp_b));
+    if (resident > ctas) resident = ctas;
+    if (w * resident > best) {
+      best = w * resident;
       h->warps = w;
-      h->ctas_per_sm = ctas;
+      h->ctas_per_sm = resident;
     }
-    if (w * ctas >= 32) break;
   }
   if (h->warps == 0)
     return fail(FPB_ERR_UNSUPPORTED,
@@ -160,7 +194,6 @@ int configure_paths(fpb_handle* h) {
                     std::to_string(cta_b + warp_b) + " bytes per CTA)");
   h->paths_smem = cta_b + (size_t)h->warps * warp_b;
   h->tasks_per_item = h->warps * 4;
-  CK(cudaFuncSetAttribute(k_paths, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->paths_smem));
   return FPB_OK;
 }
 
@@ -287,7 +320,8 @@ int run_pipeline(fpb_handle* h, long long T, int stage, bool gen, uint64_t seed,
       CK(cudaMemsetAsync(h->counter.p, 0, sizeof(int), st));
       long long grid = (long long)h->sm_count * h->ctas_per_sm;
       if (grid > total_items) grid = total_items;
-      k_paths<<<(unsigned)grid, h->warps * 32, h->paths_smem, st>>>(pp);
+      int mw_unused = 0;
+      pick_paths_kernel(h->S_max, &mw_unused)<<<(unsigned)grid, h->warps * 32, h->paths_smem, st>>>(pp);
       ++launches;
       h->tm.graph_ctas = (int)grid;
     }
@@ -609,11 +643,12 @@ int fpb_paths_toggle(fpb_handle* h, int64_t n_queries, const int32_t* trial, con
     if (warps < 1) return fail(FPB_ERR_UNSUPPORTED, "lattice too large for the path-toggle kernel");
     if (warps > 8) warps = 8;
     const size_t smem = (size_t)warps * per_warp;
-    CK(cudaFuncSetAttribute(k_path_toggle, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    toggle_fn tfn = pick_toggle_kernel(h->S_max);
+    CK(cudaFuncSetAttribute(tfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long long grid = (n_queries + warps - 1) / warps;
     const long long cap = (long long)h->sm_count * 4;
     if (grid > cap) grid = cap;
-    k_path_toggle<<<(unsigned)grid, warps * 32, smem, st>>>(pp);
+    tfn<<<(unsigned)grid, warps * 32, smem, st>>>(pp);
     CK(cudaGetLastError());
   }
   CK(cudaMemcpyAsync(flips_host, h->flips.p, nflip * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));

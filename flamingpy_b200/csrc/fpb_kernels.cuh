@@ -396,7 +396,7 @@ struct PathsParams {
 
 constexpr int NRING = 32;       // ring slots: bucket index mod 32 is kept in one byte per cube
 constexpr int STAGE_CAP = 512;  // per-warp staging list of the cubes of the current bucket
-constexpr int MAX_CHUNKS = 16;  // 16-cube chunks per lane in one scan: S <= 16 * 32 * 16 = 8192
+constexpr int MAX_CHUNKS = 16;  // 16-cube chunks per lane in one scan: S <= 16 * 32 * 16 = 8192 (template NCH)
 
 struct WarpMem {
   double* dist;     // [S]
@@ -483,7 +483,15 @@ __device__ __forceinline__ uint32_t seed_cube(const WarpMem& wm, int c, double d
 // bucket re-files cubes improved inside it.  Cubes more than 31 buckets ahead are parked in the
 // farthest slot and moved on when that slot comes up.  If `stop_at` >= 0 the search ends as
 // soon as that cube is settled.
-template <bool PRED>
+// byte-wise equality of four packed bytes with r4 -> 4-bit mask (exact, no cross-byte carries)
+__device__ __forceinline__ uint32_t eq_mask4(uint32_t word, uint32_t r4) {
+  const uint32_t x = word ^ r4;
+  const uint32_t t = (x & 0x7f7f7f7fu) + 0x7f7f7f7fu;
+  const uint32_t z = ~(t | x | 0x7f7f7f7fu);  // 0x80 in every byte of x that is zero
+  return (z * 0x00204081u) >> 28;              // gather bits 7,15,23,31 into bits 0..3
+}
+
+template <bool PRED, int NCH, int NV>
 __device__ __forceinline__ void warp_search(const CtaMem& cm, const WarpMem& wm, const DirTab& dt, int S,
                                             double step, uint32_t present, int lane, int stop_at) {
   const double inv = 1.0 / step;
@@ -500,23 +508,19 @@ __device__ __forceinline__ void warp_search(const CtaMem& cm, const WarpMem& wm,
     while ((present >> r) & 1u) {
       present &= ~(1u << r);
       // ---------------- scan: stage the cubes filed under slot r ----------------
-      uint32_t masks[MAX_CHUNKS];
+      uint32_t masks[NCH];
       int cnt = 0;
       const uint32_t r4 = (uint32_t)r * 0x01010101u;
 #pragma unroll
-      for (int j = 0; j < MAX_CHUNKS; ++j) {
+      for (int j = 0; j < NCH; ++j) {
         const int ch = j * 32 + lane;
         uint32_t m = 0;
         if (ch < n16) {
           const uint4 q = b4[ch];
-          const uint32_t e0 = __vcmpeq4(q.x, r4), e1 = __vcmpeq4(q.y, r4);
-          const uint32_t e2 = __vcmpeq4(q.z, r4), e3 = __vcmpeq4(q.w, r4);
-          m = (((e0 & 0x08040201u) * 0x01010101u) >> 24) | ((((e1 & 0x08040201u) * 0x01010101u) >> 24) << 4) |
-              ((((e2 & 0x08040201u) * 0x01010101u) >> 24) << 8) | ((((e3 & 0x08040201u) * 0x01010101u) >> 24) << 12);
+          m = eq_mask4(q.x, r4) | (eq_mask4(q.y, r4) << 4) | (eq_mask4(q.z, r4) << 8) | (eq_mask4(q.w, r4) << 12);
         }
         masks[j] = m;
         cnt += __popc(m);
-        if ((j + 1) * 32 >= n16) break;
       }
       int incl = cnt;
 #pragma unroll
@@ -527,7 +531,7 @@ __device__ __forceinline__ void warp_search(const CtaMem& cm, const WarpMem& wm,
       const int total = __shfl_sync(0xffffffffu, incl, 31);
       int pos = incl - cnt;
 #pragma unroll
-      for (int j = 0; j < MAX_CHUNKS; ++j) {
+      for (int j = 0; j < NCH; ++j) {
         uint32_t m = masks[j];
         const int base = (j * 32 + lane) << 4;
         while (m) {
@@ -539,69 +543,78 @@ __device__ __forceinline__ void warp_search(const CtaMem& cm, const WarpMem& wm,
           }
           ++pos;
         }
-        if ((j + 1) * 32 >= n16) break;
       }
       if (total > STAGE_CAP) present |= 1u << r;  // the rest stays filed; scan again afterwards
       const int nst = total < STAGE_CAP ? total : STAGE_CAP;
       __syncwarp();
-      // ---------------- relax the staged cubes, 32 at a time ----------------
+      // ---------------- relax the staged cubes, 32 * NV at a time ----------------
       uint32_t lp = 0;  // slots this lane filed cubes under
-      for (int cb = 0; cb < nst; cb += 32) {
-        const bool valid = cb + lane < nst;
-        const int v = valid ? wm.stage[cb + lane] : 0;
-        const double dv = valid ? wm.dist[v] : 0.0;
-        const int bt = bucket_of(dv, inv);
-        if (valid && bt > cur) {  // a parked cube: move it towards its real bucket
-          const int s2 = (bt < far ? bt : far) & (NRING - 1);
-          wm.bkt[v] = (uint8_t)s2;
-          lp |= 1u << s2;
-        }
-        const bool act = valid && bt <= cur;
-        const uint32_t info = act ? (uint32_t)cm.ninfo[v] : 0xaaau;  // inactive lanes: every face "none"
-        const int sb = cm.sbase[v];
-        int u[6];
-        double nd[6];
-        bool imp[6];
+      for (int cb = 0; cb < nst; cb += 32 * NV) {
+        int u[NV][6];
+        double nd[NV][6];
+        bool imp[NV][6];
 #pragma unroll
-        for (int d = 0; d < 6; ++d) {
-          const uint32_t kind = (info >> (2 * d)) & 3u;
-          const bool a = kind < 2u;
-          u[d] = v + (kind ? dt.dwrap[d] : dt.dreg[d]);
-          const int slot = sb + (kind ? dt.swrap[d] : dt.sreg[d]);
-          const double w = a ? cm.wslot[slot] : 0.0;
-          const double old = a ? wm.dist[u[d]] : 0.0;
-          nd[d] = dv + w;
-          imp[d] = a && nd[d] < old;
+        for (int k = 0; k < NV; ++k) {
+          const bool valid = cb + k * 32 + lane < nst;
+          const int v = valid ? wm.stage[cb + k * 32 + lane] : 0;
+          const double dv = wm.dist[v];
+          const int bt = bucket_of(dv, inv);
+          if (valid && bt > cur) {  // a parked cube: move it towards its real bucket
+            const int s2 = (bt < far ? bt : far) & (NRING - 1);
+            wm.bkt[v] = (uint8_t)s2;
+            lp |= 1u << s2;
+          }
+          const bool act = valid && bt <= cur;
+          const uint32_t info = act ? (uint32_t)cm.ninfo[v] : 0xaaau;  // inactive lanes: every face "none"
+          const int sb = cm.sbase[v];
+#pragma unroll
+          for (int d = 0; d < 6; ++d) {
+            const uint32_t kind = (info >> (2 * d)) & 3u;
+            const bool a = kind < 2u;
+            // inactive faces read harmless in-range addresses (their own cube, slot 0)
+            u[k][d] = a ? v + (kind ? dt.dwrap[d] : dt.dreg[d]) : v;
+            const int slot = a ? sb + (kind ? dt.swrap[d] : dt.sreg[d]) : 0;
+            nd[k][d] = dv + cm.wslot[slot];
+            imp[k][d] = a && nd[k][d] < wm.dist[u[k][d]];
+          }
         }
 #pragma unroll
         for (int d = 0; d < 6; ++d)
-          if (imp[d]) wm.dist[u[d]] = nd[d];
+#pragma unroll
+          for (int k = 0; k < NV; ++k)
+            if (imp[k][d]) wm.dist[u[k][d]] = nd[k][d];
         __syncwarp();
-        double fin[6];
+        double fin[NV][6];
         bool redo;
         do {
           redo = false;
 #pragma unroll
-          for (int d = 0; d < 6; ++d) fin[d] = imp[d] ? wm.dist[u[d]] : 0.0;
+          for (int k = 0; k < NV; ++k)
+#pragma unroll
+            for (int d = 0; d < 6; ++d) fin[k][d] = wm.dist[u[k][d]];
 #pragma unroll
           for (int d = 0; d < 6; ++d)
-            if (imp[d] && fin[d] > nd[d]) {
-              wm.dist[u[d]] = nd[d];
-              redo = true;
-            }
+#pragma unroll
+            for (int k = 0; k < NV; ++k)
+              if (imp[k][d] && fin[k][d] > nd[k][d]) {
+                wm.dist[u[k][d]] = nd[k][d];
+                redo = true;
+              }
           redo = __any_sync(0xffffffffu, redo);
         } while (redo);
 #pragma unroll
-        for (int d = 0; d < 6; ++d)
-          if (imp[d]) {
-            const int bi = bucket_of(fin[d], inv);
-            const int s2 = (bi < far ? bi : far) & (NRING - 1);
-            wm.bkt[u[d]] = (uint8_t)s2;
-            lp |= 1u << s2;
-            if (PRED) {
-              if (fin[d] == nd[d]) wm.pred[u[d]] = (uint8_t)d;
+        for (int k = 0; k < NV; ++k)
+#pragma unroll
+          for (int d = 0; d < 6; ++d)
+            if (imp[k][d]) {
+              const int bi = bucket_of(fin[k][d], inv);
+              const int s2 = (bi < far ? bi : far) & (NRING - 1);
+              wm.bkt[u[k][d]] = (uint8_t)s2;
+              lp |= 1u << s2;
+              if (PRED) {
+                if (fin[k][d] == nd[k][d]) wm.pred[u[k][d]] = (uint8_t)d;
+              }
             }
-          }
         __syncwarp();
       }
       present |= __reduce_or_sync(0xffffffffu, lp);
@@ -627,7 +640,8 @@ __device__ __forceinline__ double bucket_step(double wmin, double factor) {
   return (wmin > 0.0 && wmin < FPB_INF) ? wmin * factor : 1.0;
 }
 
-__global__ void __launch_bounds__(512) k_paths(const __grid_constant__ PathsParams p) {
+template <int NCH, int NV, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) k_paths(const __grid_constant__ PathsParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ int item_s;
   __shared__ double red_s[32];
@@ -701,35 +715,40 @@ __global__ void __launch_bounds__(512) k_paths(const __grid_constant__ PathsPara
     const long long ooff = c.odd_off[t];
     const int task_end = min(n_tasks, (chunk + 1) * p.tasks_per_item);
     for (int task = chunk * p.tasks_per_item + wid; task < task_end; task += (nthreads >> 5)) {
-      warp_clear(wm, S, lane);
-      if (task < K - 1) {
-        // single-source search from odd cube `task`; row `task` of the packed upper triangle
-        const int src = odd[task];
-        uint32_t present = 0;
-        if (lane == 0) present = seed_cube(wm, src, 0.0, inv, 0);
-        present = __shfl_sync(0xffffffffu, present, 0);
-        __syncwarp();
-        warp_search<false>(cm, wm, dt, S, step, present, lane, -1);
-        const long long row = poff + (long long)task * K - (long long)task * (task + 1) / 2;
-        for (int b = task + 1 + lane; b < K; b += 32) c.pair_len[row + (b - task - 1)] = wm.dist[odd[b]];
-      } else {
-        // LOW then HIGH connector searches; keep the nearer one (ties -> low, matching.py:149-150)
-        uint32_t present = warp_seed_connector(cm, wm, c.n_low, c.low_cube, c.low_slot, inv, lane);
-        warp_search<false>(cm, wm, dt, S, step, present, lane, -1);
-        for (int b = lane; b < K; b += 32) c.bnd_len[ooff + b] = wm.dist[odd[b]];
-        __syncwarp();
+      // task < K-1: single-source search from odd cube `task` (row `task` of the packed upper
+      // triangle); task == K-1: LOW then HIGH connector searches, keeping the nearer one
+      // (ties -> low, matching.py:149-150)
+      const bool pair_task = task < K - 1;
+      const int n_phase = pair_task ? 1 : 2;
+      for (int ph = 0; ph < n_phase; ++ph) {
         warp_clear(wm, S, lane);
-        present = warp_seed_connector(cm, wm, c.n_high, c.high_cube, c.high_slot, inv, lane);
-        warp_search<false>(cm, wm, dt, S, step, present, lane, -1);
-        for (int b = lane; b < K; b += 32) {
-          const double lo_d = c.bnd_len[ooff + b];
-          const double hi_d = wm.dist[odd[b]];
-          const bool high = hi_d < lo_d;
-          c.bnd_len[ooff + b] = high ? hi_d : lo_d;
-          c.bnd_side[ooff + b] = high ? 1 : 0;
+        uint32_t present = 0;
+        if (pair_task) {
+          if (lane == 0) present = seed_cube(wm, odd[task], 0.0, inv, 0);
+          present = __shfl_sync(0xffffffffu, present, 0);
+          __syncwarp();
+        } else if (ph == 0) {
+          present = warp_seed_connector(cm, wm, c.n_low, c.low_cube, c.low_slot, inv, lane);
+        } else {
+          present = warp_seed_connector(cm, wm, c.n_high, c.high_cube, c.high_slot, inv, lane);
         }
+        warp_search<false, NCH, NV>(cm, wm, dt, S, step, present, lane, -1);
+        if (pair_task) {
+          const long long row = poff + (long long)task * K - (long long)task * (task + 1) / 2;
+          for (int b = task + 1 + lane; b < K; b += 32) c.pair_len[row + (b - task - 1)] = wm.dist[odd[b]];
+        } else if (ph == 0) {
+          for (int b = lane; b < K; b += 32) c.bnd_len[ooff + b] = wm.dist[odd[b]];
+        } else {
+          for (int b = lane; b < K; b += 32) {
+            const double lo_d = c.bnd_len[ooff + b];
+            const double hi_d = wm.dist[odd[b]];
+            const bool high = hi_d < lo_d;
+            c.bnd_len[ooff + b] = high ? hi_d : lo_d;
+            c.bnd_side[ooff + b] = high ? 1 : 0;
+          }
+        }
+        __syncwarp();
       }
-      __syncwarp();
     }
     __syncthreads();
   }
@@ -743,6 +762,7 @@ __host__ __device__ inline size_t toggle_warp_bytes(int S_max, int slots_max) {
   return align16((size_t)slots_max * 8) + paths_warp_bytes(S_max, true);
 }
 
+template <int NCH>
 __global__ void __launch_bounds__(256) k_path_toggle(const __grid_constant__ PathsParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -776,23 +796,21 @@ __global__ void __launch_bounds__(256) k_path_toggle(const __grid_constant__ Pat
     const bool pair_query = p.q_dst[qi] >= 0;
     uint32_t* flips = p.flips + (long long)t * p.bit_words;
     warp_clear(wm, S, lane);
-    int walk_from, side = 0;
+    int walk_from, stop, side = 0;
+    uint32_t present = 0;
     if (pair_query) {
-      const int dst = odd[p.q_dst[qi]];
-      uint32_t present = 0;
       if (lane == 0) present = seed_cube(wm, src, 0.0, inv, 6);
       present = __shfl_sync(0xffffffffu, present, 0);
       __syncwarp();
-      warp_search<true>(cm, wm, dt, S, step, present, lane, dst);
-      walk_from = dst;
+      stop = walk_from = odd[p.q_dst[qi]];
     } else {
       // to the nearer connector, as recorded by the matching-graph run
       side = c.bnd_side[c.odd_off[t] + p.q_src[qi]];
-      const uint32_t present = side ? warp_seed_connector(cm, wm, c.n_high, c.high_cube, c.high_slot, inv, lane)
-                                    : warp_seed_connector(cm, wm, c.n_low, c.low_cube, c.low_slot, inv, lane);
-      warp_search<true>(cm, wm, dt, S, step, present, lane, src);
-      walk_from = src;
+      present = side ? warp_seed_connector(cm, wm, c.n_high, c.high_cube, c.high_slot, inv, lane)
+                     : warp_seed_connector(cm, wm, c.n_low, c.low_cube, c.low_slot, inv, lane);
+      stop = walk_from = src;
     }
+    warp_search<true, NCH, 1>(cm, wm, dt, S, step, present, lane, stop);
     __syncwarp();
     if (lane == 0) {
       int u = walk_from;

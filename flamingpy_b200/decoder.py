@@ -1,0 +1,173 @@
+"""Reference-compatible decoding front end (``flamingpy/decoders/decoder.py``).
+
+``correct(code, decoder="MWPM", weight_options=..., decoder_opts=...)`` keeps the
+reference's signature and result.  Weight assignment, syndrome evaluation and
+matching-graph construction run on the GPU for the noise realisation the last
+``CVLayer.apply_noise`` call produced; the minimum-weight perfect matching is
+solved on the host (north star: "the final MWPM solve still hands the GPU-built
+graph to the reference's own matcher"), then the matched pairs' correction
+paths are extracted on the GPU and the logical check is evaluated.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib
+from .matching import GpuMatchingGraph, solve_matching
+
+
+def _require_trial(code):
+    if code._trial is None:
+        raise RuntimeError("no noise realisation: call CVLayer.apply_noise(rng) first")
+    return code._trial
+
+
+def assign_weights(code, decoder="MWPM", **kwargs):
+    """``assign_weights`` (``decoders/decoder.py:31-119``) for the MWPM decoder:
+    writes the ``weight`` attribute of every syndrome qubit."""
+    if decoder != "MWPM":
+        raise NotImplementedError("only the MWPM decoder is on the accelerated path")
+    wo = {"method": "uniform", "integer": False, "multiplier": 1}
+    wo.update(kwargs)
+    if wo.get("prob_precomputed"):
+        raise NotImplementedError("prob_precomputed weights belong to CVMacroLayer (out of scope, SURVEY.md 8f)")
+    x, state, delta, p_swap = _require_trial(code)
+    wo.pop("prob_precomputed", None)
+    eng = code.engine(delta, p_swap, wo)
+    batch = eng.run_injected(x[None, :], state[None, :], stage=_lib.STAGE_NOISE)
+    g = code.graph
+    g._ensure_arrays()
+    off = 0
+    for e in code.ec:
+        ct = code.lattice.complexes[e]
+        w = batch.weights[0, off : off + ct.Q]
+        g.weight[ct.qubits] = w
+        off += ct.Q
+    return eng
+
+
+def build_match_graph(code, ec, matching_backend="networkx", weight_options=None):
+    """``build_match_graph`` (``decoders/mwpm/algos.py:23-47``): the matching graph of the
+    current noise realisation, built on the GPU."""
+    x, state, delta, p_swap = _require_trial(code)
+    wo = {"method": "uniform", "integer": False, "multiplier": 1}
+    wo.update(weight_options or {})
+    eng = code.engine(delta, p_swap, wo)
+    batch = eng.run_injected(x[None, :], state[None, :], stage=_lib.STAGE_GRAPH)
+    return GpuMatchingGraph.from_batch(code, ec, eng, batch, 0, backend=matching_backend)
+
+
+def recovery(qubits_to_flip, code, ec, sanity_check=False):
+    """``recovery`` (``decoders/decoder.py:122-148``)."""
+    g = code.graph
+    for q in qubits_to_flip:
+        g.bit_val[g.to_indices[tuple(q)]] ^= 1
+    if sanity_check:
+        odd = list(getattr(code, ec + "_stab_graph").odd_parity_stabilizers())
+        if odd:
+            print("Unsatisfied " + ec + " stabilizers:", odd)
+        else:
+            print(ec.capitalize() + " recovery succeeded - no unsatisfied stabilizers.")
+
+
+def check_correction(code, sanity_check=False):
+    """``check_correction`` (``decoders/decoder.py:151-224``): parity of the corrected
+    bits over the first correlation surface of each checked direction."""
+    g = code.graph
+    ec_checks, truth_dicts = [], []
+    for ec in code.ec:
+        ct = code.lattice.complexes[ec]
+        truth = {"x": [], "y": [], "z": []}
+        qcoords = code.lattice.coords[ct.qubits]
+        minimum = 0 if ec == "primal" else 1
+        for name in ct.plane_names:
+            a = "xyz".index(name)
+            maximum = 2 * code.dims[a] if sanity_check else minimum + 2
+            for sheet in range(minimum, maximum, 2):
+                sel = ct.qubits[qcoords[:, a] == sheet]
+                parity = int(np.bitwise_xor.reduce(g.bit_val[sel].astype(np.int64))) if len(sel) else 0
+                truth[name].append(bool(1 - parity))
+        if sanity_check:
+            print(ec.capitalize() + " error correction check --", truth)
+        ec_checks.append(bool(np.all([truth[n][0] for n in ct.plane_names])))
+        truth_dicts.append(truth)
+    if sanity_check:
+        return ec_checks, truth_dicts
+    return ec_checks
+
+
+def correct(code, decoder="MWPM", weight_options=None, sanity_check=False, decoder_opts=None, draw=False,
+            drawing_opts=None):
+    """``correct`` (``decoders/decoder.py:227-288``).  Returns True if error correction
+    succeeded.  ``decoder_opts["backend"]`` picks the host matcher ("networkx" by
+    default here: rustworkx / lemon are not installable offline)."""
+    if decoder != "MWPM":
+        raise NotImplementedError("only the MWPM decoder is on the accelerated path")
+    if draw:
+        raise NotImplementedError("drawing is out of scope for the accelerated path")
+    weight_options = dict(weight_options or {})
+    opts = {"backend": "networkx"}
+    opts.update(decoder_opts or {})
+    if opts["backend"] == "rustworkx":
+        opts["backend"] = "networkx"
+    x, state, delta, p_swap = _require_trial(code)
+    wo = {"method": "uniform", "integer": False, "multiplier": 1}
+    wo.update(weight_options)
+    eng = code.engine(delta, p_swap, wo)
+    batch = eng.run_injected(x[None, :], state[None, :], stage=_lib.STAGE_GRAPH)
+    g = code.graph
+    g._ensure_arrays()
+    off = 0
+    for e in code.ec:
+        ct = code.lattice.complexes[e]
+        g.weight[ct.qubits] = batch.weights[0, off : off + ct.Q]
+        g.hom_val_p[ct.qubits] = batch.hom[0, off : off + ct.Q]
+        g.bit_val[ct.qubits] = batch.bits[0, off : off + ct.Q]
+        off += ct.Q
+    flips = decode_batch(code, eng, batch, backend=opts["backend"])
+    off = 0
+    for e in code.ec:
+        ct = code.lattice.complexes[e]
+        g.bit_val[ct.qubits] ^= flips[0, off : off + ct.Q].astype(np.int8)
+        off += ct.Q
+        if sanity_check:
+            recovery([], code, e, sanity_check=True)
+    result = check_correction(code, sanity_check=sanity_check)
+    if sanity_check:
+        return bool(np.all(result[0]))
+    return bool(np.all(result))
+
+
+def decode_batch(code, eng, batch, backend="networkx"):
+    """Host matching + device path extraction for every trial of ``batch``.
+    Returns the recovery as uint8[T, Qtot] bit flips."""
+    trial, cx, src, dst = [], [], [], []
+    for ci, e in enumerate(code.ec):
+        ct = code.lattice.complexes[e]
+        cb = batch.complexes[e]
+        for t in range(batch.n_trials):
+            K = int(cb.odd_count[t])
+            if K == 0:
+                continue
+            bl = cb.boundary(t)[0] if ct.has_boundary else None
+            for u, v in solve_matching(K, cb.pairs(t), bl, backend=backend):
+                trial.append(t)
+                cx.append(ci)
+                src.append(u)
+                dst.append(v)
+    return eng.paths_toggle(trial, cx, src, dst)
+
+
+def logical_failures(code, batch, flips):
+    """Vectorised ``check_correction`` over a batch: bool[T], True where any checked
+    correlation surface of any complex has odd parity after the recovery."""
+    corrected = batch.bits ^ flips
+    fail = np.zeros(batch.n_trials, bool)
+    off = 0
+    for e in code.ec:
+        ct = code.lattice.complexes[e]
+        for plane in ct.planes:
+            fail |= (corrected[:, off + plane].sum(axis=1) % 2).astype(bool)
+        off += ct.Q
+    return fail
