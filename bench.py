@@ -168,7 +168,7 @@ def run_reference_arm(args, cfg, lat):
         return
     fresh = args.mode == "fresh"
     cores = os.cpu_count() or 1
-    per_step = args.cpu_trials if args.cpu_trials > 0 else max(8, 2 * cores)
+    per_step = args.cpu_trials if args.cpu_trials > 0 else max(8, 32 * cores)
     for _ in range(args.warmup):
         time_cpu_port(lat, cfg, max(2, per_step // 4), fresh)
     t_tot = 0.0
@@ -348,7 +348,7 @@ def run_gpu_arm(args, cfg, lat):
         }
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
-            n_cpu = args.cpu_trials if args.cpu_trials > 0 else max(8, 2 * cores)
+            n_cpu = args.cpu_trials if args.cpu_trials > 0 else max(8, 64 * cores)
             dt, threads = time_cpu_port(lat, cfg, n_cpu, fresh)
             line["cpu_baseline"] = {
                 "value": n_cpu / dt, "unit": "trials/s", "cores": threads, "kind": "port",
@@ -372,7 +372,7 @@ def main():
     ap.add_argument("--batch", type=int, default=2048, help="trials per GPU per step (device-resident arm)")
     ap.add_argument("--e2e-batch", type=int, default=512, help="trials per GPU per step (end-to-end arm)")
     ap.add_argument("--delta-step", type=float, default=0.0)
-    ap.add_argument("--cpu-trials", type=int, default=0, help="CPU sample size (0: 2 x cores)")
+    ap.add_argument("--cpu-trials", type=int, default=0, help="CPU sample size in trials (0: 64 x cores for cpu_baseline, 32 x cores per step for --impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":

@@ -378,7 +378,7 @@ struct PathsParams {
   int tasks_per_item;
   int S_max, slots_max;       // smem sizing (max over complexes)
   int warps;                  // warps per CTA
-  double step_factor;         // bucket width in units of the trial's minimum weight
+  double step_factor;         // bucket width in units of the trial's mean weight
   const double* weights;      // [T][Qtot]
   const int* item_off;        // [T * n_complex + 1]
   int total_items;
@@ -483,20 +483,49 @@ __device__ __forceinline__ uint32_t seed_cube(const WarpMem& wm, int c, double d
 // bucket re-files cubes improved inside it.  Cubes more than 31 buckets ahead are parked in the
 // farthest slot and moved on when that slot comes up.  If `stop_at` >= 0 the search ends as
 // soon as that cube is settled.
-// byte-wise equality of four packed bytes with r4 -> 4-bit mask (exact, no cross-byte carries)
-__device__ __forceinline__ uint32_t eq_mask4(uint32_t word, uint32_t r4) {
+// ---- explicit shared-memory accessors (32-bit shared-window addresses; volatile keeps the
+// program order of the search's loads and stores, which the conflict resolution relies on) ----
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ double lds_f64(uint32_t a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_f64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v)); }
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
+  uint16_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((uint16_t)v)); }
+__device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v)); }
+__device__ __forceinline__ uint4 lds_v4(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_v4(uint32_t a, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
+}
+
+// bytes of `word` equal to the byte replicated in r4: returns 0x80 in each matching byte
+// (exact: no carries cross a byte boundary)
+__device__ __forceinline__ uint32_t eq_bytes(uint32_t word, uint32_t r4) {
   const uint32_t x = word ^ r4;
   const uint32_t t = (x & 0x7f7f7f7fu) + 0x7f7f7f7fu;
-  const uint32_t z = ~(t | x | 0x7f7f7f7fu);  // 0x80 in every byte of x that is zero
-  return (z * 0x00204081u) >> 28;              // gather bits 7,15,23,31 into bits 0..3
+  return ~(t | x | 0x7f7f7f7fu);
 }
+// gather bits 7,15,23,31 into bits 0..3
+__device__ __forceinline__ uint32_t movemask4(uint32_t z) { return (z * 0x00204081u) >> 28; }
 
 template <bool PRED, int NCH, int NV>
 __device__ __forceinline__ void warp_search(const CtaMem& cm, const WarpMem& wm, const DirTab& dt, int S,
                                             double step, uint32_t present, int lane, int stop_at) {
   const double inv = 1.0 / step;
   const int n16 = (S + 15) >> 4;
-  const uint4* b4 = reinterpret_cast<const uint4*>(wm.bkt);
+  const uint32_t dist_a = smem_addr(wm.dist), bkt_a = smem_addr(wm.bkt), stage_a = smem_addr(wm.stage);
+  const uint32_t pred_a = PRED ? smem_addr(wm.pred) : 0u;
+  const uint32_t wslot_a = smem_addr(cm.wslot);
   int cur = 0;
   while (present) {
     {
@@ -508,6 +537,7 @@ __device__ __forceinline__ void warp_search(const CtaMem& cm, const WarpMem& wm,
     while ((present >> r) & 1u) {
       present &= ~(1u << r);
       // ---------------- scan: stage the cubes filed under slot r ----------------
+      // matching bytes are cleared (0xFF) in the same pass, one 16-byte store per chunk
       uint32_t masks[NCH];
       int cnt = 0;
       const uint32_t r4 = (uint32_t)r * 0x01010101u;
@@ -516,8 +546,16 @@ __device__ __forceinline__ void warp_search(const CtaMem& cm, const WarpMem& wm,
         const int ch = j * 32 + lane;
         uint32_t m = 0;
         if (ch < n16) {
-          const uint4 q = b4[ch];
-          m = eq_mask4(q.x, r4) | (eq_mask4(q.y, r4) << 4) | (eq_mask4(q.z, r4) << 8) | (eq_mask4(q.w, r4) << 12);
+          uint4 q = lds_v4(bkt_a + (ch << 4));
+          const uint32_t z0 = eq_bytes(q.x, r4), z1 = eq_bytes(q.y, r4), z2 = eq_bytes(q.z, r4), z3 = eq_bytes(q.w, r4);
+          m = movemask4(z0) | (movemask4(z1) << 4) | (movemask4(z2) << 8) | (movemask4(z3) << 12);
+          if (m) {
+            q.x |= (z0 >> 7) * 0xffu;
+            q.y |= (z1 >> 7) * 0xffu;
+            q.z |= (z2 >> 7) * 0xffu;
+            q.w |= (z3 >> 7) * 0xffu;
+            sts_v4(bkt_a + (ch << 4), q);
+          }
         }
         masks[j] = m;
         cnt += __popc(m);
@@ -535,54 +573,54 @@ __device__ __forceinline__ void warp_search(const CtaMem& cm, const WarpMem& wm,
         uint32_t m = masks[j];
         const int base = (j * 32 + lane) << 4;
         while (m) {
-          const int b = __ffs(m) - 1;
+          const int cube = base + __ffs(m) - 1;
           m &= m - 1;
-          if (pos < STAGE_CAP) {
-            wm.stage[pos] = (uint16_t)(base + b);
-            wm.bkt[base + b] = 0xff;
-          }
+          if (pos < STAGE_CAP) sts_u16(stage_a + 2 * pos, cube);
+          else sts_u8(bkt_a + cube, r);  // staging list full: leave it filed for the next scan
           ++pos;
         }
       }
-      if (total > STAGE_CAP) present |= 1u << r;  // the rest stays filed; scan again afterwards
+      if (total > STAGE_CAP) present |= 1u << r;
       const int nst = total < STAGE_CAP ? total : STAGE_CAP;
       __syncwarp();
       // ---------------- relax the staged cubes, 32 * NV at a time ----------------
       uint32_t lp = 0;  // slots this lane filed cubes under
       for (int cb = 0; cb < nst; cb += 32 * NV) {
-        int u[NV][6];
+        uint32_t ua[NV][6];  // shared address of the neighbour's distance
         double nd[NV][6];
         bool imp[NV][6];
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
-          const bool valid = cb + k * 32 + lane < nst;
-          const int v = valid ? wm.stage[cb + k * 32 + lane] : 0;
-          const double dv = wm.dist[v];
+          const int idx = cb + k * 32 + lane;
+          const bool valid = idx < nst;
+          const int v = valid ? (int)lds_u16(stage_a + 2 * idx) : 0;
+          const uint32_t va = dist_a + 8u * v;
+          const double dv = lds_f64(va);
           const int bt = bucket_of(dv, inv);
           if (valid && bt > cur) {  // a parked cube: move it towards its real bucket
             const int s2 = (bt < far ? bt : far) & (NRING - 1);
-            wm.bkt[v] = (uint8_t)s2;
+            sts_u8(bkt_a + v, s2);
             lp |= 1u << s2;
           }
           const bool act = valid && bt <= cur;
           const uint32_t info = act ? (uint32_t)cm.ninfo[v] : 0xaaau;  // inactive lanes: every face "none"
-          const int sb = cm.sbase[v];
+          const uint32_t sb = wslot_a + 8u * cm.sbase[v];
 #pragma unroll
           for (int d = 0; d < 6; ++d) {
             const uint32_t kind = (info >> (2 * d)) & 3u;
             const bool a = kind < 2u;
-            // inactive faces read harmless in-range addresses (their own cube, slot 0)
-            u[k][d] = a ? v + (kind ? dt.dwrap[d] : dt.dreg[d]) : v;
-            const int slot = a ? sb + (kind ? dt.swrap[d] : dt.sreg[d]) : 0;
-            nd[k][d] = dv + cm.wslot[slot];
-            imp[k][d] = a && nd[k][d] < wm.dist[u[k][d]];
+            // absent faces read harmless in-range addresses (their own cube, slot 0)
+            ua[k][d] = a ? va + 8 * (kind ? dt.dwrap[d] : dt.dreg[d]) : va;
+            const uint32_t wa = a ? sb + 8 * (kind ? dt.swrap[d] : dt.sreg[d]) : wslot_a;
+            nd[k][d] = dv + lds_f64(wa);
+            imp[k][d] = a && nd[k][d] < lds_f64(ua[k][d]);
           }
         }
 #pragma unroll
         for (int d = 0; d < 6; ++d)
 #pragma unroll
           for (int k = 0; k < NV; ++k)
-            if (imp[k][d]) wm.dist[u[k][d]] = nd[k][d];
+            if (imp[k][d]) sts_f64(ua[k][d], nd[k][d]);
         __syncwarp();
         double fin[NV][6];
         bool redo;
@@ -591,30 +629,30 @@ __device__ __forceinline__ void warp_search(const CtaMem& cm, const WarpMem& wm,
 #pragma unroll
           for (int k = 0; k < NV; ++k)
 #pragma unroll
-            for (int d = 0; d < 6; ++d) fin[k][d] = wm.dist[u[k][d]];
+            for (int d = 0; d < 6; ++d) fin[k][d] = lds_f64(ua[k][d]);
 #pragma unroll
           for (int d = 0; d < 6; ++d)
 #pragma unroll
-            for (int k = 0; k < NV; ++k)
-              if (imp[k][d] && fin[k][d] > nd[k][d]) {
-                wm.dist[u[k][d]] = nd[k][d];
-                redo = true;
-              }
+            for (int k = 0; k < NV; ++k) {
+              const bool lost = imp[k][d] && fin[k][d] > nd[k][d];
+              if (lost) sts_f64(ua[k][d], nd[k][d]);
+              redo |= lost;
+            }
           redo = __any_sync(0xffffffffu, redo);
         } while (redo);
 #pragma unroll
         for (int k = 0; k < NV; ++k)
 #pragma unroll
-          for (int d = 0; d < 6; ++d)
-            if (imp[k][d]) {
-              const int bi = bucket_of(fin[k][d], inv);
-              const int s2 = (bi < far ? bi : far) & (NRING - 1);
-              wm.bkt[u[k][d]] = (uint8_t)s2;
-              lp |= 1u << s2;
-              if (PRED) {
-                if (fin[k][d] == nd[k][d]) wm.pred[u[k][d]] = (uint8_t)d;
-              }
+          for (int d = 0; d < 6; ++d) {
+            const int bi = bucket_of(fin[k][d], inv);
+            const int s2 = (bi < far ? bi : far) & (NRING - 1);
+            const uint32_t ui = (ua[k][d] - dist_a) >> 3;
+            if (imp[k][d]) sts_u8(bkt_a + ui, s2);
+            lp |= imp[k][d] ? (1u << s2) : 0u;
+            if (PRED) {
+              if (imp[k][d] && fin[k][d] == nd[k][d]) sts_u8(pred_a + ui, d);
             }
+          }
         __syncwarp();
       }
       present |= __reduce_or_sync(0xffffffffu, lp);
@@ -636,8 +674,10 @@ __device__ __forceinline__ uint32_t warp_seed_connector(const CtaMem& cm, const 
   return __reduce_or_sync(0xffffffffu, lp);
 }
 
-__device__ __forceinline__ double bucket_step(double wmin, double factor) {
-  return (wmin > 0.0 && wmin < FPB_INF) ? wmin * factor : 1.0;
+// bucket width = factor x the trial's mean edge weight (any positive width is correct; about
+// 1.5 mean weights measured fastest on B200 across the BASELINE configurations)
+__device__ __forceinline__ double bucket_step(double wmean, double factor) {
+  return (wmean > 0.0 && wmean < FPB_INF) ? wmean * factor : 1.0;
 }
 
 template <int NCH, int NV, int MAXT, int MINB>
@@ -688,20 +728,20 @@ __global__ void __launch_bounds__(MAXT, MINB) k_paths(const __grid_constant__ Pa
     }
     if (staged_tc != tc) {
       const double* w = p.weights + (long long)t * p.Qtot + c.qoff;
-      double mn = FPB_INF;
+      double sum = 0.0;
       for (int s = threadIdx.x; s < c.n_slots; s += nthreads) {
         const int q = c.slot_qubit[s];
         const double ws = (q >= 0) ? w[q] : FPB_INF;
         wslot[s] = ws;
-        mn = fmin(mn, ws);
+        sum += (q >= 0) ? ws : 0.0;
       }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-      if (lane == 0) red_s[wid] = mn;
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      if (lane == 0) red_s[wid] = sum;
       __syncthreads();
-      mn = FPB_INF;
-      for (int w2 = 0; w2 < (nthreads >> 5); ++w2) mn = fmin(mn, red_s[w2]);
-      step = bucket_step(mn, p.step_factor);
+      sum = 0.0;
+      for (int w2 = 0; w2 < (nthreads >> 5); ++w2) sum += red_s[w2];
+      step = bucket_step(sum / (double)c.Q, p.step_factor);
       staged_tc = tc;
     }
     __syncthreads();
@@ -778,16 +818,16 @@ __global__ void __launch_bounds__(256) k_path_toggle(const __grid_constant__ Pat
     const int S = c.S;
     const DirTab dt = load_dirtab(c);
     const double* w = p.weights + (long long)t * p.Qtot + c.qoff;
-    double mn = FPB_INF;
+    double sum = 0.0;
     for (int s = lane; s < c.n_slots; s += 32) {
       const int q = c.slot_qubit[s];
       const double ws = (q >= 0) ? w[q] : FPB_INF;
       wslot[s] = ws;
-      mn = fmin(mn, ws);
+      sum += (q >= 0) ? ws : 0.0;
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-    const double step = bucket_step(mn, p.step_factor);
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const double step = bucket_step(sum / (double)c.Q, p.step_factor);
     const double inv = 1.0 / step;
     CtaMem cm;
     cm.wslot = wslot; cm.ninfo = c.ninfo; cm.sbase = c.sbase;

@@ -98,7 +98,7 @@ typedef struct fpb_config {
   double weight_multiplier; /* weight_options["multiplier"] */
   int32_t label_mode;   /* FPB_MODE_* (device RNG only) */
   int64_t chain_len;    /* trials per reused-layer chain in compat mode; <=0: one chain */
-  double delta_step;    /* shortest-path bucket width in units of the trial's minimum weight; <=0: default */
+  double delta_step;    /* shortest-path bucket width in units of the trial's mean weight; <=0: default (2.0) */
 } fpb_config;
 
 typedef struct fpb_handle fpb_handle;

@@ -13,11 +13,21 @@ subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, che
 cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
 dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
 # walk the function of interest
+# pick the one function whose instruction count equals the report's
+funcs = {}; name = None
+for l in dis.splitlines():
+    m = re.match(r"\s*\.text\.(\S+):", l)
+    if m:
+        name = m.group(1); funcs[name] = 0; continue
+    if name and re.match(r"\s+/\*[0-9a-f]{4,}\*/", l): funcs[name] += 1
+target = [f for f, n in funcs.items() if re.search(kern, f) and n == len(body)]
+target = target[0] if target else None
+print("function", target, file=sys.stderr)
 lines = []; cur = None; infn = False
 for l in dis.splitlines():
     m = re.match(r"\s*\.text\.(\S+):", l)
     if m:
-        infn = re.search(kern, m.group(1)) is not None
+        infn = (m.group(1) == target) if target else re.search(kern, m.group(1)) is not None
         continue
     if not infn: continue
     m = re.search(r'//## File "([^"]+)", line (\d+)', l)
