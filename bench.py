@@ -155,11 +155,13 @@ def time_cpu_port(lat, cfg, n_trials, fresh, threads=0, seed=SEED):
     from oracle import c_oracle  # checker / baseline leg only
 
     c_oracle.load()
+    if threads <= 0:
+        threads = os.cpu_count() or 1  # explicit: torchrun exports OMP_NUM_THREADS=1
     t0 = time.perf_counter()
     x, st = host_inputs(lat, cfg, n_trials, seed, fresh)
     c_oracle.run(lat, cfg["delta"], cfg["p_swap"], cfg["weight_opts"], x, st, n_threads=threads, copy_out=False)
     dt = time.perf_counter() - t0
-    return dt, (threads if threads > 0 else c_oracle.max_threads())
+    return dt, threads
 
 
 def run_reference_arm(args, cfg, lat):

@@ -1,0 +1,155 @@
+"""Edge cases of the C ABI path: empty syndromes, single odd cubes, tiny batches, ragged
+batches mixing silent and noisy trials, argument errors."""
+
+import numpy as np
+import pytest
+
+from flamingpy_b200 import _lib
+from flamingpy_b200.lattice import build_lattice
+from oracle import c_oracle, restate
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(lat, delta, p_swap, wopts=None, **kw):
+    from flamingpy_b200.engine import TrialEngine
+
+    return TrialEngine(lat, delta, p_swap, wopts or {"method": "blueprint", "delta": delta}, **kw)
+
+
+def _same_as_oracle(lat, batch, ref):
+    assert np.array_equal(batch.hom, ref.hom)
+    assert np.array_equal(batch.bits, ref.bits)
+    np.testing.assert_allclose(batch.weights, ref.weights, rtol=1e-9, atol=0)
+    for e in lat.ec:
+        a, b = batch.complexes[e], ref.complexes[e]
+        assert np.array_equal(a.parity, b.parity)
+        assert np.array_equal(a.odd_count, b.odd_count)
+        assert np.array_equal(a.odd_ids, b.odd_ids)
+        np.testing.assert_allclose(a.pair_len, b.pair_len, rtol=1e-9, atol=0)
+        np.testing.assert_allclose(a.bnd_len, b.bnd_len, rtol=1e-9, atol=0)
+        assert np.array_equal(a.bnd_side, b.bnd_side)
+
+
+def test_all_silent_batch_has_empty_graph():
+    lat = build_lattice(5, "primal", "open")
+    eng = _engine(lat, 0.09, 0)
+    N = lat.N
+    batch = eng.run_injected(np.zeros((3, 2 * N)), np.zeros((3, N), np.uint8))
+    cb = batch.complexes["primal"]
+    assert not batch.bits.any() and not cb.parity.any()
+    assert cb.odd_count.tolist() == [0, 0, 0]
+    assert cb.odd_ids.size == 0 and cb.pair_len.size == 0 and cb.bnd_len.size == 0
+    assert eng.timings()["graph_ctas"] == 0
+    assert eng.paths_toggle([], [], [], []).sum() == 0
+
+
+def test_single_trial_and_single_odd_cube():
+    """One flipped boundary qubit: K = 1, no pairs, one connector edge."""
+    lat = build_lattice(4, "primal", "open")
+    ct = lat.complexes["primal"]
+    N = lat.N
+    x = np.zeros((1, 2 * N))
+    q = int(ct.low_points[0])
+    x[0, N + q] = np.sqrt(np.pi)  # p homodyne one bin over -> bit 1 on a LOW boundary qubit
+    st = np.ones((1, N), np.uint8)
+    wo = {"method": "blueprint", "delta": 0.09}
+    eng = _engine(lat, 0.09, 0, wo)
+    batch = eng.run_injected(x, st)
+    cb = batch.complexes["primal"]
+    assert cb.odd_count.tolist() == [1] and cb.pair_len.size == 0
+    ref = c_oracle.run(lat, 0.09, 0, wo, x, st)
+    _same_as_oracle(lat, batch, ref)
+    assert cb.bnd_side.tolist() == [0]
+    flips = eng.paths_toggle([0], [0], [0], [-1])
+    local = int(np.nonzero(ct.qubits == q)[0][0])
+    assert np.nonzero(flips[0])[0].tolist() == [local]
+
+
+def test_ragged_batch_mixing_silent_and_noisy_trials_full_size():
+    """Compat chain at d=13 (silent / noisy alternate) against the C oracle, all outputs."""
+    lat = build_lattice(13, "primal", "open")
+    delta = 0.09
+    wo = {"method": "blueprint", "delta": delta}
+    chain = restate.LabelChain(lat.N, 0)
+    rng = np.random.default_rng(77)
+    st = np.stack([chain.next(rng) for _ in range(4)])
+    x = np.stack([restate.draw_quadratures(rng, restate.sigma_from_state(s, delta)) for s in st])
+    eng = _engine(lat, delta, 0, wo)
+    batch = eng.run_injected(x, st)
+    ref = c_oracle.run(lat, delta, 0, wo, x, st)
+    _same_as_oracle(lat, batch, ref)
+    assert batch.complexes["primal"].odd_count[1] == 0 and batch.complexes["primal"].odd_count[0] > 100
+
+
+def test_both_complexes_full_size_against_c_oracle():
+    """BASELINE configs[2] lattice (d=13 periodic, ec=both), two noisy trials, every pair length."""
+    lat = build_lattice(13, "both", "periodic")
+    delta = 0.09
+    wo = {"method": "blueprint", "delta": delta}
+    eng = _engine(lat, delta, 0, wo, mode="fresh")
+    batch = eng.run_rng(5, 0, 2, want_draws=True)
+    ref = c_oracle.run(lat, delta, 0, wo, batch.x, batch.state)
+    _same_as_oracle(lat, batch, ref)
+    assert batch.complexes["primal"].pair_len.size > 200000
+
+
+def test_config4_lattice_noise_stage_d21():
+    """d=21 open, p_swap=1 (configs[3]): noise / syndrome stages at full size; the graph stage
+    reports that the lattice does not fit the shared-memory kernel instead of falling back."""
+    lat = build_lattice(21, "primal", "open")
+    delta = 0.09
+    wo = {"method": "blueprint", "delta": delta}
+    eng = _engine(lat, delta, 1, wo)
+    batch = eng.run_rng(1, 0, 2, stage=_lib.STAGE_SYNDROME, want_draws=True)
+    assert (batch.state == 2).all()
+    ref = c_oracle.run(lat, delta, 1, wo, batch.x, batch.state, stage=_lib.STAGE_SYNDROME)
+    assert np.array_equal(batch.hom, ref.hom) and np.array_equal(batch.bits, ref.bits)
+    np.testing.assert_allclose(batch.weights, ref.weights, rtol=1e-9)
+    assert np.array_equal(batch.complexes["primal"].odd_ids, ref.complexes["primal"].odd_ids)
+    # all-p lattice: weights are the constants -ln{1/4, 1/3, 2/5} (decoder.py:86)
+    assert set(np.round(np.unique(batch.weights), 12)) <= set(np.round(-np.log([0.25, 1 / 3, 0.4]), 12))
+    with pytest.raises(_lib.FpbError, match="shortest-path kernel"):
+        eng.run_rng(1, 0, 2, stage=_lib.STAGE_GRAPH)
+
+
+def test_argument_errors_are_loud():
+    lat = build_lattice(3, "primal", "open")
+    eng = _engine(lat, 0.09, 0.25)
+    with pytest.raises(_lib.FpbError):
+        eng.run_rng(1, 0, 0)
+    with pytest.raises(_lib.FpbError):
+        eng.run_rng(1, -5, 4)
+    with pytest.raises(ValueError):
+        eng.run_injected(np.zeros((2, 7)), np.zeros((2, lat.N), np.uint8))
+    eng.run_rng(1, 0, 4, stage=_lib.STAGE_NOISE)
+    with pytest.raises(_lib.FpbError):
+        eng.fetch(_lib.STAGE_GRAPH)  # graph outputs of a noise-only run
+    with pytest.raises(_lib.FpbError):
+        eng.paths_toggle([0], [0], [0], [1])
+    b = eng.run_rng(1, 0, 4)
+    K = int(b.complexes["primal"].odd_count[0])
+    with pytest.raises(_lib.FpbError):
+        eng.paths_toggle([0], [0], [K], [0])  # endpoint out of range
+    from flamingpy_b200.engine import TrialEngine
+
+    with pytest.raises(_lib.FpbError):
+        TrialEngine(lat, -1.0, 0.25)
+    with pytest.raises(_lib.FpbError):
+        TrialEngine(lat, 0.09, 0.25, device=99)
+
+
+def test_uniform_and_integer_weights_with_zero_weight_edges():
+    """Integer weights with a tiny multiplier round to 0 on many edges: zero-weight edges must
+    not break the bucketed search (fallback bucket width, label correcting)."""
+    lat = build_lattice(5, "primal", "open")
+    delta = 0.09
+    wo = {"method": "blueprint", "delta": delta, "integer": True, "multiplier": 0.4}
+    eng = _engine(lat, delta, 0.3, wo, mode="fresh")
+    batch = eng.run_rng(3, 0, 6, want_draws=True)
+    assert (batch.weights == 0).any()
+    ref = c_oracle.run(lat, delta, 0.3, wo, batch.x, batch.state)
+    assert np.array_equal(batch.weights, ref.weights)
+    cb, rb = batch.complexes["primal"], ref.complexes["primal"]
+    assert np.array_equal(cb.pair_len, rb.pair_len)
+    assert np.array_equal(cb.bnd_len, rb.bnd_len)
