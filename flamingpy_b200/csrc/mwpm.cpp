@@ -1,0 +1,381 @@
+// Native minimum-weight perfect matching for the matching graphs the CUDA pipeline builds.
+//
+// Replaces the reference's only native component, the LEMON wrapper
+// flamingpy/cpp/lemonpy.cpp:13-41 (and rx.max_weight_matching, decoders/mwpm/matching.py:286-292),
+// neither of which can be installed offline.  Host-side C++, C ABI, OpenMP over trials.
+//
+// Algorithm: Edmonds' blossom algorithm with dual variables for dense graphs, O(n^3), the
+// classical primal-dual formulation (Galil 1986): grow alternating trees from free vertices
+// along tight edges, shrink odd cycles into blossoms, adjust duals by the minimum slack,
+// expand blossoms whose dual reaches zero.  Lengths are scaled to 64-bit integers (2^-32
+// resolution) so that all dual arithmetic is exact; maximum-weight matching on C - w with C
+// large makes the optimum a minimum-weight perfect matching.
+//
+// Matching-graph structure used (decoders/mwpm/matching.py:97-173): K odd cubes, pairwise
+// lengths d_ab; with boundary points one private virtual partner per cube at length b_a and a
+// zero-weight clique among virtual nodes.  That graph is equivalent to a complete graph on the K
+// real nodes with weights min(d_ab, b_a + b_b) (plus one dummy node at weight b_a when K is
+// odd): a pair whose minimum is b_a + b_b means "both go to their connector".  This halves n.
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <queue>
+#include <vector>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace {
+
+typedef long long ll;
+
+struct Edge {
+  int u, v;
+  ll w;
+};
+
+class Blossom {
+ public:
+  explicit Blossom(int n) : n(n), nx(n), m(2 * n + 1) {
+    g.assign((size_t)m * m, Edge{0, 0, 0});
+    lab.assign(m, 0);
+    match.assign(m, 0);
+    slack.assign(m, 0);
+    st.assign(m, 0);
+    pa.assign(m, 0);
+    S.assign(m, 0);
+    vis.assign(m, 0);
+    flower.assign(m, std::vector<int>());
+    flower_from.assign((size_t)m * (n + 1), 0);
+    for (int u = 1; u <= n; ++u)
+      for (int v = 1; v <= n; ++v) G(u, v) = Edge{u, v, 0};
+  }
+  void set_weight(int u, int v, ll w) {  // 1-based, w > 0
+    G(u, v).w = w;
+    G(v, u).w = w;
+  }
+  // returns mate[1..n] (0 = unmatched)
+  const std::vector<int>& solve() {
+    std::fill(match.begin(), match.end(), 0);
+    nx = n;
+    for (int u = 0; u <= n; ++u) {
+      st[u] = u;
+      flower[u].clear();
+    }
+    ll w_max = 0;
+    for (int u = 1; u <= n; ++u)
+      for (int v = 1; v <= n; ++v) {
+        FF(u, v) = (u == v ? u : 0);
+        w_max = std::max(w_max, G(u, v).w);
+      }
+    for (int u = 1; u <= n; ++u) lab[u] = w_max;
+    while (matching()) {
+    }
+    return match;
+  }
+
+ private:
+  int n, nx, m;
+  std::vector<Edge> g;
+  std::vector<ll> lab;
+  std::vector<int> match, slack, st, pa, S, vis;
+  std::vector<std::vector<int>> flower;
+  std::vector<int> flower_from;
+  std::queue<int> q;
+  int vis_t = 0;
+
+  Edge& G(int u, int v) { return g[(size_t)u * m + v]; }
+  int& FF(int b, int x) { return flower_from[(size_t)b * (n + 1) + x]; }
+  ll e_delta(const Edge& e) { return lab[e.u] + lab[e.v] - G(e.u, e.v).w * 2; }
+  void update_slack(int u, int x) {
+    if (!slack[x] || e_delta(G(u, x)) < e_delta(G(slack[x], x))) slack[x] = u;
+  }
+  void set_slack(int x) {
+    slack[x] = 0;
+    for (int u = 1; u <= n; ++u)
+      if (G(u, x).w > 0 && st[u] != x && S[st[u]] == 0) update_slack(u, x);
+  }
+  void q_push(int x) {
+    if (x <= n) q.push(x);
+    else
+      for (size_t i = 0; i < flower[x].size(); ++i) q_push(flower[x][i]);
+  }
+  void set_st(int x, int b) {
+    st[x] = b;
+    if (x > n)
+      for (size_t i = 0; i < flower[x].size(); ++i) set_st(flower[x][i], b);
+  }
+  int get_pr(int b, int xr) {
+    int pr = (int)(std::find(flower[b].begin(), flower[b].end(), xr) - flower[b].begin());
+    if (pr % 2 == 1) {
+      std::reverse(flower[b].begin() + 1, flower[b].end());
+      return (int)flower[b].size() - pr;
+    }
+    return pr;
+  }
+  void set_match(int u, int v) {
+    match[u] = G(u, v).v;
+    if (u <= n) return;
+    Edge e = G(u, v);
+    int xr = FF(u, e.u), pr = get_pr(u, xr);
+    for (int i = 0; i < pr; ++i) set_match(flower[u][i], flower[u][i ^ 1]);
+    set_match(xr, v);
+    std::rotate(flower[u].begin(), flower[u].begin() + pr, flower[u].end());
+  }
+  void augment(int u, int v) {
+    for (;;) {
+      int xnv = st[match[u]];
+      set_match(u, v);
+      if (!xnv) return;
+      set_match(xnv, st[pa[xnv]]);
+      u = st[pa[xnv]];
+      v = xnv;
+    }
+  }
+  int get_lca(int u, int v) {
+    for (++vis_t; u || v; std::swap(u, v)) {
+      if (u == 0) continue;
+      if (vis[u] == vis_t) return u;
+      vis[u] = vis_t;
+      u = st[match[u]];
+      if (u) u = st[pa[u]];
+    }
+    return 0;
+  }
+  void add_blossom(int u, int lca, int v) {
+    int b = n + 1;
+    while (b <= nx && st[b]) ++b;
+    if (b > nx) ++nx;
+    lab[b] = 0;
+    S[b] = 0;
+    match[b] = match[lca];
+    flower[b].clear();
+    flower[b].push_back(lca);
+    for (int x = u, y; x != lca; x = st[pa[y]]) {
+      flower[b].push_back(x);
+      flower[b].push_back(y = st[match[x]]);
+      q_push(y);
+    }
+    std::reverse(flower[b].begin() + 1, flower[b].end());
+    for (int x = v, y; x != lca; x = st[pa[y]]) {
+      flower[b].push_back(x);
+      flower[b].push_back(y = st[match[x]]);
+      q_push(y);
+    }
+    set_st(b, b);
+    for (int x = 1; x <= nx; ++x) G(b, x).w = G(x, b).w = 0;
+    for (int x = 1; x <= n; ++x) FF(b, x) = 0;
+    for (size_t i = 0; i < flower[b].size(); ++i) {
+      int xs = flower[b][i];
+      for (int x = 1; x <= nx; ++x)
+        if (G(b, x).w == 0 || e_delta(G(xs, x)) < e_delta(G(b, x))) {
+          G(b, x) = G(xs, x);
+          G(x, b) = G(x, xs);
+        }
+      for (int x = 1; x <= n; ++x)
+        if (FF(xs, x)) FF(b, x) = xs;
+    }
+    set_slack(b);
+  }
+  void expand_blossom(int b) {
+    for (size_t i = 0; i < flower[b].size(); ++i) set_st(flower[b][i], flower[b][i]);
+    int xr = FF(b, G(b, pa[b]).u), pr = get_pr(b, xr);
+    for (int i = 0; i < pr; i += 2) {
+      int xs = flower[b][i], xns = flower[b][i + 1];
+      pa[xs] = G(xns, xs).u;
+      S[xs] = 1;
+      S[xns] = 0;
+      slack[xs] = 0;
+      set_slack(xns);
+      q_push(xns);
+    }
+    S[xr] = 1;
+    pa[xr] = pa[b];
+    for (size_t i = pr + 1; i < flower[b].size(); ++i) {
+      int xs = flower[b][i];
+      S[xs] = -1;
+      set_slack(xs);
+    }
+    st[b] = 0;
+  }
+  bool on_found_edge(const Edge& e) {
+    int u = st[e.u], v = st[e.v];
+    if (S[v] == -1) {
+      pa[v] = e.u;
+      S[v] = 1;
+      int nu = st[match[v]];
+      slack[v] = slack[nu] = 0;
+      S[nu] = 0;
+      q_push(nu);
+    } else if (S[v] == 0) {
+      int lca = get_lca(u, v);
+      if (!lca) {
+        augment(u, v);
+        augment(v, u);
+        return true;
+      }
+      add_blossom(u, lca, v);
+    }
+    return false;
+  }
+  bool matching() {
+    std::fill(S.begin() + 1, S.begin() + nx + 1, -1);
+    std::fill(slack.begin() + 1, slack.begin() + nx + 1, 0);
+    q = std::queue<int>();
+    for (int x = 1; x <= nx; ++x)
+      if (st[x] == x && !match[x]) {
+        pa[x] = 0;
+        S[x] = 0;
+        q_push(x);
+      }
+    if (q.empty()) return false;
+    for (;;) {
+      while (!q.empty()) {
+        int u = q.front();
+        q.pop();
+        if (S[st[u]] == 1) continue;
+        for (int v = 1; v <= n; ++v)
+          if (G(u, v).w > 0 && st[u] != st[v]) {
+            if (e_delta(G(u, v)) == 0) {
+              if (on_found_edge(G(u, v))) return true;
+            } else {
+              update_slack(u, st[v]);
+            }
+          }
+      }
+      ll d = INT64_MAX;
+      for (int b = n + 1; b <= nx; ++b)
+        if (st[b] == b && S[b] == 1) d = std::min(d, lab[b] / 2);
+      for (int x = 1; x <= nx; ++x)
+        if (st[x] == x && slack[x]) {
+          if (S[x] == -1) d = std::min(d, e_delta(G(slack[x], x)));
+          else if (S[x] == 0) d = std::min(d, e_delta(G(slack[x], x)) / 2);
+        }
+      for (int u = 1; u <= n; ++u) {
+        if (S[st[u]] == 0) {
+          if (lab[u] <= d) return false;
+          lab[u] -= d;
+        } else if (S[st[u]] == 1) {
+          lab[u] += d;
+        }
+      }
+      for (int b = n + 1; b <= nx; ++b)
+        if (st[b] == b) {
+          if (S[st[b]] == 0) lab[b] += d * 2;
+          else if (S[st[b]] == 1) lab[b] -= d * 2;
+        }
+      q = std::queue<int>();
+      for (int x = 1; x <= nx; ++x)
+        if (st[x] == x && slack[x] && st[slack[x]] != x && e_delta(G(slack[x], x)) == 0)
+          if (on_found_edge(G(slack[x], x))) return true;
+      for (int b = n + 1; b <= nx; ++b)
+        if (st[b] == b && S[b] == 1 && lab[b] == 0) expand_blossom(b);
+    }
+    return false;
+  }
+};
+
+// One matching graph.  pair_len: packed upper triangle (row-major, a < b); bnd_len: K lengths or
+// null.  Writes out_src / out_dst (dst = -1: matched to its connector); returns the number of
+// queries written (<= K) or a negative code.
+int solve_one(int K, const double* pair_len, const double* bnd_len, int* out_src, int* out_dst) {
+  if (K <= 0) return 0;
+  if (!bnd_len && (K & 1)) return -1;  // no perfect matching
+  if (K == 1) {
+    out_src[0] = 0;
+    out_dst[0] = -1;
+    return 1;
+  }
+  const int n = (bnd_len && (K & 1)) ? K + 1 : K;
+  // scale so that every weight is an even positive integer (duals halve) with ~2^-32 resolution
+  double wmax = 0;
+  const long long npairs = (long long)K * (K - 1) / 2;
+  for (long long i = 0; i < npairs; ++i) wmax = std::max(wmax, pair_len[i]);
+  if (bnd_len)
+    for (int a = 0; a < K; ++a) wmax = std::max(wmax, 2 * bnd_len[a]);
+  if (!(wmax < 1e15)) return -2;
+  int shift = 32;
+  while (shift > 0 && std::ldexp(wmax + 1.0, shift) * (double)(n + 2) > 1e17) --shift;
+  const double scale = std::ldexp(1.0, shift);
+  const ll wmax_i = (ll)std::llround(wmax * scale) + 1;
+  const ll C = wmax_i * (ll)(n + 1);  // C - w > 0 and large enough that cardinality dominates
+  Blossom bl(n);
+  std::vector<char> via_boundary((size_t)K * K, 0);
+  long long pos = 0;
+  for (int a = 0; a < K - 1; ++a)
+    for (int b = a + 1; b < K; ++b, ++pos) {
+      double w = pair_len[pos];
+      if (bnd_len) {
+        const double wb = bnd_len[a] + bnd_len[b];
+        if (wb < w) {
+          w = wb;
+          via_boundary[(size_t)a * K + b] = 1;
+        }
+      }
+      bl.set_weight(a + 1, b + 1, 2 * (C - (ll)std::llround(w * scale)));
+    }
+  if (n > K)
+    for (int a = 0; a < K; ++a) bl.set_weight(a + 1, n, 2 * (C - (ll)std::llround(bnd_len[a] * scale)));
+  const std::vector<int>& mate = bl.solve();
+  int nq = 0;
+  for (int a = 0; a < K; ++a) {
+    const int b = mate[a + 1] - 1;
+    if (b < 0) return -3;
+    if (b >= K) {  // dummy
+      out_src[nq] = a;
+      out_dst[nq++] = -1;
+    } else if (a < b) {
+      if (via_boundary[(size_t)a * K + b]) {
+        out_src[nq] = a; out_dst[nq++] = -1;
+        out_src[nq] = b; out_dst[nq++] = -1;
+      } else {
+        out_src[nq] = a;
+        out_dst[nq++] = b;
+      }
+    }
+  }
+  return nq;
+}
+
+}  // namespace
+
+extern "C" {
+
+// Single graph (see solve_one).  out_src / out_dst need room for K entries.
+int fpb_mwpm(int K, const double* pair_len, const double* bnd_len, int* out_src, int* out_dst) {
+  return solve_one(K, pair_len, bnd_len, out_src, out_dst);
+}
+
+// T graphs in the ragged layout of fpb_outputs (odd_count[T], pair_len / bnd_len concatenated).
+// q_off[T+1] must hold the exclusive prefix of odd_count (each trial writes at most K queries);
+// n_queries[T] receives the counts.  OpenMP over trials.
+int fpb_mwpm_batch(int T, const int* odd_count, const double* pair_len, const double* bnd_len,
+                   const long long* q_off, int* out_src, int* out_dst, int* n_queries, int n_threads) {
+  std::vector<long long> poff((size_t)T + 1, 0);
+  for (int t = 0; t < T; ++t) poff[t + 1] = poff[t] + (long long)odd_count[t] * (odd_count[t] - 1) / 2;
+  int bad = 0;
+#ifdef _OPENMP
+  if (n_threads > 0) omp_set_num_threads(n_threads);
+#endif
+#pragma omp parallel for schedule(dynamic, 1) reduction(| : bad)
+  for (int t = 0; t < T; ++t) {
+    const int K = odd_count[t];
+    const int r = solve_one(K, pair_len + poff[t], bnd_len ? bnd_len + q_off[t] : nullptr, out_src + q_off[t],
+                            out_dst + q_off[t]);
+    if (r < 0) bad |= 1;
+    n_queries[t] = r < 0 ? 0 : r;
+  }
+  return bad ? -1 : 0;
+}
+
+int fpb_mwpm_max_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+}  // extern "C"

@@ -141,22 +141,37 @@ def correct(code, decoder="MWPM", weight_options=None, sanity_check=False, decod
 
 def decode_batch(code, eng, batch, backend="networkx"):
     """Host matching + device path extraction for every trial of ``batch``.
-    Returns the recovery as uint8[T, Qtot] bit flips."""
+    Returns the recovery as uint8[T, Qtot] bit flips.  ``backend="native"`` solves all trials
+    with the C++ blossom matcher (OpenMP over trials); "networkx" is the reference's fallback."""
     trial, cx, src, dst = [], [], [], []
     for ci, e in enumerate(code.ec):
         ct = code.lattice.complexes[e]
         cb = batch.complexes[e]
+        if backend == "native":
+            from . import mwpm_native
+
+            t_, s_, d_ = mwpm_native.solve_batch(cb.odd_count, cb.pair_len, cb.bnd_len if ct.has_boundary else None)
+            trial.append(t_)
+            cx.append(np.full(len(t_), ci, np.int32))
+            src.append(s_)
+            dst.append(d_)
+            continue
+        tt, ss, dd = [], [], []
         for t in range(batch.n_trials):
             K = int(cb.odd_count[t])
             if K == 0:
                 continue
             bl = cb.boundary(t)[0] if ct.has_boundary else None
             for u, v in solve_matching(K, cb.pairs(t), bl, backend=backend):
-                trial.append(t)
-                cx.append(ci)
-                src.append(u)
-                dst.append(v)
-    return eng.paths_toggle(trial, cx, src, dst)
+                tt.append(t)
+                ss.append(u)
+                dd.append(v)
+        trial.append(np.array(tt, np.int32))
+        cx.append(np.full(len(tt), ci, np.int32))
+        src.append(np.array(ss, np.int32))
+        dst.append(np.array(dd, np.int32))
+    cat = lambda parts: np.concatenate(parts) if parts else np.empty(0, np.int32)  # noqa: E731
+    return eng.paths_toggle(cat(trial), cat(cx), cat(src), cat(dst))
 
 
 def logical_failures(code, batch, flips):

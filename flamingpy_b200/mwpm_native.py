@@ -1,0 +1,88 @@
+"""ctypes binding of the native minimum-weight perfect matcher (``csrc/mwpm.cpp`` ->
+``libfpb_mwpm.so``), the host-side replacement of the reference's LEMON plugin
+(``flamingpy/cpp/lemonpy.cpp``, ``decoders/mwpm/lemon.py:25-40``)."""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libfpb_mwpm.so")
+_lib = None
+
+_i32p = C.POINTER(C.c_int32)
+_f64p = C.POINTER(C.c_double)
+_i64p = C.POINTER(C.c_int64)
+
+
+def load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} not found: run __graft_entry__.build()")
+        lib = C.CDLL(LIB_PATH)
+        lib.fpb_mwpm.restype = C.c_int
+        lib.fpb_mwpm.argtypes = [C.c_int, _f64p, _f64p, _i32p, _i32p]
+        lib.fpb_mwpm_batch.restype = C.c_int
+        lib.fpb_mwpm_batch.argtypes = [C.c_int, _i32p, _f64p, _f64p, _i64p, _i32p, _i32p, _i32p, C.c_int]
+        lib.fpb_mwpm_max_threads.restype = C.c_int
+        _lib = lib
+    return _lib
+
+
+def _p(a, typ):
+    return a.ctypes.data_as(typ) if a is not None else None
+
+
+def solve(K: int, pair_len: np.ndarray, bnd_len: Optional[np.ndarray]):
+    """Matched queries [(u, v)] with v == -1 for "to its connector" (one matching graph)."""
+    if K == 0:
+        return []
+    lib = load()
+    pl = np.ascontiguousarray(pair_len, np.float64)
+    bl = None if bnd_len is None else np.ascontiguousarray(bnd_len, np.float64)
+    src = np.empty(max(K, 1), np.int32)
+    dst = np.empty(max(K, 1), np.int32)
+    n = lib.fpb_mwpm(K, _p(pl, _f64p), _p(bl, _f64p), _p(src, _i32p), _p(dst, _i32p))
+    if n < 0:
+        raise ValueError(f"native matcher failed ({n}): no perfect matching or weights out of range")
+    return [(int(src[i]), int(dst[i])) for i in range(n)]
+
+
+def min_weight_perfect_matching(K, pair_len, bnd_len):
+    """mate dict in the node numbering of ``matching.solve_matching`` (virtual node of u is K+u)."""
+    mate = {}
+    for u, v in solve(K, pair_len, bnd_len):
+        if v < 0:
+            mate[u] = K + u
+        else:
+            mate[u], mate[v] = v, u
+    return mate
+
+
+def solve_batch(odd_count: np.ndarray, pair_len: np.ndarray, bnd_len: Optional[np.ndarray], threads: int = 0):
+    """All trials of a batch at once (OpenMP over trials).  Returns (trial, src, dst) int32 arrays
+    of the matched queries, ready for ``TrialEngine.paths_toggle``."""
+    lib = load()
+    T = len(odd_count)
+    oc = np.ascontiguousarray(odd_count, np.int32)
+    q_off = np.concatenate([[0], np.cumsum(oc.astype(np.int64))]).astype(np.int64)
+    total = int(q_off[-1])
+    src = np.empty(max(total, 1), np.int32)
+    dst = np.empty(max(total, 1), np.int32)
+    nq = np.zeros(T, np.int32)
+    pl = np.ascontiguousarray(pair_len, np.float64)
+    bl = None if (bnd_len is None or len(bnd_len) == 0) else np.ascontiguousarray(bnd_len, np.float64)
+    if threads <= 0:
+        threads = os.cpu_count() or 1
+    rc = lib.fpb_mwpm_batch(T, _p(oc, _i32p), _p(pl, _f64p), _p(bl, _f64p), _p(q_off, _i64p), _p(src, _i32p),
+                            _p(dst, _i32p), _p(nq, _i32p), threads)
+    if rc != 0:
+        raise ValueError("native matcher failed on at least one trial")
+    keep = np.concatenate([np.arange(q_off[t], q_off[t] + nq[t]) for t in range(T)]) if T else np.empty(0, np.int64)
+    keep = keep.astype(np.int64)
+    trial = np.repeat(np.arange(T, dtype=np.int32), nq)
+    return trial, src[keep], dst[keep]

@@ -57,7 +57,7 @@ def trial_range(trials: int, rank: int, size: int):
 
 
 def ec_monte_carlo(trials, code_instance, noise_instance, decoder, decoder_args, world_comm=None, mpi_rank=0,
-                   mpi_size=1, *, seed=None, batch=1024, mode="compat", backend="networkx", device=None,
+                   mpi_size=1, *, seed=None, batch=1024, mode="compat", backend="native", device=None,
                    return_stats=False):
     """Run ``trials`` Monte-Carlo trials of the complete error-correction procedure and
     return the number of logical errors.

@@ -153,3 +153,31 @@ def test_failure_rate_consistent_with_reference(d, b, delta, ps, mode, ref_fail,
     z = (p1 - p2) / np.sqrt(pooled * (1 - pooled) * (1 / n + 1 / ref_n))
     print(f"d={d} ps={ps} {mode}: gpu {errors}/{n}={p1:.5f} reference {ref_fail}/{ref_n}={p2:.5f} z={z:+.2f}")
     assert abs(z) < 3.29, (errors, n, p1, p2, z)
+
+
+def test_native_matcher_end_to_end_agrees_with_networkx():
+    """Same device trials decoded with the native blossom matcher and with networkx: equal
+    matching weights imply equal corrections up to ties; with continuous weights (p_swap=0)
+    the logical verdicts must agree trial by trial."""
+    from flamingpy_b200.decoder import decode_batch, logical_failures
+
+    code = SurfaceCode(5, "primal", "open")
+    wo = {"method": "blueprint", "delta": 0.1}
+    eng = code.engine(0.1, 0, wo, mode="fresh")
+    b = eng.run_rng(8, 0, 400)
+    f_nat = logical_failures(code, b, decode_batch(code, eng, b, backend="native"))
+    f_nx = logical_failures(code, b, decode_batch(code, eng, b, backend="networkx"))
+    assert np.array_equal(f_nat, f_nx)
+    assert 0 < f_nat.sum() < 200
+
+
+def test_monte_carlo_d9_with_native_matcher():
+    """BASELINE configs[1] lattice end to end (d=9 open, delta 0.08, p_swap 0.5): far too slow
+    for the networkx matcher (11 s per trial); runs with the native one and gives a failure rate
+    in (0, 1)."""
+    code = SurfaceCode(9, "primal", "open")
+    noise = CVLayer(code, delta=0.08, p_swap=0.5)
+    errors, stats = ec_monte_carlo(64, code, noise, "MWPM", {"weight_opts": {"method": "blueprint", "delta": 0.08}},
+                                   seed=3, batch=64, backend="native", return_stats=True)
+    assert stats["trials_done"] == 64
+    assert 0 <= errors <= 64

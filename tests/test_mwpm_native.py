@@ -1,0 +1,75 @@
+"""Native blossom matcher against networkx on random matching graphs (the reference's own
+cross-backend check, tests/decoders/test_matching.py:74-131: equal total weight)."""
+
+import itertools as it
+
+import numpy as np
+import pytest
+
+from flamingpy_b200 import mwpm_native
+from flamingpy_b200.matching import solve_matching, tri_index
+
+
+def total_weight(K, pairs, pair_len, bnd_len):
+    tot = 0.0
+    seen = set()
+    for u, v in pairs:
+        assert u not in seen
+        seen.add(u)
+        if v >= 0:
+            assert v not in seen
+            seen.add(v)
+            a, b = (u, v) if u < v else (v, u)
+            tot += pair_len[tri_index(a, b, K)]
+        else:
+            tot += bnd_len[u]
+    assert seen == set(range(K))  # perfect
+    return tot
+
+
+@pytest.mark.parametrize("K", [1, 2, 3, 4, 7, 10, 17, 30, 41])
+@pytest.mark.parametrize("boundary", [False, True])
+def test_native_equals_networkx_total_weight(K, boundary):
+    if not boundary and K % 2:
+        pytest.skip("odd K without boundary has no perfect matching")
+    rng = np.random.default_rng(K * 2 + boundary)
+    for rep in range(6):
+        if rep % 3 == 0:
+            pair = rng.integers(0, 10, K * (K - 1) // 2).astype(float)  # many ties (reference uses 0..9)
+            bnd = rng.integers(0, 6, K).astype(float)
+        elif rep % 3 == 1:
+            # metric-like: points in 3-D with L1 distances, boundary = distance to a wall
+            pts = rng.uniform(0, 10, (K, 3))
+            pair = np.array([np.abs(pts[a] - pts[b]).sum() for a, b in it.combinations(range(K), 2)])
+            bnd = np.minimum(pts[:, 0], 10 - pts[:, 0]) + 0.1
+        else:
+            pair = rng.uniform(0.5, 60, K * (K - 1) // 2)
+            bnd = rng.uniform(0.5, 30, K)
+        b = bnd if boundary else None
+        got = mwpm_native.solve(K, pair, b)
+        ref = solve_matching(K, pair, b, backend="networkx")
+        wg, wr = total_weight(K, got, pair, bnd), total_weight(K, ref, pair, bnd)
+        assert wg == pytest.approx(wr, rel=1e-9, abs=1e-9), (K, rep)
+        assert sorted(solve_matching(K, pair, b, backend="native")) == sorted(got)
+
+
+def test_batch_interface_matches_single_calls():
+    rng = np.random.default_rng(0)
+    Ks = [0, 4, 1, 9, 6, 0, 13]
+    pairs = [rng.uniform(1, 20, k * (k - 1) // 2) for k in Ks]
+    bnds = [rng.uniform(1, 10, k) for k in Ks]
+    trial, src, dst = mwpm_native.solve_batch(np.array(Ks, np.int32), np.concatenate(pairs), np.concatenate(bnds), 2)
+    for t, k in enumerate(Ks):
+        sel = trial == t
+        got = sorted(zip(src[sel].tolist(), dst[sel].tolist()))
+        assert got == sorted(mwpm_native.solve(k, pairs[t], bnds[t]))
+    # without boundary lengths
+    Ks2 = [2, 6, 0, 8]
+    pairs2 = [rng.uniform(1, 20, k * (k - 1) // 2) for k in Ks2]
+    trial, src, dst = mwpm_native.solve_batch(np.array(Ks2, np.int32), np.concatenate(pairs2), None, 2)
+    assert np.all(dst >= 0) and len(trial) == sum(Ks2) // 2
+
+
+def test_odd_graph_without_boundary_is_an_error():
+    with pytest.raises(ValueError):
+        mwpm_native.solve(3, np.ones(3), None)
