@@ -110,6 +110,8 @@ struct fpb_handle {
   // shortest-path launch configuration
   int warps = 0, ctas_per_sm = 0, tasks_per_item = 0;
   size_t paths_smem = 0;
+  bool paths_wg = false;  // weights / tables in global memory (large lattices)
+  DevBuf<double> wscratch;
 };
 
 namespace {
@@ -135,38 +137,43 @@ typedef void (*toggle_fn)(const PathsParams);
 // kernel variant by lattice size: NCH = 16-cube chunks each lane scans, NV = cubes relaxed per
 // lane per batch, MINB = CTAs per SM the register budget is sized for
 // (NV = 2 variants are compiled for at most 384 threads so that they get 170 registers)
-paths_fn pick_paths_kernel(int S, int* max_warps) {
+paths_fn pick_paths_kernel(int S, bool wg, int* max_warps) {
+  if (wg) {  // weights and face tables in global memory: lattices that do not fit shared memory
+    *max_warps = 8;
+    if (S <= 4096) return k_paths<8, 1, 256, 1, true>;
+    if (S <= 8192) return k_paths<16, 1, 256, 1, true>;
+    return k_paths<32, 1, 256, 1, true>;
+  }
   *max_warps = 16;
-  if (S <= 1024) return k_paths<2, 1, 512, 2>;
-  if (S <= 1536) return k_paths<3, 1, 512, 1>;
+  if (S <= 1024) return k_paths<2, 1, 512, 2, false>;
+  if (S <= 1536) return k_paths<3, 1, 512, 1, false>;
   *max_warps = 12;
-  if (S <= 2560) return k_paths<5, 2, 384, 1>;
-  if (S <= 4096) return k_paths<8, 2, 384, 1>;
-  return k_paths<16, 2, 384, 1>;
+  if (S <= 2560) return k_paths<5, 2, 384, 1, false>;
+  if (S <= 4096) return k_paths<8, 2, 384, 1, false>;
+  return k_paths<16, 2, 384, 1, false>;
 }
-toggle_fn pick_toggle_kernel(int S) {
-  if (S <= 1024) return k_path_toggle<2>;
-  if (S <= 1536) return k_path_toggle<3>;
-  if (S <= 2560) return k_path_toggle<5>;
-  if (S <= 4096) return k_path_toggle<8>;
-  return k_path_toggle<16>;
+toggle_fn pick_toggle_kernel(int S, bool wg) {
+  if (wg) {
+    if (S <= 4096) return k_path_toggle<8, true>;
+    if (S <= 8192) return k_path_toggle<16, true>;
+    return k_path_toggle<32, true>;
+  }
+  if (S <= 1024) return k_path_toggle<2, false>;
+  if (S <= 1536) return k_path_toggle<3, false>;
+  if (S <= 2560) return k_path_toggle<5, false>;
+  if (S <= 4096) return k_path_toggle<8, false>;
+  return k_path_toggle<16, false>;
 }
 
-int configure_paths(fpb_handle* h) {
-  // shared-memory budget: one CTA-wide copy of the trial's weights and the face tables, plus a
-  // distance array, bucket bytes and a staging list per warp (= per concurrent search)
+int configure_variant(fpb_handle* h, bool wg) {
   int max_optin = 0;
   CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
   int smem_per_sm = 0;
   CK(cudaDeviceGetAttribute(&smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, h->device));
-  const size_t cta_b = paths_cta_bytes(h->S_max, h->slots_max);
+  const size_t cta_b = wg ? 0 : paths_cta_bytes(h->S_max, h->slots_max);
   const size_t warp_b = paths_warp_bytes(h->S_max, false);
-  h->warps = 0;
-  h->ctas_per_sm = 0;
-  if (h->S_max > 16 * 32 * MAX_CHUNKS)
-    return fail(FPB_ERR_UNSUPPORTED, "lattice too large for the shortest-path kernel's bucket scan");
   int max_warps = 16;
-  paths_fn fn = pick_paths_kernel(h->S_max, &max_warps);
+  paths_fn fn = pick_paths_kernel(h->S_max, wg, &max_warps);
   cudaFuncAttributes fattr;
   CK(cudaFuncGetAttributes(&fattr, fn));
   max_optin -= (int)fattr.sharedSizeBytes;  // static shared memory counts against the opt-in limit
@@ -188,12 +195,29 @@ int configure_paths(fpb_handle* h) {
       h->ctas_per_sm = resident;
     }
   }
-  if (h->warps == 0)
-    return fail(FPB_ERR_UNSUPPORTED,
-                "lattice too large for the shared-memory shortest-path kernel (needs " +
-                    std::to_string(cta_b + warp_b) + " bytes per CTA)");
+  if (best == 0) return FPB_OK;  // does not fit; caller decides
+  h->paths_wg = wg;
   h->paths_smem = cta_b + (size_t)h->warps * warp_b;
   h->tasks_per_item = h->warps * 4;
+  return FPB_OK;
+}
+
+int configure_paths(fpb_handle* h) {
+  // shared-memory budget: one CTA-wide copy of the trial's weights and the face tables, plus a
+  // distance array, bucket bytes and a staging list per warp (= per concurrent search).  Lattices
+  // whose weights do not fit next to at least one search fall back to the variant that keeps
+  // weights and tables in global memory (L2) and only the per-search state in shared memory.
+  h->warps = 0;
+  h->ctas_per_sm = 0;
+  if (h->S_max > 16 * 32 * MAX_CHUNKS || h->S_max > 65535)
+    return fail(FPB_ERR_UNSUPPORTED, "lattice too large for the shortest-path kernel's bucket scan");
+  int rc = FPB_OK;
+  if (h->S_max <= 16 * 32 * 16) rc = configure_variant(h, false);
+  if (rc) return rc;
+  if (h->warps == 0) rc = configure_variant(h, true);
+  if (rc) return rc;
+  if (h->warps == 0)
+    return fail(FPB_ERR_UNSUPPORTED, "lattice too large for the shared-memory shortest-path kernel");
   return FPB_OK;
 }
 
@@ -320,8 +344,13 @@ int run_pipeline(fpb_handle* h, long long T, int stage, bool gen, uint64_t seed,
       CK(cudaMemsetAsync(h->counter.p, 0, sizeof(int), st));
       long long grid = (long long)h->sm_count * h->ctas_per_sm;
       if (grid > total_items) grid = total_items;
+      if (h->paths_wg) {
+        int rc2 = h->wscratch.ensure((size_t)grid * h->slots_max);
+        if (rc2) return rc2;
+        pp.wscratch = h->wscratch.p;
+      }
       int mw_unused = 0;
-      pick_paths_kernel(h->S_max, &mw_unused)<<<(unsigned)grid, h->warps * 32, h->paths_smem, st>>>(pp);
+      pick_paths_kernel(h->S_max, h->paths_wg, &mw_unused)<<<(unsigned)grid, h->warps * 32, h->paths_smem, st>>>(pp);
       ++launches;
       h->tm.graph_ctas = (int)grid;
     }
@@ -464,7 +493,7 @@ int fpb_destroy(fpb_handle* h) {
   }
   h->x.release(); h->hom.release(); h->weights.release(); h->state.release(); h->bits.release();
   h->flips.release(); h->item_off.release(); h->counter.release(); h->totals.release();
-  h->q_trial.release(); h->q_cx.release(); h->q_src.release(); h->q_dst.release();
+  h->q_trial.release(); h->q_cx.release(); h->q_src.release(); h->q_dst.release(); h->wscratch.release();
   if (h->totals_host) cudaFreeHost(h->totals_host);
   for (auto& ev : h->ev)
     if (ev) cudaEventDestroy(ev);
@@ -638,16 +667,21 @@ int fpb_paths_toggle(fpb_handle* h, int64_t n_queries, const int32_t* trial, con
     pp.flips = h->flips.p; pp.bit_words = h->bit_words;
     int max_optin = 0;
     CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
-    const size_t per_warp = toggle_warp_bytes(h->S_max, h->slots_max);
+    const bool wg = h->paths_wg;
+    const size_t per_warp = wg ? paths_warp_bytes(h->S_max, true) : toggle_warp_bytes(h->S_max, h->slots_max);
     int warps = (int)((size_t)max_optin / per_warp);
     if (warps < 1) return fail(FPB_ERR_UNSUPPORTED, "lattice too large for the path-toggle kernel");
     if (warps > 8) warps = 8;
     const size_t smem = (size_t)warps * per_warp;
-    toggle_fn tfn = pick_toggle_kernel(h->S_max);
+    toggle_fn tfn = pick_toggle_kernel(h->S_max, wg);
     CK(cudaFuncSetAttribute(tfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long long grid = (n_queries + warps - 1) / warps;
     const long long cap = (long long)h->sm_count * 4;
     if (grid > cap) grid = cap;
+    if (wg) {
+      if ((rc = h->wscratch.ensure((size_t)grid * warps * h->slots_max))) return rc;
+      pp.wscratch = h->wscratch.p;
+    }
     tfn<<<(unsigned)grid, warps * 32, smem, st>>>(pp);
     CK(cudaGetLastError());
   }

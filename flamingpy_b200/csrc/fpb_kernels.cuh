@@ -392,11 +392,12 @@ struct PathsParams {
   const int* q_dst;
   uint32_t* flips;            // [T][bit_words]
   int bit_words;
+  double* wscratch;           // [grid][slots_max] slot-ordered weights (global-weights variant only)
 };
 
 constexpr int NRING = 32;       // ring slots: bucket index mod 32 is kept in one byte per cube
 constexpr int STAGE_CAP = 512;  // per-warp staging list of the cubes of the current bucket
-constexpr int MAX_CHUNKS = 16;  // 16-cube chunks per lane in one scan: S <= 16 * 32 * 16 = 8192 (template NCH)
+constexpr int MAX_CHUNKS = 32;  // 16-cube chunks per lane in one scan: S <= 16 * 32 * 32 = 16384 (template NCH)
 
 struct WarpMem {
   double* dist;     // [S]
@@ -518,14 +519,15 @@ __device__ __forceinline__ uint32_t eq_bytes(uint32_t word, uint32_t r4) {
 // gather bits 7,15,23,31 into bits 0..3
 __device__ __forceinline__ uint32_t movemask4(uint32_t z) { return (z * 0x00204081u) >> 28; }
 
-template <bool PRED, int NCH, int NV>
+template <bool PRED, int NCH, int NV, bool WG>
 __device__ __forceinline__ void warp_search(const CtaMem& cm, const WarpMem& wm, const DirTab& dt, int S,
                                             double step, uint32_t present, int lane, int stop_at) {
   const double inv = 1.0 / step;
   const int n16 = (S + 15) >> 4;
   const uint32_t dist_a = smem_addr(wm.dist), bkt_a = smem_addr(wm.bkt), stage_a = smem_addr(wm.stage);
   const uint32_t pred_a = PRED ? smem_addr(wm.pred) : 0u;
-  const uint32_t wslot_a = smem_addr(cm.wslot);
+  // WG: the trial's weights (and the face tables) live in global memory instead of shared memory
+  const uint32_t wslot_a = WG ? 0u : smem_addr(cm.wslot);
   int cur = 0;
   while (present) {
     {
@@ -604,15 +606,15 @@ __device__ __forceinline__ void warp_search(const CtaMem& cm, const WarpMem& wm,
           }
           const bool act = valid && bt <= cur;
           const uint32_t info = act ? (uint32_t)cm.ninfo[v] : 0xaaau;  // inactive lanes: every face "none"
-          const uint32_t sb = wslot_a + 8u * cm.sbase[v];
+          const int sb = cm.sbase[v];
 #pragma unroll
           for (int d = 0; d < 6; ++d) {
             const uint32_t kind = (info >> (2 * d)) & 3u;
             const bool a = kind < 2u;
             // absent faces read harmless in-range addresses (their own cube, slot 0)
             ua[k][d] = a ? va + 8 * (kind ? dt.dwrap[d] : dt.dreg[d]) : va;
-            const uint32_t wa = a ? sb + 8 * (kind ? dt.swrap[d] : dt.sreg[d]) : wslot_a;
-            nd[k][d] = dv + lds_f64(wa);
+            const int slot = a ? sb + (kind ? dt.swrap[d] : dt.sreg[d]) : 0;
+            nd[k][d] = dv + (WG ? cm.wslot[slot] : lds_f64(wslot_a + 8u * slot));
             imp[k][d] = a && nd[k][d] < lds_f64(ua[k][d]);
           }
         }
@@ -680,7 +682,7 @@ __device__ __forceinline__ double bucket_step(double wmean, double factor) {
   return (wmean > 0.0 && wmean < FPB_INF) ? wmean * factor : 1.0;
 }
 
-template <int NCH, int NV, int MAXT, int MINB>
+template <int NCH, int NV, int MAXT, int MINB, bool WG>
 __global__ void __launch_bounds__(MAXT, MINB) k_paths(const __grid_constant__ PathsParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ int item_s;
@@ -688,10 +690,19 @@ __global__ void __launch_bounds__(MAXT, MINB) k_paths(const __grid_constant__ Pa
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int nthreads = blockDim.x;
 
+  // shared variant: weights + face tables per CTA in shared memory, then the per-warp state;
+  // WG variant (large lattices): weights in a per-CTA global scratch row, tables read in place
   unsigned char* ptr = smem;
-  double* wslot = (double*)ptr; ptr += align16((size_t)p.slots_max * 8);
-  uint16_t* ninfo_s = (uint16_t*)ptr; ptr += align16((size_t)p.S_max * 2);
-  uint16_t* sbase_s = (uint16_t*)ptr; ptr += align16((size_t)p.S_max * 2);
+  double* wslot;
+  uint16_t* ninfo_s = nullptr;
+  uint16_t* sbase_s = nullptr;
+  if (WG) {
+    wslot = p.wscratch + (size_t)blockIdx.x * p.slots_max;
+  } else {
+    wslot = (double*)ptr; ptr += align16((size_t)p.slots_max * 8);
+    ninfo_s = (uint16_t*)ptr; ptr += align16((size_t)p.S_max * 2);
+    sbase_s = (uint16_t*)ptr; ptr += align16((size_t)p.S_max * 2);
+  }
   CtaMem cm;
   cm.wslot = wslot; cm.ninfo = ninfo_s; cm.sbase = sbase_s;
   const WarpMem wm = carve_warp(ptr + (size_t)wid * paths_warp_bytes(p.S_max, false), p.S_max, false);
@@ -719,9 +730,14 @@ __global__ void __launch_bounds__(MAXT, MINB) k_paths(const __grid_constant__ Pa
     const int S = c.S;
 
     if (staged_c != ci) {
-      for (int v = threadIdx.x; v < S; v += nthreads) {
-        ninfo_s[v] = c.ninfo[v];
-        sbase_s[v] = c.sbase[v];
+      if (WG) {
+        cm.ninfo = c.ninfo;
+        cm.sbase = c.sbase;
+      } else {
+        for (int v = threadIdx.x; v < S; v += nthreads) {
+          ninfo_s[v] = c.ninfo[v];
+          sbase_s[v] = c.sbase[v];
+        }
       }
       dt = load_dirtab(c);
       staged_c = ci;
@@ -743,6 +759,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_paths(const __grid_constant__ Pa
       for (int w2 = 0; w2 < (nthreads >> 5); ++w2) sum += red_s[w2];
       step = bucket_step(sum / (double)c.Q, p.step_factor);
       staged_tc = tc;
+      if (WG) __threadfence_block();
     }
     __syncthreads();
 
@@ -772,7 +789,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_paths(const __grid_constant__ Pa
         } else {
           present = warp_seed_connector(cm, wm, c.n_high, c.high_cube, c.high_slot, inv, lane);
         }
-        warp_search<false, NCH, NV>(cm, wm, dt, S, step, present, lane, -1);
+        warp_search<false, NCH, NV, WG>(cm, wm, dt, S, step, present, lane, -1);
         if (pair_task) {
           const long long row = poff + (long long)task * K - (long long)task * (task + 1) / 2;
           for (int b = task + 1 + lane; b < K; b += 32) c.pair_len[row + (b - task - 1)] = wm.dist[odd[b]];
@@ -802,15 +819,22 @@ __host__ __device__ inline size_t toggle_warp_bytes(int S_max, int slots_max) {
   return align16((size_t)slots_max * 8) + paths_warp_bytes(S_max, true);
 }
 
-template <int NCH>
+template <int NCH, bool WG>
 __global__ void __launch_bounds__(256) k_path_toggle(const __grid_constant__ PathsParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int nwarps = blockDim.x >> 5;
   // queries of one CTA mix trials, so every warp keeps its own copy of the trial's weights;
   // the static face tables are read from global memory (L1/L2 resident)
-  unsigned char* wp = smem + (size_t)wid * toggle_warp_bytes(p.S_max, p.slots_max);
-  double* wslot = (double*)wp; wp += align16((size_t)p.slots_max * 8);
+  unsigned char* wp;
+  double* wslot;
+  if (WG) {
+    wp = smem + (size_t)wid * paths_warp_bytes(p.S_max, true);
+    wslot = p.wscratch + ((size_t)blockIdx.x * nwarps + wid) * p.slots_max;
+  } else {
+    wp = smem + (size_t)wid * toggle_warp_bytes(p.S_max, p.slots_max);
+    wslot = (double*)wp; wp += align16((size_t)p.slots_max * 8);
+  }
   const WarpMem wm = carve_warp(wp, p.S_max, true);
   for (int qi = blockIdx.x * nwarps + wid; qi < p.n_queries; qi += gridDim.x * nwarps) {
     const int t = p.q_trial[qi], ci = p.q_cx[qi];
@@ -827,6 +851,8 @@ __global__ void __launch_bounds__(256) k_path_toggle(const __grid_constant__ Pat
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (WG) __threadfence_block();
+    __syncwarp();
     const double step = bucket_step(sum / (double)c.Q, p.step_factor);
     const double inv = 1.0 / step;
     CtaMem cm;
@@ -850,7 +876,7 @@ __global__ void __launch_bounds__(256) k_path_toggle(const __grid_constant__ Pat
                      : warp_seed_connector(cm, wm, c.n_low, c.low_cube, c.low_slot, inv, lane);
       stop = walk_from = src;
     }
-    warp_search<true, NCH, 1>(cm, wm, dt, S, step, present, lane, stop);
+    warp_search<true, NCH, 1, WG>(cm, wm, dt, S, step, present, lane, stop);
     __syncwarp();
     if (lane == 0) {
       int u = walk_from;
