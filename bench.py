@@ -36,6 +36,13 @@ WORKLOADS = {
                            weight_opts={"method": "blueprint", "delta": 0.08}),
     "d13_open_primal": dict(distance=13, ec="primal", boundaries="open", delta=0.09, p_swap=0.0,
                             weight_opts={"method": "blueprint", "delta": 0.09}),
+    # BASELINE.json configs[3]: all nodes p-squeezed -> trial-independent weights -> table gather
+    "d21_open_allp_blueprint": dict(distance=21, ec="primal", boundaries="open", delta=0.09, p_swap=1.0,
+                                    weight_opts={"method": "blueprint", "delta": 0.09}),
+    "d21_open_allp_uniform": dict(distance=21, ec="primal", boundaries="open", delta=0.09, p_swap=1.0,
+                                  weight_opts={"method": "uniform"}),
+    "d17_periodic_primal": dict(distance=17, ec="primal", boundaries="periodic", delta=0.09, p_swap=0.0,
+                                weight_opts={"method": "blueprint", "delta": 0.09}),
     "d3_open_primal": dict(distance=3, ec="primal", boundaries="open", delta=0.09, p_swap=0.25,
                            weight_opts={"method": "blueprint", "delta": 0.09}),
 }
@@ -219,6 +226,9 @@ def run_gpu_arm(args, cfg, lat):
     B = args.batch
     eng = TrialEngine(lat, cfg["delta"], cfg["p_swap"], cfg["weight_opts"], mode=args.mode, device=local,
                       delta_step=args.delta_step)
+    static = cfg["weight_opts"]["method"] == "uniform" or cfg["p_swap"] == 1.0
+    if static and not args.no_table:
+        eng.build_table()  # trial-independent weights: the matching graph becomes a table gather
 
     def barrier():
         if use_dist:
@@ -321,6 +331,9 @@ def run_gpu_arm(args, cfg, lat):
     if rank == 0:
         peak, peak_src = load_peaks()
         kb = paths_kernel_bytes(lat, B * args.steps, tot_odd, tot_pairs)
+        if eng.uses_table:  # gather: reads one table entry and writes one length per pair / connector
+            kb = sum(4 * tot_odd[i] + 16 * tot_pairs[i] + (18 * tot_odd[i] if lat.complexes[e].has_boundary else 0)
+                     for i, e in enumerate(lat.ec))
         achieved = kb / (graph_ms * 1e-3) / 1e9 if graph_ms > 0 else 0.0
         pipe_b = algorithmic_bytes(lat, B * args.steps, tot_odd, tot_pairs)
         line = {
@@ -340,10 +353,11 @@ def run_gpu_arm(args, cfg, lat):
                     "d2h_bytes_per_step": d2h_bytes // max(1, args.steps), "trials_per_gpu_per_step": Be,
                     "api": "TrialEngine.run_injected(host x, host labels) + fetch_into(pinned host buffers)"},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "k_paths", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "k_gather" if eng.uses_table else "k_paths", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "share_of_step": graph_ms / dev_ms if dev_ms else None,
-                         "note": "k_paths is bound by shared-memory latency/issue, not HBM (DESIGN.md)",
+                         "note": ("static-weight table gather (HBM / L2 bound)" if eng.uses_table else
+                                  "k_paths is bound by shared-memory latency/issue, not HBM (DESIGN.md)"),
                          "pipeline_achieved": pipe_b / (dev_ms * 1e-3) / 1e9,
                          "pipeline_frac": pipe_b / (dev_ms * 1e-3) / 1e9 / peak},
             "clocks": clk,
@@ -376,6 +390,7 @@ def main():
     ap.add_argument("--delta-step", type=float, default=0.0)
     ap.add_argument("--cpu-trials", type=int, default=0, help="CPU sample size in trials (0: 64 x cores for cpu_baseline, 32 x cores per step for --impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-table", action="store_true", help="static-weight workloads: search instead of the table gather")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         print("bench.py: note: fewer than 3 warm-up steps requested", file=sys.stderr)

@@ -126,6 +126,7 @@ EXPORTS = {
     "fpb_device_outputs": (C.c_int, [C.c_void_p, C.POINTER(Outputs)]),
     "fpb_get_timings": (C.c_int, [C.c_void_p, C.POINTER(Timings)]),
     "fpb_synchronize": (C.c_int, [C.c_void_p]),
+    "fpb_build_table": (C.c_int, [C.c_void_p]),
     "fpb_mark": (C.c_int, [C.c_void_p, C.c_int]),
     "fpb_elapsed_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "fpb_paths_toggle": (C.c_int, [C.c_void_p, C.c_int64, _i32p, _i32p, _i32p, _i32p, _u32p]),

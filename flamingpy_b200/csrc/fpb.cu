@@ -79,6 +79,8 @@ struct ComplexHost {
   DevBuf<double> pair_len, bnd_len;
   DevBuf<uint8_t> bnd_side;
   long long total_odd = 0, total_pairs = 0;
+  DevBuf<double> tab_pair, tab_bnd;  // all-pairs table of the static-weight path
+  DevBuf<uint8_t> tab_side;
 };
 
 }  // namespace
@@ -112,6 +114,12 @@ struct fpb_handle {
   size_t paths_smem = 0;
   bool paths_wg = false;  // weights / tables in global memory (large lattices)
   DevBuf<double> wscratch;
+  // static-weight fast path (fpb_build_table)
+  bool use_table = false;
+  std::vector<int> qubit_degree;  // host copy: lattice degree of every syndrome qubit
+  DevBuf<double> static_w;        // [Qtot]
+  DevBuf<int> static_flag;
+  int* static_flag_host = nullptr;  // pinned
 };
 
 namespace {
@@ -242,6 +250,68 @@ int ensure_batch(fpb_handle* h, long long T) {
   return FPB_OK;
 }
 
+int launch_paths(fpb_handle* h, long long T, int* launches) {
+  cudaStream_t st = h->stream;
+  const long long total_items = h->totals_host[2 * MAXC];
+  if (total_items <= 0) return FPB_OK;
+  PathsParams pp;
+  memset(&pp, 0, sizeof pp);
+  pp.n_complex = h->ncx; pp.T = (int)T; pp.Qtot = h->Qtot;
+  pp.tasks_per_item = h->tasks_per_item;
+  pp.S_max = h->S_max; pp.slots_max = h->slots_max; pp.warps = h->warps;
+  pp.step_factor = h->step_factor;
+  pp.weights = h->weights.p;
+  pp.item_off = h->item_off.p;
+  pp.total_items = (int)total_items;
+  pp.counter = h->counter.p;
+  for (int c = 0; c < h->ncx; ++c) pp.cx[c] = make_dev(h->cx[c]);
+  CK(cudaMemsetAsync(h->counter.p, 0, sizeof(int), st));
+  long long grid = (long long)h->sm_count * h->ctas_per_sm;
+  if (grid > total_items) grid = total_items;
+  if (h->paths_wg) {
+    int rc2 = h->wscratch.ensure((size_t)grid * h->slots_max);
+    if (rc2) return rc2;
+    pp.wscratch = h->wscratch.p;
+  }
+  int mw_unused = 0;
+  pick_paths_kernel(h->S_max, h->paths_wg, &mw_unused)<<<(unsigned)grid, h->warps * 32, h->paths_smem, st>>>(pp);
+  ++*launches;
+  h->tm.graph_ctas = (int)grid;
+  return FPB_OK;
+}
+
+// scan the odd counts, read the totals back, size the ragged outputs, compact the odd lists
+int post_syndrome(fpb_handle* h, long long T, int stage, int* launches) {
+  cudaStream_t st = h->stream;
+  ScanParams sc;
+  sc.n_complex = h->ncx;
+  sc.tasks_per_item = h->tasks_per_item > 0 ? h->tasks_per_item : 1;
+  for (int c = 0; c < h->ncx; ++c) {
+    sc.cx[c] = make_dev(h->cx[c]);
+    sc.has_boundary[c] = h->cx[c].n_low > 0;
+  }
+  sc.item_off = h->item_off.p;
+  sc.totals = h->totals.p;
+  k_scan<<<1, 1024, 0, st>>>(sc, (int)T);
+  ++*launches;
+  CK(cudaMemcpyAsync(h->totals_host, h->totals.p, (2 * MAXC + 1) * sizeof(long long), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  int rc;
+  for (int c = 0; c < h->ncx; ++c) {
+    ComplexHost& cx = h->cx[c];
+    cx.total_odd = h->totals_host[c];
+    cx.total_pairs = h->totals_host[MAXC + c];
+    if ((rc = cx.odd_ids.ensure((size_t)cx.total_odd + 1))) return rc;
+    if ((rc = cx.bnd_len.ensure((size_t)cx.total_odd + 1))) return rc;
+    if ((rc = cx.bnd_side.ensure((size_t)cx.total_odd + 1))) return rc;
+    if (stage >= FPB_STAGE_GRAPH)
+      if ((rc = cx.pair_len.ensure((size_t)cx.total_pairs + 1))) return rc;
+    k_compact_odd<<<(unsigned)T, 256, 0, st>>>(make_dev(cx), (int)T);
+    ++*launches;
+  }
+  return FPB_OK;
+}
+
 int run_pipeline(fpb_handle* h, long long T, int stage, bool gen, uint64_t seed, long long first_trial) {
   if (T <= 0) return fail(FPB_ERR_ARG, "n_trials must be positive");
   if (T > 0x7fffffffll / (h->ncx > 0 ? h->ncx : 1) / 2) return fail(FPB_ERR_ARG, "n_trials too large for one batch");
@@ -297,62 +367,31 @@ int run_pipeline(fpb_handle* h, long long T, int stage, bool gen, uint64_t seed,
     for (int c = 0; c < h->ncx; ++c) sp.cx[c] = make_dev(h->cx[c]);
     k_syndrome<<<dim3((unsigned)T, h->ncx), 256, 0, st>>>(sp);
     ++launches;
-    ScanParams sc;
-    sc.n_complex = h->ncx;
-    sc.tasks_per_item = h->tasks_per_item > 0 ? h->tasks_per_item : 1;
-    for (int c = 0; c < h->ncx; ++c) {
-      sc.cx[c] = sp.cx[c];
-      sc.has_boundary[c] = h->cx[c].n_low > 0;
-    }
-    sc.item_off = h->item_off.p;
-    sc.totals = h->totals.p;
-    k_scan<<<1, 1024, 0, st>>>(sc, (int)T);
-    ++launches;
-    CK(cudaMemcpyAsync(h->totals_host, h->totals.p, (2 * MAXC + 1) * sizeof(long long),
-                       cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    int rc;
-    for (int c = 0; c < h->ncx; ++c) {
-      ComplexHost& cx = h->cx[c];
-      cx.total_odd = h->totals_host[c];
-      cx.total_pairs = h->totals_host[MAXC + c];
-      if ((rc = cx.odd_ids.ensure((size_t)cx.total_odd + 1))) return rc;
-      if ((rc = cx.bnd_len.ensure((size_t)cx.total_odd + 1))) return rc;
-      if ((rc = cx.bnd_side.ensure((size_t)cx.total_odd + 1))) return rc;
-      if (stage >= FPB_STAGE_GRAPH)
-        if ((rc = cx.pair_len.ensure((size_t)cx.total_pairs + 1))) return rc;
-      k_compact_odd<<<(unsigned)T, 256, 0, st>>>(make_dev(cx), (int)T);
-      ++launches;
-    }
+    int rcs = post_syndrome(h, T, stage, &launches);
+    if (rcs) return rcs;
   }
   CK(cudaEventRecord(h->ev[3], st));
   if (stage >= FPB_STAGE_GRAPH) {
     if (h->warps == 0) return fail(FPB_ERR_UNSUPPORTED, "shortest-path kernel not configured for this lattice");
-    const long long total_items = h->totals_host[2 * MAXC];
-    if (total_items > 0) {
-      PathsParams pp;
-      memset(&pp, 0, sizeof pp);
-      pp.n_complex = h->ncx; pp.T = (int)T; pp.Qtot = h->Qtot;
-      pp.tasks_per_item = h->tasks_per_item;
-      pp.S_max = h->S_max; pp.slots_max = h->slots_max; pp.warps = h->warps;
-      pp.step_factor = h->step_factor;
-      pp.weights = h->weights.p;
-      pp.item_off = h->item_off.p;
-      pp.total_items = (int)total_items;
-      pp.counter = h->counter.p;
-      for (int c = 0; c < h->ncx; ++c) pp.cx[c] = make_dev(h->cx[c]);
-      CK(cudaMemsetAsync(h->counter.p, 0, sizeof(int), st));
-      long long grid = (long long)h->sm_count * h->ctas_per_sm;
-      if (grid > total_items) grid = total_items;
-      if (h->paths_wg) {
-        int rc2 = h->wscratch.ensure((size_t)grid * h->slots_max);
-        if (rc2) return rc2;
-        pp.wscratch = h->wscratch.p;
+    if (h->use_table) {
+      // static weights: gather the matching graph from the all-pairs table
+      if (h->weight_method == FPB_WEIGHT_BLUEPRINT) {
+        CK(cudaMemsetAsync(h->static_flag.p, 0, sizeof(int), st));
+        k_check_static<<<h->sm_count * 4, 256, 0, st>>>(h->weights.p, h->static_w.p, h->Qtot, T, h->static_flag.p);
+        CK(cudaMemcpyAsync(h->static_flag_host, h->static_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        ++launches;
       }
-      int mw_unused = 0;
-      pick_paths_kernel(h->S_max, h->paths_wg, &mw_unused)<<<(unsigned)grid, h->warps * 32, h->paths_smem, st>>>(pp);
-      ++launches;
-      h->tm.graph_ctas = (int)grid;
+      for (int c = 0; c < h->ncx; ++c) {
+        ComplexHost& cx = h->cx[c];
+        if (cx.total_odd == 0) continue;
+        dim3 grid((unsigned)T, (unsigned)((cx.S + GATHER_ROWS - 1) / GATHER_ROWS));
+        k_gather<<<grid, GATHER_ROWS * 32, (size_t)cx.S * 2, st>>>(make_dev(cx), cx.tab_pair.p,
+                                                                  cx.n_low > 0 ? cx.tab_bnd.p : nullptr, cx.tab_side.p);
+        ++launches;
+      }
+    } else {
+      int rc2 = launch_paths(h, T, &launches);
+      if (rc2) return rc2;
     }
   }
   CK(cudaEventRecord(h->ev[4], st));
@@ -363,6 +402,8 @@ int run_pipeline(fpb_handle* h, long long T, int stage, bool gen, uint64_t seed,
   CK(cudaEventElapsedTime(&h->tm.syndrome_ms, h->ev[2], h->ev[3]));
   CK(cudaEventElapsedTime(&h->tm.graph_ms, h->ev[3], h->ev[4]));
   CK(cudaEventElapsedTime(&h->tm.total_ms, h->ev[0], h->ev[4]));
+  if (stage >= FPB_STAGE_GRAPH && h->use_table && h->weight_method == FPB_WEIGHT_BLUEPRINT && *h->static_flag_host)
+    return fail(FPB_ERR_STATE, "static-weight table in use but a trial's labels are not all p-squeezed");
   h->tm.launches = launches;
   h->tm.graph_warps_per_cta = h->warps;
   h->tm.graph_smem_bytes = (int)h->paths_smem;
@@ -427,6 +468,8 @@ int fpb_create(const fpb_config* cfg, fpb_handle** out) {
     if (cudaEventCreate(&ev) != cudaSuccess) return bail(fail(FPB_ERR_CUDA, "event creation failed"));
   if (cudaMallocHost(&h->totals_host, (2 * MAXC + 1) * sizeof(long long)) != cudaSuccess) return bail(fail(FPB_ERR_CUDA, "pinned allocation failed"));
   memset(h->totals_host, 0, (2 * MAXC + 1) * sizeof(long long));
+  if (cudaMallocHost(&h->static_flag_host, sizeof(int)) != cudaSuccess) return bail(fail(FPB_ERR_CUDA, "pinned allocation failed"));
+  *h->static_flag_host = 0;
 
   const int N = h->N;
   const int nnz = cfg->adj_indptr[N];
@@ -451,6 +494,7 @@ int fpb_create(const fpb_config* cfg, fpb_handle** out) {
     for (int q = 0; q < d.n_qubits; ++q) {
       if (d.qubit_node[q] < 0 || d.qubit_node[q] >= N) return bail(fail(FPB_ERR_ARG, "qubit node index out of range"));
       qnode.push_back(d.qubit_node[q]);
+      h->qubit_degree.push_back(cfg->adj_indptr[d.qubit_node[q] + 1] - cfg->adj_indptr[d.qubit_node[q]]);
     }
     std::vector<uint16_t> sb16(d.n_cubes);
     for (int s = 0; s < d.n_cubes; ++s) {
@@ -489,12 +533,14 @@ int fpb_destroy(fpb_handle* h) {
     cudaFree(cx.low_cube); cudaFree(cx.low_slot); cudaFree(cx.high_cube); cudaFree(cx.high_slot);
     cx.parity.release(); cx.odd_count.release(); cx.odd_fixed.release(); cx.odd_ids.release();
     cx.odd_off.release(); cx.pair_off.release(); cx.pair_len.release(); cx.bnd_len.release();
-    cx.bnd_side.release();
+    cx.bnd_side.release(); cx.tab_pair.release(); cx.tab_bnd.release(); cx.tab_side.release();
   }
   h->x.release(); h->hom.release(); h->weights.release(); h->state.release(); h->bits.release();
   h->flips.release(); h->item_off.release(); h->counter.release(); h->totals.release();
   h->q_trial.release(); h->q_cx.release(); h->q_src.release(); h->q_dst.release(); h->wscratch.release();
   if (h->totals_host) cudaFreeHost(h->totals_host);
+  if (h->static_flag_host) cudaFreeHost(h->static_flag_host);
+  h->static_w.release(); h->static_flag.release();
   for (auto& ev : h->ev)
     if (ev) cudaEventDestroy(ev);
   for (auto& ev : h->mark)
@@ -604,6 +650,55 @@ int fpb_synchronize(fpb_handle* h) {
   if (!h) return fail(FPB_ERR_ARG, "null handle");
   CK(cudaSetDevice(h->device));
   CK(cudaStreamSynchronize(h->stream));
+  return FPB_OK;
+}
+
+int fpb_build_table(fpb_handle* h) {
+  if (!h) return fail(FPB_ERR_ARG, "null handle");
+  const bool uniform = h->weight_method == FPB_WEIGHT_UNIFORM;
+  if (!uniform && !(h->weight_method == FPB_WEIGHT_BLUEPRINT && h->p_swap >= 1.0))
+    return fail(FPB_ERR_UNSUPPORTED, "weights are trial-dependent: the static table needs uniform weights or p_swap == 1");
+  if (h->warps == 0) return fail(FPB_ERR_UNSUPPORTED, "shortest-path kernel not configured for this lattice");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  // trial-independent weights (decoders/decoder.py:86-93 with p_count = degree, :115-116)
+  std::vector<double> w((size_t)h->Qtot, 1.0);
+  if (!uniform)
+    for (int q = 0; q < h->Qtot; ++q) {
+      const int deg = h->qubit_degree[q];
+      if (deg < 2 || deg > 4) return fail(FPB_ERR_UNSUPPORTED, "a syndrome qubit with fewer than 2 neighbours has hom-dependent weight");
+      const double err = deg == 2 ? 0.25 : (deg == 3 ? 1.0 / 3.0 : 0.4);
+      w[q] = h->weight_integer ? std::rint(-h->weight_multiplier * std::log(err)) : -std::log(err);
+    }
+  int rc;
+  if ((rc = ensure_batch(h, 1))) return rc;
+  if ((rc = h->static_w.ensure((size_t)h->Qtot))) return rc;
+  if ((rc = h->static_flag.ensure(1))) return rc;
+  CK(cudaMemcpyAsync(h->static_w.p, w.data(), (size_t)h->Qtot * sizeof(double), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(h->weights.p, h->static_w.p, (size_t)h->Qtot * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  // pseudo-trial in which every cube is odd: its matching graph is the all-pairs table
+  h->use_table = false;
+  for (int c = 0; c < h->ncx; ++c) k_iota_odd<<<64, 256, 0, st>>>(make_dev(h->cx[c]));
+  int launches = 0;
+  h->T = 1;
+  h->last_stage = FPB_STAGE_GRAPH;
+  if ((rc = post_syndrome(h, 1, FPB_STAGE_GRAPH, &launches))) return rc;
+  if ((rc = launch_paths(h, 1, &launches))) return rc;
+  for (int c = 0; c < h->ncx; ++c) {
+    ComplexHost& cx = h->cx[c];
+    if ((rc = cx.tab_pair.ensure((size_t)cx.total_pairs + 1))) return rc;
+    if ((rc = cx.tab_bnd.ensure((size_t)cx.S + 1))) return rc;
+    if ((rc = cx.tab_side.ensure((size_t)cx.S + 1))) return rc;
+    CK(cudaMemcpyAsync(cx.tab_pair.p, cx.pair_len.p, (size_t)cx.total_pairs * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (cx.n_low > 0) {
+      CK(cudaMemcpyAsync(cx.tab_bnd.p, cx.bnd_len.p, (size_t)cx.S * sizeof(double), cudaMemcpyDeviceToDevice, st));
+      CK(cudaMemcpyAsync(cx.tab_side.p, cx.bnd_side.p, (size_t)cx.S, cudaMemcpyDeviceToDevice, st));
+    }
+  }
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(st));
+  h->use_table = true;
+  h->T = 0;  // the pseudo-trial is not a result
   return FPB_OK;
 }
 

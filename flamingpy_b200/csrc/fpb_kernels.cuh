@@ -911,4 +911,59 @@ __global__ void __launch_bounds__(256) k_path_toggle(const __grid_constant__ Pat
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Static-weight path (uniform weights, or blueprint weights with every node p-squeezed:
+// decoder.py:86-93,115-116 make the weights trial-independent).  The all-pairs distances of the
+// cube grid are computed once with k_paths (odd list = every cube) into a packed upper triangle;
+// a trial's matching graph is then a pure gather - the HBM-bound case of SURVEY.md section 7.
+// ------------------------------------------------------------------------------------------
+__global__ void k_fill_static(double* weights, const double* static_w, int Qtot, long long T) {
+  const long long n = T * Qtot;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    weights[i] = static_w[i % Qtot];
+}
+
+// flag != 0 if any trial's weights differ from the static ones (labels were not all "p")
+__global__ void k_check_static(const double* weights, const double* static_w, int Qtot, long long T, int* flag) {
+  const long long n = T * Qtot;
+  bool bad = false;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    bad |= weights[i] != static_w[i % Qtot];
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
+
+__global__ void k_iota_odd(ComplexDev c) {  // the "every cube is odd" pseudo-trial of the table build
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < c.S; i += gridDim.x * blockDim.x) c.odd_fixed[i] = i;
+  if (blockIdx.x == 0 && threadIdx.x == 0) c.odd_count[0] = c.S;
+}
+
+constexpr int GATHER_ROWS = 8;  // rows (= warps) per CTA
+
+__global__ void __launch_bounds__(GATHER_ROWS * 32) k_gather(ComplexDev c, const double* tab_pair,
+                                                              const double* tab_bnd, const uint8_t* tab_side) {
+  const int t = blockIdx.x;
+  const int K = c.odd_count[t];
+  const int a0 = blockIdx.y * GATHER_ROWS;
+  if (a0 >= K) return;
+  extern __shared__ uint16_t odd_s[];  // the trial's odd list
+  const int* odd = c.odd_fixed + (long long)t * c.S;
+  for (int i = threadIdx.x; i < K; i += blockDim.x) odd_s[i] = (uint16_t)odd[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, a = a0 + (threadIdx.x >> 5);
+  if (a >= K) return;
+  const long long S = c.S;
+  const long long src = odd_s[a];
+  if (a < K - 1) {
+    // row `src` of the table triangle holds (src, j), j > src, contiguously
+    const double* trow = tab_pair + (src * S - src * (src + 1) / 2 - src - 1);
+    double* orow = c.pair_len + c.pair_off[t] + ((long long)a * K - (long long)a * (a + 1) / 2 - a - 1);
+    for (int b = a + 1 + lane; b < K; b += 32) orow[b] = trow[odd_s[b]];
+  }
+  if (tab_bnd && lane == 0) {
+    const long long o = c.odd_off[t] + a;
+    c.bnd_len[o] = tab_bnd[src];
+    c.bnd_side[o] = tab_side[src];
+  }
+}
+
 }  // namespace fpb

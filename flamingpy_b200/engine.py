@@ -155,6 +155,7 @@ class TrialEngine:
         _lib.check(lib.fpb_create(C.byref(cfg), C.byref(handle)))
         self._h = handle
         self._keep = []
+        self.uses_table = False
 
     # ------------------------------------------------------------------ lifecycle
     def close(self):
@@ -198,6 +199,12 @@ class TrialEngine:
         t = _lib.Timings()
         _lib.check(self._lib.fpb_get_timings(self._h, C.byref(t)))
         return {name: getattr(t, name) for name, _ in _lib.Timings._fields_}
+
+    def build_table(self):
+        """Precompute the all-pairs distance table for trial-independent weights (uniform, or
+        blueprint with ``p_swap == 1``); later graph-stage runs gather from it."""
+        _lib.check(self._lib.fpb_build_table(self._h))
+        self.uses_table = True
 
     def mark(self, which: int):
         """Record timing mark 0 / 1 on the handle's stream."""

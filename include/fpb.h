@@ -180,6 +180,14 @@ int fpb_synchronize(fpb_handle* h);
 int fpb_mark(fpb_handle* h, int which);
 int fpb_elapsed_ms(fpb_handle* h, float* ms);
 
+/* Static-weight fast path.  With uniform weights, or blueprint weights and p_swap == 1 (every
+ * node p-squeezed), assign_weights gives trial-independent weights (decoders/decoder.py:86-93,
+ * 115-116), so the shortest-path lengths between all cubes are computed once here and every later
+ * graph-stage run gathers its matching graph from that table instead of searching (results are
+ * bit-identical to the search path).  Fails with FPB_ERR_UNSUPPORTED for other weight options;
+ * a later injected run whose labels are not all "p" fails with FPB_ERR_STATE. */
+int fpb_build_table(fpb_handle* h);
+
 /* Correction paths for matched pairs of the last run.  Query i asks, in trial
  * trial[i] and complex cx[i], for the shortest path from odd cube src[i] to
  * odd cube dst[i] (dst >= 0), or to its nearer connector (dst == -1).  The local

@@ -171,3 +171,43 @@ def test_uniform_and_integer_weights_with_zero_weight_edges():
     cb, rb = batch.complexes["primal"], ref.complexes["primal"]
     assert np.array_equal(cb.pair_len, rb.pair_len)
     assert np.array_equal(cb.bnd_len, rb.bnd_len)
+
+
+@pytest.mark.parametrize("d,ec,b,wo", [
+    (7, "primal", "open", {"method": "blueprint", "delta": 0.09}),
+    (6, "dual", "open", {"method": "uniform"}),
+    (5, "both", "periodic", {"method": "blueprint", "delta": 0.09, "integer": True, "multiplier": 100}),
+])
+def test_static_weight_table_is_bit_identical_to_search(d, ec, b, wo):
+    """p_swap = 1 (or uniform weights): weights are trial-independent, the matching graph gathered
+    from the precomputed all-pairs table equals the per-trial search bit for bit."""
+    lat = build_lattice(d, ec, b)
+    search = _engine(lat, 0.09, 1, wo)
+    table = _engine(lat, 0.09, 1, wo)
+    table.build_table()
+    a = search.run_rng(4, 0, 24)
+    t = table.run_rng(4, 0, 24)
+    for e in lat.ec:
+        ca, ct_ = a.complexes[e], t.complexes[e]
+        assert np.array_equal(ca.odd_ids, ct_.odd_ids)
+        assert np.array_equal(ca.pair_len, ct_.pair_len)
+        assert np.array_equal(ca.bnd_len, ct_.bnd_len)
+        assert np.array_equal(ca.bnd_side, ct_.bnd_side)
+    assert a.complexes[lat.ec[0]].pair_len.size > 0
+    # and against the oracle
+    full = table.run_rng(4, 0, 3, want_draws=True)
+    ref = c_oracle.run(lat, 0.09, 1, wo, full.x, full.state)
+    _same_as_oracle(lat, full, ref)
+
+
+def test_static_table_guards():
+    lat = build_lattice(4, "primal", "open")
+    with pytest.raises(_lib.FpbError, match="trial-dependent"):
+        _engine(lat, 0.09, 0.5, {"method": "blueprint", "delta": 0.09}).build_table()
+    eng = _engine(lat, 0.09, 1, {"method": "blueprint", "delta": 0.09})
+    eng.build_table()
+    N = lat.N
+    x = np.random.default_rng(0).normal(0, 0.3, (2, 2 * N))
+    eng.run_injected(x, np.full((2, N), 2, np.uint8))  # all p: fine
+    with pytest.raises(_lib.FpbError, match="not all p"):
+        eng.run_injected(x, np.ones((2, N), np.uint8))  # GKP labels: weights differ from the table
