@@ -276,7 +276,11 @@ def run_gpu_arm(args, cfg, lat):
     value = total_trials / (dev_ms_max * 1e-3)
 
     # ---------------- end to end through the public API with host buffers (`e2e`) ----------------
+    # Every step copies its inputs from pinned host memory (H2D) and all contract outputs back to
+    # pinned host buffers (D2H).  Two engines on two streams, driven by two host threads, let one
+    # step's copies overlap the other's kernels (ctypes releases the GIL inside the calls).
     Be = args.e2e_batch
+    n_lanes = max(1, args.e2e_lanes)
     n_sets = min(args.steps + args.warmup, 3)
     N, Q = lat.N, eng.Qtot
     pin = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True).numpy()  # noqa: E731
@@ -288,38 +292,61 @@ def run_gpu_arm(args, cfg, lat):
     rng = np.random.default_rng(SEED + 1000 * rank)
     for i in range(n_sets):
         sample_batch(rng, N, cfg["delta"], cfg["p_swap"], Be, sampler=sampler, out_x=xs[i], out_state=sts[i])
+    engines = [eng]
+    for _ in range(n_lanes - 1):
+        e2 = TrialEngine(lat, cfg["delta"], cfg["p_swap"], cfg["weight_opts"], mode=args.mode, device=local,
+                         delta_step=args.delta_step)
+        if eng.uses_table:
+            e2.build_table()
+        engines.append(e2)
     # host result buffers sized from a probe run
     eng.run_injected(xs[0], sts[0], fetch=False)
     sz = eng.sizes()
-    bufs = {"hom": pin((Be * Q,), torch.float64), "weights": pin((Be * Q,), torch.float64),
-            "bits": pin((Be * eng.bit_words,), torch.int32).view(np.uint32)}
-    for i, e in enumerate(lat.ec):
-        ct = lat.complexes[e]
-        mo = int(sz.total_odd[i] * 1.25) + 1024
-        mp = int(sz.total_pairs[i] * 1.25) + 1024
-        bufs[f"parity{i}"] = pin((Be * ((ct.S + 31) // 32),), torch.int32).view(np.uint32)
-        bufs[f"odd_count{i}"] = pin((Be,), torch.int32)
-        bufs[f"odd_ids{i}"] = pin((mo,), torch.int32)
-        bufs[f"pair_len{i}"] = pin((mp,), torch.float64)
-        if ct.has_boundary:
-            bufs[f"bnd_len{i}"] = pin((mo,), torch.float64)
-            bufs[f"bnd_side{i}"] = pin((mo,), torch.uint8)
 
-    def e2e_step(i):
-        eng.run_injected(xs[i % n_sets], sts[i % n_sets], fetch=False)  # H2D inside
-        s_ = eng.fetch_into(bufs)  # D2H inside
-        d2h = Be * (16 * Q + 4 * eng.bit_words) + sum(
+    def alloc_bufs():
+        bufs = {"hom": pin((Be * Q,), torch.float64), "weights": pin((Be * Q,), torch.float64),
+                "bits": pin((Be * eng.bit_words,), torch.int32).view(np.uint32)}
+        for i, e in enumerate(lat.ec):
+            ct = lat.complexes[e]
+            mo = int(sz.total_odd[i] * 1.25) + 1024
+            mp = int(sz.total_pairs[i] * 1.25) + 1024
+            bufs[f"parity{i}"] = pin((Be * ((ct.S + 31) // 32),), torch.int32).view(np.uint32)
+            bufs[f"odd_count{i}"] = pin((Be,), torch.int32)
+            bufs[f"odd_ids{i}"] = pin((mo,), torch.int32)
+            bufs[f"pair_len{i}"] = pin((mp,), torch.float64)
+            if ct.has_boundary:
+                bufs[f"bnd_len{i}"] = pin((mo,), torch.float64)
+                bufs[f"bnd_side{i}"] = pin((mo,), torch.uint8)
+        return bufs
+
+    lane_bufs = [alloc_bufs() for _ in engines]
+
+    def e2e_step(lane, i):
+        en = engines[lane]
+        en.run_injected(xs[i % n_sets], sts[i % n_sets], fetch=False)  # H2D inside
+        s_ = en.fetch_into(lane_bufs[lane])  # D2H inside
+        return Be * (16 * Q + 4 * eng.bit_words) + sum(
             Be * (4 * ((lat.complexes[e].S + 31) // 32) + 4) + 4 * int(s_.total_odd[j]) + 8 * int(s_.total_pairs[j])
             + (9 * int(s_.total_odd[j]) if lat.complexes[e].has_boundary else 0) for j, e in enumerate(lat.ec))
-        return d2h
 
-    for s in range(max(1, args.warmup)):
-        e2e_step(s)
+    def run_steps(first, count):
+        done = [0] * len(engines)
+
+        def work(lane):
+            for i in range(first + lane, first + count, len(engines)):
+                done[lane] += e2e_step(lane, i)
+
+        ths = [threading.Thread(target=work, args=(ln,)) for ln in range(len(engines))]
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join()
+        return sum(done)
+
+    run_steps(0, max(len(engines), args.warmup))
     barrier()
     t0 = time.perf_counter()
-    d2h_bytes = 0
-    for s in range(args.steps):
-        d2h_bytes += e2e_step(s)
+    d2h_bytes = run_steps(args.warmup, args.steps)
     barrier()
     e2e_wall = time.perf_counter() - t0
     e2e_t = torch.tensor([e2e_wall], dtype=torch.float64, device="cuda")
@@ -351,7 +378,8 @@ def run_gpu_arm(args, cfg, lat):
             "wall_ms_per_step": wall_ms_max / args.steps,
             "e2e": {"value": e2e_value, "unit": "trials/s", "h2d_bytes_per_step": h2d_per_step,
                     "d2h_bytes_per_step": d2h_bytes // max(1, args.steps), "trials_per_gpu_per_step": Be,
-                    "api": "TrialEngine.run_injected(host x, host labels) + fetch_into(pinned host buffers)"},
+                    "api": "TrialEngine.run_injected(host x, host labels) + fetch_into(pinned host buffers)",
+                    "host_threads": len(engines)},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "k_gather" if eng.uses_table else "k_paths", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
@@ -371,7 +399,8 @@ def run_gpu_arm(args, cfg, lat):
                 "sample": f"{n_cpu} trials of the same workload, oracle/fpb_oracle.c (C + OpenMP restatement of "
                           f"the reference path), host NumPy sampling included, {dt:.1f} s"}
         print(json.dumps(line), flush=True)
-    eng.close()
+    for en in engines:
+        en.close()
     if use_dist:
         dist.destroy_process_group()
 
@@ -387,6 +416,7 @@ def main():
                     help="compat = one reused CVLayer per chain like simulations.ec_monte_carlo; fresh = new layer per trial")
     ap.add_argument("--batch", type=int, default=2048, help="trials per GPU per step (device-resident arm)")
     ap.add_argument("--e2e-batch", type=int, default=512, help="trials per GPU per step (end-to-end arm)")
+    ap.add_argument("--e2e-lanes", type=int, default=2, help="engines / host threads overlapping copies and kernels")
     ap.add_argument("--delta-step", type=float, default=0.0)
     ap.add_argument("--cpu-trials", type=int, default=0, help="CPU sample size in trials (0: 64 x cores for cpu_baseline, 32 x cores per step for --impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
