@@ -7,6 +7,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -113,6 +114,7 @@ struct fpb_handle {
   int warps = 0, ctas_per_sm = 0, tasks_per_item = 0;
   size_t paths_smem = 0;
   bool paths_wg = false;  // weights / tables in global memory (large lattices)
+  bool paths_team = false;  // two warps per search (k_paths_team)
   DevBuf<double> wscratch;
   // static-weight fast path (fpb_build_table)
   bool use_table = false;
@@ -159,6 +161,13 @@ paths_fn pick_paths_kernel(int S, bool wg, int* max_warps) {
   if (S <= 2560) return k_paths<5, 2, 384, 1, false>;
   if (S <= 4096) return k_paths<8, 2, 384, 1, false>;
   return k_paths<16, 2, 384, 1, false>;
+}
+// two-warp-team variant (shared-memory lattices with more than 1024 cubes): NCH2 = chunks per warp
+paths_fn pick_team_kernel(int S) {
+  if (S <= 2048) return k_paths_team<2, 2, 512, 1>;
+  if (S <= 3072) return k_paths_team<3, 2, 512, 1>;
+  if (S <= 4096) return k_paths_team<4, 2, 512, 1>;
+  return k_paths_team<8, 2, 512, 1>;
 }
 toggle_fn pick_toggle_kernel(int S, bool wg) {
   if (wg) {
@@ -222,6 +231,29 @@ int configure_paths(fpb_handle* h) {
   int rc = FPB_OK;
   if (h->S_max <= 16 * 32 * 16) rc = configure_variant(h, false);
   if (rc) return rc;
+  h->paths_team = false;
+  if (h->warps > 0 && !h->paths_wg && h->S_max > 1024 && h->S_max <= 8192 && h->ctas_per_sm == 1 &&
+      !getenv("FPB_NO_TEAM")) {
+    // same shared-memory states, two warps each (at most 8 teams = 512 threads per CTA)
+    paths_fn tf = pick_team_kernel(h->S_max);
+    int teams = h->warps < 8 ? h->warps : 8;
+    cudaFuncAttributes fattr;
+    CK(cudaFuncGetAttributes(&fattr, tf));
+    int max_optin = 0;
+    CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+    const size_t need = paths_cta_bytes(h->S_max, h->slots_max) + (size_t)teams * paths_warp_bytes(h->S_max, false);
+    if (need + fattr.sharedSizeBytes <= (size_t)max_optin) {
+      CK(cudaFuncSetAttribute(tf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+      int resident = 0;
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, tf, teams * 64, need));
+      if (resident >= 1) {
+        h->paths_team = true;
+        h->warps = teams;  // searches in flight per CTA
+        h->paths_smem = need;
+        h->tasks_per_item = teams * 4;
+      }
+    }
+  }
   if (h->warps == 0) rc = configure_variant(h, true);
   if (rc) return rc;
   if (h->warps == 0)
@@ -274,7 +306,10 @@ int launch_paths(fpb_handle* h, long long T, int* launches) {
     pp.wscratch = h->wscratch.p;
   }
   int mw_unused = 0;
-  pick_paths_kernel(h->S_max, h->paths_wg, &mw_unused)<<<(unsigned)grid, h->warps * 32, h->paths_smem, st>>>(pp);
+  if (h->paths_team)
+    pick_team_kernel(h->S_max)<<<(unsigned)grid, h->warps * 64, h->paths_smem, st>>>(pp);
+  else
+    pick_paths_kernel(h->S_max, h->paths_wg, &mw_unused)<<<(unsigned)grid, h->warps * 32, h->paths_smem, st>>>(pp);
   ++*launches;
   h->tm.graph_ctas = (int)grid;
   return FPB_OK;

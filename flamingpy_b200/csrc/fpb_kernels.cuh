@@ -812,6 +812,320 @@ __global__ void __launch_bounds__(MAXT, MINB) k_paths(const __grid_constant__ Pa
 }
 
 // ------------------------------------------------------------------------------------------
+// Two-warp teams: the same search as warp_search, run by a pair of warps that share one
+// distance / bucket / staging state.  Warp `half` scans its half of the bucket chunks and
+// relaxes directions 3*half .. 3*half+2 of every staged cube, so each warp executes about half
+// of the instruction stream and an SM holds twice as many warps for the same shared memory.
+// The store-then-verify protocol extends across the pair with named barriers (bar.sync id, 64):
+// all stores of a batch precede every verify load, and the redo flag, staging counts and filed
+// slots are exchanged through a few shared words.  Control flow is identical in both warps.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void team_bar(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
+struct TeamX {      // exchange words of one team (shared memory)
+  int cnt[2];       // staged cubes per half
+  int lp[2];        // slots filed by each half during a sub-round
+  int redo[2][2];   // [round parity][half]
+};
+
+template <int NCH2, int NV>
+__device__ __forceinline__ void team_search(const CtaMem& cm, const WarpMem& wm, const ComplexDev& c, int S,
+                                            double step, uint32_t present, int lane, int half, int bar_id,
+                                            volatile TeamX* tx) {
+  const double inv = 1.0 / step;
+  const int n16 = (S + 15) >> 4;
+  const uint32_t dist_a = smem_addr(wm.dist), bkt_a = smem_addr(wm.bkt);
+  const uint32_t stage_a = smem_addr(wm.stage) + (uint32_t)half * STAGE_CAP;  // own half of the staging list
+  const uint32_t stage0_a = smem_addr(wm.stage), stage1_a = stage0_a + STAGE_CAP;
+  const uint32_t wslot_a = smem_addr(cm.wslot);
+  constexpr int HCAP = STAGE_CAP / 2;  // entries per half
+  // this warp's three directions
+  int dreg[3], dwrap[3], sreg[3], swrap[3];
+  const int d0 = 3 * half;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    dreg[i] = c.d_off[2 * (d0 + i)];
+    dwrap[i] = c.d_off[2 * (d0 + i) + 1];
+    sreg[i] = c.s_off[2 * (d0 + i)];
+    swrap[i] = c.s_off[2 * (d0 + i) + 1];
+  }
+  int cur = 0;
+  while (present) {
+    {
+      const uint32_t rot = __funnelshift_r(present, present, cur & (NRING - 1));
+      cur += __ffs(rot) - 1;
+    }
+    const int r = cur & (NRING - 1);
+    const int far = cur + NRING - 1;
+    while ((present >> r) & 1u) {
+      present &= ~(1u << r);
+      // ---------------- scan (this warp's chunks): stage cubes filed under slot r ----------------
+      uint32_t masks[NCH2];
+      int cnt = 0;
+      const uint32_t r4 = (uint32_t)r * 0x01010101u;
+#pragma unroll
+      for (int j = 0; j < NCH2; ++j) {
+        const int ch = (2 * j + half) * 32 + lane;
+        uint32_t m = 0;
+        if (ch < n16) {
+          uint4 q = lds_v4(bkt_a + (ch << 4));
+          const uint32_t z0 = eq_bytes(q.x, r4), z1 = eq_bytes(q.y, r4), z2 = eq_bytes(q.z, r4), z3 = eq_bytes(q.w, r4);
+          m = movemask4(z0) | (movemask4(z1) << 4) | (movemask4(z2) << 8) | (movemask4(z3) << 12);
+          if (m) {
+            q.x |= (z0 >> 7) * 0xffu;
+            q.y |= (z1 >> 7) * 0xffu;
+            q.z |= (z2 >> 7) * 0xffu;
+            q.w |= (z3 >> 7) * 0xffu;
+            sts_v4(bkt_a + (ch << 4), q);
+          }
+        }
+        masks[j] = m;
+        cnt += __popc(m);
+      }
+      int incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+      }
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      int pos = incl - cnt;
+      uint32_t lp = 0;  // slots this lane filed cubes under
+#pragma unroll
+      for (int j = 0; j < NCH2; ++j) {
+        uint32_t m = masks[j];
+        const int base = ((2 * j + half) * 32 + lane) << 4;
+        while (m) {
+          const int cube = base + __ffs(m) - 1;
+          m &= m - 1;
+          if (pos < HCAP) sts_u16(stage_a + 2 * pos, cube);
+          else sts_u8(bkt_a + cube, r);  // staging half full: leave it filed for the next scan
+          ++pos;
+        }
+      }
+      if (total > HCAP) lp |= 1u << r;
+      if (lane == 0) tx->cnt[half] = total < HCAP ? total : HCAP;
+      team_bar(bar_id);  // (a) both halves of the staging list are complete
+      const int n0 = tx->cnt[0], n1 = tx->cnt[1];
+      const int nst = n0 + n1;
+      // ---------------- relax: every staged cube, this warp's three directions ----------------
+      int parity = 0;
+      for (int cb = 0; cb < nst; cb += 32 * NV) {
+        uint32_t ua[NV][3], wa[NV][3];
+        double nd[NV][3], old[NV][3], dvs[NV];
+        bool imp[NV][3];
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+          const int idx = cb + k * 32 + lane;
+          const bool valid = idx < nst;
+          const uint32_t sa = idx < n0 ? stage0_a + 2 * idx : stage1_a + 2 * (idx - n0);
+          const int v = valid ? (int)lds_u16(sa) : 0;
+          const uint32_t va = dist_a + 8u * v;
+          const double dv = lds_f64(va);
+          dvs[k] = dv;
+          const int bt = bucket_of(dv, inv);
+          if (valid && bt > cur && half == 0) {  // a parked cube: move it towards its real bucket
+            const int s2 = (bt < far ? bt : far) & (NRING - 1);
+            sts_u8(bkt_a + v, s2);
+            lp |= 1u << s2;
+          }
+          const bool act = valid && bt <= cur;
+          const uint32_t info = act ? ((uint32_t)cm.ninfo[v] >> (6 * half)) : 0xaaau;
+          const int sb = cm.sbase[v];
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            const uint32_t kind = (info >> (2 * i)) & 3u;
+            const bool a = kind < 2u;
+            ua[k][i] = va + 8 * (kind ? dwrap[i] : dreg[i]);
+            wa[k][i] = wslot_a + 8u * (sb + (kind ? swrap[i] : sreg[i]));
+            // shared-memory pipe is the limiter: only existing faces load, and the weight is
+            // fetched only if the neighbour is farther from the source than this cube
+            old[k][i] = a ? lds_f64(ua[k][i]) : 0.0;
+            imp[k][i] = a && old[k][i] > dv;
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < NV; ++k)
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            nd[k][i] = imp[k][i] ? dvs[k] + lds_f64(wa[k][i]) : 0.0;
+            imp[k][i] = imp[k][i] && nd[k][i] < old[k][i];
+          }
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int k = 0; k < NV; ++k)
+            if (imp[k][i]) sts_f64(ua[k][i], nd[k][i]);
+        team_bar(bar_id);  // (b) all stores of the batch, from both warps, precede the verify loads
+        // verify: a store may have been overwritten by a later, larger one; every improving
+        // candidate re-reads its target until no store was lost, so that the bucket each cube is
+        // filed under is the bucket of its final distance (filing late costs cascades of rework)
+        double fin[NV][3];
+        bool redo;
+        do {
+          bool mine = false;
+#pragma unroll
+          for (int k = 0; k < NV; ++k)
+#pragma unroll
+            for (int i = 0; i < 3; ++i) fin[k][i] = imp[k][i] ? lds_f64(ua[k][i]) : 0.0;
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int k = 0; k < NV; ++k) {
+              const bool lost = imp[k][i] && fin[k][i] > nd[k][i];
+              if (lost) sts_f64(ua[k][i], nd[k][i]);
+              mine |= lost;
+            }
+          mine = __any_sync(0xffffffffu, mine);
+          if (lane == 0) tx->redo[parity][half] = mine;
+          team_bar(bar_id);  // (c) re-stores visible; exchange the redo flags
+          redo = tx->redo[parity][0] | tx->redo[parity][1];
+          parity ^= 1;
+        } while (redo);
+#pragma unroll
+        for (int k = 0; k < NV; ++k)
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            const int bi = bucket_of(fin[k][i], inv);
+            const int s2 = (bi < far ? bi : far) & (NRING - 1);
+            const uint32_t ui = (ua[k][i] - dist_a) >> 3;
+            if (imp[k][i]) sts_u8(bkt_a + ui, s2);
+            lp |= imp[k][i] ? (1u << s2) : 0u;
+          }
+      }
+      lp = __reduce_or_sync(0xffffffffu, lp);
+      if (lane == 0) tx->lp[half] = (int)lp;
+      team_bar(bar_id);  // (d) filed slots exchanged, bucket bytes visible to the next scan
+      present |= (uint32_t)tx->lp[0] | (uint32_t)tx->lp[1];
+    }
+  }
+}
+
+template <int NCH2, int NV, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) k_paths_team(const __grid_constant__ PathsParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ int item_s;
+  __shared__ double red_s[32];
+  __shared__ TeamX tx_s[16];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int team = wid >> 1, half = wid & 1, n_teams = blockDim.x >> 6;
+  const int bar_id = 1 + team;
+  const int nthreads = blockDim.x;
+  volatile TeamX* tx = &tx_s[team];
+
+  unsigned char* ptr = smem;
+  double* wslot = (double*)ptr; ptr += align16((size_t)p.slots_max * 8);
+  uint16_t* ninfo_s = (uint16_t*)ptr; ptr += align16((size_t)p.S_max * 2);
+  uint16_t* sbase_s = (uint16_t*)ptr; ptr += align16((size_t)p.S_max * 2);
+  CtaMem cm;
+  cm.wslot = wslot; cm.ninfo = ninfo_s; cm.sbase = sbase_s;
+  const WarpMem wm = carve_warp(ptr + (size_t)team * paths_warp_bytes(p.S_max, false), p.S_max, false);
+
+  int staged_tc = -1, staged_c = -1;
+  double step = 1.0;
+
+  while (true) {
+    if (threadIdx.x == 0) item_s = atomicAdd(p.counter, 1);
+    __syncthreads();
+    const int item = item_s;
+    __syncthreads();
+    if (item >= p.total_items) break;
+    int lo = 0, hi = p.T * p.n_complex;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (p.item_off[mid] <= item) lo = mid; else hi = mid;
+    }
+    const int tc = lo;
+    const int t = tc / p.n_complex, ci = tc - t * p.n_complex;
+    const ComplexDev& c = p.cx[ci];
+    const int chunk = item - p.item_off[tc];
+    const int S = c.S;
+
+    if (staged_c != ci) {
+      for (int v = threadIdx.x; v < S; v += nthreads) {
+        ninfo_s[v] = c.ninfo[v];
+        sbase_s[v] = c.sbase[v];
+      }
+      staged_c = ci;
+    }
+    if (staged_tc != tc) {
+      const double* w = p.weights + (long long)t * p.Qtot + c.qoff;
+      double sum = 0.0;
+      for (int s = threadIdx.x; s < c.n_slots; s += nthreads) {
+        const int q = c.slot_qubit[s];
+        const double ws = (q >= 0) ? w[q] : FPB_INF;
+        wslot[s] = ws;
+        sum += (q >= 0) ? ws : 0.0;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      if (lane == 0) red_s[wid] = sum;
+      __syncthreads();
+      sum = 0.0;
+      for (int w2 = 0; w2 < (nthreads >> 5); ++w2) sum += red_s[w2];
+      step = bucket_step(sum / (double)c.Q, p.step_factor);
+      staged_tc = tc;
+    }
+    __syncthreads();
+
+    const double inv = 1.0 / step;
+    const int K = c.odd_count[t];
+    const int* odd = c.odd_fixed + (long long)t * S;
+    const int has_bnd = c.n_low > 0;
+    const int n_tasks = n_tasks_of(K, has_bnd);
+    const long long poff = c.pair_off[t];
+    const long long ooff = c.odd_off[t];
+    const int task_end = min(n_tasks, (chunk + 1) * p.tasks_per_item);
+    for (int task = chunk * p.tasks_per_item + team; task < task_end; task += n_teams) {
+      const bool pair_task = task < K - 1;
+      const int n_phase = pair_task ? 1 : 2;
+      for (int ph = 0; ph < n_phase; ++ph) {
+        // clear the shared state, half each
+        for (int v = half * 32 + lane; v < S; v += 64) wm.dist[v] = FPB_INF;
+        {
+          const int n16 = (S + 15) >> 4;
+          uint4* b4 = reinterpret_cast<uint4*>(wm.bkt);
+          for (int i = half * 32 + lane; i < n16; i += 64) b4[i] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+        }
+        team_bar(bar_id);
+        uint32_t present = 0;
+        if (half == 0) {
+          if (pair_task) {
+            if (lane == 0) present = seed_cube(wm, odd[task], 0.0, inv, 0);
+            present = __shfl_sync(0xffffffffu, present, 0);
+          } else if (ph == 0) {
+            present = warp_seed_connector(cm, wm, c.n_low, c.low_cube, c.low_slot, inv, lane);
+          } else {
+            present = warp_seed_connector(cm, wm, c.n_high, c.high_cube, c.high_slot, inv, lane);
+          }
+          if (lane == 0) tx->lp[0] = (int)present;
+        }
+        team_bar(bar_id);
+        present = (uint32_t)tx->lp[0];
+        team_bar(bar_id);  // lp[0] is rewritten inside the search
+        team_search<NCH2, NV>(cm, wm, c, S, step, present, lane, half, bar_id, tx);
+        if (pair_task) {
+          const long long row = poff + (long long)task * K - (long long)task * (task + 1) / 2;
+          for (int b = task + 1 + half * 32 + lane; b < K; b += 64) c.pair_len[row + (b - task - 1)] = wm.dist[odd[b]];
+        } else if (ph == 0) {
+          for (int b = half * 32 + lane; b < K; b += 64) c.bnd_len[ooff + b] = wm.dist[odd[b]];
+        } else {
+          for (int b = half * 32 + lane; b < K; b += 64) {
+            const double lo_d = c.bnd_len[ooff + b];
+            const double hi_d = wm.dist[odd[b]];
+            const bool high = hi_d < lo_d;
+            c.bnd_len[ooff + b] = high ? hi_d : lo_d;
+            c.bnd_side[ooff + b] = high ? 1 : 0;
+          }
+        }
+        team_bar(bar_id);  // outputs read before the state is cleared again
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // k_path_toggle: one warp per query; search with early stop, then walk the tree back and
 // XOR-toggle the crossed qubits (mwpm/algos.py:88-95)
 // ------------------------------------------------------------------------------------------
