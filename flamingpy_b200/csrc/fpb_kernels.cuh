@@ -828,9 +828,17 @@ struct TeamX {      // exchange words of one team (shared memory)
   int redo[2][2];   // [round parity][half]
 };
 
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+
+// cinfo_a: shared address of one 32-bit word per cube = face kinds (low 12 bits) | weight-slot
+// base << 16.  Each warp of the pair relaxes half of the staged cubes (all six directions).
 template <int NCH2, int NV>
-__device__ __forceinline__ void team_search(const CtaMem& cm, const WarpMem& wm, const ComplexDev& c, int S,
-                                            double step, uint32_t present, int lane, int half, int bar_id,
+__device__ __forceinline__ void team_search(const CtaMem& cm, uint32_t cinfo_a, const WarpMem& wm, const DirTab& dt,
+                                            int S, double step, uint32_t present, int lane, int half, int bar_id,
                                             volatile TeamX* tx) {
   const double inv = 1.0 / step;
   const int n16 = (S + 15) >> 4;
@@ -839,16 +847,6 @@ __device__ __forceinline__ void team_search(const CtaMem& cm, const WarpMem& wm,
   const uint32_t stage0_a = smem_addr(wm.stage), stage1_a = stage0_a + STAGE_CAP;
   const uint32_t wslot_a = smem_addr(cm.wslot);
   constexpr int HCAP = STAGE_CAP / 2;  // entries per half
-  // this warp's three directions
-  int dreg[3], dwrap[3], sreg[3], swrap[3];
-  const int d0 = 3 * half;
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    dreg[i] = c.d_off[2 * (d0 + i)];
-    dwrap[i] = c.d_off[2 * (d0 + i) + 1];
-    sreg[i] = c.s_off[2 * (d0 + i)];
-    swrap[i] = c.s_off[2 * (d0 + i) + 1];
-  }
   int cur = 0;
   while (present) {
     {
@@ -908,74 +906,62 @@ __device__ __forceinline__ void team_search(const CtaMem& cm, const WarpMem& wm,
       team_bar(bar_id);  // (a) both halves of the staging list are complete
       const int n0 = tx->cnt[0], n1 = tx->cnt[1];
       const int nst = n0 + n1;
-      // ---------------- relax: every staged cube, this warp's three directions ----------------
+      // ---------------- relax: 64 staged cubes per round, 32 per warp, all six directions ----------------
       int parity = 0;
-      for (int cb = 0; cb < nst; cb += 32 * NV) {
-        uint32_t ua[NV][3], wa[NV][3];
-        double nd[NV][3], old[NV][3], dvs[NV];
-        bool imp[NV][3];
+      for (int cb = 0; cb < nst; cb += 64) {
+        uint32_t ua[6], wa[6];
+        double nd[6], old[6];
+        bool imp[6];
+        const int idx = cb + half * 32 + lane;
+        const bool valid = idx < nst;
+        const uint32_t sa = idx < n0 ? stage0_a + 2 * idx : stage1_a + 2 * (idx - n0);
+        const int v = valid ? (int)lds_u16(sa) : 0;
+        const uint32_t va = dist_a + 8u * v;
+        const double dv = lds_f64(va);
+        const int bt = bucket_of(dv, inv);
+        if (valid && bt > cur) {  // a parked cube: move it towards its real bucket
+          const int s2 = (bt < far ? bt : far) & (NRING - 1);
+          sts_u8(bkt_a + v, s2);
+          lp |= 1u << s2;
+        }
+        const bool act = valid && bt <= cur;
+        const uint32_t ci = act ? lds_u32(cinfo_a + 4u * v) : 0xaaau;  // inactive lanes: every face "none"
+        const uint32_t sb = wslot_a + 8u * (ci >> 16);
 #pragma unroll
-        for (int k = 0; k < NV; ++k) {
-          const int idx = cb + k * 32 + lane;
-          const bool valid = idx < nst;
-          const uint32_t sa = idx < n0 ? stage0_a + 2 * idx : stage1_a + 2 * (idx - n0);
-          const int v = valid ? (int)lds_u16(sa) : 0;
-          const uint32_t va = dist_a + 8u * v;
-          const double dv = lds_f64(va);
-          dvs[k] = dv;
-          const int bt = bucket_of(dv, inv);
-          if (valid && bt > cur && half == 0) {  // a parked cube: move it towards its real bucket
-            const int s2 = (bt < far ? bt : far) & (NRING - 1);
-            sts_u8(bkt_a + v, s2);
-            lp |= 1u << s2;
-          }
-          const bool act = valid && bt <= cur;
-          const uint32_t info = act ? ((uint32_t)cm.ninfo[v] >> (6 * half)) : 0xaaau;
-          const int sb = cm.sbase[v];
-#pragma unroll
-          for (int i = 0; i < 3; ++i) {
-            const uint32_t kind = (info >> (2 * i)) & 3u;
-            const bool a = kind < 2u;
-            ua[k][i] = va + 8 * (kind ? dwrap[i] : dreg[i]);
-            wa[k][i] = wslot_a + 8u * (sb + (kind ? swrap[i] : sreg[i]));
-            // shared-memory pipe is the limiter: only existing faces load, and the weight is
-            // fetched only if the neighbour is farther from the source than this cube
-            old[k][i] = a ? lds_f64(ua[k][i]) : 0.0;
-            imp[k][i] = a && old[k][i] > dv;
-          }
+        for (int d = 0; d < 6; ++d) {
+          const uint32_t kind = (ci >> (2 * d)) & 3u;
+          const bool a = kind < 2u;
+          ua[d] = va + 8 * (kind ? dt.dwrap[d] : dt.dreg[d]);
+          wa[d] = sb + 8 * (kind ? dt.swrap[d] : dt.sreg[d]);
+          // the shared-memory pipe is the limiter: only existing faces load, and the weight is
+          // fetched only if the neighbour is farther from the source than this cube
+          old[d] = a ? lds_f64(ua[d]) : 0.0;
+          imp[d] = a && old[d] > dv;
         }
 #pragma unroll
-        for (int k = 0; k < NV; ++k)
+        for (int d = 0; d < 6; ++d) {
+          nd[d] = imp[d] ? dv + lds_f64(wa[d]) : 0.0;
+          imp[d] = imp[d] && nd[d] < old[d];
+        }
 #pragma unroll
-          for (int i = 0; i < 3; ++i) {
-            nd[k][i] = imp[k][i] ? dvs[k] + lds_f64(wa[k][i]) : 0.0;
-            imp[k][i] = imp[k][i] && nd[k][i] < old[k][i];
-          }
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-#pragma unroll
-          for (int k = 0; k < NV; ++k)
-            if (imp[k][i]) sts_f64(ua[k][i], nd[k][i]);
-        team_bar(bar_id);  // (b) all stores of the batch, from both warps, precede the verify loads
+        for (int d = 0; d < 6; ++d)
+          if (imp[d]) sts_f64(ua[d], nd[d]);
+        team_bar(bar_id);  // (b) all stores of the round, from both warps, precede the verify loads
         // verify: a store may have been overwritten by a later, larger one; every improving
         // candidate re-reads its target until no store was lost, so that the bucket each cube is
         // filed under is the bucket of its final distance (filing late costs cascades of rework)
-        double fin[NV][3];
+        double fin[6];
         bool redo;
         do {
           bool mine = false;
 #pragma unroll
-          for (int k = 0; k < NV; ++k)
+          for (int d = 0; d < 6; ++d) fin[d] = imp[d] ? lds_f64(ua[d]) : 0.0;
 #pragma unroll
-            for (int i = 0; i < 3; ++i) fin[k][i] = imp[k][i] ? lds_f64(ua[k][i]) : 0.0;
-#pragma unroll
-          for (int i = 0; i < 3; ++i)
-#pragma unroll
-            for (int k = 0; k < NV; ++k) {
-              const bool lost = imp[k][i] && fin[k][i] > nd[k][i];
-              if (lost) sts_f64(ua[k][i], nd[k][i]);
-              mine |= lost;
-            }
+          for (int d = 0; d < 6; ++d) {
+            const bool lost = imp[d] && fin[d] > nd[d];
+            if (lost) sts_f64(ua[d], nd[d]);
+            mine |= lost;
+          }
           mine = __any_sync(0xffffffffu, mine);
           if (lane == 0) tx->redo[parity][half] = mine;
           team_bar(bar_id);  // (c) re-stores visible; exchange the redo flags
@@ -983,15 +969,13 @@ __device__ __forceinline__ void team_search(const CtaMem& cm, const WarpMem& wm,
           parity ^= 1;
         } while (redo);
 #pragma unroll
-        for (int k = 0; k < NV; ++k)
-#pragma unroll
-          for (int i = 0; i < 3; ++i) {
-            const int bi = bucket_of(fin[k][i], inv);
-            const int s2 = (bi < far ? bi : far) & (NRING - 1);
-            const uint32_t ui = (ua[k][i] - dist_a) >> 3;
-            if (imp[k][i]) sts_u8(bkt_a + ui, s2);
-            lp |= imp[k][i] ? (1u << s2) : 0u;
-          }
+        for (int d = 0; d < 6; ++d) {
+          const int bi = bucket_of(fin[d], inv);
+          const int s2 = (bi < far ? bi : far) & (NRING - 1);
+          const uint32_t ui = (ua[d] - dist_a) >> 3;
+          if (imp[d]) sts_u8(bkt_a + ui, s2);
+          lp |= imp[d] ? (1u << s2) : 0u;
+        }
       }
       lp = __reduce_or_sync(0xffffffffu, lp);
       if (lane == 0) tx->lp[half] = (int)lp;
@@ -1015,11 +999,12 @@ __global__ void __launch_bounds__(MAXT, MINB) k_paths_team(const __grid_constant
 
   unsigned char* ptr = smem;
   double* wslot = (double*)ptr; ptr += align16((size_t)p.slots_max * 8);
-  uint16_t* ninfo_s = (uint16_t*)ptr; ptr += align16((size_t)p.S_max * 2);
-  uint16_t* sbase_s = (uint16_t*)ptr; ptr += align16((size_t)p.S_max * 2);
+  uint32_t* cinfo_s = (uint32_t*)ptr; ptr += 2 * align16((size_t)p.S_max * 2);  // ninfo | sbase << 16
   CtaMem cm;
-  cm.wslot = wslot; cm.ninfo = ninfo_s; cm.sbase = sbase_s;
+  cm.wslot = wslot; cm.ninfo = nullptr; cm.sbase = nullptr;
+  const uint32_t cinfo_a = smem_addr(cinfo_s);
   const WarpMem wm = carve_warp(ptr + (size_t)team * paths_warp_bytes(p.S_max, false), p.S_max, false);
+  DirTab dt = load_dirtab(p.cx[0]);
 
   int staged_tc = -1, staged_c = -1;
   double step = 1.0;
@@ -1042,10 +1027,8 @@ __global__ void __launch_bounds__(MAXT, MINB) k_paths_team(const __grid_constant
     const int S = c.S;
 
     if (staged_c != ci) {
-      for (int v = threadIdx.x; v < S; v += nthreads) {
-        ninfo_s[v] = c.ninfo[v];
-        sbase_s[v] = c.sbase[v];
-      }
+      for (int v = threadIdx.x; v < S; v += nthreads) cinfo_s[v] = (uint32_t)c.ninfo[v] | ((uint32_t)c.sbase[v] << 16);
+      dt = load_dirtab(c);
       staged_c = ci;
     }
     if (staged_tc != tc) {
@@ -1103,7 +1086,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_paths_team(const __grid_constant
         team_bar(bar_id);
         present = (uint32_t)tx->lp[0];
         team_bar(bar_id);  // lp[0] is rewritten inside the search
-        team_search<NCH2, NV>(cm, wm, c, S, step, present, lane, half, bar_id, tx);
+        team_search<NCH2, NV>(cm, cinfo_a, wm, dt, S, step, present, lane, half, bar_id, tx);
         if (pair_task) {
           const long long row = poff + (long long)task * K - (long long)task * (task + 1) / 2;
           for (int b = task + 1 + half * 32 + lane; b < K; b += 64) c.pair_len[row + (b - task - 1)] = wm.dist[odd[b]];
