@@ -163,11 +163,15 @@ paths_fn pick_paths_kernel(int S, bool wg, int* max_warps) {
   return k_paths<16, 2, 384, 1, false>;
 }
 // two-warp-team variant (shared-memory lattices with more than 1024 cubes): NCH2 = chunks per warp
-paths_fn pick_team_kernel(int S) {
-  if (S <= 2048) return k_paths_team<2, 2, 512, 1>;
-  if (S <= 3072) return k_paths_team<3, 2, 512, 1>;
-  if (S <= 4096) return k_paths_team<4, 2, 512, 1>;
-  return k_paths_team<8, 2, 512, 1>;
+paths_fn pick_team_kernel(int S, bool wg) {
+  if (wg) {
+    if (S <= 4096) return k_paths_team<4, 2, 512, 1, true>;
+    return k_paths_team<8, 2, 512, 1, true>;
+  }
+  if (S <= 2048) return k_paths_team<2, 2, 512, 1, false>;
+  if (S <= 3072) return k_paths_team<3, 2, 512, 1, false>;
+  if (S <= 4096) return k_paths_team<4, 2, 512, 1, false>;
+  return k_paths_team<8, 2, 512, 1, false>;
 }
 toggle_fn pick_toggle_kernel(int S, bool wg) {
   if (wg) {
@@ -229,29 +233,37 @@ int configure_paths(fpb_handle* h) {
   if (h->S_max > 16 * 32 * MAX_CHUNKS || h->S_max > 65535)
     return fail(FPB_ERR_UNSUPPORTED, "lattice too large for the shortest-path kernel's bucket scan");
   int rc = FPB_OK;
-  if (h->S_max <= 16 * 32 * 16) rc = configure_variant(h, false);
+  if (h->S_max <= 16 * 32 * 16 && !getenv("FPB_FORCE_WG")) rc = configure_variant(h, false);
   if (rc) return rc;
   h->paths_team = false;
   if (h->warps > 0 && !h->paths_wg && h->S_max > 1024 && h->S_max <= 8192 && h->ctas_per_sm == 1 &&
       !getenv("FPB_NO_TEAM")) {
-    // same shared-memory states, two warps each (at most 8 teams = 512 threads per CTA)
-    paths_fn tf = pick_team_kernel(h->S_max);
-    int teams = h->warps < 8 ? h->warps : 8;
-    cudaFuncAttributes fattr;
-    CK(cudaFuncGetAttributes(&fattr, tf));
+    // two warps per search on the same shared-memory states (at most 8 teams = 512 threads per
+    // CTA).  If the CTA-wide weight copy leaves room for fewer than 8 searches, the team variant
+    // that keeps weights and face tables in global memory holds more of them.
     int max_optin = 0;
     CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
-    const size_t need = paths_cta_bytes(h->S_max, h->slots_max) + (size_t)teams * paths_warp_bytes(h->S_max, false);
-    if (need + fattr.sharedSizeBytes <= (size_t)max_optin) {
+    const size_t warp_b = paths_warp_bytes(h->S_max, false);
+    for (int wg = 0; wg <= 1; ++wg) {
+      paths_fn tf = pick_team_kernel(h->S_max, wg != 0);
+      cudaFuncAttributes fattr;
+      CK(cudaFuncGetAttributes(&fattr, tf));
+      const size_t cta_b = wg ? 0 : paths_cta_bytes(h->S_max, h->slots_max);
+      const size_t room = (size_t)max_optin - fattr.sharedSizeBytes;
+      if (room < cta_b + warp_b) continue;
+      int teams = (int)((room - cta_b) / warp_b);
+      if (teams > 8) teams = 8;
+      if (h->paths_team && teams <= h->warps) continue;  // the shared-weights variant already holds as many
+      const size_t need = cta_b + (size_t)teams * warp_b;
       CK(cudaFuncSetAttribute(tf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
       int resident = 0;
       CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, tf, teams * 64, need));
-      if (resident >= 1) {
-        h->paths_team = true;
-        h->warps = teams;  // searches in flight per CTA
-        h->paths_smem = need;
-        h->tasks_per_item = teams * 4;
-      }
+      if (resident < 1) continue;
+      h->paths_team = true;
+      h->paths_wg = wg != 0;
+      h->warps = teams;  // searches in flight per CTA
+      h->paths_smem = need;
+      h->tasks_per_item = teams * 4;
     }
   }
   if (h->warps == 0) rc = configure_variant(h, true);
@@ -307,7 +319,7 @@ int launch_paths(fpb_handle* h, long long T, int* launches) {
   }
   int mw_unused = 0;
   if (h->paths_team)
-    pick_team_kernel(h->S_max)<<<(unsigned)grid, h->warps * 64, h->paths_smem, st>>>(pp);
+    pick_team_kernel(h->S_max, h->paths_wg)<<<(unsigned)grid, h->warps * 64, h->paths_smem, st>>>(pp);
   else
     pick_paths_kernel(h->S_max, h->paths_wg, &mw_unused)<<<(unsigned)grid, h->warps * 32, h->paths_smem, st>>>(pp);
   ++*launches;

@@ -836,7 +836,7 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
 
 // cinfo_a: shared address of one 32-bit word per cube = face kinds (low 12 bits) | weight-slot
 // base << 16.  Each warp of the pair relaxes half of the staged cubes (all six directions).
-template <int NCH2, int NV>
+template <int NCH2, int NV, bool WG>
 __device__ __forceinline__ void team_search(const CtaMem& cm, uint32_t cinfo_a, const WarpMem& wm, const DirTab& dt,
                                             int S, double step, uint32_t present, int lane, int half, int bar_id,
                                             volatile TeamX* tx) {
@@ -845,7 +845,7 @@ __device__ __forceinline__ void team_search(const CtaMem& cm, uint32_t cinfo_a, 
   const uint32_t dist_a = smem_addr(wm.dist), bkt_a = smem_addr(wm.bkt);
   const uint32_t stage_a = smem_addr(wm.stage) + (uint32_t)half * STAGE_CAP;  // own half of the staging list
   const uint32_t stage0_a = smem_addr(wm.stage), stage1_a = stage0_a + STAGE_CAP;
-  const uint32_t wslot_a = smem_addr(cm.wslot);
+  const uint32_t wslot_a = WG ? 0u : smem_addr(cm.wslot);  // WG: weights and face tables in global memory
   constexpr int HCAP = STAGE_CAP / 2;  // entries per half
   int cur = 0;
   while (present) {
@@ -925,14 +925,15 @@ __device__ __forceinline__ void team_search(const CtaMem& cm, uint32_t cinfo_a, 
           lp |= 1u << s2;
         }
         const bool act = valid && bt <= cur;
-        const uint32_t ci = act ? lds_u32(cinfo_a + 4u * v) : 0xaaau;  // inactive lanes: every face "none"
-        const uint32_t sb = wslot_a + 8u * (ci >> 16);
+        uint32_t ci = 0xaaau;  // inactive lanes: every face "none"
+        if (act) ci = WG ? ((uint32_t)cm.ninfo[v] | ((uint32_t)cm.sbase[v] << 16)) : lds_u32(cinfo_a + 4u * v);
+        const uint32_t sb = WG ? (ci >> 16) : wslot_a + 8u * (ci >> 16);  // slot index (WG) or shared address
 #pragma unroll
         for (int d = 0; d < 6; ++d) {
           const uint32_t kind = (ci >> (2 * d)) & 3u;
           const bool a = kind < 2u;
           ua[d] = va + 8 * (kind ? dt.dwrap[d] : dt.dreg[d]);
-          wa[d] = sb + 8 * (kind ? dt.swrap[d] : dt.sreg[d]);
+          wa[d] = sb + (WG ? 1 : 8) * (kind ? dt.swrap[d] : dt.sreg[d]);
           // the shared-memory pipe is the limiter: only existing faces load, and the weight is
           // fetched only if the neighbour is farther from the source than this cube
           old[d] = a ? lds_f64(ua[d]) : 0.0;
@@ -940,7 +941,7 @@ __device__ __forceinline__ void team_search(const CtaMem& cm, uint32_t cinfo_a, 
         }
 #pragma unroll
         for (int d = 0; d < 6; ++d) {
-          nd[d] = imp[d] ? dv + lds_f64(wa[d]) : 0.0;
+          nd[d] = imp[d] ? dv + (WG ? cm.wslot[wa[d]] : lds_f64(wa[d])) : 0.0;
           imp[d] = imp[d] && nd[d] < old[d];
         }
 #pragma unroll
@@ -985,7 +986,7 @@ __device__ __forceinline__ void team_search(const CtaMem& cm, uint32_t cinfo_a, 
   }
 }
 
-template <int NCH2, int NV, int MAXT, int MINB>
+template <int NCH2, int NV, int MAXT, int MINB, bool WG>
 __global__ void __launch_bounds__(MAXT, MINB) k_paths_team(const __grid_constant__ PathsParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ int item_s;
@@ -998,11 +999,17 @@ __global__ void __launch_bounds__(MAXT, MINB) k_paths_team(const __grid_constant
   volatile TeamX* tx = &tx_s[team];
 
   unsigned char* ptr = smem;
-  double* wslot = (double*)ptr; ptr += align16((size_t)p.slots_max * 8);
-  uint32_t* cinfo_s = (uint32_t*)ptr; ptr += 2 * align16((size_t)p.S_max * 2);  // ninfo | sbase << 16
+  double* wslot;
+  uint32_t* cinfo_s = nullptr;
+  if (WG) {
+    wslot = p.wscratch + (size_t)blockIdx.x * p.slots_max;
+  } else {
+    wslot = (double*)ptr; ptr += align16((size_t)p.slots_max * 8);
+    cinfo_s = (uint32_t*)ptr; ptr += 2 * align16((size_t)p.S_max * 2);  // ninfo | sbase << 16
+  }
   CtaMem cm;
   cm.wslot = wslot; cm.ninfo = nullptr; cm.sbase = nullptr;
-  const uint32_t cinfo_a = smem_addr(cinfo_s);
+  const uint32_t cinfo_a = WG ? 0u : smem_addr(cinfo_s);
   const WarpMem wm = carve_warp(ptr + (size_t)team * paths_warp_bytes(p.S_max, false), p.S_max, false);
   DirTab dt = load_dirtab(p.cx[0]);
 
@@ -1027,7 +1034,12 @@ __global__ void __launch_bounds__(MAXT, MINB) k_paths_team(const __grid_constant
     const int S = c.S;
 
     if (staged_c != ci) {
-      for (int v = threadIdx.x; v < S; v += nthreads) cinfo_s[v] = (uint32_t)c.ninfo[v] | ((uint32_t)c.sbase[v] << 16);
+      if (WG) {
+        cm.ninfo = c.ninfo;
+        cm.sbase = c.sbase;
+      } else {
+        for (int v = threadIdx.x; v < S; v += nthreads) cinfo_s[v] = (uint32_t)c.ninfo[v] | ((uint32_t)c.sbase[v] << 16);
+      }
       dt = load_dirtab(c);
       staged_c = ci;
     }
@@ -1048,6 +1060,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_paths_team(const __grid_constant
       for (int w2 = 0; w2 < (nthreads >> 5); ++w2) sum += red_s[w2];
       step = bucket_step(sum / (double)c.Q, p.step_factor);
       staged_tc = tc;
+      if (WG) __threadfence_block();
     }
     __syncthreads();
 
@@ -1086,7 +1099,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_paths_team(const __grid_constant
         team_bar(bar_id);
         present = (uint32_t)tx->lp[0];
         team_bar(bar_id);  // lp[0] is rewritten inside the search
-        team_search<NCH2, NV>(cm, cinfo_a, wm, dt, S, step, present, lane, half, bar_id, tx);
+        team_search<NCH2, NV, WG>(cm, cinfo_a, wm, dt, S, step, present, lane, half, bar_id, tx);
         if (pair_task) {
           const long long row = poff + (long long)task * K - (long long)task * (task + 1) / 2;
           for (int b = task + 1 + half * 32 + lane; b < K; b += 64) c.pair_len[row + (b - task - 1)] = wm.dist[odd[b]];
