@@ -105,7 +105,8 @@ struct fpb_handle {
   DevBuf<uint32_t> bits, flips;
   DevBuf<int> item_off, counter, q_trial, q_cx, q_src, q_dst;
   DevBuf<long long> totals;
-  long long* totals_host = nullptr;  // pinned
+  long long* totals_host = nullptr;  // pinned + mapped: kernels write it directly (no copy-engine hop)
+  long long* totals_map = nullptr;   // device alias of totals_host
   long long T = 0;
   int last_stage = 0;
   bool have_rng = false;
@@ -121,7 +122,8 @@ struct fpb_handle {
   std::vector<int> qubit_degree;  // host copy: lattice degree of every syndrome qubit
   DevBuf<double> static_w;        // [Qtot]
   DevBuf<int> static_flag;
-  int* static_flag_host = nullptr;  // pinned
+  int* static_flag_host = nullptr;  // pinned + mapped
+  int* static_flag_map = nullptr;
 };
 
 namespace {
@@ -338,10 +340,11 @@ int post_syndrome(fpb_handle* h, long long T, int stage, int* launches) {
     sc.has_boundary[c] = h->cx[c].n_low > 0;
   }
   sc.item_off = h->item_off.p;
-  sc.totals = h->totals.p;
+  // the totals go straight to mapped host memory: a D2H copy would queue on the copy engine behind
+  // another handle's bulk result transfer and stall this handle's next launch
+  sc.totals = h->totals_map;
   k_scan<<<1, 1024, 0, st>>>(sc, (int)T);
   ++*launches;
-  CK(cudaMemcpyAsync(h->totals_host, h->totals.p, (2 * MAXC + 1) * sizeof(long long), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   int rc;
   for (int c = 0; c < h->ncx; ++c) {
@@ -423,9 +426,8 @@ int run_pipeline(fpb_handle* h, long long T, int stage, bool gen, uint64_t seed,
     if (h->use_table) {
       // static weights: gather the matching graph from the all-pairs table
       if (h->weight_method == FPB_WEIGHT_BLUEPRINT) {
-        CK(cudaMemsetAsync(h->static_flag.p, 0, sizeof(int), st));
-        k_check_static<<<h->sm_count * 4, 256, 0, st>>>(h->weights.p, h->static_w.p, h->Qtot, T, h->static_flag.p);
-        CK(cudaMemcpyAsync(h->static_flag_host, h->static_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        *h->static_flag_host = 0;
+        k_check_static<<<h->sm_count * 4, 256, 0, st>>>(h->weights.p, h->static_w.p, h->Qtot, T, h->static_flag_map);
         ++launches;
       }
       for (int c = 0; c < h->ncx; ++c) {
@@ -513,9 +515,13 @@ int fpb_create(const fpb_config* cfg, fpb_handle** out) {
     if (cudaEventCreate(&ev) != cudaSuccess) return bail(fail(FPB_ERR_CUDA, "event creation failed"));
   for (auto& ev : h->mark)
     if (cudaEventCreate(&ev) != cudaSuccess) return bail(fail(FPB_ERR_CUDA, "event creation failed"));
-  if (cudaMallocHost(&h->totals_host, (2 * MAXC + 1) * sizeof(long long)) != cudaSuccess) return bail(fail(FPB_ERR_CUDA, "pinned allocation failed"));
+  if (cudaHostAlloc(&h->totals_host, (2 * MAXC + 1) * sizeof(long long), cudaHostAllocMapped) != cudaSuccess ||
+      cudaHostGetDevicePointer(&h->totals_map, h->totals_host, 0) != cudaSuccess)
+    return bail(fail(FPB_ERR_CUDA, "mapped pinned allocation failed"));
   memset(h->totals_host, 0, (2 * MAXC + 1) * sizeof(long long));
-  if (cudaMallocHost(&h->static_flag_host, sizeof(int)) != cudaSuccess) return bail(fail(FPB_ERR_CUDA, "pinned allocation failed"));
+  if (cudaHostAlloc(&h->static_flag_host, sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
+      cudaHostGetDevicePointer(&h->static_flag_map, h->static_flag_host, 0) != cudaSuccess)
+    return bail(fail(FPB_ERR_CUDA, "mapped pinned allocation failed"));
   *h->static_flag_host = 0;
 
   const int N = h->N;
