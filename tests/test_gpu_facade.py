@@ -181,3 +181,20 @@ def test_monte_carlo_d9_with_native_matcher():
                                    seed=3, batch=64, backend="native", return_stats=True)
     assert stats["trials_done"] == 64
     assert 0 <= errors <= 64
+
+
+def test_threshold_sweep_driver(tmp_path):
+    """configs[4]-style sweep at toy size: CSV rows, errors fall with the code distance below
+    threshold (delta = 0.06) and rise with delta."""
+    from flamingpy_b200.sweep import COLUMNS, sweep
+
+    f = tmp_path / "sweep.csv"
+    rows = sweep([3, 5], [0.06, 0.12], 600, fname=str(f), mode="fresh", batch=600)
+    assert len(rows) == 4
+    lines = f.read_text().strip().splitlines()
+    assert lines[0].split(",") == COLUMNS and len(lines) == 5
+    err = {(r[1], r[5]): r[9] for r in rows}
+    assert err[(5, 0.06)] <= err[(3, 0.06)]
+    assert err[(3, 0.12)] > err[(3, 0.06)] and err[(5, 0.12)] > err[(5, 0.06)]
+    g = sweep([9], [0.09], 256, graph_only=True, batch=256)
+    assert g[0][9] == -1 and float(g[0][-1]) > 1000
