@@ -952,16 +952,20 @@ __device__ __forceinline__ void team_search(const CtaMem& cm, uint32_t cinfo_a, 
         // candidate re-reads its target until no store was lost, so that the bucket each cube is
         // filed under is the bucket of its final distance (filing late costs cascades of rework)
         double fin[6];
+        bool chk[6];  // still a possible owner of the target's final value
+#pragma unroll
+        for (int d = 0; d < 6; ++d) chk[d] = imp[d];
         bool redo;
         do {
           bool mine = false;
 #pragma unroll
-          for (int d = 0; d < 6; ++d) fin[d] = imp[d] ? lds_f64(ua[d]) : 0.0;
+          for (int d = 0; d < 6; ++d) fin[d] = chk[d] ? lds_f64(ua[d]) : 0.0;
 #pragma unroll
           for (int d = 0; d < 6; ++d) {
-            const bool lost = imp[d] && fin[d] > nd[d];
+            const bool lost = chk[d] && fin[d] > nd[d];
             if (lost) sts_f64(ua[d], nd[d]);
             mine |= lost;
+            chk[d] = chk[d] && !(fin[d] < nd[d]);  // beaten by a smaller value: its owner files the cube
           }
           mine = __any_sync(0xffffffffu, mine);
           if (lane == 0) tx->redo[parity][half] = mine;
@@ -969,13 +973,16 @@ __device__ __forceinline__ void team_search(const CtaMem& cm, uint32_t cinfo_a, 
           redo = tx->redo[parity][0] | tx->redo[parity][1];
           parity ^= 1;
         } while (redo);
+        // after the last round every surviving candidate saw its own value in place: it owns the
+        // target's final distance and files the cube under that distance's bucket
 #pragma unroll
         for (int d = 0; d < 6; ++d) {
-          const int bi = bucket_of(fin[d], inv);
+          const bool own = chk[d] && fin[d] == nd[d];
+          const int bi = bucket_of(nd[d], inv);
           const int s2 = (bi < far ? bi : far) & (NRING - 1);
           const uint32_t ui = (ua[d] - dist_a) >> 3;
-          if (imp[d]) sts_u8(bkt_a + ui, s2);
-          lp |= imp[d] ? (1u << s2) : 0u;
+          if (own) sts_u8(bkt_a + ui, s2);
+          lp |= own ? (1u << s2) : 0u;
         }
       }
       lp = __reduce_or_sync(0xffffffffu, lp);
