@@ -139,6 +139,19 @@ def paths_kernel_bytes(lat, n_trials, total_odd, total_pairs):
     return b
 
 
+def recorded_traffic(workload, mode, batch):
+    """DRAM bytes per k_paths launch from the committed ncu capture, if it was taken on this
+    very configuration (profiles/r1_k_paths_traffic.json); None otherwise."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_k_paths_traffic.json")) as f:
+            t = json.load(f)
+        if t["workload"] == workload and t["mode"] == mode and t["trials_per_gpu_per_step"] == batch:
+            return t["traffic_bytes_per_launch"]
+    except Exception:
+        pass
+    return None
+
+
 def dist_env():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -382,7 +395,9 @@ def run_gpu_arm(args, cfg, lat):
                     "host_threads": len(engines)},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "k_gather" if eng.uses_table else "k_paths", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak,
+                         "traffic": None if eng.uses_table else recorded_traffic(args.workload, args.mode, B),
+                         "algorithmic_bytes_per_launch": kb / args.steps, "peak_source": peak_src,
                          "share_of_step": graph_ms / dev_ms if dev_ms else None,
                          "note": ("static-weight table gather (HBM / L2 bound)" if eng.uses_table else
                                   "k_paths is bound by shared-memory latency/issue, not HBM (DESIGN.md)"),
