@@ -211,3 +211,69 @@ def test_static_table_guards():
     eng.run_injected(x, np.full((2, N), 2, np.uint8))  # all p: fine
     with pytest.raises(_lib.FpbError, match="not all p"):
         eng.run_injected(x, np.ones((2, N), np.uint8))  # GKP labels: weights differ from the table
+
+
+@pytest.mark.parametrize("delta", [1e-4, 1e-3, 0.3, 2.0, 10.0])
+def test_weight_limits_at_extreme_delta(delta):
+    """reference tests/cv/test_gkp.py:80-102: Z_err_cond -> 0 at tiny delta (weight -> -ln(float_min)
+    where the series underflows) and -> 0.5 (weight ln 2) at huge delta; same values as the oracle."""
+    lat = build_lattice(4, "primal", "open")
+    wo = {"method": "blueprint", "delta": delta}
+    eng = _engine(lat, delta, 0, wo, mode="fresh")
+    batch = eng.run_rng(21, 0, 8, stage=_lib.STAGE_SYNDROME, want_draws=True)
+    ref = c_oracle.run(lat, delta, 0, wo, batch.x, batch.state, stage=_lib.STAGE_SYNDROME)
+    assert np.array_equal(batch.hom, ref.hom) and np.array_equal(batch.bits, ref.bits)
+    w, wr = batch.weights, ref.weights
+    normal = wr < 700  # numerator is a normal double there (see DESIGN.md on denormals)
+    np.testing.assert_allclose(w[normal], wr[normal], rtol=1e-9, atol=0)
+    # denormal numerators carry a few bits only, and at the very edge of underflow one exp() may
+    # return the smallest denormal (weight ~744) where the other returns 0 (weight -ln(float_min) =
+    # 708.4): not a 1e-9 quantity (DESIGN.md); both sides must agree that the weight is "huge"
+    edge = (~normal) & ((w > 740) | (wr > 740))
+    np.testing.assert_allclose(w[~normal & ~edge], wr[~normal & ~edge], rtol=0, atol=0.75)
+    assert np.all(w[edge] > 700) and np.all(wr[edge] > 700)
+    assert np.all(w >= np.log(2) - 1e-12)
+    if delta >= 2.0:
+        assert np.all(w < 2.0)  # error probability close to 1/2 everywhere
+    if delta <= 1e-3:
+        assert np.median(w) > 50
+
+
+def test_engine_reuse_across_batch_sizes_and_handles():
+    """Buffers grow and shrink logically across runs; two handles on one device are independent."""
+    lat = build_lattice(5, "primal", "open")
+    wo = {"method": "blueprint", "delta": 0.09}
+    a = _engine(lat, 0.09, 0.25, wo, mode="fresh")
+    b = _engine(lat, 0.09, 0.25, wo, mode="fresh")
+    big = a.run_rng(3, 0, 300)
+    small = a.run_rng(3, 100, 7)
+    other = b.run_rng(3, 100, 7)
+    again = a.run_rng(3, 0, 300)
+    for x, y in ((small, other), (big, again)):
+        assert np.array_equal(x.hom, y.hom)
+        assert np.array_equal(x.complexes["primal"].pair_len, y.complexes["primal"].pair_len)
+    cb, cs = big.complexes["primal"], small.complexes["primal"]
+    assert np.array_equal(cb.pair_len[cb.pair_off[100]:cb.pair_off[107]], cs.pair_len)
+    a.close()
+    a.close()  # idempotent
+    assert b.run_rng(3, 0, 2).n_trials == 2
+
+
+def test_two_host_threads_two_engines():
+    """The e2e arm of bench.py drives two engines from two threads; results are unaffected."""
+    import threading
+
+    lat = build_lattice(7, "primal", "open")
+    wo = {"method": "blueprint", "delta": 0.09}
+    engs = [_engine(lat, 0.09, 0, wo, mode="fresh") for _ in range(2)]
+    ref = engs[0].run_rng(5, 0, 64).complexes["primal"].pair_len.copy()
+    out = [None, None]
+
+    def work(j):
+        for _ in range(5):
+            out[j] = engs[j].run_rng(5, 0, 64).complexes["primal"].pair_len
+
+    ths = [threading.Thread(target=work, args=(j,)) for j in range(2)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    assert np.array_equal(out[0], ref) and np.array_equal(out[1], ref)
