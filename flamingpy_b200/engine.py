@@ -220,6 +220,40 @@ class TrialEngine:
         _lib.check(self._lib.fpb_device_outputs(self._h, C.byref(o)))
         return o
 
+    def device_tensors(self) -> dict:
+        """Zero-copy ``torch`` views of the last run's result buffers on the GPU (valid until the
+        next run of this engine).  PyTorch is used for plumbing only: the tensors alias the
+        handle's own device memory through ``__cuda_array_interface__``."""
+        import torch
+
+        o = self.device_outputs()
+        s = self.sizes()
+        T = int(s.n_trials)
+
+        class _View:
+            def __init__(self, ptr, shape, typestr):
+                self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False),
+                                                 "version": 2, "strides": None}
+
+        def view(ptr, shape, typestr):
+            addr = C.cast(ptr, C.c_void_p).value
+            if not addr or 0 in shape:
+                return None
+            return torch.as_tensor(_View(addr, shape, typestr), device=torch.device("cuda", self.device))
+
+        out = {"hom": view(o.hom, (T, self.Qtot), "<f8"), "weights": view(o.weights, (T, self.Qtot), "<f8"),
+               "bits": view(o.bits, (T, self.bit_words), "<i4")}
+        for i, ec in enumerate(self.ec):
+            ct = self.lat.complexes[ec]
+            out[ec] = {
+                "parity": view(o.parity[i], (T, (ct.S + 31) // 32), "<i4"),
+                "odd_count": view(o.odd_count[i], (T,), "<i4"),
+                "odd_ids": view(o.odd_ids[i], (int(s.total_odd[i]),), "<i4"),
+                "pair_len": view(o.pair_len[i], (int(s.total_pairs[i]),), "<f8"),
+                "bnd_len": view(o.bnd_len[i], (int(s.total_odd[i]),), "<f8"),
+            }
+        return out
+
     def fetch(self, stage: int = _lib.STAGE_GRAPH, want_draws: bool = False, want_noise: bool = True) -> TrialBatch:
         """Copy the last run's results to host arrays."""
         s = self.sizes()

@@ -90,13 +90,43 @@ def ec_monte_carlo(trials, code_instance, noise_instance, decoder, decoder_args,
     failures = 0
     done = 0
     t_dev = 0.0
-    for first in range(lo, hi, batch):
-        n = min(batch, hi - first)
-        b = eng.run_rng(seed, first, n, stage=_lib.STAGE_GRAPH)
+    # two engines alternate: while the host matches batch i (all cores) and extracts its paths, the
+    # other engine's GPU stage of batch i + 1 is already running on its own stream
+    engines = [eng]
+    starts = list(range(lo, hi, batch))
+    if len(starts) > 1:
+        from .engine import TrialEngine
+
+        eng2 = TrialEngine(code.lattice, noise_instance.delta, noise_instance.p_swap, weight_opts, mode=mode,
+                           device=device)
+        if eng.uses_table:
+            eng2.build_table()
+        engines.append(eng2)
+    import threading
+
+    slots = {}
+
+    def produce(k):
+        first = starts[k]
+        slots[k] = engines[k % len(engines)].run_rng(seed, first, min(batch, hi - first), stage=_lib.STAGE_GRAPH)
+
+    worker = None
+    if starts:
+        produce(0)
+    for k, first in enumerate(starts):
+        if k + 1 < len(starts):
+            worker = threading.Thread(target=produce, args=(k + 1,))
+            worker.start()
+        b = slots.pop(k)
         t_dev += b.timings["total_ms"]
-        flips = decode_batch(code, eng, b, backend=backend)
+        flips = decode_batch(code, engines[k % len(engines)], b, backend=backend)
         failures += int(logical_failures(code, b, flips).sum())
-        done += n
+        done += b.n_trials
+        if worker is not None:
+            worker.join()
+            worker = None
+    for extra in engines[1:]:
+        extra.close()
     counts = np.array([failures, done], np.int64)
     if dist is not None and size > 1:
         import torch

@@ -277,3 +277,22 @@ def test_two_host_threads_two_engines():
     [t.start() for t in ths]
     [t.join() for t in ths]
     assert np.array_equal(out[0], ref) and np.array_equal(out[1], ref)
+
+
+def test_device_tensors_are_zero_copy_views():
+    """torch views over the handle's device buffers (no host round trip) match the fetched arrays."""
+    import torch
+
+    lat = build_lattice(5, "primal", "open")
+    eng = _engine(lat, 0.09, 0.25, {"method": "blueprint", "delta": 0.09}, mode="fresh")
+    batch = eng.run_rng(2, 0, 16)
+    dv = eng.device_tensors()
+    assert dv["hom"].is_cuda and dv["hom"].dtype == torch.float64
+    assert np.array_equal(dv["hom"].cpu().numpy(), batch.hom)
+    assert np.array_equal(dv["weights"].cpu().numpy(), batch.weights)
+    cb = batch.complexes["primal"]
+    assert np.array_equal(dv["primal"]["odd_ids"].cpu().numpy(), cb.odd_ids)
+    assert np.array_equal(dv["primal"]["pair_len"].cpu().numpy(), cb.pair_len)
+    assert np.array_equal(dv["primal"]["bnd_len"].cpu().numpy(), cb.bnd_len)
+    # a device-side reduction without leaving the GPU
+    assert float(dv["primal"]["pair_len"].min()) == float(cb.pair_len.min())
