@@ -519,7 +519,7 @@ __device__ __forceinline__ uint32_t eq_bytes(uint32_t word, uint32_t r4) {
 // gather bits 7,15,23,31 into bits 0..3
 __device__ __forceinline__ uint32_t movemask4(uint32_t z) { return (z * 0x00204081u) >> 28; }
 
-template <bool PRED, int NCH, int NV, bool WG>
+template <bool PRED, int NCH, int NV, bool WG, bool LEAN = false>
 __device__ __forceinline__ void warp_search(const CtaMem& cm, const WarpMem& wm, const DirTab& dt, int S,
                                             double step, uint32_t present, int lane, int stop_at) {
   const double inv = 1.0 / step;
@@ -614,8 +614,17 @@ __device__ __forceinline__ void warp_search(const CtaMem& cm, const WarpMem& wm,
             // absent faces read harmless in-range addresses (their own cube, slot 0)
             ua[k][d] = a ? va + 8 * (kind ? dt.dwrap[d] : dt.dreg[d]) : va;
             const int slot = a ? sb + (kind ? dt.swrap[d] : dt.sreg[d]) : 0;
-            nd[k][d] = dv + (WG ? cm.wslot[slot] : lds_f64(wslot_a + 8u * slot));
-            imp[k][d] = a && nd[k][d] < lds_f64(ua[k][d]);
+            if (LEAN) {
+              // many resident warps, shared-memory pipe is the limiter: only existing faces load, and
+              // the weight is fetched only if the neighbour is farther from the source than this cube
+              const double old = a ? lds_f64(ua[k][d]) : 0.0;
+              const bool cand = a && old > dv;
+              nd[k][d] = cand ? dv + (WG ? cm.wslot[slot] : lds_f64(wslot_a + 8u * slot)) : 0.0;
+              imp[k][d] = cand && nd[k][d] < old;
+            } else {
+              nd[k][d] = dv + (WG ? cm.wslot[slot] : lds_f64(wslot_a + 8u * slot));
+              imp[k][d] = a && nd[k][d] < lds_f64(ua[k][d]);
+            }
           }
         }
 #pragma unroll
@@ -631,7 +640,7 @@ __device__ __forceinline__ void warp_search(const CtaMem& cm, const WarpMem& wm,
 #pragma unroll
           for (int k = 0; k < NV; ++k)
 #pragma unroll
-            for (int d = 0; d < 6; ++d) fin[k][d] = lds_f64(ua[k][d]);
+            for (int d = 0; d < 6; ++d) fin[k][d] = (!LEAN || imp[k][d]) ? lds_f64(ua[k][d]) : 0.0;
 #pragma unroll
           for (int d = 0; d < 6; ++d)
 #pragma unroll
@@ -789,7 +798,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_paths(const __grid_constant__ Pa
         } else {
           present = warp_seed_connector(cm, wm, c.n_high, c.high_cube, c.high_slot, inv, lane);
         }
-        warp_search<false, NCH, NV, WG>(cm, wm, dt, S, step, present, lane, -1);
+        warp_search<false, NCH, NV, WG, (MINB > 1)>(cm, wm, dt, S, step, present, lane, -1);
         if (pair_task) {
           const long long row = poff + (long long)task * K - (long long)task * (task + 1) / 2;
           for (int b = task + 1 + lane; b < K; b += 32) c.pair_len[row + (b - task - 1)] = wm.dist[odd[b]];
