@@ -368,8 +368,8 @@ int run_pipeline(fpb_handle* h, long long T, int stage, bool gen, uint64_t seed,
   if (stage < FPB_STAGE_NOISE || stage > FPB_STAGE_GRAPH) return fail(FPB_ERR_ARG, "bad stage");
   cudaStream_t st = h->stream;
   memset(&h->tm, 0, sizeof h->tm);
-  h->T = T;
-  h->last_stage = stage;
+  h->T = 0;  // no valid result until every stage below has completed
+  h->last_stage = 0;
   for (int c = 0; c < h->ncx; ++c) h->cx[c].total_odd = h->cx[c].total_pairs = 0;
   int launches = 0;
 
@@ -453,6 +453,8 @@ int run_pipeline(fpb_handle* h, long long T, int stage, bool gen, uint64_t seed,
   CK(cudaEventElapsedTime(&h->tm.total_ms, h->ev[0], h->ev[4]));
   if (stage >= FPB_STAGE_GRAPH && h->use_table && h->weight_method == FPB_WEIGHT_BLUEPRINT && *h->static_flag_host)
     return fail(FPB_ERR_STATE, "static-weight table in use but a trial's labels are not all p-squeezed");
+  h->T = T;
+  h->last_stage = stage;
   h->tm.launches = launches;
   h->tm.graph_warps_per_cta = h->warps;
   h->tm.graph_smem_bytes = (int)h->paths_smem;

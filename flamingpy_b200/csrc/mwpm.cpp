@@ -64,13 +64,30 @@ class Blossom {
       st[u] = u;
       flower[u].clear();
     }
-    ll w_max = 0;
-    for (int u = 1; u <= n; ++u)
+    // Jump start.  Duals only have to be feasible (lab[u] + lab[v] >= 2 w(u, v)); with
+    // lab[u] = max_v w(u, v) every vertex already has a tight edge to its best partner, and
+    // matching mutually unmatched best partners greedily leaves few free vertices for the
+    // O(n^2) augmentation phases.  Optimality follows from complementary slackness once the
+    // matching is perfect, whatever the starting duals were.
+    std::vector<int> best(n + 1, 0);
+    for (int u = 1; u <= n; ++u) {
+      ll mx = 0;
       for (int v = 1; v <= n; ++v) {
         FF(u, v) = (u == v ? u : 0);
-        w_max = std::max(w_max, G(u, v).w);
+        if (v != u && G(u, v).w > mx) {
+          mx = G(u, v).w;
+          best[u] = v;
+        }
       }
-    for (int u = 1; u <= n; ++u) lab[u] = w_max;
+      lab[u] = mx;
+    }
+    for (int u = 1; u <= n; ++u) {
+      const int v = best[u];
+      if (v && !match[u] && !match[v] && lab[u] + lab[v] == 2 * G(u, v).w) {
+        match[u] = v;
+        match[v] = u;
+      }
+    }
     while (matching()) {
     }
     return match;
