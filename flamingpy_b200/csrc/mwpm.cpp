@@ -20,8 +20,11 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <atomic>
 #include <queue>
 #include <vector>
+
+#include "mwpm_sparse.h"
 
 #ifdef _OPENMP
 #include <omp.h>
@@ -356,13 +359,215 @@ int solve_one(int K, const double* pair_len, const double* bnd_len, int* out_src
   return nq;
 }
 
+// Tuning / statistics of the sparse solver (process-wide).
+std::atomic<int> g_mode(0);   // 0: sparse from SPARSE_MIN_K cubes on, 1: always dense, 2: always sparse
+std::atomic<int> g_knn(12);    // nearest partners per cube in the first candidate graph
+std::atomic<long long> g_stats[4];  // sparse solves, dense fallbacks, pricing rounds, priced-in edges
+const int SPARSE_MIN_K = 48;
+
+// Same problem as solve_one, solved on a sparse candidate graph and proved optimal for the
+// complete graph by pricing (mwpm_sparse.h).  Returns -100 when the caller should fall back to
+// the dense solver (candidate graph without a perfect matching, or too many pricing rounds).
+int solve_one_sparse(int K, const double* pair_len, const double* bnd_len, int* out_src, int* out_dst) {
+  using fpb_sparse::SparseBlossom;
+  const int n = (bnd_len && (K & 1)) ? K + 1 : K;
+  double wmax = 0;
+  const long long npairs = (long long)K * (K - 1) / 2;
+  for (long long i = 0; i < npairs; ++i) wmax = std::max(wmax, pair_len[i]);
+  if (bnd_len)
+    for (int a = 0; a < K; ++a) wmax = std::max(wmax, 2 * bnd_len[a]);
+  if (!(wmax < 1e15)) return -2;
+  int shift = 32;
+  while (shift > 0 && std::ldexp(wmax + 1.0, shift) * (double)(n + 2) > 1e17) --shift;
+  const double scale = std::ldexp(1.0, shift);
+  // One pass over the packed triangle: integer lengths of the reduced complete graph (see the
+  // header comment of this file) and, per vertex, its knn nearest partners.  Length and partner
+  // are packed in one 64-bit key (len * (n + 2) < 1e17 by the choice of the scale); thr[u] is the
+  // current knn-th smallest key of u, so almost every pair costs two compares.
+  const int knn = std::max(2, g_knn.load());
+  int vbits = 1;
+  while ((1 << vbits) < n) ++vbits;
+  std::vector<ll> len((size_t)npairs);
+  std::vector<unsigned long long> top((size_t)n * knn), thr((size_t)n, ~0ull);
+  std::vector<int> cnt((size_t)n, 0);
+  auto offer = [&](int u, unsigned long long key) {  // insert into u's ascending list
+    unsigned long long* t = top.data() + (size_t)u * knn;
+    int i = cnt[u] < knn ? cnt[u]++ : knn - 1;
+    for (; i > 0 && t[i - 1] > key; --i) t[i] = t[i - 1];
+    t[i] = key;
+    if (cnt[u] == knn) thr[u] = t[knn - 1];
+  };
+  {
+    long long pos = 0;
+    for (int a = 0; a < K - 1; ++a) {
+      const double ba = bnd_len ? bnd_len[a] : 0.0;
+      for (int b = a + 1; b < K; ++b, ++pos) {
+        double w = pair_len[pos];
+        if (bnd_len) w = std::min(w, ba + bnd_len[b]);
+        const ll L = (ll)std::llround(w * scale);
+        len[pos] = L;
+        const unsigned long long kb = ((unsigned long long)L << vbits) | (unsigned)b;
+        const unsigned long long ka = ((unsigned long long)L << vbits) | (unsigned)a;
+        if (kb < thr[a]) offer(a, kb);
+        if (ka < thr[b]) offer(b, ka);
+      }
+    }
+  }
+  std::vector<ll> dlen;
+  if (n > K) {
+    dlen.resize(K);
+    for (int a = 0; a < K; ++a) {
+      dlen[a] = (ll)std::llround(bnd_len[a] * scale);
+      const unsigned long long kd = ((unsigned long long)dlen[a] << vbits) | (unsigned)K;
+      const unsigned long long ka = ((unsigned long long)dlen[a] << vbits) | (unsigned)a;
+      if (kd < thr[a]) offer(a, kd);
+      if (ka < thr[K]) offer(K, ka);
+    }
+  }
+  auto wt = [&](int u, int v) -> ll {  // matcher weight (maximised) of edge u < v
+    if (v >= K) return -2 * dlen[u];
+    return -2 * len[(size_t)((ll)u * K - (ll)u * (u + 1) / 2 + (v - u - 1))];
+  };
+  std::vector<unsigned long long> keys;
+  for (int u = 0; u < n; ++u)
+    for (int i = 0; i < cnt[u]; ++i) {
+      const int v = (int)(top[(size_t)u * knn + i] & ((1ull << vbits) - 1));
+      const unsigned long long lo = std::min(u, v), hi = std::max(u, v);
+      keys.push_back((lo << 32) | hi);
+    }
+  std::sort(keys.begin(), keys.end());
+  keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+  SparseBlossom sb;
+  sb.reset(n);
+  for (size_t i = 0; i < keys.size(); ++i) {
+    const int u = (int)(keys[i] >> 32), v = (int)(keys[i] & 0xffffffffu);
+    sb.add_edge(u, v, wt(u, v));
+  }
+  sb.build_adjacency();
+  std::vector<ll> y;
+  std::vector<int> vmate;
+  // cold start (the usual greedy jump start of primal-dual matchers): feasible duals y_u = best
+  // incident weight; then every free vertex lowers its dual until its first edge becomes tight
+  // and takes that partner if it is still free.  All weights are even, so all duals stay even.
+  auto cold_start = [&]() -> bool {
+    y.assign(n, INT64_MIN);
+    vmate.assign(n, -1);
+    for (int k = 0; k < sb.n_edges(); ++k) {
+      y[sb.eu[k]] = std::max(y[sb.eu[k]], sb.ew[k]);
+      y[sb.ev[k]] = std::max(y[sb.ev[k]], sb.ew[k]);
+    }
+    for (int u = 0; u < n; ++u)
+      if (y[u] == INT64_MIN) return false;
+    for (int u = 0; u < n; ++u) {
+      if (vmate[u] >= 0) continue;
+      ll smin = INT64_MAX;
+      int pick = -1;
+      sb.for_neighbours(u, [&](int v, ll w) {
+        const ll sl = y[u] + y[v] - 2 * w;
+        if (sl < smin || (sl == smin && pick >= 0 && vmate[pick] >= 0 && vmate[v] < 0)) {
+          smin = sl;
+          pick = v;
+        }
+      });
+      y[u] -= smin;
+      if (vmate[pick] < 0) {
+        vmate[u] = pick;
+        vmate[pick] = u;
+      }
+    }
+    sb.start(y, vmate);
+    return true;
+  };
+  if (!cold_start()) return -100;
+  g_stats[0].fetch_add(1);
+  struct Viol { ll s; int u, v; };
+  std::vector<Viol> viol;
+  bool done = false;
+  for (int round = 0; round < 40 && !done; ++round) {
+    if (!sb.solve()) return -100;
+    // pricing: reduced cost of every edge of the complete graph under the sparse optimum's duals
+    viol.clear();
+    for (int u = 0; u < n - 1; ++u) {
+      const ll du = sb.dual[u];
+      for (int v = u + 1; v < n; ++v) {
+        ll s = du + sb.dual[v] - 2 * wt(u, v);
+        if (s < 0) {
+          s += sb.common_blossom_dual(u, v);
+          if (s < 0) viol.push_back(Viol{s, u, v});
+        }
+      }
+    }
+    if (viol.empty()) {
+      done = true;
+      break;
+    }
+    g_stats[2].fetch_add(1);
+    const size_t cap = (size_t)4 * n;
+    if (viol.size() > cap) {
+      std::nth_element(viol.begin(), viol.begin() + cap, viol.end(), [](const Viol& a, const Viol& b) { return a.s < b.s; });
+      viol.resize(cap);
+    }
+    g_stats[3].fetch_add((long long)viol.size());
+    // restart on the enlarged candidate graph (the greedy start leaves fewer free vertices than
+    // repairing the previous duals would: dropping the blossoms unmatches all their vertices)
+    for (size_t i = 0; i < viol.size(); ++i) sb.add_edge(viol[i].u, viol[i].v, wt(viol[i].u, viol[i].v));
+    sb.build_adjacency();
+    if (!cold_start()) return -100;
+  }
+  if (!done) return -100;
+  int nq = 0;
+  for (int a = 0; a < K; ++a) {
+    const int b = sb.mate_vertex(a);
+    if (b < 0) return -3;
+    if (b >= K) {
+      out_src[nq] = a;
+      out_dst[nq++] = -1;
+    } else if (a < b) {
+      const long long pos = (ll)a * K - (ll)a * (a + 1) / 2 + (b - a - 1);
+      if (bnd_len && bnd_len[a] + bnd_len[b] < pair_len[pos]) {
+        out_src[nq] = a; out_dst[nq++] = -1;
+        out_src[nq] = b; out_dst[nq++] = -1;
+      } else {
+        out_src[nq] = a;
+        out_dst[nq++] = b;
+      }
+    }
+  }
+  return nq;
+}
+
+int solve_auto(int K, const double* pair_len, const double* bnd_len, int* out_src, int* out_dst) {
+  const int mode = g_mode.load();
+  if (K >= 4 && (bnd_len || !(K & 1)) && (mode == 2 || (mode == 0 && K >= SPARSE_MIN_K))) {
+    const int r = solve_one_sparse(K, pair_len, bnd_len, out_src, out_dst);
+    if (r != -100) return r;
+    g_stats[1].fetch_add(1);
+  }
+  return solve_one(K, pair_len, bnd_len, out_src, out_dst);
+}
+
 }  // namespace
 
 extern "C" {
 
+// mode 0: automatic (sparse + pricing for large graphs), 1: dense O(n^3) solver only, 2: sparse only
+// (dense fallback stays).  knn > 0 sets the nearest-partner count of the first candidate graph.
+void fpb_mwpm_configure(int mode, int knn) {
+  g_mode.store(mode);
+  if (knn > 0) g_knn.store(knn);
+}
+
+// out[0..3] = sparse solves, dense fallbacks, pricing rounds, priced-in edges since load / last reset.
+void fpb_mwpm_stats(long long* out, int reset) {
+  for (int i = 0; i < 4; ++i) {
+    out[i] = g_stats[i].load();
+    if (reset) g_stats[i].store(0);
+  }
+}
+
 // Single graph (see solve_one).  out_src / out_dst need room for K entries.
 int fpb_mwpm(int K, const double* pair_len, const double* bnd_len, int* out_src, int* out_dst) {
-  return solve_one(K, pair_len, bnd_len, out_src, out_dst);
+  return solve_auto(K, pair_len, bnd_len, out_src, out_dst);
 }
 
 // T graphs in the ragged layout of fpb_outputs (odd_count[T], pair_len / bnd_len concatenated).
@@ -379,7 +584,7 @@ int fpb_mwpm_batch(int T, const int* odd_count, const double* pair_len, const do
 #pragma omp parallel for schedule(dynamic, 1) reduction(| : bad)
   for (int t = 0; t < T; ++t) {
     const int K = odd_count[t];
-    const int r = solve_one(K, pair_len + poff[t], bnd_len ? bnd_len + q_off[t] : nullptr, out_src + q_off[t],
+    const int r = solve_auto(K, pair_len + poff[t], bnd_len ? bnd_len + q_off[t] : nullptr, out_src + q_off[t],
                             out_dst + q_off[t]);
     if (r < 0) bad |= 1;
     n_queries[t] = r < 0 ? 0 : r;

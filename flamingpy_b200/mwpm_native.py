@@ -29,8 +29,29 @@ def load():
         lib.fpb_mwpm_batch.restype = C.c_int
         lib.fpb_mwpm_batch.argtypes = [C.c_int, _i32p, _f64p, _f64p, _i64p, _i32p, _i32p, _i32p, C.c_int]
         lib.fpb_mwpm_max_threads.restype = C.c_int
+        lib.fpb_mwpm_configure.restype = None
+        lib.fpb_mwpm_configure.argtypes = [C.c_int, C.c_int]
+        lib.fpb_mwpm_stats.restype = None
+        lib.fpb_mwpm_stats.argtypes = [_i64p, C.c_int]
         _lib = lib
     return _lib
+
+
+MODES = {"auto": 0, "dense": 1, "sparse": 2}
+
+
+def configure(mode: str = "auto", knn: int = 0) -> None:
+    """Choose the solver: ``"auto"`` (sparse candidate graph + pricing from 48 cubes on, dense
+    O(n^3) below), ``"dense"`` or ``"sparse"``; ``knn`` = nearest partners per cube in the first
+    candidate graph (0 keeps the current value).  Both solvers return a minimum-weight perfect
+    matching of the same complete graph; only the choice among ties can differ."""
+    load().fpb_mwpm_configure(MODES[mode], int(knn))
+
+
+def stats(reset: bool = False) -> dict:
+    out = np.zeros(4, np.int64)
+    load().fpb_mwpm_stats(_p(out, _i64p), int(reset))
+    return dict(zip(("sparse_solves", "dense_fallbacks", "pricing_rounds", "priced_edges"), out.tolist()))
 
 
 def _p(a, typ):

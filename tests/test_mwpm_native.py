@@ -73,3 +73,72 @@ def test_batch_interface_matches_single_calls():
 def test_odd_graph_without_boundary_is_an_error():
     with pytest.raises(ValueError):
         mwpm_native.solve(3, np.ones(3), None)
+
+
+def _random_graph(rng, K, kind):
+    if kind == 0:  # small integers: many ties
+        return rng.integers(0, 10, K * (K - 1) // 2).astype(float), rng.integers(0, 6, K).astype(float)
+    if kind == 1:  # metric, continuous
+        pts = rng.uniform(0, 10, (K, 3))
+        d = np.abs(pts[:, None, :] - pts[None, :, :]).sum(-1)
+        return d[np.triu_indices(K, 1)], np.minimum(pts[:, 0], 10 - pts[:, 0]) + 0.1
+    if kind == 2:  # no structure at all
+        return rng.uniform(0.5, 60, K * (K - 1) // 2), rng.uniform(0.5, 30, K)
+    pts = rng.integers(0, 7, (K, 3)).astype(float)  # lattice points: metric with massive ties
+    d = np.abs(pts[:, None, :] - pts[None, :, :]).sum(-1)
+    return d[np.triu_indices(K, 1)], np.minimum(pts[:, 0], 6 - pts[:, 0]) + 1.0
+
+
+@pytest.mark.parametrize("K", [4, 5, 6, 9, 16, 23, 38, 60, 97, 150])
+@pytest.mark.parametrize("boundary", [False, True])
+def test_sparse_pricing_solver_finds_the_dense_optimum(K, boundary):
+    """The sparse solver (k-nearest candidate graph + pricing against the complete graph) must
+    return a perfect matching of exactly the dense solver's total weight."""
+    if not boundary and K % 2:
+        pytest.skip("odd K without boundary has no perfect matching")
+    rng = np.random.default_rng(100 + K)
+    try:
+        for rep in range(8):
+            pair, bnd = _random_graph(rng, K, rep % 4)
+            b = bnd if boundary else None
+            mwpm_native.configure("dense")
+            ref = mwpm_native.solve(K, pair, b)
+            mwpm_native.configure("sparse", knn=int(rng.integers(2, 14)))
+            got = mwpm_native.solve(K, pair, b)
+            wr, wg = total_weight(K, ref, pair, bnd), total_weight(K, got, pair, bnd)
+            assert wg == pytest.approx(wr, rel=1e-12, abs=1e-9), (K, rep)
+    finally:
+        mwpm_native.configure("auto", knn=12)
+
+
+def test_sparse_solver_on_oracle_matching_graphs():
+    """Matching graphs of real trials (C oracle, d=7 periodic and open): the sparse solver's
+    matchings weigh what the dense solver's do, and it rarely needs the dense fallback."""
+    from flamingpy_b200.lattice import build_lattice
+    from flamingpy_b200.noise import sample_batch
+    from oracle import c_oracle
+
+    try:
+        for bnd_kind in ("periodic", "open"):
+            lat = build_lattice(7, "primal", bnd_kind)
+            rng = np.random.default_rng(3)
+            x, st = sample_batch(rng, lat.N, 0.1, 0.3, 12, fresh=True)
+            b = c_oracle.run(lat, 0.1, 0.3, {"method": "blueprint", "delta": 0.1}, x, st)
+            cb = b.complexes[lat.ec[0]]
+            has = len(cb.bnd_len) > 0
+            mwpm_native.stats(reset=True)
+            for t in range(12):
+                K = int(cb.odd_count[t])
+                if K < 4:
+                    continue
+                pl = cb.pair_len[cb.pair_off[t]:cb.pair_off[t + 1]]
+                bl = cb.bnd_len[cb.odd_off[t]:cb.odd_off[t + 1]] if has else None
+                mwpm_native.configure("dense")
+                ref = mwpm_native.solve(K, pl, bl)
+                mwpm_native.configure("sparse", knn=12)
+                got = mwpm_native.solve(K, pl, bl)
+                assert total_weight(K, got, pl, bl) == pytest.approx(total_weight(K, ref, pl, bl), rel=1e-12, abs=1e-9)
+            s = mwpm_native.stats()
+            assert s["sparse_solves"] > 0 and s["dense_fallbacks"] <= s["sparse_solves"] // 4
+    finally:
+        mwpm_native.configure("auto", knn=12)
