@@ -39,6 +39,9 @@ struct Edge {
   ll w;
 };
 
+// non-negative scaled length -> integer, round half up (one cvttsd2si instead of a libm call)
+inline ll to_fixed(double v) { return (ll)(v + 0.5); }
+
 class Blossom {
  public:
   explicit Blossom(int n) : n(n), nx(n), m(2 * n + 1) {
@@ -319,7 +322,7 @@ int solve_one(int K, const double* pair_len, const double* bnd_len, int* out_src
   int shift = 32;
   while (shift > 0 && std::ldexp(wmax + 1.0, shift) * (double)(n + 2) > 1e17) --shift;
   const double scale = std::ldexp(1.0, shift);
-  const ll wmax_i = (ll)std::llround(wmax * scale) + 1;
+  const ll wmax_i = to_fixed(wmax * scale) + 1;
   const ll C = wmax_i * (ll)(n + 1);  // C - w > 0 and large enough that cardinality dominates
   Blossom bl(n);
   std::vector<char> via_boundary((size_t)K * K, 0);
@@ -334,10 +337,10 @@ int solve_one(int K, const double* pair_len, const double* bnd_len, int* out_src
           via_boundary[(size_t)a * K + b] = 1;
         }
       }
-      bl.set_weight(a + 1, b + 1, 2 * (C - (ll)std::llround(w * scale)));
+      bl.set_weight(a + 1, b + 1, 2 * (C - to_fixed(w * scale)));
     }
   if (n > K)
-    for (int a = 0; a < K; ++a) bl.set_weight(a + 1, n, 2 * (C - (ll)std::llround(bnd_len[a] * scale)));
+    for (int a = 0; a < K; ++a) bl.set_weight(a + 1, n, 2 * (C - to_fixed(bnd_len[a] * scale)));
   const std::vector<int>& mate = bl.solve();
   int nq = 0;
   for (int a = 0; a < K; ++a) {
@@ -362,13 +365,13 @@ int solve_one(int K, const double* pair_len, const double* bnd_len, int* out_src
 // Tuning / statistics of the sparse solver (process-wide).
 std::atomic<int> g_mode(0);   // 0: sparse from SPARSE_MIN_K cubes on, 1: always dense, 2: always sparse
 std::atomic<int> g_knn(12);    // nearest partners per cube in the first candidate graph
-std::atomic<long long> g_stats[4];  // sparse solves, dense fallbacks, pricing rounds, priced-in edges
+std::atomic<long long> g_stats[4];  // sparse solves, retries with a denser candidate graph, pricing rounds, priced-in edges
 const int SPARSE_MIN_K = 48;
 
 // Same problem as solve_one, solved on a sparse candidate graph and proved optimal for the
 // complete graph by pricing (mwpm_sparse.h).  Returns -100 when the caller should fall back to
 // the dense solver (candidate graph without a perfect matching, or too many pricing rounds).
-int solve_one_sparse(int K, const double* pair_len, const double* bnd_len, int* out_src, int* out_dst) {
+int solve_one_sparse(int K, const double* pair_len, const double* bnd_len, int* out_src, int* out_dst, int knn) {
   using fpb_sparse::SparseBlossom;
   const int n = (bnd_len && (K & 1)) ? K + 1 : K;
   double wmax = 0;
@@ -384,7 +387,6 @@ int solve_one_sparse(int K, const double* pair_len, const double* bnd_len, int* 
   // header comment of this file) and, per vertex, its knn nearest partners.  Length and partner
   // are packed in one 64-bit key (len * (n + 2) < 1e17 by the choice of the scale); thr[u] is the
   // current knn-th smallest key of u, so almost every pair costs two compares.
-  const int knn = std::max(2, g_knn.load());
   int vbits = 1;
   while ((1 << vbits) < n) ++vbits;
   std::vector<ll> len((size_t)npairs);
@@ -404,7 +406,7 @@ int solve_one_sparse(int K, const double* pair_len, const double* bnd_len, int* 
       for (int b = a + 1; b < K; ++b, ++pos) {
         double w = pair_len[pos];
         if (bnd_len) w = std::min(w, ba + bnd_len[b]);
-        const ll L = (ll)std::llround(w * scale);
+        const ll L = to_fixed(w * scale);
         len[pos] = L;
         const unsigned long long kb = ((unsigned long long)L << vbits) | (unsigned)b;
         const unsigned long long ka = ((unsigned long long)L << vbits) | (unsigned)a;
@@ -417,7 +419,7 @@ int solve_one_sparse(int K, const double* pair_len, const double* bnd_len, int* 
   if (n > K) {
     dlen.resize(K);
     for (int a = 0; a < K; ++a) {
-      dlen[a] = (ll)std::llround(bnd_len[a] * scale);
+      dlen[a] = to_fixed(bnd_len[a] * scale);
       const unsigned long long kd = ((unsigned long long)dlen[a] << vbits) | (unsigned)K;
       const unsigned long long ka = ((unsigned long long)dlen[a] << vbits) | (unsigned)a;
       if (kd < thr[a]) offer(a, kd);
@@ -474,6 +476,24 @@ int solve_one_sparse(int K, const double* pair_len, const double* bnd_len, int* 
         vmate[u] = pick;
         vmate[pick] = u;
       }
+    }
+    // augmenting paths of three tight edges (free - matched = matched - free) need no search
+    for (int u = 0; u < n; ++u) {
+      if (vmate[u] >= 0) continue;
+      bool found = false;
+      sb.for_neighbours(u, [&](int v, ll w) {
+        if (found || vmate[v] < 0 || y[u] + y[v] != 2 * w) return;
+        const int v2 = vmate[v];
+        int x = -1;
+        sb.for_neighbours(v2, [&](int c, ll w2) {
+          if (x < 0 && c != u && vmate[c] < 0 && y[v2] + y[c] == 2 * w2) x = c;
+        });
+        if (x >= 0) {
+          vmate[u] = v; vmate[v] = u;
+          vmate[v2] = x; vmate[x] = v2;
+          found = true;
+        }
+      });
     }
     sb.start(y, vmate);
     return true;
@@ -539,9 +559,14 @@ int solve_one_sparse(int K, const double* pair_len, const double* bnd_len, int* 
 int solve_auto(int K, const double* pair_len, const double* bnd_len, int* out_src, int* out_dst) {
   const int mode = g_mode.load();
   if (K >= 4 && (bnd_len || !(K & 1)) && (mode == 2 || (mode == 0 && K >= SPARSE_MIN_K))) {
-    const int r = solve_one_sparse(K, pair_len, bnd_len, out_src, out_dst);
-    if (r != -100) return r;
-    g_stats[1].fetch_add(1);
+    // a candidate graph without a perfect matching (or one that needs too many pricing rounds)
+    // is retried with four times the partners; with K - 1 partners it is the complete graph
+    for (int knn = std::max(2, g_knn.load());; knn *= 4) {
+      const int r = solve_one_sparse(K, pair_len, bnd_len, out_src, out_dst, std::min(knn, K));
+      if (r != -100) return r;
+      g_stats[1].fetch_add(1);
+      if (knn >= K) break;
+    }
   }
   return solve_one(K, pair_len, bnd_len, out_src, out_dst);
 }
@@ -557,7 +582,7 @@ void fpb_mwpm_configure(int mode, int knn) {
   if (knn > 0) g_knn.store(knn);
 }
 
-// out[0..3] = sparse solves, dense fallbacks, pricing rounds, priced-in edges since load / last reset.
+// out[0..3] = sparse solves, retries with a denser candidate graph, pricing rounds, priced-in edges since load / last reset.
 void fpb_mwpm_stats(long long* out, int reset) {
   for (int i = 0; i < 4; ++i) {
     out[i] = g_stats[i].load();

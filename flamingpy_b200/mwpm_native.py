@@ -51,7 +51,7 @@ def configure(mode: str = "auto", knn: int = 0) -> None:
 def stats(reset: bool = False) -> dict:
     out = np.zeros(4, np.int64)
     load().fpb_mwpm_stats(_p(out, _i64p), int(reset))
-    return dict(zip(("sparse_solves", "dense_fallbacks", "pricing_rounds", "priced_edges"), out.tolist()))
+    return dict(zip(("sparse_solves", "retries", "pricing_rounds", "priced_edges"), out.tolist()))
 
 
 def _p(a, typ):
