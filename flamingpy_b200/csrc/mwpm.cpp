@@ -437,6 +437,20 @@ int solve_one_sparse(int K, const double* pair_len, const double* bnd_len, int* 
       const unsigned long long lo = std::min(u, v), hi = std::max(u, v);
       keys.push_back((lo << 32) | hi);
     }
+  if (bnd_len) {
+    // Cubes that end at their connector are paired with EACH OTHER in the reduced graph, at
+    // b_a + b_b whatever the pairing.  Nearest partners alone give that group a star (everyone
+    // points at the few cubes closest to the boundary), which has no perfect matching; a chain
+    // through the cubes in order of their boundary length lets neighbours in that order pair up.
+    std::vector<int> order(K);
+    for (int a = 0; a < K; ++a) order[a] = a;
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return bnd_len[a] < bnd_len[b] || (bnd_len[a] == bnd_len[b] && a < b); });
+    for (int i = 0; i < K; ++i)
+      for (int j = 1; j <= 3 && i + j < K; ++j) {
+        const unsigned long long lo = std::min(order[i], order[i + j]), hi = std::max(order[i], order[i + j]);
+        keys.push_back((lo << 32) | hi);
+      }
+  }
   std::sort(keys.begin(), keys.end());
   keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
   SparseBlossom sb;
