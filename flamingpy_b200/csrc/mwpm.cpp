@@ -390,14 +390,19 @@ int solve_one_sparse(int K, const double* pair_len, const double* bnd_len, int* 
   int vbits = 1;
   while ((1 << vbits) < n) ++vbits;
   std::vector<ll> len((size_t)npairs);
-  std::vector<unsigned long long> top((size_t)n * knn), thr((size_t)n, ~0ull);
+  // per vertex a buffer of 2 * knn keys: offers are appended, a full buffer is cut back to its knn
+  // smallest keys (nth_element), which also tightens the threshold - O(1) amortised per offer
+  const int cap2 = 2 * knn;
+  std::vector<unsigned long long> top((size_t)n * cap2), thr((size_t)n, ~0ull);
   std::vector<int> cnt((size_t)n, 0);
-  auto offer = [&](int u, unsigned long long key) {  // insert into u's ascending list
-    unsigned long long* t = top.data() + (size_t)u * knn;
-    int i = cnt[u] < knn ? cnt[u]++ : knn - 1;
-    for (; i > 0 && t[i - 1] > key; --i) t[i] = t[i - 1];
-    t[i] = key;
-    if (cnt[u] == knn) thr[u] = t[knn - 1];
+  auto offer = [&](int u, unsigned long long key) {
+    unsigned long long* t = top.data() + (size_t)u * cap2;
+    t[cnt[u]++] = key;
+    if (cnt[u] == cap2) {
+      std::nth_element(t, t + (knn - 1), t + cap2);
+      thr[u] = t[knn - 1];
+      cnt[u] = knn;
+    }
   };
   {
     long long pos = 0;
@@ -426,17 +431,24 @@ int solve_one_sparse(int K, const double* pair_len, const double* bnd_len, int* 
       if (ka < thr[K]) offer(K, ka);
     }
   }
+  int wshift = 0;  // weights and duals are doubled at every warm restart (see below)
   auto wt = [&](int u, int v) -> ll {  // matcher weight (maximised) of edge u < v
-    if (v >= K) return -2 * dlen[u];
-    return -2 * len[(size_t)((ll)u * K - (ll)u * (u + 1) / 2 + (v - u - 1))];
+    if (v >= K) return -((2 * dlen[u]) << wshift);
+    return -((2 * len[(size_t)((ll)u * K - (ll)u * (u + 1) / 2 + (v - u - 1))]) << wshift);
   };
   std::vector<unsigned long long> keys;
-  for (int u = 0; u < n; ++u)
+  for (int u = 0; u < n; ++u) {
+    unsigned long long* t = top.data() + (size_t)u * cap2;
+    if (cnt[u] > knn) {
+      std::nth_element(t, t + (knn - 1), t + cnt[u]);
+      cnt[u] = knn;
+    }
     for (int i = 0; i < cnt[u]; ++i) {
-      const int v = (int)(top[(size_t)u * knn + i] & ((1ull << vbits) - 1));
+      const int v = (int)(t[i] & ((1ull << vbits) - 1));
       const unsigned long long lo = std::min(u, v), hi = std::max(u, v);
       keys.push_back((lo << 32) | hi);
     }
+  }
   if (bnd_len) {
     // Cubes that end at their connector are paired with EACH OTHER in the reduced graph, at
     // b_a + b_b whatever the pairing.  Nearest partners alone give that group a star (everyone
@@ -516,6 +528,7 @@ int solve_one_sparse(int K, const double* pair_len, const double* bnd_len, int* 
   g_stats[0].fetch_add(1);
   struct Viol { ll s; int u, v; };
   std::vector<Viol> viol;
+  std::vector<int> marked;
   bool done = false;
   for (int round = 0; round < 40 && !done; ++round) {
     if (!sb.solve()) return -100;
@@ -542,11 +555,39 @@ int solve_one_sparse(int K, const double* pair_len, const double* bnd_len, int* 
       viol.resize(cap);
     }
     g_stats[3].fetch_add((long long)viol.size());
-    // restart on the enlarged candidate graph (the greedy start leaves fewer free vertices than
-    // repairing the previous duals would: dropping the blossoms unmatches all their vertices)
-    for (size_t i = 0; i < viol.size(); ++i) sb.add_edge(viol[i].u, viol[i].v, wt(viol[i].u, viol[i].v));
-    sb.build_adjacency();
-    if (!cold_start()) return -100;
+    // Warm restart: keep matching, duals and blossoms.  Everything is doubled first, so that all
+    // duals are even again (the stages need the free vertices' duals to share one parity).  A
+    // violated edge becomes feasible by raising the dual of one endpoint (after dissolving the
+    // blossoms around it) - that only adds slack to its other edges - and that vertex and its
+    // partner become free: the next solve() runs a few stages instead of starting over.
+    bool warm = wshift < 6;
+    if (warm) {
+      sb.double_all();
+      ++wshift;
+      marked.clear();
+      for (size_t i = 0; i < viol.size() && warm; ++i) {
+        const int u = viol[i].u, v = viol[i].v;
+        if (sb.dual[u] + sb.dual[v] - 2 * wt(u, v) + sb.common_blossom_dual(u, v) >= 0) continue;  // covered by an earlier raise
+        const int x = sb.is_bare(u) ? u : (sb.is_bare(v) ? v : u);
+        sb.make_bare(x);  // dissolves the blossoms around x (their bases become free)
+        const ll rc = sb.dual[u] + sb.dual[v] - 2 * wt(u, v) + sb.common_blossom_dual(u, v);
+        if (rc >= 0) continue;
+        sb.dual[x] -= rc;
+        marked.push_back(x);
+      }
+    }
+    if (warm) {
+      for (size_t i = 0; i < viol.size(); ++i) sb.add_edge(viol[i].u, viol[i].v, wt(viol[i].u, viol[i].v));
+      sb.build_adjacency();
+      for (size_t i = 0; i < marked.size(); ++i) sb.unmatch(marked[i]);
+    } else {
+      // too many doublings: start over on the enlarged graph
+      wshift = 0;
+      for (int k = 0; k < sb.n_edges(); ++k) sb.ew[k] = wt(sb.eu[k], sb.ev[k]);
+      for (size_t i = 0; i < viol.size(); ++i) sb.add_edge(viol[i].u, viol[i].v, wt(viol[i].u, viol[i].v));
+      sb.build_adjacency();
+      if (!cold_start()) return -100;
+    }
   }
   if (!done) return -100;
   int nq = 0;

@@ -62,6 +62,33 @@ class SparseBlossom {
     }
   }
 
+  bool is_bare(int v) const { return inblossom[v] == v; }  // top-level, not inside a blossom
+  void double_all() {
+    for (size_t i = 0; i < dual.size(); ++i) dual[i] *= 2;
+    for (size_t k = 0; k < ew.size(); ++k) ew[k] *= 2;
+  }
+  // Dissolve the blossoms around v: a blossom's dual z moves onto its vertices (z / 2 each in LP
+  // units), which keeps every inner edge's reduced cost, adds slack to the edges leaving it and
+  // breaks only the tightness of the base's matched edge - so the base and its partner become free.
+  void make_bare(int v) {
+    while (inblossom[v] != v) {
+      const int b = inblossom[v];
+      const ll z = dual[b];
+      if (z != 0) {
+        leaves(b, [&](int x) { dual[x] += z; });
+        dual[b] = 0;
+        unmatch(blossombase[b]);
+      }
+      expand_blossom(b, true);
+    }
+  }
+  void unmatch(int v) {
+    if (mate[v] < 0) return;
+    const int m = endpoint(mate[v]);
+    mate[v] = -1;
+    mate[m] = -1;
+  }
+
   template <class F>
   void for_neighbours(int u, F&& f) const {
     for (int i = adj_off[u]; i < adj_off[u + 1]; ++i) f(endpoint(adj[i]), ew[adj[i] >> 1]);
