@@ -389,14 +389,24 @@ int solve_one_sparse(int K, const double* pair_len, const double* bnd_len, int* 
   // current knn-th smallest key of u, so almost every pair costs two compares.
   int vbits = 1;
   while ((1 << vbits) < n) ++vbits;
-  std::vector<ll> len((size_t)npairs);
+  // scratch is kept per thread: fresh megabyte-sized vectors would be mmap'ed and page-faulted per graph
+  static thread_local std::vector<ll> len_tls;
+  len_tls.resize((size_t)npairs);
+  ll* const len = len_tls.data();  // (thread_local objects cost a TLS lookup per access)
   // per vertex a buffer of 2 * knn keys: offers are appended, a full buffer is cut back to its knn
   // smallest keys (nth_element), which also tightens the threshold - O(1) amortised per offer
   const int cap2 = 2 * knn;
-  std::vector<unsigned long long> top((size_t)n * cap2), thr((size_t)n, ~0ull);
-  std::vector<int> cnt((size_t)n, 0);
+  static thread_local std::vector<unsigned long long> top_tls, thr_tls, keys_tls;
+  static thread_local std::vector<int> cnt_tls;
+  top_tls.resize((size_t)n * cap2);
+  thr_tls.assign((size_t)n, ~0ull);
+  cnt_tls.assign((size_t)n, 0);
+  unsigned long long* const top = top_tls.data();
+  unsigned long long* const thr = thr_tls.data();
+  int* const cnt = cnt_tls.data();
+  std::vector<unsigned long long>& keys = keys_tls;
   auto offer = [&](int u, unsigned long long key) {
-    unsigned long long* t = top.data() + (size_t)u * cap2;
+    unsigned long long* t = top + (size_t)u * cap2;
     t[cnt[u]++] = key;
     if (cnt[u] == cap2) {
       std::nth_element(t, t + (knn - 1), t + cap2);
@@ -436,9 +446,9 @@ int solve_one_sparse(int K, const double* pair_len, const double* bnd_len, int* 
     if (v >= K) return -((2 * dlen[u]) << wshift);
     return -((2 * len[(size_t)((ll)u * K - (ll)u * (u + 1) / 2 + (v - u - 1))]) << wshift);
   };
-  std::vector<unsigned long long> keys;
+  keys.clear();
   for (int u = 0; u < n; ++u) {
-    unsigned long long* t = top.data() + (size_t)u * cap2;
+    unsigned long long* t = top + (size_t)u * cap2;
     if (cnt[u] > knn) {
       std::nth_element(t, t + (knn - 1), t + cnt[u]);
       cnt[u] = knn;
@@ -465,15 +475,18 @@ int solve_one_sparse(int K, const double* pair_len, const double* bnd_len, int* 
   }
   std::sort(keys.begin(), keys.end());
   keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
-  SparseBlossom sb;
+  static thread_local SparseBlossom sb_tls;
+  SparseBlossom& sb = sb_tls;
   sb.reset(n);
   for (size_t i = 0; i < keys.size(); ++i) {
     const int u = (int)(keys[i] >> 32), v = (int)(keys[i] & 0xffffffffu);
     sb.add_edge(u, v, wt(u, v));
   }
   sb.build_adjacency();
-  std::vector<ll> y;
-  std::vector<int> vmate;
+  static thread_local std::vector<ll> y_tls;
+  static thread_local std::vector<int> vmate_tls;
+  std::vector<ll>& y = y_tls;
+  std::vector<int>& vmate = vmate_tls;
   // cold start (the usual greedy jump start of primal-dual matchers): feasible duals y_u = best
   // incident weight; then every free vertex lowers its dual until its first edge becomes tight
   // and takes that partner if it is still free.  All weights are even, so all duals stay even.

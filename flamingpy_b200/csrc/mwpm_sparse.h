@@ -37,6 +37,7 @@ class SparseBlossom {
   void reset(int n_) {
     n = n_;
     eu.clear(); ev.clear(); ew.clear();
+    n_stages = n_deltas = 0;
   }
   int n_edges() const { return (int)eu.size(); }
   void add_edge(int u, int v, ll w) {
@@ -118,13 +119,22 @@ class SparseBlossom {
     blossombase.assign(m, -1);
     for (int v = 0; v < n; ++v) blossombase[v] = v;
     bestedge.assign(m, -1);
-    childs.assign(m, std::vector<int>());
-    endps.assign(m, std::vector<int>());
-    bestedges.assign(m, std::vector<int>());
+    if ((int)childs.size() < m) {
+      childs.resize(m);
+      endps.resize(m);
+      bestedges.resize(m);
+    }
+    for (int b = 0; b < m; ++b) {
+      childs[b].clear();
+      endps[b].clear();
+      bestedges[b].clear();
+    }
     has_bestedges.assign(m, 0);
     unused.clear();
     for (int b = m - 1; b >= n; --b) unused.push_back(b);
     bestedgeto.assign(m, -1);
+    stamp.assign(m, 0);
+    stamp_t = 0;
   }
 
   // Stages: label every free vertex S, grow the alternating forest along tight edges, adjust the
@@ -241,7 +251,6 @@ class SparseBlossom {
   ll common_blossom_dual(int u, int v) {
     if (inblossom[u] != inblossom[v] || inblossom[u] < n) return 0;
     ++stamp_t;
-    if (stamp.size() != (size_t)2 * n) stamp.assign(2 * (size_t)n, 0);
     for (int b = blossomparent[u]; b >= 0; b = blossomparent[b]) stamp[b] = stamp_t;
     ll s = 0;
     bool in = false;
