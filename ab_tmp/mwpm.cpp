@@ -21,7 +21,6 @@
 #include <cstdint>
 #include <cstring>
 #include <atomic>
-#include <chrono>
 #include <queue>
 #include <vector>
 
@@ -366,12 +365,7 @@ int solve_one(int K, const double* pair_len, const double* bnd_len, int* out_src
 // Tuning / statistics of the sparse solver (process-wide).
 std::atomic<int> g_mode(0);   // 0: sparse from SPARSE_MIN_K cubes on, 1: always dense, 2: always sparse
 std::atomic<int> g_knn(12);    // nearest partners per cube in the first candidate graph
-// sparse solves, retries with a denser candidate graph, pricing rounds, priced-in edges, then ns
-// spent in: candidate scan, graph build + jump start, solve stages, pricing (summed over threads)
-std::atomic<long long> g_stats[8];
-inline long long now_ns() {
-  return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
-}
+std::atomic<long long> g_stats[4];  // sparse solves, retries with a denser candidate graph, pricing rounds, priced-in edges
 const int SPARSE_MIN_K = 48;
 
 // Same problem as solve_one, solved on a sparse candidate graph and proved optimal for the
@@ -380,7 +374,6 @@ const int SPARSE_MIN_K = 48;
 int solve_one_sparse(int K, const double* pair_len, const double* bnd_len, int* out_src, int* out_dst, int knn) {
   using fpb_sparse::SparseBlossom;
   const int n = (bnd_len && (K & 1)) ? K + 1 : K;
-  const long long t_begin = now_ns();
   double wmax = 0;
   const long long npairs = (long long)K * (K - 1) / 2;
   for (long long i = 0; i < npairs; ++i) wmax = std::max(wmax, pair_len[i]);
@@ -396,30 +389,15 @@ int solve_one_sparse(int K, const double* pair_len, const double* bnd_len, int* 
   // current knn-th smallest key of u, so almost every pair costs two compares.
   int vbits = 1;
   while ((1 << vbits) < n) ++vbits;
-  // scratch is kept per thread: fresh megabyte-sized vectors would be mmap'ed and page-faulted per graph
-  static thread_local std::vector<ll> len_tls;
-  len_tls.resize((size_t)npairs);
-  ll* const len = len_tls.data();  // (thread_local objects cost a TLS lookup per access)
-  // per vertex a buffer of 2 * knn keys: offers are appended, a full buffer is cut back to its knn
-  // smallest keys (nth_element), which also tightens the threshold - O(1) amortised per offer
-  const int cap2 = 2 * knn;
-  static thread_local std::vector<unsigned long long> top_tls, thr_tls, keys_tls;
-  static thread_local std::vector<int> cnt_tls;
-  top_tls.resize((size_t)n * cap2);
-  thr_tls.assign((size_t)n, ~0ull);
-  cnt_tls.assign((size_t)n, 0);
-  unsigned long long* const top = top_tls.data();
-  unsigned long long* const thr = thr_tls.data();
-  int* const cnt = cnt_tls.data();
-  std::vector<unsigned long long>& keys = keys_tls;
-  auto offer = [&](int u, unsigned long long key) {
-    unsigned long long* t = top + (size_t)u * cap2;
-    t[cnt[u]++] = key;
-    if (cnt[u] == cap2) {
-      std::nth_element(t, t + (knn - 1), t + cap2);
-      thr[u] = t[knn - 1];
-      cnt[u] = knn;
-    }
+  std::vector<ll> len((size_t)npairs);
+  std::vector<unsigned long long> top((size_t)n * knn), thr((size_t)n, ~0ull);
+  std::vector<int> cnt((size_t)n, 0);
+  auto offer = [&](int u, unsigned long long key) {  // insert into u's ascending list
+    unsigned long long* t = top.data() + (size_t)u * knn;
+    int i = cnt[u] < knn ? cnt[u]++ : knn - 1;
+    for (; i > 0 && t[i - 1] > key; --i) t[i] = t[i - 1];
+    t[i] = key;
+    if (cnt[u] == knn) thr[u] = t[knn - 1];
   };
   {
     long long pos = 0;
@@ -448,26 +426,17 @@ int solve_one_sparse(int K, const double* pair_len, const double* bnd_len, int* 
       if (ka < thr[K]) offer(K, ka);
     }
   }
-  int wshift = 0;  // weights and duals are doubled at every warm restart (see below)
   auto wt = [&](int u, int v) -> ll {  // matcher weight (maximised) of edge u < v
-    if (v >= K) return -((2 * dlen[u]) << wshift);
-    return -((2 * len[(size_t)((ll)u * K - (ll)u * (u + 1) / 2 + (v - u - 1))]) << wshift);
+    if (v >= K) return -2 * dlen[u];
+    return -2 * len[(size_t)((ll)u * K - (ll)u * (u + 1) / 2 + (v - u - 1))];
   };
-  const long long t_scan = now_ns();
-  g_stats[4].fetch_add(t_scan - t_begin);
-  keys.clear();
-  for (int u = 0; u < n; ++u) {
-    unsigned long long* t = top + (size_t)u * cap2;
-    if (cnt[u] > knn) {
-      std::nth_element(t, t + (knn - 1), t + cnt[u]);
-      cnt[u] = knn;
-    }
+  std::vector<unsigned long long> keys;
+  for (int u = 0; u < n; ++u)
     for (int i = 0; i < cnt[u]; ++i) {
-      const int v = (int)(t[i] & ((1ull << vbits) - 1));
+      const int v = (int)(top[(size_t)u * knn + i] & ((1ull << vbits) - 1));
       const unsigned long long lo = std::min(u, v), hi = std::max(u, v);
       keys.push_back((lo << 32) | hi);
     }
-  }
   if (bnd_len) {
     // Cubes that end at their connector are paired with EACH OTHER in the reduced graph, at
     // b_a + b_b whatever the pairing.  Nearest partners alone give that group a star (everyone
@@ -484,18 +453,15 @@ int solve_one_sparse(int K, const double* pair_len, const double* bnd_len, int* 
   }
   std::sort(keys.begin(), keys.end());
   keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
-  static thread_local SparseBlossom sb_tls;
-  SparseBlossom& sb = sb_tls;
+  SparseBlossom sb;
   sb.reset(n);
   for (size_t i = 0; i < keys.size(); ++i) {
     const int u = (int)(keys[i] >> 32), v = (int)(keys[i] & 0xffffffffu);
     sb.add_edge(u, v, wt(u, v));
   }
   sb.build_adjacency();
-  static thread_local std::vector<ll> y_tls;
-  static thread_local std::vector<int> vmate_tls;
-  std::vector<ll>& y = y_tls;
-  std::vector<int>& vmate = vmate_tls;
+  std::vector<ll> y;
+  std::vector<int> vmate;
   // cold start (the usual greedy jump start of primal-dual matchers): feasible duals y_u = best
   // incident weight; then every free vertex lowers its dual until its first edge becomes tight
   // and takes that partner if it is still free.  All weights are even, so all duals stay even.
@@ -548,16 +514,11 @@ int solve_one_sparse(int K, const double* pair_len, const double* bnd_len, int* 
   };
   if (!cold_start()) return -100;
   g_stats[0].fetch_add(1);
-  g_stats[5].fetch_add(now_ns() - t_scan);
   struct Viol { ll s; int u, v; };
   std::vector<Viol> viol;
-  std::vector<int> marked;
   bool done = false;
   for (int round = 0; round < 40 && !done; ++round) {
-    const long long t_a = now_ns();
     if (!sb.solve()) return -100;
-    const long long t_b = now_ns();
-    g_stats[6].fetch_add(t_b - t_a);
     // pricing: reduced cost of every edge of the complete graph under the sparse optimum's duals
     viol.clear();
     for (int u = 0; u < n - 1; ++u) {
@@ -570,7 +531,6 @@ int solve_one_sparse(int K, const double* pair_len, const double* bnd_len, int* 
         }
       }
     }
-    g_stats[7].fetch_add(now_ns() - t_b);
     if (viol.empty()) {
       done = true;
       break;
@@ -582,39 +542,11 @@ int solve_one_sparse(int K, const double* pair_len, const double* bnd_len, int* 
       viol.resize(cap);
     }
     g_stats[3].fetch_add((long long)viol.size());
-    // Warm restart: keep matching, duals and blossoms.  Everything is doubled first, so that all
-    // duals are even again (the stages need the free vertices' duals to share one parity).  A
-    // violated edge becomes feasible by raising the dual of one endpoint (after dissolving the
-    // blossoms around it) - that only adds slack to its other edges - and that vertex and its
-    // partner become free: the next solve() runs a few stages instead of starting over.
-    bool warm = wshift < 6;
-    if (warm) {
-      sb.double_all();
-      ++wshift;
-      marked.clear();
-      for (size_t i = 0; i < viol.size() && warm; ++i) {
-        const int u = viol[i].u, v = viol[i].v;
-        if (sb.dual[u] + sb.dual[v] - 2 * wt(u, v) + sb.common_blossom_dual(u, v) >= 0) continue;  // covered by an earlier raise
-        const int x = sb.is_bare(u) ? u : (sb.is_bare(v) ? v : u);
-        sb.make_bare(x);  // dissolves the blossoms around x (their bases become free)
-        const ll rc = sb.dual[u] + sb.dual[v] - 2 * wt(u, v) + sb.common_blossom_dual(u, v);
-        if (rc >= 0) continue;
-        sb.dual[x] -= rc;
-        marked.push_back(x);
-      }
-    }
-    if (warm) {
-      for (size_t i = 0; i < viol.size(); ++i) sb.add_edge(viol[i].u, viol[i].v, wt(viol[i].u, viol[i].v));
-      sb.build_adjacency();
-      for (size_t i = 0; i < marked.size(); ++i) sb.unmatch(marked[i]);
-    } else {
-      // too many doublings: start over on the enlarged graph
-      wshift = 0;
-      for (int k = 0; k < sb.n_edges(); ++k) sb.ew[k] = wt(sb.eu[k], sb.ev[k]);
-      for (size_t i = 0; i < viol.size(); ++i) sb.add_edge(viol[i].u, viol[i].v, wt(viol[i].u, viol[i].v));
-      sb.build_adjacency();
-      if (!cold_start()) return -100;
-    }
+    // restart on the enlarged candidate graph (the greedy start leaves fewer free vertices than
+    // repairing the previous duals would: dropping the blossoms unmatches all their vertices)
+    for (size_t i = 0; i < viol.size(); ++i) sb.add_edge(viol[i].u, viol[i].v, wt(viol[i].u, viol[i].v));
+    sb.build_adjacency();
+    if (!cold_start()) return -100;
   }
   if (!done) return -100;
   int nq = 0;
@@ -664,9 +596,9 @@ void fpb_mwpm_configure(int mode, int knn) {
   if (knn > 0) g_knn.store(knn);
 }
 
-// out[0..7] = sparse solves, retries with a denser candidate graph, pricing rounds, priced-in edges since load / last reset.
+// out[0..3] = sparse solves, retries with a denser candidate graph, pricing rounds, priced-in edges since load / last reset.
 void fpb_mwpm_stats(long long* out, int reset) {
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < 4; ++i) {
     out[i] = g_stats[i].load();
     if (reset) g_stats[i].store(0);
   }

@@ -1,0 +1,486 @@
+// Sparse primal-dual blossom matcher with pricing, for large matching graphs.
+//
+// The matching graphs of this path are complete graphs on the K odd cubes (reference:
+// decoders/mwpm/matching.py:125-173), but their weights are lattice path lengths: the optimal
+// matching almost only uses edges between near neighbours.  So the optimum is computed on a
+// sparse candidate graph (the k nearest partners of every cube) and then PROVED optimal for the
+// complete graph by pricing: the dual solution of the sparse problem is checked against every
+// one of the K(K-1)/2 edges, edges with negative reduced cost are added, and the solver is
+// warm-started from the repaired duals until no edge is violated.  By LP duality (Edmonds'
+// perfect-matching polytope: vertex duals free, blossom duals >= 0) the final matching is a
+// minimum-weight perfect matching of the complete graph - the same optimum the dense solver in
+// mwpm.cpp finds, only the choice among ties may differ.
+//
+// The solver is the classical primal-dual formulation with adjacency lists (labels S/T on
+// top-level blossoms, least-slack edge tracking per blossom, dual adjustment by the minimum of
+// the free-vertex / S-S / T-blossom slacks, blossom expansion during and at the end of a stage),
+// one augmentation per stage with every free vertex as a root, on weights -2*len so that vertex
+// duals stay integral and S-S slacks stay even.
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <vector>
+
+namespace fpb_sparse {
+
+typedef long long ll;
+
+class SparseBlossom {
+ public:
+  int n = 0;
+  std::vector<int> eu, ev;
+  std::vector<ll> ew;
+  std::vector<ll> dual;   // [0, n): vertices (2 x LP dual); [n, 2n): blossoms
+  std::vector<int> mate;  // remote endpoint of the matched edge, -1 = free
+  long long n_stages = 0, n_deltas = 0;
+
+  void reset(int n_) {
+    n = n_;
+    eu.clear(); ev.clear(); ew.clear();
+  }
+  int n_edges() const { return (int)eu.size(); }
+  void add_edge(int u, int v, ll w) {
+    eu.push_back(u); ev.push_back(v); ew.push_back(w);
+  }
+  int endpoint(int p) const { return (p & 1) ? ev[p >> 1] : eu[p >> 1]; }
+  ll slack(int k) const { return dual[eu[k]] + dual[ev[k]] - 2 * ew[k]; }
+  int mate_vertex(int v) const { return mate[v] < 0 ? -1 : endpoint(mate[v]); }
+
+  void build_adjacency() {
+    const int ne = n_edges();
+    adj_off.assign(n + 1, 0);
+    for (int k = 0; k < ne; ++k) {
+      ++adj_off[eu[k] + 1];
+      ++adj_off[ev[k] + 1];
+    }
+    for (int v = 0; v < n; ++v) adj_off[v + 1] += adj_off[v];
+    adj.resize(2 * (size_t)ne);
+    std::vector<int> fill(adj_off.begin(), adj_off.end() - 1);
+    for (int k = 0; k < ne; ++k) {
+      adj[fill[eu[k]]++] = 2 * k + 1;
+      adj[fill[ev[k]]++] = 2 * k;
+    }
+  }
+
+  template <class F>
+  void for_neighbours(int u, F&& f) const {
+    for (int i = adj_off[u]; i < adj_off[u + 1]; ++i) f(endpoint(adj[i]), ew[adj[i] >> 1]);
+  }
+
+  // Start state: vertex duals y (feasible on every edge) and a matching on tight edges given as
+  // vertex mates (-1 = free).  Free vertices must share the parity of their duals.
+  void start(const std::vector<ll>& y, const std::vector<int>& vmate) {
+    const int m = 2 * n;
+    dual.assign(m, 0);
+    for (int v = 0; v < n; ++v) dual[v] = y[v];
+    mate.assign(n, -1);
+    for (int v = 0; v < n; ++v) {
+      if (vmate[v] < 0 || mate[v] >= 0) continue;
+      for (int i = adj_off[v]; i < adj_off[v + 1]; ++i)
+        if (endpoint(adj[i]) == vmate[v]) {
+          mate[v] = adj[i];
+          mate[vmate[v]] = adj[i] ^ 1;
+          break;
+        }
+    }
+    label.assign(m, 0);
+    labelend.assign(m, -1);
+    inblossom.resize(n);
+    for (int v = 0; v < n; ++v) inblossom[v] = v;
+    blossomparent.assign(m, -1);
+    blossombase.assign(m, -1);
+    for (int v = 0; v < n; ++v) blossombase[v] = v;
+    bestedge.assign(m, -1);
+    childs.assign(m, std::vector<int>());
+    endps.assign(m, std::vector<int>());
+    bestedges.assign(m, std::vector<int>());
+    has_bestedges.assign(m, 0);
+    unused.clear();
+    for (int b = m - 1; b >= n; --b) unused.push_back(b);
+    bestedgeto.assign(m, -1);
+  }
+
+  // Stages: label every free vertex S, grow the alternating forest along tight edges, adjust the
+  // duals when it is stuck, until one augmenting path is found; repeat until none exists.
+  // Returns true when the matching is perfect.
+  bool solve() {
+    const int m = 2 * n, ne = n_edges();
+    allow.assign(ne, 0);
+    for (;;) {
+      std::fill(label.begin(), label.end(), 0);
+      std::fill(bestedge.begin(), bestedge.end(), -1);
+      for (int b = n; b < m; ++b) {
+        has_bestedges[b] = 0;
+        bestedges[b].clear();
+      }
+      std::fill(allow.begin(), allow.end(), 0);
+      queue.clear();
+      for (int v = 0; v < n; ++v)
+        if (mate[v] < 0 && label[inblossom[v]] == 0) assign_label(v, 1, -1);
+      if (queue.empty()) break;
+      ++n_stages;
+      bool augmented = false;
+      for (;;) {
+        while (!queue.empty() && !augmented) {
+          const int v = queue.back();
+          queue.pop_back();
+          for (int ai = adj_off[v]; ai < adj_off[v + 1]; ++ai) {
+            const int p = adj[ai], k = p >> 1, w = endpoint(p);
+            if (inblossom[v] == inblossom[w]) continue;
+            ll kslack = 0;
+            if (!allow[k]) {
+              kslack = slack(k);
+              if (kslack <= 0) allow[k] = 1;
+            }
+            if (allow[k]) {
+              if (label[inblossom[w]] == 0) {
+                assign_label(w, 2, p ^ 1);
+              } else if (label[inblossom[w]] == 1) {
+                const int base = scan_blossom(v, w);
+                if (base >= 0) {
+                  add_blossom(base, k);
+                } else {
+                  augment_matching(k);
+                  augmented = true;
+                  break;
+                }
+              } else if (label[w] == 0) {
+                label[w] = 2;
+                labelend[w] = p ^ 1;
+              }
+            } else if (label[inblossom[w]] == 1) {
+              const int b = inblossom[v];
+              if (bestedge[b] < 0 || kslack < slack(bestedge[b])) bestedge[b] = k;
+            } else if (label[w] == 0) {
+              if (bestedge[w] < 0 || kslack < slack(bestedge[w])) bestedge[w] = k;
+            }
+          }
+        }
+        if (augmented) break;
+        int deltatype = -1, deltaedge = -1, deltablossom = -1;
+        ll delta = 0;
+        for (int v = 0; v < n; ++v)
+          if (label[inblossom[v]] == 0 && bestedge[v] >= 0) {
+            const ll d = slack(bestedge[v]);
+            if (deltatype < 0 || d < delta) {
+              delta = d; deltatype = 2; deltaedge = bestedge[v];
+            }
+          }
+        for (int b = 0; b < m; ++b)
+          if (blossomparent[b] < 0 && label[b] == 1 && bestedge[b] >= 0) {
+            const ll d = slack(bestedge[b]) / 2;
+            if (deltatype < 0 || d < delta) {
+              delta = d; deltatype = 3; deltaedge = bestedge[b];
+            }
+          }
+        for (int b = n; b < m; ++b)
+          if (blossombase[b] >= 0 && blossomparent[b] < 0 && label[b] == 2 && (deltatype < 0 || dual[b] < delta)) {
+            delta = dual[b]; deltatype = 4; deltablossom = b;
+          }
+        if (deltatype < 0) break;  // the candidate graph has no perfect matching
+        ++n_deltas;
+        for (int v = 0; v < n; ++v) {
+          const int l = label[inblossom[v]];
+          if (l == 1) dual[v] -= delta;
+          else if (l == 2) dual[v] += delta;
+        }
+        for (int b = n; b < m; ++b)
+          if (blossombase[b] >= 0 && blossomparent[b] < 0) {
+            if (label[b] == 1) dual[b] += delta;
+            else if (label[b] == 2) dual[b] -= delta;
+          }
+        if (deltatype == 2) {
+          allow[deltaedge] = 1;
+          int i = eu[deltaedge];
+          if (label[inblossom[i]] == 0) i = ev[deltaedge];
+          queue.push_back(i);
+        } else if (deltatype == 3) {
+          allow[deltaedge] = 1;
+          queue.push_back(eu[deltaedge]);
+        } else {
+          expand_blossom(deltablossom, false);
+        }
+      }
+      if (!augmented) break;
+      for (int b = n; b < m; ++b)
+        if (blossomparent[b] < 0 && blossombase[b] >= 0 && label[b] == 1 && dual[b] == 0) expand_blossom(b, true);
+    }
+    for (int v = 0; v < n; ++v)
+      if (mate[v] < 0) return false;
+    return true;
+  }
+
+  // 2 x (sum of the duals of the blossoms that contain both u and v)
+  ll common_blossom_dual(int u, int v) {
+    if (inblossom[u] != inblossom[v] || inblossom[u] < n) return 0;
+    ++stamp_t;
+    if (stamp.size() != (size_t)2 * n) stamp.assign(2 * (size_t)n, 0);
+    for (int b = blossomparent[u]; b >= 0; b = blossomparent[b]) stamp[b] = stamp_t;
+    ll s = 0;
+    bool in = false;
+    for (int b = blossomparent[v]; b >= 0; b = blossomparent[b]) {
+      in = in || stamp[b] == stamp_t;
+      if (in) s += dual[b];
+    }
+    return 2 * s;
+  }
+
+ private:
+  std::vector<int> adj_off, adj;
+  std::vector<int> label, labelend, inblossom, blossomparent, blossombase, bestedge;
+  std::vector<std::vector<int>> childs, endps, bestedges;
+  std::vector<char> has_bestedges, allow;
+  std::vector<int> unused, queue, bestedgeto, touched, stamp;
+  int stamp_t = 0;
+
+  static int wrap(int j, int len) { return j < 0 ? j + len : j; }
+
+  template <class F>
+  void leaves(int b, F&& f) {
+    if (b < n) {
+      f(b);
+    } else {
+      for (size_t i = 0; i < childs[b].size(); ++i) leaves(childs[b][i], f);
+    }
+  }
+
+  void assign_label(int w, int t, int p) {
+    const int b = inblossom[w];
+    label[w] = label[b] = t;
+    labelend[w] = labelend[b] = p;
+    bestedge[w] = bestedge[b] = -1;
+    if (t == 1) {
+      leaves(b, [&](int v) { queue.push_back(v); });
+    } else {
+      const int base = blossombase[b];
+      assign_label(endpoint(mate[base]), 1, mate[base] ^ 1);
+    }
+  }
+
+  // Trace back from v and w towards the roots; returns the base vertex of the first common
+  // blossom (a new blossom closes) or -1 (the two trees differ: an augmenting path).
+  int scan_blossom(int v, int w) {
+    path.clear();
+    int base = -1;
+    while (v != -1 || w != -1) {
+      int b = inblossom[v];
+      if (label[b] & 4) {
+        base = blossombase[b];
+        break;
+      }
+      path.push_back(b);
+      label[b] = 5;
+      if (labelend[b] == -1) {
+        v = -1;
+      } else {
+        v = endpoint(labelend[b]);
+        b = inblossom[v];
+        v = endpoint(labelend[b]);
+      }
+      if (w != -1) std::swap(v, w);
+    }
+    for (size_t i = 0; i < path.size(); ++i) label[path[i]] = 1;
+    return base;
+  }
+  std::vector<int> path;
+
+  void add_blossom(int base, int k) {
+    int v = eu[k], w = ev[k];
+    const int bb = inblossom[base];
+    int bv = inblossom[v], bw = inblossom[w];
+    const int b = unused.back();
+    unused.pop_back();
+    blossombase[b] = base;
+    blossomparent[b] = -1;
+    blossomparent[bb] = b;
+    std::vector<int>& pth = childs[b];
+    std::vector<int>& eps = endps[b];
+    pth.clear();
+    eps.clear();
+    while (bv != bb) {
+      blossomparent[bv] = b;
+      pth.push_back(bv);
+      eps.push_back(labelend[bv]);
+      v = endpoint(labelend[bv]);
+      bv = inblossom[v];
+    }
+    pth.push_back(bb);
+    std::reverse(pth.begin(), pth.end());
+    std::reverse(eps.begin(), eps.end());
+    eps.push_back(2 * k);
+    while (bw != bb) {
+      blossomparent[bw] = b;
+      pth.push_back(bw);
+      eps.push_back(labelend[bw] ^ 1);
+      w = endpoint(labelend[bw]);
+      bw = inblossom[w];
+    }
+    label[b] = 1;
+    labelend[b] = labelend[bb];
+    dual[b] = 0;
+    leaves(b, [&](int x) {
+      if (label[inblossom[x]] == 2) queue.push_back(x);
+      inblossom[x] = b;
+    });
+    // least-slack edges from the new blossom to every neighbouring S-blossom
+    touched.clear();
+    auto consider = [&](int e) {
+      int j = ev[e];
+      if (inblossom[j] == b) j = eu[e];
+      const int bj = inblossom[j];
+      if (bj != b && label[bj] == 1) {
+        if (bestedgeto[bj] < 0) {
+          bestedgeto[bj] = e;
+          touched.push_back(bj);
+        } else if (slack(e) < slack(bestedgeto[bj])) {
+          bestedgeto[bj] = e;
+        }
+      }
+    };
+    for (size_t i = 0; i < pth.size(); ++i) {
+      const int c = pth[i];
+      if (c >= n && has_bestedges[c]) {
+        for (size_t q = 0; q < bestedges[c].size(); ++q) consider(bestedges[c][q]);
+      } else {
+        leaves(c, [&](int x) {
+          for (int ai = adj_off[x]; ai < adj_off[x + 1]; ++ai) consider(adj[ai] >> 1);
+        });
+      }
+      if (c >= n) {
+        has_bestedges[c] = 0;
+        bestedges[c].clear();
+      }
+      bestedge[c] = -1;
+    }
+    bestedges[b].clear();
+    bestedge[b] = -1;
+    for (size_t i = 0; i < touched.size(); ++i) {
+      const int e = bestedgeto[touched[i]];
+      bestedgeto[touched[i]] = -1;
+      bestedges[b].push_back(e);
+      if (bestedge[b] < 0 || slack(e) < slack(bestedge[b])) bestedge[b] = e;
+    }
+    has_bestedges[b] = 1;
+  }
+
+  void expand_blossom(int b, bool endstage) {
+    for (size_t i = 0; i < childs[b].size(); ++i) {
+      const int s = childs[b][i];
+      blossomparent[s] = -1;
+      if (s < n) {
+        inblossom[s] = s;
+      } else if (endstage && dual[s] == 0) {
+        expand_blossom(s, endstage);
+      } else {
+        leaves(s, [&](int x) { inblossom[x] = s; });
+      }
+    }
+    if (!endstage && label[b] == 2) {
+      // the blossom was a T-node of a tree: relabel the even-length half of its cycle that
+      // leads from the entry child to the base, and re-examine the rest
+      const int len = (int)childs[b].size();
+      const int entrychild = inblossom[endpoint(labelend[b] ^ 1)];
+      int j = (int)(std::find(childs[b].begin(), childs[b].end(), entrychild) - childs[b].begin());
+      int jstep, endptrick;
+      if (j & 1) {
+        j -= len; jstep = 1; endptrick = 0;
+      } else {
+        jstep = -1; endptrick = 1;
+      }
+      int p = labelend[b];
+      while (j != 0) {
+        label[endpoint(p ^ 1)] = 0;
+        label[endpoint(endps[b][wrap(j - endptrick, len)] ^ endptrick ^ 1)] = 0;
+        assign_label(endpoint(p ^ 1), 2, p);
+        allow[endps[b][wrap(j - endptrick, len)] >> 1] = 1;
+        j += jstep;
+        p = endps[b][wrap(j - endptrick, len)] ^ endptrick;
+        allow[p >> 1] = 1;
+        j += jstep;
+      }
+      int bv = childs[b][wrap(j, len)];
+      label[endpoint(p ^ 1)] = label[bv] = 2;
+      labelend[endpoint(p ^ 1)] = labelend[bv] = p;
+      bestedge[bv] = -1;
+      j += jstep;
+      while (childs[b][wrap(j, len)] != entrychild) {
+        bv = childs[b][wrap(j, len)];
+        if (label[bv] == 1) {
+          j += jstep;
+          continue;
+        }
+        int found = -1;
+        leaves(bv, [&](int x) {
+          if (found < 0 && label[x] != 0) found = x;
+        });
+        if (found >= 0) {
+          label[found] = 0;
+          label[endpoint(mate[blossombase[bv]])] = 0;
+          assign_label(found, 2, labelend[found]);
+        }
+        j += jstep;
+      }
+    }
+    label[b] = -1;
+    labelend[b] = -1;
+    childs[b].clear();
+    endps[b].clear();
+    blossombase[b] = -1;
+    has_bestedges[b] = 0;
+    bestedges[b].clear();
+    bestedge[b] = -1;
+    unused.push_back(b);
+  }
+
+  // Swap matched / unmatched edges over the alternating path through blossom b between
+  // vertex v and the base, making v the new base.
+  void augment_blossom(int b, int v) {
+    int t = v;
+    while (blossomparent[t] != b) t = blossomparent[t];
+    if (t >= n) augment_blossom(t, v);
+    const int len = (int)childs[b].size();
+    const int i = (int)(std::find(childs[b].begin(), childs[b].end(), t) - childs[b].begin());
+    int j = i, jstep, endptrick;
+    if (i & 1) {
+      j -= len; jstep = 1; endptrick = 0;
+    } else {
+      jstep = -1; endptrick = 1;
+    }
+    while (j != 0) {
+      j += jstep;
+      t = childs[b][wrap(j, len)];
+      const int p = endps[b][wrap(j - endptrick, len)] ^ endptrick;
+      if (t >= n) augment_blossom(t, endpoint(p));
+      j += jstep;
+      t = childs[b][wrap(j, len)];
+      if (t >= n) augment_blossom(t, endpoint(p ^ 1));
+      mate[endpoint(p)] = p ^ 1;
+      mate[endpoint(p ^ 1)] = p;
+    }
+    std::rotate(childs[b].begin(), childs[b].begin() + i, childs[b].end());
+    std::rotate(endps[b].begin(), endps[b].begin() + i, endps[b].end());
+    blossombase[b] = blossombase[childs[b][0]];
+  }
+
+  void augment_matching(int k) {
+    for (int side = 0; side < 2; ++side) {
+      int s = side ? ev[k] : eu[k];
+      int p = side ? 2 * k : 2 * k + 1;
+      for (;;) {
+        const int bs = inblossom[s];
+        if (bs >= n) augment_blossom(bs, s);
+        mate[s] = p;
+        if (labelend[bs] == -1) break;
+        const int t = endpoint(labelend[bs]);
+        const int bt = inblossom[t];
+        s = endpoint(labelend[bt]);
+        const int j = endpoint(labelend[bt] ^ 1);
+        if (bt >= n) augment_blossom(bt, j);
+        mate[j] = labelend[bt];
+        p = labelend[bt] ^ 1;
+      }
+    }
+  }
+};
+
+}  // namespace fpb_sparse

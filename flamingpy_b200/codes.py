@@ -268,15 +268,18 @@ class SurfaceCode:
         raise NotImplementedError
 
     # ------------------------------------------------------------------ engine cache
-    def engine(self, delta, p_swap, weight_opts=None, device=0, mode="compat"):
-        """The ``TrialEngine`` for these noise / weight options (created once)."""
+    def engine(self, delta, p_swap, weight_opts=None, device=0, mode="compat", lane=0):
+        """The ``TrialEngine`` for these noise / weight options (created once).  ``lane`` > 0
+        gives further engines with the same options (own stream and buffers) for pipelining."""
         from .engine import TrialEngine
 
         wo = dict(weight_opts or {})
-        key = (float(delta), float(p_swap or 0.0), tuple(sorted(wo.items())), device, mode)
+        key = (float(delta), float(p_swap or 0.0), tuple(sorted(wo.items())), device, mode, lane)
         eng = self._engines.get(key)
         if eng is None:
             eng = TrialEngine(self.lattice, delta, p_swap, wo, mode=mode, device=device)
+            if lane and self.engine(delta, p_swap, weight_opts, device, mode).uses_table:
+                eng.build_table()
             self._engines[key] = eng
         return eng
 

@@ -347,6 +347,48 @@ class TrialEngine:
         _lib.check(self._lib.fpb_fetch(self._h, C.byref(out), 0))
         return s
 
+    def fetch_decode(self, bufs: Optional[dict] = None) -> "TrialBatch":
+        """What the host decoder needs of the last run - bits, odd counts, pair and boundary
+        lengths - copied into reusable pinned buffers (``bufs``, grown on demand and owned by
+        the caller; the returned arrays are views into them, valid until the next call)."""
+        import torch
+
+        bufs = {} if bufs is None else bufs
+        s = self.sizes()
+        T = int(s.n_trials)
+
+        def room(key, n, dtype):
+            a = bufs.get(key)
+            if a is None or a.size < n:
+                cap = max(int(n * 1.3) + 1024, 1)
+                t = torch.empty(cap, dtype=dtype, pin_memory=torch.cuda.is_available())
+                a = bufs[key] = t.numpy().view(np.uint32) if key == "bits" else t.numpy()
+                bufs["_keep_" + key] = t
+            return a
+
+        room("bits", T * self.bit_words, torch.int32)
+        for i, ec in enumerate(self.ec):
+            room(f"odd_count{i}", T, torch.int32)
+            room(f"pair_len{i}", int(s.total_pairs[i]), torch.float64)
+            if self.lat.complexes[ec].has_boundary:
+                room(f"bnd_len{i}", int(s.total_odd[i]), torch.float64)
+        self.fetch_into({k: v for k, v in bufs.items() if not k.startswith("_keep_")})
+        batch = TrialBatch(T, _lib.STAGE_GRAPH)
+        batch.bits = unpack_bits(bufs["bits"][: T * self.bit_words].reshape(T, self.bit_words), self.Qtot)
+        batch.complexes = {}
+        for i, ec in enumerate(self.ec):
+            cb = ComplexBatch()
+            cb.odd_count = bufs[f"odd_count{i}"][:T]
+            k64 = cb.odd_count.astype(np.int64)
+            cb.odd_off = np.concatenate([[0], np.cumsum(k64)])
+            cb.pair_off = np.concatenate([[0], np.cumsum(k64 * (k64 - 1) // 2)])
+            cb.pair_len = bufs[f"pair_len{i}"][: int(s.total_pairs[i])]
+            cb.bnd_len = (bufs[f"bnd_len{i}"][: int(s.total_odd[i])] if self.lat.complexes[ec].has_boundary
+                          else np.empty(0, np.float64))
+            batch.complexes[ec] = cb
+        batch.timings = self.timings()
+        return batch
+
     def paths_toggle(self, trial, cx, src, dst) -> np.ndarray:
         """XOR-toggle the qubits on the shortest paths of the given (trial,
         complex, odd-index src, odd-index dst | -1) queries of the last run.

@@ -10,7 +10,7 @@ from typing import Optional
 
 import numpy as np
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libfpb_mwpm.so")
+LIB_PATH = os.environ.get("FPB_MWPM_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libfpb_mwpm.so")
 _lib = None
 
 _i32p = C.POINTER(C.c_int32)
@@ -49,9 +49,11 @@ def configure(mode: str = "auto", knn: int = 0) -> None:
 
 
 def stats(reset: bool = False) -> dict:
-    out = np.zeros(4, np.int64)
+    out = np.zeros(8, np.int64)
     load().fpb_mwpm_stats(_p(out, _i64p), int(reset))
-    return dict(zip(("sparse_solves", "retries", "pricing_rounds", "priced_edges"), out.tolist()))
+    d = dict(zip(("sparse_solves", "retries", "pricing_rounds", "priced_edges"), out[:4].tolist()))
+    d.update(zip(("scan_ms", "build_ms", "stages_ms", "pricing_ms"), (out[4:] / 1e6).round(1).tolist()))  # summed over threads
+    return d
 
 
 def _p(a, typ):

@@ -95,20 +95,18 @@ def ec_monte_carlo(trials, code_instance, noise_instance, decoder, decoder_args,
     engines = [eng]
     starts = list(range(lo, hi, batch))
     if len(starts) > 1:
-        from .engine import TrialEngine
-
-        eng2 = TrialEngine(code.lattice, noise_instance.delta, noise_instance.p_swap, weight_opts, mode=mode,
-                           device=device)
-        if eng.uses_table:
-            eng2.build_table()
-        engines.append(eng2)
+        engines.append(code.engine(noise_instance.delta, noise_instance.p_swap, weight_opts, device=device,
+                                   mode=mode, lane=1))
     import threading
 
     slots = {}
+    # pinned host buffers, one set per engine, reused by every batch and every later call
+    lane_bufs = [e.__dict__.setdefault("_decode_bufs", {}) for e in engines]
 
     def produce(k):
-        first = starts[k]
-        slots[k] = engines[k % len(engines)].run_rng(seed, first, min(batch, hi - first), stage=_lib.STAGE_GRAPH)
+        first, lane = starts[k], k % len(engines)
+        engines[lane].run_rng(seed, first, min(batch, hi - first), stage=_lib.STAGE_GRAPH, fetch=False)
+        slots[k] = engines[lane].fetch_decode(lane_bufs[lane])
 
     worker = None
     if starts:
@@ -125,8 +123,6 @@ def ec_monte_carlo(trials, code_instance, noise_instance, decoder, decoder_args,
         if worker is not None:
             worker.join()
             worker = None
-    for extra in engines[1:]:
-        extra.close()
     counts = np.array([failures, done], np.int64)
     if dist is not None and size > 1:
         import torch
