@@ -390,48 +390,71 @@ int solve_one_sparse(int K, const double* pair_len, const double* bnd_len, int* 
   int shift = 32;
   while (shift > 0 && std::ldexp(wmax + 1.0, shift) * (double)(n + 2) > 1e17) --shift;
   const double scale = std::ldexp(1.0, shift);
-  // One pass over the packed triangle: integer lengths of the reduced complete graph (see the
-  // header comment of this file) and, per vertex, its knn nearest partners.  Length and partner
-  // are packed in one 64-bit key (len * (n + 2) < 1e17 by the choice of the scale); thr[u] is the
-  // current knn-th smallest key of u, so almost every pair costs two compares.
+  // One pass over the packed triangle selects, per vertex, its knn nearest partners in the reduced
+  // complete graph (see the header comment of this file).  Length and partner are packed in one
+  // 64-bit key (len * (n + 2) < 1e17 by the choice of the scale); thr[u] is the current knn-th
+  // smallest key of u and thrd[u] a double-precision bound on the lengths that can still beat it,
+  // so that almost every pair is rejected by two floating-point compares in a vectorisable loop.
   int vbits = 1;
   while ((1 << vbits) < n) ++vbits;
-  // scratch is kept per thread: fresh megabyte-sized vectors would be mmap'ed and page-faulted per graph
-  static thread_local std::vector<ll> len_tls;
-  len_tls.resize((size_t)npairs);
-  ll* const len = len_tls.data();  // (thread_local objects cost a TLS lookup per access)
   // per vertex a buffer of 2 * knn keys: offers are appended, a full buffer is cut back to its knn
-  // smallest keys (nth_element), which also tightens the threshold - O(1) amortised per offer
+  // smallest keys (nth_element), which also tightens the threshold - O(1) amortised per offer.
+  // Scratch is kept per thread (fresh megabyte-sized vectors would be mmap'ed and page-faulted per
+  // graph) and used through local pointers (thread_local objects cost a TLS lookup per access).
   const int cap2 = 2 * knn;
   static thread_local std::vector<unsigned long long> top_tls, thr_tls, keys_tls;
   static thread_local std::vector<int> cnt_tls;
+  static thread_local std::vector<double> thrd_tls, wrow_tls;
+  static thread_local std::vector<unsigned char> flag_tls;
   top_tls.resize((size_t)n * cap2);
   thr_tls.assign((size_t)n, ~0ull);
   cnt_tls.assign((size_t)n, 0);
+  thrd_tls.assign((size_t)n, HUGE_VAL);
+  wrow_tls.resize((size_t)K + 8);
+  flag_tls.resize((size_t)K + 8);
   unsigned long long* const top = top_tls.data();
   unsigned long long* const thr = thr_tls.data();
   int* const cnt = cnt_tls.data();
+  double* const thrd = thrd_tls.data();
+  double* const wrow = wrow_tls.data();
+  unsigned char* const flag = flag_tls.data();
   std::vector<unsigned long long>& keys = keys_tls;
+  const double inv_scale = 1.0 / scale;
   auto offer = [&](int u, unsigned long long key) {
     unsigned long long* t = top + (size_t)u * cap2;
     t[cnt[u]++] = key;
     if (cnt[u] == cap2) {
       std::nth_element(t, t + (knn - 1), t + cap2);
       thr[u] = t[knn - 1];
+      // key < thr[u] needs len <= len(thr[u]), i.e. w * scale < len(thr[u]) + 0.5
+      thrd[u] = ((double)(thr[u] >> vbits) + 1.0) * inv_scale;
       cnt[u] = knn;
     }
+  };
+  auto reduced = [&](int u, int v) -> double {  // u < v < K
+    const double w = pair_len[(size_t)((ll)u * K - (ll)u * (u + 1) / 2 + (v - u - 1))];
+    return bnd_len ? std::min(w, bnd_len[u] + bnd_len[v]) : w;
   };
   {
     long long pos = 0;
     for (int a = 0; a < K - 1; ++a) {
-      const double ba = bnd_len ? bnd_len[a] : 0.0;
-      for (int b = a + 1; b < K; ++b, ++pos) {
-        double w = pair_len[pos];
-        if (bnd_len) w = std::min(w, ba + bnd_len[b]);
-        const ll L = to_fixed(w * scale);
-        len[pos] = L;
-        const unsigned long long kb = ((unsigned long long)L << vbits) | (unsigned)b;
-        const unsigned long long ka = ((unsigned long long)L << vbits) | (unsigned)a;
+      const int nb = K - 1 - a;
+      const double* row = pair_len + pos;
+      pos += nb;
+      if (bnd_len) {
+        const double ba = bnd_len[a];
+        const double* bb = bnd_len + a + 1;
+        for (int j = 0; j < nb; ++j) wrow[j] = std::min(row[j], ba + bb[j]);
+        row = wrow;
+      }
+      const double ta = thrd[a];  // may go stale (too large) during the row: only costs exact checks
+      const double* tb = thrd + a + 1;
+      for (int j = 0; j < nb; ++j) flag[j] = (unsigned char)((row[j] < ta) | (row[j] < tb[j]));
+      for (int j = 0; j < nb; ++j) {
+        if (!flag[j]) continue;
+        const int b = a + 1 + j;
+        const unsigned long long L = (unsigned long long)to_fixed(row[j] * scale);
+        const unsigned long long kb = (L << vbits) | (unsigned)b, ka = (L << vbits) | (unsigned)a;
         if (kb < thr[a]) offer(a, kb);
         if (ka < thr[b]) offer(b, ka);
       }
@@ -451,7 +474,7 @@ int solve_one_sparse(int K, const double* pair_len, const double* bnd_len, int* 
   int wshift = 0;  // weights and duals are doubled at every warm restart (see below)
   auto wt = [&](int u, int v) -> ll {  // matcher weight (maximised) of edge u < v
     if (v >= K) return -((2 * dlen[u]) << wshift);
-    return -((2 * len[(size_t)((ll)u * K - (ll)u * (u + 1) / 2 + (v - u - 1))]) << wshift);
+    return -((2 * to_fixed(reduced(u, v) * scale)) << wshift);
   };
   const long long t_scan = now_ns();
   g_stats[4].fetch_add(t_scan - t_begin);
@@ -558,17 +581,47 @@ int solve_one_sparse(int K, const double* pair_len, const double* bnd_len, int* 
     if (!sb.solve()) return -100;
     const long long t_b = now_ns();
     g_stats[6].fetch_add(t_b - t_a);
-    // pricing: reduced cost of every edge of the complete graph under the sparse optimum's duals
+    // pricing: reduced cost of every edge of the complete graph under the sparse optimum's duals.
+    // A double-precision estimate with a safety margin clears almost every edge in a vectorisable
+    // loop; the few near or below zero are recomputed exactly in integers.
     viol.clear();
-    for (int u = 0; u < n - 1; ++u) {
-      const ll du = sb.dual[u];
-      for (int v = u + 1; v < n; ++v) {
-        ll s = du + sb.dual[v] - 2 * wt(u, v);
-        if (s < 0) {
-          s += sb.common_blossom_dual(u, v);
-          if (s < 0) viol.push_back(Viol{s, u, v});
-        }
+    {
+      static thread_local std::vector<double> duald_tls;
+      duald_tls.resize((size_t)n);
+      double* const duald = duald_tls.data();
+      double dmax = 0;
+      for (int v = 0; v < n; ++v) {
+        duald[v] = (double)sb.dual[v];
+        dmax = std::max(dmax, std::fabs(duald[v]));
       }
+      const double c4 = std::ldexp(4.0 * scale, wshift);  // reduced cost = y_u + y_v + 4 * 2^wshift * len
+      const double margin = std::ldexp(8.0, wshift) + 1e-13 * (2 * dmax + c4 * wmax) + 64.0;
+      auto exact = [&](int u, int v) {
+        ll sl = sb.dual[u] + sb.dual[v] - 2 * wt(u, v);
+        if (sl < 0) {
+          sl += sb.common_blossom_dual(u, v);
+          if (sl < 0) viol.push_back(Viol{sl, u, v});
+        }
+      };
+      long long pos = 0;
+      for (int u = 0; u < K - 1; ++u) {
+        const int nb = K - 1 - u;
+        const double* row = pair_len + pos;
+        pos += nb;
+        if (bnd_len) {
+          const double bu = bnd_len[u];
+          const double* bb = bnd_len + u + 1;
+          for (int j = 0; j < nb; ++j) wrow[j] = std::min(row[j], bu + bb[j]);
+          row = wrow;
+        }
+        const double du = duald[u] - margin;
+        const double* dv = duald + u + 1;
+        for (int j = 0; j < nb; ++j) flag[j] = (unsigned char)(du + dv[j] + c4 * row[j] < 0.0);
+        for (int j = 0; j < nb; ++j)
+          if (flag[j]) exact(u, u + 1 + j);
+      }
+      if (n > K)
+        for (int u = 0; u < K; ++u) exact(u, K);
     }
     g_stats[7].fetch_add(now_ns() - t_b);
     if (viol.empty()) {
