@@ -435,6 +435,27 @@ int solve_one_sparse(int K, const double* pair_len, const double* bnd_len, int* 
     const double w = pair_len[(size_t)((ll)u * K - (ll)u * (u + 1) / 2 + (v - u - 1))];
     return bnd_len ? std::min(w, bnd_len[u] + bnd_len[v]) : w;
   };
+  // Start every threshold at 1.3 x the median knn-th reduced length of a few sampled vertices:
+  // a vertex whose true knn-th length is larger ends the scan with fewer than knn offers and is
+  // redone exactly below; for all others the filter cannot drop one of their knn nearest.
+  auto gather_row = [&](int u, double* out) {  // reduced lengths from u to every v != u (v < K)
+    int c = 0;
+    for (int v = 0; v < u; ++v) out[c++] = reduced(v, u);
+    for (int v = u + 1; v < K; ++v) out[c++] = reduced(u, v);
+    return c;
+  };
+  if (K - 1 > 2 * knn) {
+    const int n_s = std::min(K, 16);
+    double d_s[16];
+    for (int i = 0; i < n_s; ++i) {
+      const int c = gather_row((int)((long long)i * K / n_s), wrow);
+      std::nth_element(wrow, wrow + (knn - 1), wrow + c);
+      d_s[i] = wrow[knn - 1];
+    }
+    std::nth_element(d_s, d_s + n_s / 2, d_s + n_s);
+    const double t0 = 1.3 * d_s[n_s / 2] + inv_scale;
+    for (int u = 0; u < K; ++u) thrd[u] = t0;
+  }
   {
     long long pos = 0;
     for (int a = 0; a < K - 1; ++a) {
@@ -458,6 +479,18 @@ int solve_one_sparse(int K, const double* pair_len, const double* bnd_len, int* 
         if (kb < thr[a]) offer(a, kb);
         if (ka < thr[b]) offer(b, ka);
       }
+    }
+  }
+  for (int u = 0; u < K; ++u) {
+    if (cnt[u] >= knn || cnt[u] >= K - 1) continue;
+    // fewer than knn partners under the starting threshold: select from the whole row
+    cnt[u] = 0;
+    thr[u] = ~0ull;
+    for (int v = 0; v < K; ++v) {
+      if (v == u) continue;
+      const unsigned long long L = (unsigned long long)to_fixed((v < u ? reduced(v, u) : reduced(u, v)) * scale);
+      const unsigned long long key = (L << vbits) | (unsigned)v;
+      if (key < thr[u]) offer(u, key);
     }
   }
   std::vector<ll> dlen;
