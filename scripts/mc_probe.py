@@ -7,13 +7,13 @@ from flamingpy_b200.noise import CVLayer
 from flamingpy_b200.simulations import ec_monte_carlo
 mode = sys.argv[1] if len(sys.argv) > 1 else "auto"
 mwpm_native.configure(mode)
-for d, b, delta, n in [(9, "open", 0.08, 4096), (13, "open", 0.09, 2048), (13, "periodic", 0.09, 2048),
-                       (17, "periodic", 0.09, 256)]:
+for d, b, delta, n in [(9, "open", 0.08, 16384), (13, "open", 0.09, 8192), (13, "periodic", 0.09, 8192),
+                       (17, "periodic", 0.09, 1024)]:
     if mode == "dense" and d > 13:
         continue
     code = SurfaceCode(d, "primal", b); noise = CVLayer(code, delta=delta, p_swap=0)
     wo = {"weight_opts": {"method": "blueprint", "delta": delta}}
-    ec_monte_carlo(64, code, noise, "MWPM", wo, seed=1, mode="fresh", batch=64)
+    ec_monte_carlo(512, code, noise, "MWPM", wo, seed=1, mode="fresh", batch=256)  # warm-up: engines, pinned buffers
     mwpm_native.stats(reset=True)
     t0 = time.perf_counter()
     e, st = ec_monte_carlo(n, code, noise, "MWPM", wo, seed=2, mode="fresh", batch=256, return_stats=True)
