@@ -139,18 +139,17 @@ class SparseBlossom {
 
   // Stages: label every free vertex S, grow the alternating forest along tight edges, adjust the
   // duals when it is stuck, until one augmenting path is found; repeat until none exists.
+  // Labels, least-slack records and allowed-edge flags are tracked in lists, so that a dual
+  // adjustment and the clean-up of a stage cost the size of the forest, not of the graph.
   // Returns true when the matching is perfect.
   bool solve() {
-    const int m = 2 * n, ne = n_edges();
-    allow.assign(ne, 0);
+    allow.assign(n_edges(), 0);
+    upd_stamp.assign(2 * (size_t)n, 0);
+    upd_t = 0;
+    lab_touched.clear();
+    be_touched.clear();
+    allow_touched.clear();
     for (;;) {
-      std::fill(label.begin(), label.end(), 0);
-      std::fill(bestedge.begin(), bestedge.end(), -1);
-      for (int b = n; b < m; ++b) {
-        has_bestedges[b] = 0;
-        bestedges[b].clear();
-      }
-      std::fill(allow.begin(), allow.end(), 0);
       queue.clear();
       for (int v = 0; v < n; ++v)
         if (mate[v] < 0 && label[inblossom[v]] == 0) assign_label(v, 1, -1);
@@ -167,7 +166,7 @@ class SparseBlossom {
             ll kslack = 0;
             if (!allow[k]) {
               kslack = slack(k);
-              if (kslack <= 0) allow[k] = 1;
+              if (kslack <= 0) set_allow(k);
             }
             if (allow[k]) {
               if (label[inblossom[w]] == 0) {
@@ -182,65 +181,75 @@ class SparseBlossom {
                   break;
                 }
               } else if (label[w] == 0) {
-                label[w] = 2;
+                set_label(w, 2);
                 labelend[w] = p ^ 1;
               }
             } else if (label[inblossom[w]] == 1) {
               const int b = inblossom[v];
-              if (bestedge[b] < 0 || kslack < slack(bestedge[b])) bestedge[b] = k;
+              if (bestedge[b] < 0 || kslack < slack(bestedge[b])) set_bestedge(b, k);
             } else if (label[w] == 0) {
-              if (bestedge[w] < 0 || kslack < slack(bestedge[w])) bestedge[w] = k;
+              if (bestedge[w] < 0 || kslack < slack(bestedge[w])) set_bestedge(w, k);
             }
           }
         }
         if (augmented) break;
         int deltatype = -1, deltaedge = -1, deltablossom = -1;
         ll delta = 0;
-        for (int v = 0; v < n; ++v)
-          if (label[inblossom[v]] == 0 && bestedge[v] >= 0) {
-            const ll d = slack(bestedge[v]);
+        for (size_t q = 0; q < be_touched.size(); ++q) {
+          const int i = be_touched[q], k = bestedge[i];
+          if (k < 0) continue;
+          if (i < n && label[inblossom[i]] == 0) {
+            const ll d = slack(k);
             if (deltatype < 0 || d < delta) {
-              delta = d; deltatype = 2; deltaedge = bestedge[v];
+              delta = d; deltatype = 2; deltaedge = k;
+            }
+          } else if (blossomparent[i] < 0 && label[i] == 1) {
+            const ll d = slack(k) / 2;
+            if (deltatype < 0 || d < delta) {
+              delta = d; deltatype = 3; deltaedge = k;
             }
           }
-        for (int b = 0; b < m; ++b)
-          if (blossomparent[b] < 0 && label[b] == 1 && bestedge[b] >= 0) {
-            const ll d = slack(bestedge[b]) / 2;
-            if (deltatype < 0 || d < delta) {
-              delta = d; deltatype = 3; deltaedge = bestedge[b];
-            }
-          }
-        for (int b = n; b < m; ++b)
-          if (blossombase[b] >= 0 && blossomparent[b] < 0 && label[b] == 2 && (deltatype < 0 || dual[b] < delta)) {
+        }
+        for (size_t q = 0; q < lab_touched.size(); ++q) {
+          const int b = lab_touched[q];
+          if (b >= n && blossombase[b] >= 0 && blossomparent[b] < 0 && label[b] == 2 && (deltatype < 0 || dual[b] < delta)) {
             delta = dual[b]; deltatype = 4; deltablossom = b;
           }
+        }
         if (deltatype < 0) break;  // the candidate graph has no perfect matching
         ++n_deltas;
-        for (int v = 0; v < n; ++v) {
-          const int l = label[inblossom[v]];
-          if (l == 1) dual[v] -= delta;
-          else if (l == 2) dual[v] += delta;
+        ++upd_t;
+        for (size_t q = 0; q < lab_touched.size(); ++q) {
+          const int i = lab_touched[q];
+          if (blossomparent[i] >= 0 || (i >= n && blossombase[i] < 0)) continue;  // not top-level
+          const int l = label[i];
+          if ((l != 1 && l != 2) || upd_stamp[i] == upd_t) continue;
+          upd_stamp[i] = upd_t;
+          const ll dv = l == 1 ? -delta : delta;
+          leaves(i, [&](int x) { dual[x] += dv; });
+          if (i >= n) dual[i] -= dv;
         }
-        for (int b = n; b < m; ++b)
-          if (blossombase[b] >= 0 && blossomparent[b] < 0) {
-            if (label[b] == 1) dual[b] += delta;
-            else if (label[b] == 2) dual[b] -= delta;
-          }
         if (deltatype == 2) {
-          allow[deltaedge] = 1;
+          set_allow(deltaedge);
           int i = eu[deltaedge];
           if (label[inblossom[i]] == 0) i = ev[deltaedge];
           queue.push_back(i);
         } else if (deltatype == 3) {
-          allow[deltaedge] = 1;
+          set_allow(deltaedge);
           queue.push_back(eu[deltaedge]);
         } else {
           expand_blossom(deltablossom, false);
         }
       }
+      if (augmented) {
+        const size_t n_lab = lab_touched.size();  // expansions at the end of a stage add no labels
+        for (size_t q = 0; q < n_lab; ++q) {
+          const int b = lab_touched[q];
+          if (b >= n && blossomparent[b] < 0 && blossombase[b] >= 0 && label[b] == 1 && dual[b] == 0) expand_blossom(b, true);
+        }
+      }
+      end_stage();
       if (!augmented) break;
-      for (int b = n; b < m; ++b)
-        if (blossomparent[b] < 0 && blossombase[b] >= 0 && label[b] == 1 && dual[b] == 0) expand_blossom(b, true);
     }
     for (int v = 0; v < n; ++v)
       if (mate[v] < 0) return false;
@@ -269,7 +278,41 @@ class SparseBlossom {
   std::vector<int> unused, queue, bestedgeto, touched, stamp;
   int stamp_t = 0;
 
+  std::vector<int> lab_touched, be_touched, allow_touched, upd_stamp;
+  int upd_t = 0;
+
   static int wrap(int j, int len) { return j < 0 ? j + len : j; }
+
+  // per-stage state is undone through these lists instead of clearing whole arrays
+  void set_label(int i, int t) {
+    lab_touched.push_back(i);
+    label[i] = t;
+  }
+  void set_bestedge(int i, int k) {
+    if (bestedge[i] < 0) be_touched.push_back(i);
+    bestedge[i] = k;
+  }
+  void set_allow(int k) {
+    if (!allow[k]) {
+      allow[k] = 1;
+      allow_touched.push_back(k);
+    }
+  }
+  void end_stage() {
+    for (size_t q = 0; q < lab_touched.size(); ++q) {
+      const int i = lab_touched[q];
+      label[i] = 0;
+      if (i >= n) {
+        has_bestedges[i] = 0;
+        bestedges[i].clear();
+      }
+    }
+    for (size_t q = 0; q < be_touched.size(); ++q) bestedge[be_touched[q]] = -1;
+    for (size_t q = 0; q < allow_touched.size(); ++q) allow[allow_touched[q]] = 0;
+    lab_touched.clear();
+    be_touched.clear();
+    allow_touched.clear();
+  }
 
   template <class F>
   void leaves(int b, F&& f) {
@@ -282,7 +325,8 @@ class SparseBlossom {
 
   void assign_label(int w, int t, int p) {
     const int b = inblossom[w];
-    label[w] = label[b] = t;
+    set_label(w, t);
+    set_label(b, t);
     labelend[w] = labelend[b] = p;
     bestedge[w] = bestedge[b] = -1;
     if (t == 1) {
@@ -351,7 +395,7 @@ class SparseBlossom {
       w = endpoint(labelend[bw]);
       bw = inblossom[w];
     }
-    label[b] = 1;
+    set_label(b, 1);
     labelend[b] = labelend[bb];
     dual[b] = 0;
     leaves(b, [&](int x) {
@@ -394,7 +438,7 @@ class SparseBlossom {
       const int e = bestedgeto[touched[i]];
       bestedgeto[touched[i]] = -1;
       bestedges[b].push_back(e);
-      if (bestedge[b] < 0 || slack(e) < slack(bestedge[b])) bestedge[b] = e;
+      if (bestedge[b] < 0 || slack(e) < slack(bestedge[b])) set_bestedge(b, e);
     }
     has_bestedges[b] = 1;
   }
@@ -428,14 +472,15 @@ class SparseBlossom {
         label[endpoint(p ^ 1)] = 0;
         label[endpoint(endps[b][wrap(j - endptrick, len)] ^ endptrick ^ 1)] = 0;
         assign_label(endpoint(p ^ 1), 2, p);
-        allow[endps[b][wrap(j - endptrick, len)] >> 1] = 1;
+        set_allow(endps[b][wrap(j - endptrick, len)] >> 1);
         j += jstep;
         p = endps[b][wrap(j - endptrick, len)] ^ endptrick;
-        allow[p >> 1] = 1;
+        set_allow(p >> 1);
         j += jstep;
       }
       int bv = childs[b][wrap(j, len)];
-      label[endpoint(p ^ 1)] = label[bv] = 2;
+      set_label(endpoint(p ^ 1), 2);
+      set_label(bv, 2);
       labelend[endpoint(p ^ 1)] = labelend[bv] = p;
       bestedge[bv] = -1;
       j += jstep;
@@ -457,7 +502,7 @@ class SparseBlossom {
         j += jstep;
       }
     }
-    label[b] = -1;
+    set_label(b, -1);
     labelend[b] = -1;
     childs[b].clear();
     endps[b].clear();
