@@ -31,6 +31,17 @@ def test_library_exports_every_declared_symbol():
     assert _lib.load().fpb_abi_version() == _lib.FPB_ABI_VERSION
 
 
+def test_matcher_library_exports_every_declared_symbol():
+    from flamingpy_b200 import mwpm_native
+
+    header = open(os.path.join(ROOT, "include", "fpb_mwpm.h")).read()
+    declared = set(re.findall(r"\b(fpb_mwpm[a-z_]*)\s*\(", header))
+    assert {"fpb_mwpm", "fpb_mwpm_batch", "fpb_mwpm_configure", "fpb_mwpm_stats", "fpb_mwpm_max_threads"} == declared
+    lib = ctypes.CDLL(mwpm_native.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
 def test_create_fails_loudly_without_gpu():
     """The product path has no CPU fallback: without a device fpb_create errors out."""
     import torch
