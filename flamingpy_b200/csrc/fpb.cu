@@ -116,6 +116,7 @@ struct fpb_handle {
   size_t paths_smem = 0;
   bool paths_wg = false;  // weights / tables in global memory (large lattices)
   bool paths_team = false;  // two warps per search (k_paths_team)
+  int team_w = 0;           // > 0: W warps per search (k_paths_teamw)
   DevBuf<double> wscratch;
   // static-weight fast path (fpb_build_table)
   bool use_table = false;
@@ -174,6 +175,22 @@ paths_fn pick_team_kernel(int S, bool wg) {
   if (S <= 3072) return k_paths_team<3, 2, 512, 1, false>;
   if (S <= 4096) return k_paths_team<4, 2, 512, 1, false>;
   return k_paths_team<8, 2, 512, 1, false>;
+}
+// W-warp teams (global-memory weights) for lattices of which at most four searches fit an SM
+paths_fn pick_teamw_kernel(int S, int W) {
+  if (W == 4) {
+    if (S <= 4096) return k_paths_teamw<2, 4, 512>;
+    if (S <= 6144) return k_paths_teamw<3, 4, 512>;
+    if (S <= 8192) return k_paths_teamw<4, 4, 512>;
+  } else if (W == 8) {
+    if (S <= 8192) return k_paths_teamw<2, 8, 512>;
+    if (S <= 12288) return k_paths_teamw<3, 8, 512>;
+    if (S <= 16384) return k_paths_teamw<4, 8, 512>;
+  } else if (W == 16) {
+    if (S <= 8192) return k_paths_teamw<1, 16, 512>;
+    if (S <= 16384) return k_paths_teamw<2, 16, 512>;
+  }
+  return nullptr;
 }
 toggle_fn pick_toggle_kernel(int S, bool wg) {
   if (wg) {
@@ -272,6 +289,42 @@ int configure_paths(fpb_handle* h) {
   if (rc) return rc;
   if (h->warps == 0)
     return fail(FPB_ERR_UNSUPPORTED, "lattice too large for the shared-memory shortest-path kernel");
+  // Very large lattices: one to five searches fit an SM, so each search gets 16 / 8 / 4 warps
+  // (FPB_TEAM_W=0 disables, FPB_TEAM_W=4|8|16 forces a width).
+  h->team_w = 0;
+  {
+    const char* ev = getenv("FPB_TEAM_W");
+    const int force_w = ev ? atoi(ev) : -1;
+    if (force_w != 0 && h->S_max > 1024) {
+      int max_optin = 0;
+      CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+      const size_t warp_b = paths_warp_bytes(h->S_max, false);
+      const int fit0 = (int)(((size_t)max_optin - 2048) / warp_b);
+      const int W = force_w > 0 ? force_w : (fit0 <= 1 ? 16 : fit0 == 2 ? 8 : fit0 <= 5 ? 4 : 0);
+      paths_fn tf = W ? pick_teamw_kernel(h->S_max, W) : nullptr;
+      if (tf) {
+        cudaFuncAttributes fattr;
+        CK(cudaFuncGetAttributes(&fattr, tf));
+        int teams = (int)(((size_t)max_optin - fattr.sharedSizeBytes) / warp_b);
+        if (teams > 16 / W) teams = 16 / W;
+        if (teams >= 1) {
+          const size_t need = (size_t)teams * warp_b;
+          CK(cudaFuncSetAttribute(tf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+          int resident = 0;
+          CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, tf, teams * W * 32, need));
+          if (resident >= 1) {
+            h->team_w = W;
+            h->paths_team = true;
+            h->paths_wg = true;
+            h->warps = teams;
+            h->ctas_per_sm = 1;
+            h->paths_smem = need;
+            h->tasks_per_item = teams * 4;
+          }
+        }
+      }
+    }
+  }
   return FPB_OK;
 }
 
@@ -320,7 +373,9 @@ int launch_paths(fpb_handle* h, long long T, int* launches) {
     pp.wscratch = h->wscratch.p;
   }
   int mw_unused = 0;
-  if (h->paths_team)
+  if (h->team_w)
+    pick_teamw_kernel(h->S_max, h->team_w)<<<(unsigned)grid, h->warps * h->team_w * 32, h->paths_smem, st>>>(pp);
+  else if (h->paths_team)
     pick_team_kernel(h->S_max, h->paths_wg)<<<(unsigned)grid, h->warps * 64, h->paths_smem, st>>>(pp);
   else
     pick_paths_kernel(h->S_max, h->paths_wg, &mw_unused)<<<(unsigned)grid, h->warps * 32, h->paths_smem, st>>>(pp);

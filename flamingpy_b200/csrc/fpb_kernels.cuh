@@ -421,8 +421,10 @@ __host__ __device__ inline size_t align16(size_t b) { return (b + 15) / 16 * 16;
 __host__ __device__ inline size_t paths_cta_bytes(int S_max, int slots_max) {
   return align16((size_t)slots_max * 8) + align16((size_t)S_max * 2) + align16((size_t)S_max * 2);
 }
+// staging-list entries per search: the wide-team kernels of very large lattices stage more cubes per scan
+__host__ __device__ inline int paths_stage_entries(int S_max) { return S_max > 6144 ? 4 * STAGE_CAP : STAGE_CAP; }
 __host__ __device__ inline size_t paths_warp_bytes(int S_max, bool pred) {
-  return align16((size_t)S_max * 8) + align16((size_t)S_max) + align16((size_t)STAGE_CAP * 2) +
+  return align16((size_t)S_max * 8) + align16((size_t)S_max) + align16((size_t)paths_stage_entries(S_max) * 2) +
          (pred ? align16((size_t)S_max) : 0);
 }
 
@@ -432,7 +434,7 @@ __device__ __forceinline__ WarpMem carve_warp(unsigned char* wp, int S_max, bool
   WarpMem wm;
   wm.dist = (double*)wp; wp += align16((size_t)S_max * 8);
   wm.bkt = (uint8_t*)wp; wp += align16((size_t)S_max);
-  wm.stage = (uint16_t*)wp; wp += align16((size_t)STAGE_CAP * 2);
+  wm.stage = (uint16_t*)wp; wp += align16((size_t)paths_stage_entries(S_max) * 2);
   wm.pred = pred ? (uint8_t*)wp : nullptr;
   return wm;
 }
@@ -1131,6 +1133,306 @@ __global__ void __launch_bounds__(MAXT, MINB) k_paths_team(const __grid_constant
           }
         }
         team_bar(bar_id);  // outputs read before the state is cleared again
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// W-warp teams (W = 4, 8, 16) for lattices so large that only one to four searches fit an SM's
+// shared memory: the same protocol as the two-warp team, with the scan chunks, the staging list
+// and every relaxation round split W ways (32 * W cubes per round), so that the few searches in
+// flight still occupy the SM.  Weights and face tables stay in global memory (WG layout).
+// ------------------------------------------------------------------------------------------
+template <int W>
+struct TeamXW {
+  int cnt[W];
+  int lp[W];
+  int redo[2][W];
+};
+template <int W>
+__device__ __forceinline__ void teamw_bar(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(32 * W) : "memory"); }
+
+template <int NCHW, int W>
+__device__ __forceinline__ void teamw_search(const CtaMem& cm, const WarpMem& wm, const DirTab& dt, int S, double step,
+                                             uint32_t present, int lane, int widx, int bar_id, int seg,
+                                             volatile TeamXW<W>* tx) {
+  const double inv = 1.0 / step;
+  const int n16 = (S + 15) >> 4;
+  const uint32_t dist_a = smem_addr(wm.dist), bkt_a = smem_addr(wm.bkt);
+  const uint32_t stage0_a = smem_addr(wm.stage);
+  const uint32_t stage_a = stage0_a + 2u * (uint32_t)(widx * seg);  // this warp's segment of the staging list
+  int cur = 0;
+  while (present) {
+    {
+      const uint32_t rot = __funnelshift_r(present, present, cur & (NRING - 1));
+      cur += __ffs(rot) - 1;
+    }
+    const int r = cur & (NRING - 1);
+    const int far = cur + NRING - 1;
+    while ((present >> r) & 1u) {
+      present &= ~(1u << r);
+      uint32_t masks[NCHW];
+      int cnt = 0;
+      const uint32_t r4 = (uint32_t)r * 0x01010101u;
+#pragma unroll
+      for (int j = 0; j < NCHW; ++j) {
+        const int ch = (W * j + widx) * 32 + lane;
+        uint32_t m = 0;
+        if (ch < n16) {
+          uint4 q = lds_v4(bkt_a + (ch << 4));
+          const uint32_t z0 = eq_bytes(q.x, r4), z1 = eq_bytes(q.y, r4), z2 = eq_bytes(q.z, r4), z3 = eq_bytes(q.w, r4);
+          m = movemask4(z0) | (movemask4(z1) << 4) | (movemask4(z2) << 8) | (movemask4(z3) << 12);
+          if (m) {
+            q.x |= (z0 >> 7) * 0xffu;
+            q.y |= (z1 >> 7) * 0xffu;
+            q.z |= (z2 >> 7) * 0xffu;
+            q.w |= (z3 >> 7) * 0xffu;
+            sts_v4(bkt_a + (ch << 4), q);
+          }
+        }
+        masks[j] = m;
+        cnt += __popc(m);
+      }
+      int incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+      }
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      int pos = incl - cnt;
+      uint32_t lp = 0;
+#pragma unroll
+      for (int j = 0; j < NCHW; ++j) {
+        uint32_t m = masks[j];
+        const int base = ((W * j + widx) * 32 + lane) << 4;
+        while (m) {
+          const int cube = base + __ffs(m) - 1;
+          m &= m - 1;
+          if (pos < seg) sts_u16(stage_a + 2 * pos, cube);
+          else sts_u8(bkt_a + cube, r);  // segment full: leave it filed for the next scan
+          ++pos;
+        }
+      }
+      if (total > seg) lp |= 1u << r;
+      if (lane == 0) tx->cnt[widx] = total < seg ? total : seg;
+      teamw_bar<W>(bar_id);  // (a) every segment of the staging list is complete
+      // lane w < W holds segment w's count and the number of cubes staged before it
+      const int my_cnt = lane < W ? tx->cnt[lane] : 0;
+      int my_end = my_cnt;
+#pragma unroll
+      for (int o = 1; o < W; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, my_end, o);
+        if (lane >= o) my_end += y;
+      }
+      const int nst = __shfl_sync(0xffffffffu, my_end, W - 1);
+      int parity = 0;
+      for (int cb = 0; cb < nst; cb += 32 * W) {
+        uint32_t ua[6], wa[6];
+        double nd[6], old[6];
+        bool imp[6];
+        const int idx = cb + widx * 32 + lane;
+        const bool valid = idx < nst;
+        // segment of idx: the first w with idx < end[w]
+        int sgm = 0, sbeg = 0;
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+          const int e = __shfl_sync(0xffffffffu, my_end, w);
+          if (idx >= e) {
+            sgm = w + 1;
+            sbeg = e;
+          }
+        }
+        const uint32_t sa = stage0_a + 2u * (uint32_t)((valid ? sgm : 0) * seg + (valid ? idx - sbeg : 0));
+        const int v = valid ? (int)lds_u16(sa) : 0;
+        const uint32_t va = dist_a + 8u * v;
+        const double dv = lds_f64(va);
+        const int bt = bucket_of(dv, inv);
+        if (valid && bt > cur) {  // a parked cube: move it towards its real bucket
+          const int s2 = (bt < far ? bt : far) & (NRING - 1);
+          sts_u8(bkt_a + v, s2);
+          lp |= 1u << s2;
+        }
+        const bool act = valid && bt <= cur;
+        uint32_t ci = 0xaaau;  // inactive lanes: every face "none"
+        if (act) ci = (uint32_t)cm.ninfo[v] | ((uint32_t)cm.sbase[v] << 16);
+        const uint32_t sb = ci >> 16;
+#pragma unroll
+        for (int d = 0; d < 6; ++d) {
+          const uint32_t kind = (ci >> (2 * d)) & 3u;
+          const bool a = kind < 2u;
+          ua[d] = va + 8 * (kind ? dt.dwrap[d] : dt.dreg[d]);
+          wa[d] = sb + (kind ? dt.swrap[d] : dt.sreg[d]);
+          old[d] = a ? lds_f64(ua[d]) : 0.0;
+          imp[d] = a && old[d] > dv;
+        }
+#pragma unroll
+        for (int d = 0; d < 6; ++d) {
+          nd[d] = imp[d] ? dv + cm.wslot[wa[d]] : 0.0;
+          imp[d] = imp[d] && nd[d] < old[d];
+        }
+#pragma unroll
+        for (int d = 0; d < 6; ++d)
+          if (imp[d]) sts_f64(ua[d], nd[d]);
+        teamw_bar<W>(bar_id);  // (b) all stores of the round precede the verify loads
+        double fin[6];
+        bool chk[6];
+#pragma unroll
+        for (int d = 0; d < 6; ++d) chk[d] = imp[d];
+        bool redo;
+        do {
+          bool mine = false;
+#pragma unroll
+          for (int d = 0; d < 6; ++d) fin[d] = chk[d] ? lds_f64(ua[d]) : 0.0;
+#pragma unroll
+          for (int d = 0; d < 6; ++d) {
+            const bool lost = chk[d] && fin[d] > nd[d];
+            if (lost) sts_f64(ua[d], nd[d]);
+            mine |= lost;
+            chk[d] = chk[d] && !(fin[d] < nd[d]);
+          }
+          mine = __any_sync(0xffffffffu, mine);
+          if (lane == 0) tx->redo[parity][widx] = mine;
+          teamw_bar<W>(bar_id);  // (c) re-stores visible; exchange the redo flags
+          redo = __any_sync(0xffffffffu, lane < W && tx->redo[parity][lane < W ? lane : 0] != 0);
+          parity ^= 1;
+        } while (redo);
+#pragma unroll
+        for (int d = 0; d < 6; ++d) {
+          const bool own = chk[d] && fin[d] == nd[d];
+          const int bi = bucket_of(nd[d], inv);
+          const int s2 = (bi < far ? bi : far) & (NRING - 1);
+          const uint32_t ui = (ua[d] - dist_a) >> 3;
+          if (own) sts_u8(bkt_a + ui, s2);
+          lp |= own ? (1u << s2) : 0u;
+        }
+      }
+      lp = __reduce_or_sync(0xffffffffu, lp);
+      if (lane == 0) tx->lp[widx] = (int)lp;
+      teamw_bar<W>(bar_id);  // (d) filed slots exchanged, bucket bytes visible to the next scan
+      present |= __reduce_or_sync(0xffffffffu, lane < W ? (uint32_t)tx->lp[lane] : 0u);
+    }
+  }
+}
+
+template <int NCHW, int W, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) k_paths_teamw(const __grid_constant__ PathsParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ int item_s;
+  __shared__ double red_s[32];
+  __shared__ TeamXW<W> tx_s[16 / W];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int team = wid / W, widx = wid % W, n_teams = blockDim.x / (32 * W);
+  const int bar_id = 1 + team;
+  const int nthreads = blockDim.x;
+  volatile TeamXW<W>* tx = &tx_s[team];
+  const int seg = paths_stage_entries(p.S_max) / W;
+
+  double* wslot = p.wscratch + (size_t)blockIdx.x * p.slots_max;
+  CtaMem cm;
+  cm.wslot = wslot; cm.ninfo = nullptr; cm.sbase = nullptr;
+  const WarpMem wm = carve_warp(smem + (size_t)team * paths_warp_bytes(p.S_max, false), p.S_max, false);
+  DirTab dt = load_dirtab(p.cx[0]);
+
+  int staged_tc = -1, staged_c = -1;
+  double step = 1.0;
+
+  while (true) {
+    if (threadIdx.x == 0) item_s = atomicAdd(p.counter, 1);
+    __syncthreads();
+    const int item = item_s;
+    __syncthreads();
+    if (item >= p.total_items) break;
+    int lo = 0, hi = p.T * p.n_complex;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (p.item_off[mid] <= item) lo = mid; else hi = mid;
+    }
+    const int tc = lo;
+    const int t = tc / p.n_complex, ci = tc - t * p.n_complex;
+    const ComplexDev& c = p.cx[ci];
+    const int chunk = item - p.item_off[tc];
+    const int S = c.S;
+
+    if (staged_c != ci) {
+      cm.ninfo = c.ninfo;
+      cm.sbase = c.sbase;
+      dt = load_dirtab(c);
+      staged_c = ci;
+    }
+    if (staged_tc != tc) {
+      const double* w = p.weights + (long long)t * p.Qtot + c.qoff;
+      double sum = 0.0;
+      for (int s = threadIdx.x; s < c.n_slots; s += nthreads) {
+        const int q = c.slot_qubit[s];
+        const double ws = (q >= 0) ? w[q] : FPB_INF;
+        wslot[s] = ws;
+        sum += (q >= 0) ? ws : 0.0;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      if (lane == 0) red_s[wid] = sum;
+      __syncthreads();
+      sum = 0.0;
+      for (int w2 = 0; w2 < (nthreads >> 5); ++w2) sum += red_s[w2];
+      step = bucket_step(sum / (double)c.Q, p.step_factor);
+      staged_tc = tc;
+      __threadfence_block();
+    }
+    __syncthreads();
+
+    const double inv = 1.0 / step;
+    const int K = c.odd_count[t];
+    const int* odd = c.odd_fixed + (long long)t * S;
+    const int has_bnd = c.n_low > 0;
+    const int n_tasks = n_tasks_of(K, has_bnd);
+    const long long poff = c.pair_off[t];
+    const long long ooff = c.odd_off[t];
+    const int task_end = min(n_tasks, (chunk + 1) * p.tasks_per_item);
+    for (int task = chunk * p.tasks_per_item + team; task < task_end; task += n_teams) {
+      const bool pair_task = task < K - 1;
+      const int n_phase = pair_task ? 1 : 2;
+      for (int ph = 0; ph < n_phase; ++ph) {
+        for (int v = widx * 32 + lane; v < S; v += 32 * W) wm.dist[v] = FPB_INF;
+        {
+          const int n16 = (S + 15) >> 4;
+          uint4* b4 = reinterpret_cast<uint4*>(wm.bkt);
+          for (int i = widx * 32 + lane; i < n16; i += 32 * W) b4[i] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+        }
+        teamw_bar<W>(bar_id);
+        uint32_t present = 0;
+        if (widx == 0) {
+          if (pair_task) {
+            if (lane == 0) present = seed_cube(wm, odd[task], 0.0, inv, 0);
+            present = __shfl_sync(0xffffffffu, present, 0);
+          } else if (ph == 0) {
+            present = warp_seed_connector(cm, wm, c.n_low, c.low_cube, c.low_slot, inv, lane);
+          } else {
+            present = warp_seed_connector(cm, wm, c.n_high, c.high_cube, c.high_slot, inv, lane);
+          }
+          if (lane == 0) tx->lp[0] = (int)present;
+        }
+        teamw_bar<W>(bar_id);
+        present = (uint32_t)tx->lp[0];
+        teamw_bar<W>(bar_id);  // lp[0] is rewritten inside the search
+        teamw_search<NCHW, W>(cm, wm, dt, S, step, present, lane, widx, bar_id, seg, tx);
+        if (pair_task) {
+          const long long row = poff + (long long)task * K - (long long)task * (task + 1) / 2;
+          for (int b = task + 1 + widx * 32 + lane; b < K; b += 32 * W) c.pair_len[row + (b - task - 1)] = wm.dist[odd[b]];
+        } else if (ph == 0) {
+          for (int b = widx * 32 + lane; b < K; b += 32 * W) c.bnd_len[ooff + b] = wm.dist[odd[b]];
+        } else {
+          for (int b = widx * 32 + lane; b < K; b += 32 * W) {
+            const double lo_d = c.bnd_len[ooff + b];
+            const double hi_d = wm.dist[odd[b]];
+            const bool high = hi_d < lo_d;
+            c.bnd_len[ooff + b] = high ? hi_d : lo_d;
+            c.bnd_side[ooff + b] = high ? 1 : 0;
+          }
+        }
+        teamw_bar<W>(bar_id);  // outputs read before the state is cleared again
       }
     }
     __syncthreads();

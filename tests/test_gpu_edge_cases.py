@@ -117,10 +117,16 @@ def test_config4_lattice_d21_all_p():
     assert set(np.nonzero(par)[0].tolist()) == {int(odd[0]), int(odd[3]), int(odd[5])}
 
 
-@pytest.mark.parametrize("d,ec,b", [(17, "both", "periodic"), (25, "primal", "open")])
-def test_sweep_lattices_d17_d25(d, ec, b):
-    """Threshold-sweep lattices of configs[4]: d=17 still fits shared memory (2 searches per SM),
-    d=25 uses the global-weights variant; one noisy trial each against the C oracle."""
+@pytest.mark.parametrize("d,ec,b,team_w", [(17, "both", "periodic", None), (19, "primal", "periodic", None),
+                                           (19, "primal", "open", "0"), (21, "primal", "periodic", None),
+                                           (21, "primal", "periodic", "16"), (25, "primal", "open", None)])
+def test_sweep_lattices_d17_to_d25(d, ec, b, team_w, monkeypatch):
+    """Threshold-sweep lattices of configs[4] and the sizes between them.  One to five searches
+    fit an SM there, so the graph stage runs the W-warp team kernel (4 warps per search at
+    d=17/19, 8 at d=21, 16 at d=25; FPB_TEAM_W overrides: "0" = the one-warp global-weights
+    variant); one noisy trial each against the C oracle."""
+    if team_w is not None:
+        monkeypatch.setenv("FPB_TEAM_W", team_w)
     lat = build_lattice(d, ec, b)
     delta = 0.1
     wo = {"method": "blueprint", "delta": delta}
