@@ -198,3 +198,36 @@ def test_threshold_sweep_driver(tmp_path):
     assert err[(3, 0.12)] > err[(3, 0.06)] and err[(5, 0.12)] > err[(5, 0.06)]
     g = sweep([9], [0.09], 256, graph_only=True, batch=256)
     assert g[0][9] == -1 and float(g[0][-1]) > 1000
+
+
+def test_fetch_decode_matches_full_fetch_and_pipelined_driver_is_batch_invariant():
+    """`fetch_decode` (pinned, reusable buffers; what the Monte-Carlo driver reads) returns the
+    same bits / odd counts / lengths as the full `fetch`; and the pipelined two-engine driver gives
+    the same failure count whatever the batch size (Philox counters follow the global trial index)
+    with the sparse and the dense matcher alike."""
+    from flamingpy_b200 import mwpm_native
+
+    code = SurfaceCode(9, "primal", "open")
+    wo = {"method": "blueprint", "delta": 0.1}
+    eng = code.engine(0.1, 0, wo, mode="fresh")
+    full = eng.run_rng(5, 100, 37)
+    bufs = {}
+    for _ in range(2):  # second call reuses the pinned buffers
+        eng.run_rng(5, 100, 37, fetch=False)
+        dec = eng.fetch_decode(bufs)
+    assert np.array_equal(dec.bits, full.bits)
+    cf, cd = full.complexes["primal"], dec.complexes["primal"]
+    assert np.array_equal(cd.odd_count, cf.odd_count)
+    assert np.array_equal(cd.pair_len, cf.pair_len) and np.array_equal(cd.bnd_len, cf.bnd_len)
+    assert np.array_equal(cd.pair_off, cf.pair_off) and np.array_equal(cd.odd_off, cf.odd_off)
+
+    noise = CVLayer(code, delta=0.1, p_swap=0)
+    counts = []
+    try:
+        for mode, batch in (("auto", 64), ("auto", 300), ("dense", 128), ("sparse", 500)):
+            mwpm_native.configure(mode)
+            counts.append(ec_monte_carlo(500, code, noise, "MWPM", {"weight_opts": wo}, seed=11, mode="fresh",
+                                         batch=batch))
+    finally:
+        mwpm_native.configure("auto")
+    assert len(set(counts)) == 1 and 0 < counts[0] < 500, counts
