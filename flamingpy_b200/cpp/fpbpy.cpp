@@ -44,6 +44,16 @@ PYBIND11_MODULE(fpbpy, m) {
     py::gil_scoped_release release;
     check(fpb_run_rng(reinterpret_cast<fpb_handle*>(h), seed, first_trial, n_trials, stage));
   });
+  m.def("run_iid", [](std::uintptr_t h, uint64_t seed, int64_t first_trial, int64_t n_trials, double p_err, int stage) {
+    py::gil_scoped_release release;
+    check(fpb_run_iid(reinterpret_cast<fpb_handle*>(h), seed, first_trial, n_trials, p_err, stage));
+  });
+  m.def("run_bits",
+        [](std::uintptr_t h, py::array_t<uint32_t, py::array::c_style | py::array::forcecast> bits, int stage) {
+          if (bits.ndim() != 2) throw std::runtime_error("bits must be uint32[n_trials][bit_words]");
+          py::gil_scoped_release release;
+          check(fpb_run_bits(reinterpret_cast<fpb_handle*>(h), bits.shape(0), bits.data(), 0, stage));
+        });
   m.def("sizes", [](std::uintptr_t h) {
     fpb_sizes s;
     check(fpb_get_sizes(reinterpret_cast<fpb_handle*>(h), &s));

@@ -417,7 +417,12 @@ int post_syndrome(fpb_handle* h, long long T, int stage, int* launches) {
   return FPB_OK;
 }
 
-int run_pipeline(fpb_handle* h, long long T, int stage, bool gen, uint64_t seed, long long first_trial) {
+// source of a batch: injected draws + labels, Philox draws + labels, injected bits, Philox i.i.d. bits
+enum { SRC_INJECTED = 0, SRC_GEN = 1, SRC_BITS = 2, SRC_IID = 3 };
+
+int run_pipeline(fpb_handle* h, long long T, int stage, int source, uint64_t seed, long long first_trial,
+                 double p_err = 0.0) {
+  const bool gen = source == SRC_GEN;
   if (T <= 0) return fail(FPB_ERR_ARG, "n_trials must be positive");
   if (T > 0x7fffffffll / (h->ncx > 0 ? h->ncx : 1) / 2) return fail(FPB_ERR_ARG, "n_trials too large for one batch");
   if (stage < FPB_STAGE_NOISE || stage > FPB_STAGE_GRAPH) return fail(FPB_ERR_ARG, "bad stage");
@@ -452,8 +457,28 @@ int run_pipeline(fpb_handle* h, long long T, int stage, bool gen, uint64_t seed,
     k_gen<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(g, T);
     ++launches;
   }
+  if (source == SRC_IID) {
+    IidParams g;
+    g.Qtot = h->Qtot; g.bit_words = h->bit_words;
+    g.seed_lo = (uint32_t)seed; g.seed_hi = (uint32_t)(seed >> 32);
+    g.first_trial = first_trial;
+    g.p_err = p_err;
+    g.qubit_node = h->qubit_node;
+    g.bits = h->bits.p;
+    const long long total = T * (long long)h->bit_words;
+    const long long blocks = (total + 255) / 256, cap = (long long)h->sm_count * 32;
+    k_iid<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(g, T);
+    ++launches;
+  }
   CK(cudaEventRecord(h->ev[1], st));
-  {
+  if (source == SRC_BITS || source == SRC_IID) {
+    // bits-only trials: no homodyne outcomes; every syndrome qubit carries the uniform weight 1
+    const long long nw = T * (long long)h->Qtot;
+    const long long blocks = (nw + 255) / 256, cap = (long long)h->sm_count * 32;
+    k_fill<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(h->weights.p, nw, 1.0);
+    CK(cudaMemsetAsync(h->hom.p, 0, (size_t)nw * sizeof(double), st));
+    ++launches;
+  } else {
     NoiseParams p;
     p.N = h->N; p.Qtot = h->Qtot; p.bit_words = h->bit_words;
     p.adj_indptr = h->adj_indptr; p.adj_indices = h->adj_indices; p.adj_vals = h->adj_vals;
@@ -670,7 +695,7 @@ int fpb_run_injected(fpb_handle* h, int64_t n_trials, const double* x, const uin
   CK(cudaMemcpyAsync(h->x.p, x, (size_t)n_trials * 2 * h->N * sizeof(double), kind, h->stream));
   CK(cudaMemcpyAsync(h->state.p, state, (size_t)n_trials * h->N, kind, h->stream));
   h->have_rng = false;
-  return run_pipeline(h, n_trials, stage, false, 0, 0);
+  return run_pipeline(h, n_trials, stage, SRC_INJECTED, 0, 0);
 }
 
 int fpb_run_rng(fpb_handle* h, uint64_t seed, int64_t first_trial, int64_t n_trials, int stage) {
@@ -680,7 +705,37 @@ int fpb_run_rng(fpb_handle* h, uint64_t seed, int64_t first_trial, int64_t n_tri
   int rc = ensure_batch(h, n_trials);
   if (rc) return rc;
   h->have_rng = true;
-  return run_pipeline(h, n_trials, stage, true, seed, first_trial);
+  return run_pipeline(h, n_trials, stage, SRC_GEN, seed, first_trial);
+}
+
+static int check_bits_run(fpb_handle* h) {
+  if (h->weight_method != FPB_WEIGHT_UNIFORM)
+    return fail(FPB_ERR_ARG, "bits-only trials carry no homodyne outcomes: the handle must use uniform weights");
+  return FPB_OK;
+}
+
+int fpb_run_bits(fpb_handle* h, int64_t n_trials, const uint32_t* bits, int on_device, int stage) {
+  if (!h || !bits) return fail(FPB_ERR_ARG, "null argument");
+  int rc = check_bits_run(h);
+  if (rc) return rc;
+  CK(cudaSetDevice(h->device));
+  if ((rc = ensure_batch(h, n_trials))) return rc;
+  CK(cudaMemcpyAsync(h->bits.p, bits, (size_t)n_trials * h->bit_words * sizeof(uint32_t),
+                     on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+  h->have_rng = false;
+  return run_pipeline(h, n_trials, stage, SRC_BITS, 0, 0);
+}
+
+int fpb_run_iid(fpb_handle* h, uint64_t seed, int64_t first_trial, int64_t n_trials, double p_err, int stage) {
+  if (!h) return fail(FPB_ERR_ARG, "null handle");
+  if (first_trial < 0) return fail(FPB_ERR_ARG, "first_trial must be >= 0");
+  if (!(p_err >= 0.0 && p_err <= 1.0)) return fail(FPB_ERR_ARG, "Probability is not between 0 and 1.");
+  int rc = check_bits_run(h);
+  if (rc) return rc;
+  CK(cudaSetDevice(h->device));
+  if ((rc = ensure_batch(h, n_trials))) return rc;
+  h->have_rng = false;
+  return run_pipeline(h, n_trials, stage, SRC_IID, seed, first_trial, p_err);
 }
 
 int fpb_get_sizes(fpb_handle* h, fpb_sizes* out) {

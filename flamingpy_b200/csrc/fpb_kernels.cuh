@@ -78,6 +78,40 @@ struct GenParams {
 };
 
 // ------------------------------------------------------------------------------------------
+// k_iid: i.i.d. Z errors (flamingpy/noise/iid.py:37-50): bit_val = (uniform < p) per node, drawn
+// from the Philox stream of (trial, node, SLOT_IID) for the syndrome qubits, packed LSB-first;
+// k_fill: constant weights for the trials of a bits-only run (uniform weights, decoder.py:115-116)
+// ------------------------------------------------------------------------------------------
+struct IidParams {
+  int Qtot, bit_words;
+  uint32_t seed_lo, seed_hi;
+  long long first_trial;
+  double p_err;
+  const int* qubit_node;  // [Qtot]
+  uint32_t* bits;         // [T][bit_words]
+};
+__global__ void __launch_bounds__(256) k_iid(IidParams g, long long n_trials) {
+  const long long total = n_trials * g.bit_words;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long t = i / g.bit_words;
+    const int wd = (int)(i - t * g.bit_words);
+    const unsigned long long trial = (unsigned long long)(g.first_trial + t);
+    uint32_t word = 0;
+    const int q0 = wd * 32;
+    const int nq = min(32, g.Qtot - q0);
+    for (int b = 0; b < nq; ++b) {
+      const Philox4 r = philox4x32_10((uint32_t)trial, (uint32_t)(trial >> 32), (uint32_t)g.qubit_node[q0 + b], SLOT_IID,
+                                      g.seed_lo, g.seed_hi);
+      word |= (u01_53(r.x, r.y) < g.p_err ? 1u : 0u) << b;
+    }
+    g.bits[i] = word;
+  }
+}
+__global__ void __launch_bounds__(256) k_fill(double* dst, long long n, double value) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) dst[i] = value;
+}
+
+// ------------------------------------------------------------------------------------------
 // k_gen: labels and draws
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool label_is_p(const GenParams& g, long long trial, uint32_t node) {

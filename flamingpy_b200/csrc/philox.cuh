@@ -45,6 +45,7 @@ __host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t 
 // slot ids of the per-(trial, node) streams
 constexpr uint32_t SLOT_QUADRATURE = 0;  // 128 bits -> one Box-Muller pair (q, p)
 constexpr uint32_t SLOT_LABEL = 1;       // 32 bits  -> Bernoulli(p_swap)
+constexpr uint32_t SLOT_IID = 2;         // 53 bits  -> Bernoulli(p_err) of the i.i.d. noise model
 
 // uniform in (0, 1) from 53 random bits (never 0, never 1)
 __host__ __device__ __forceinline__ double u01_53(uint32_t hi, uint32_t lo) {

@@ -19,8 +19,24 @@ from .matching import GpuMatchingGraph, solve_matching
 
 def _require_trial(code):
     if code._trial is None:
-        raise RuntimeError("no noise realisation: call CVLayer.apply_noise(rng) first")
+        raise RuntimeError("no noise realisation: call the noise model's apply_noise(rng) first")
     return code._trial
+
+
+def _run_trial(code, wo, stage):
+    """Run the last noise realisation (one trial) through the device pipeline up to ``stage``.
+    CVLayer realisations are (x, state, delta, p_swap); bit-level ones (IidNoise) are
+    ("bits", bit values of all nodes) and need uniform weights."""
+    trial = _require_trial(code)
+    if isinstance(trial[0], str) and trial[0] == "bits":
+        if wo.get("method", "uniform") != "uniform":
+            raise ValueError("IidNoise has no homodyne outcomes: use weight_options {'method': 'uniform'}")
+        eng = code.engine(1.0, 0.0, wo)
+        qn = np.concatenate([code.lattice.complexes[e].qubits for e in code.ec])
+        return eng, eng.run_bits(trial[1][qn][None, :], stage=stage)
+    x, state, delta, p_swap = trial
+    eng = code.engine(delta, p_swap, wo)
+    return eng, eng.run_injected(x[None, :], state[None, :], stage=stage)
 
 
 def assign_weights(code, decoder="MWPM", **kwargs):
@@ -32,10 +48,8 @@ def assign_weights(code, decoder="MWPM", **kwargs):
     wo.update(kwargs)
     if wo.get("prob_precomputed"):
         raise NotImplementedError("prob_precomputed weights belong to CVMacroLayer (out of scope, SURVEY.md 8f)")
-    x, state, delta, p_swap = _require_trial(code)
     wo.pop("prob_precomputed", None)
-    eng = code.engine(delta, p_swap, wo)
-    batch = eng.run_injected(x[None, :], state[None, :], stage=_lib.STAGE_NOISE)
+    eng, batch = _run_trial(code, wo, _lib.STAGE_NOISE)
     g = code.graph
     g._ensure_arrays()
     off = 0
@@ -50,11 +64,9 @@ def assign_weights(code, decoder="MWPM", **kwargs):
 def build_match_graph(code, ec, matching_backend="networkx", weight_options=None):
     """``build_match_graph`` (``decoders/mwpm/algos.py:23-47``): the matching graph of the
     current noise realisation, built on the GPU."""
-    x, state, delta, p_swap = _require_trial(code)
     wo = {"method": "uniform", "integer": False, "multiplier": 1}
     wo.update(weight_options or {})
-    eng = code.engine(delta, p_swap, wo)
-    batch = eng.run_injected(x[None, :], state[None, :], stage=_lib.STAGE_GRAPH)
+    eng, batch = _run_trial(code, wo, _lib.STAGE_GRAPH)
     return GpuMatchingGraph.from_batch(code, ec, eng, batch, 0, backend=matching_backend)
 
 
@@ -111,18 +123,18 @@ def correct(code, decoder="MWPM", weight_options=None, sanity_check=False, decod
     opts.update(decoder_opts or {})
     if opts["backend"] == "rustworkx":
         opts["backend"] = "networkx"
-    x, state, delta, p_swap = _require_trial(code)
     wo = {"method": "uniform", "integer": False, "multiplier": 1}
     wo.update(weight_options)
-    eng = code.engine(delta, p_swap, wo)
-    batch = eng.run_injected(x[None, :], state[None, :], stage=_lib.STAGE_GRAPH)
+    eng, batch = _run_trial(code, wo, _lib.STAGE_GRAPH)
+    is_cv = not isinstance(code._trial[0], str)
     g = code.graph
     g._ensure_arrays()
     off = 0
     for e in code.ec:
         ct = code.lattice.complexes[e]
         g.weight[ct.qubits] = batch.weights[0, off : off + ct.Q]
-        g.hom_val_p[ct.qubits] = batch.hom[0, off : off + ct.Q]
+        if is_cv:
+            g.hom_val_p[ct.qubits] = batch.hom[0, off : off + ct.Q]
         g.bit_val[ct.qubits] = batch.bits[0, off : off + ct.Q]
         off += ct.Q
     flips = decode_batch(code, eng, batch, backend=opts["backend"])

@@ -190,6 +190,31 @@ class TrialEngine:
         return self.fetch(stage, want_draws=want_draws) if fetch else TrialBatch(
             n_trials, stage, timings=self.timings())
 
+    def run_bits(self, bits, stage: int = _lib.STAGE_GRAPH, fetch: bool = True) -> TrialBatch:
+        """Trials given directly as bit values of the syndrome qubits - the i.i.d. Pauli-noise model
+        (``flamingpy/noise/iid.py``) or any other bit-level sampler.  ``bits``: uint8[T, Qtot] (0/1)
+        or already packed uint32[T, bit_words] (LSB first).  Needs uniform weights."""
+        bits = np.asarray(bits)
+        if bits.dtype != np.uint32:
+            if bits.ndim != 2 or bits.shape[1] != self.Qtot:
+                raise ValueError(f"bits must have shape (n_trials, {self.Qtot})")
+            pad = np.zeros((bits.shape[0], self.bit_words * 32), np.uint8)
+            pad[:, : self.Qtot] = bits != 0
+            bits = np.packbits(pad, axis=1, bitorder="little").view(np.uint32)
+        if bits.ndim != 2 or bits.shape[1] != self.bit_words:
+            raise ValueError(f"packed bits must have shape (n_trials, {self.bit_words})")
+        bits = np.ascontiguousarray(bits)
+        n_trials = bits.shape[0]
+        _lib.check(self._lib.fpb_run_bits(self._h, n_trials, bits.ctypes.data, 0, stage))
+        return self.fetch(stage) if fetch else TrialBatch(n_trials, stage, timings=self.timings())
+
+    def run_iid(self, seed: int, first_trial: int, n_trials: int, p_err: float, stage: int = _lib.STAGE_GRAPH,
+                fetch: bool = True) -> TrialBatch:
+        """Trials ``[first_trial, first_trial + n_trials)`` of i.i.d. Z errors with probability
+        ``p_err`` per qubit, drawn on the device (Philox stream ``seed``).  Needs uniform weights."""
+        _lib.check(self._lib.fpb_run_iid(self._h, seed & (2**64 - 1), first_trial, n_trials, float(p_err), stage))
+        return self.fetch(stage) if fetch else TrialBatch(n_trials, stage, timings=self.timings())
+
     def sizes(self) -> _lib.Sizes:
         s = _lib.Sizes()
         _lib.check(self._lib.fpb_get_sizes(self._h, C.byref(s)))

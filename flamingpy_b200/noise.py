@@ -187,3 +187,38 @@ class CVLayer:
     @property
     def gkp_inds(self):
         return self.states.get("GKP")
+
+
+class IidNoise:
+    """Reference-compatible i.i.d. Z-error model (``flamingpy/noise/iid.py:19-50``):
+    ``IidNoise(code, error_probability).apply_noise(rng)`` sets ``bit_val = int(rng.random() < p)``
+    on every node of the lattice.  Decoding such a realisation needs uniform weights
+    (``weight_options={"method": "uniform"}``, the reference's default).
+
+    One documented difference: the draws are consumed in node-index order (sorted coordinates), as
+    one ``rng.random(N)`` call; the reference walks ``egraph.nodes`` in the insertion order its
+    ``RHG_graph`` happens to produce from a Python ``set`` (``surface_code.py:186-226``), which
+    is an artefact of tuple hashing, not a specification.  Same distribution; to replay a reference
+    realisation inject its bits (``TrialEngine.run_bits`` or ``IidNoise.set_bits``).
+    """
+
+    def __init__(self, code, error_probability):
+        if error_probability < 0.0 or error_probability > 1.0:
+            raise ValueError("Probability is not between 0 and 1.")
+        self.code = code
+        self.egraph = code.graph
+        self.error_probability = float(error_probability)
+
+    def set_bits(self, bit_val):
+        """Install a given realisation: ``bit_val`` for all N nodes in node-index order."""
+        bits = (np.asarray(bit_val).reshape(-1) != 0).astype(np.int8)
+        if bits.shape[0] != self.code.lattice.N:
+            raise ValueError(f"need one bit per node ({self.code.lattice.N})")
+        g = self.egraph
+        g._ensure_arrays()
+        g.bit_val[:] = bits
+        self.code._trial = ("bits", bits.astype(np.uint8))
+
+    def apply_noise(self, rng=None):
+        rng = np.random.default_rng() if rng is None else rng
+        self.set_bits(rng.random(self.code.lattice.N) < self.error_probability)

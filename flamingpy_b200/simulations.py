@@ -26,7 +26,7 @@ import numpy as np
 from . import _lib
 from .codes import SurfaceCode
 from .decoder import correct, decode_batch, logical_failures
-from .noise import CVLayer
+from .noise import CVLayer, IidNoise
 
 int_time = int(str(datetime.now().timestamp()).replace(".", ""))
 
@@ -68,9 +68,16 @@ def ec_monte_carlo(trials, code_instance, noise_instance, decoder, decoder_args,
     """
     if decoder != "MWPM":
         raise NotImplementedError("only the MWPM decoder is on the accelerated path")
-    if not isinstance(noise_instance, CVLayer):
-        raise NotImplementedError("the batched driver accelerates CVLayer noise")
+    if not isinstance(noise_instance, (CVLayer, IidNoise)):
+        raise NotImplementedError("the batched driver accelerates CVLayer and IidNoise")
     weight_opts = dict(decoder_args.get("weight_opts") or {})
+    iid = isinstance(noise_instance, IidNoise)
+    if iid:
+        if weight_opts.get("method", "uniform") != "uniform":
+            raise ValueError("IidNoise has no homodyne outcomes: use weight_opts {'method': 'uniform'}")
+        n_delta, n_pswap, mode = 1.0, 0.0, "fresh"  # engine parameters that bit-level trials never read
+    else:
+        n_delta, n_pswap = noise_instance.delta, noise_instance.p_swap
     dist, rank, size = _dist_info()
     if dist is None and mpi_size > 1:
         rank, size = mpi_rank, mpi_size
@@ -85,7 +92,9 @@ def ec_monte_carlo(trials, code_instance, noise_instance, decoder, decoder_args,
             pass
     seed = int_time if seed is None else int(seed)
     code = code_instance
-    eng = code.engine(noise_instance.delta, noise_instance.p_swap, weight_opts, device=device, mode=mode)
+    eng = code.engine(n_delta, n_pswap, weight_opts, device=device, mode=mode)
+    if iid and not eng.uses_table:
+        eng.build_table()  # uniform weights: every matching graph is a gather from one all-pairs table
     lo, hi = trial_range(trials, rank, size)
     failures = 0
     done = 0
@@ -95,8 +104,7 @@ def ec_monte_carlo(trials, code_instance, noise_instance, decoder, decoder_args,
     engines = [eng]
     starts = list(range(lo, hi, batch))
     if len(starts) > 1:
-        engines.append(code.engine(noise_instance.delta, noise_instance.p_swap, weight_opts, device=device,
-                                   mode=mode, lane=1))
+        engines.append(code.engine(n_delta, n_pswap, weight_opts, device=device, mode=mode, lane=1))
     import threading
 
     slots = {}
@@ -105,7 +113,11 @@ def ec_monte_carlo(trials, code_instance, noise_instance, decoder, decoder_args,
 
     def produce(k):
         first, lane = starts[k], k % len(engines)
-        engines[lane].run_rng(seed, first, min(batch, hi - first), stage=_lib.STAGE_GRAPH, fetch=False)
+        if iid:
+            engines[lane].run_iid(seed, first, min(batch, hi - first), noise_instance.error_probability,
+                                  stage=_lib.STAGE_GRAPH, fetch=False)
+        else:
+            engines[lane].run_rng(seed, first, min(batch, hi - first), stage=_lib.STAGE_GRAPH, fetch=False)
         slots[k] = engines[lane].fetch_decode(lane_bufs[lane])
 
     worker = None
@@ -198,7 +210,7 @@ def main(argv=None):
         dec = "MWPM"
     else:
         raise ValueError(f"Decoder {args.decoder} is either invalid or not yet implemented.")
-    classes = {"SurfaceCode": SurfaceCode, "CVLayer": CVLayer}
+    classes = {"SurfaceCode": SurfaceCode, "CVLayer": CVLayer, "IidNoise": IidNoise}
     return run_ec_simulation(args.trials, classes[args.code], l_eval(args.code_args), classes[args.noise],
                              l_eval(args.noise_args), dec, l_eval(args.decoder_args), fname=args.fname,
                              mode=args.mode)

@@ -167,6 +167,16 @@ int fpb_run_injected(fpb_handle* h, int64_t n_trials, const double* x, const uin
  * matching graph (flamingpy/simulations.py:46-59). */
 int fpb_run_rng(fpb_handle* h, uint64_t seed, int64_t first_trial, int64_t n_trials, int stage);
 
+/* Trials of the i.i.d. Z-error model (flamingpy/noise/iid.py:19-50: bit_val = rng.random() < p
+ * per node), which has no homodyne outcomes: the handle must have been created with
+ * weight_method = FPB_WEIGHT_UNIFORM (decoders/decoder.py:115-116); `hom` reads back as zeros and
+ * `weights` as ones.  fpb_run_bits takes the bits of the syndrome qubits, [n_trials][bit_words]
+ * uint32 words, LSB first, in the qubit order of fpb_outputs.bits; fpb_run_iid draws them on the
+ * device from the Philox stream (seed; trial, node), independent of batching and GPU count.
+ * With static weights every later graph stage can come from fpb_build_table's gather. */
+int fpb_run_bits(fpb_handle* h, int64_t n_trials, const uint32_t* bits, int on_device, int stage);
+int fpb_run_iid(fpb_handle* h, uint64_t seed, int64_t first_trial, int64_t n_trials, double p_err, int stage);
+
 int fpb_get_sizes(fpb_handle* h, fpb_sizes* out);
 /* Copy results of the last run into caller buffers (host if on_device == 0). */
 int fpb_fetch(fpb_handle* h, const fpb_outputs* dst, int on_device);

@@ -105,3 +105,48 @@ def make_layer(code, delta, p_swap):
     from flamingpy.noise import CVLayer
 
     return CVLayer(code, delta=delta, p_swap=p_swap)
+
+
+def capture_iid_trial(code, lat, rng, error_probability, run_correct=True):
+    """One reference trial of ``IidNoise`` (``flamingpy/noise/iid.py``) decoded with uniform
+    weights: the bit of every node in ``flamingpy_b200.lattice`` index order, per complex the
+    parities / odd cubes / matching-graph lengths of ``NxMatchingGraph``, and ``correct``'s verdict."""
+    ref_shim.load()
+    from flamingpy.decoders.decoder import assign_weights, correct
+    from flamingpy.decoders.mwpm.matching import NxMatchingGraph
+    from flamingpy.noise import IidNoise
+
+    IidNoise(code, error_probability).apply_noise(rng)
+    pts = [tuple(int(v) for v in c) for c in lat.coords]
+    nodes = code.graph.nodes
+    bit_val = np.array([int(nodes[p]["bit_val"]) for p in pts], np.uint8)
+    wo = {"method": "uniform", "integer": False, "multiplier": 1}
+    assign_weights(code, "MWPM", **wo)
+    out = {"bit_val": bit_val, "complex": {}}
+    for ec in code.ec:
+        ct = lat.complexes[ec]
+        stabs = getattr(code, ec + "_stabilizers")
+        parity = np.array([s.parity for s in stabs], np.uint8)
+        mg = NxMatchingGraph(ec, code)
+        odd = np.nonzero(parity)[0].astype(np.int32)
+        K = len(odd)
+        pair_len = np.empty(K * (K - 1) // 2, np.float64)
+        k = 0
+        for a in range(K - 1):
+            for b in range(a + 1, K):
+                pair_len[k] = mg.edge_weight((stabs[odd[a]], stabs[odd[b]]))
+                k += 1
+        bnd_len = np.empty(0, np.float64)
+        bnd_side = np.empty(0, np.uint8)
+        if ct.has_boundary and K:
+            low = set(getattr(code, ec + "_stab_graph").low_bound_points)
+            bnd_len = np.empty(K, np.float64)
+            bnd_side = np.empty(K, np.uint8)
+            for i, vp in enumerate(mg.virtual_points):
+                bnd_len[i] = mg.edge_weight((stabs[odd[i]], vp))
+                bnd_side[i] = 0 if vp[0] in low else 1
+        out["complex"][ec] = {"parity": parity, "odd": odd, "pair_len": pair_len, "bnd_len": bnd_len,
+                              "bnd_side": bnd_side}
+    if run_correct:
+        out["success"] = bool(correct(code, "MWPM", weight_options=wo, decoder_opts={"backend": "networkx"}))
+    return out

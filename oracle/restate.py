@@ -397,6 +397,42 @@ def trial_from_draws(lat, state, x, delta, weight_opts=None, want_graph=True, wa
     return TrialResult(state, x, hom_all, out)
 
 
+def iid_bits(rng, n_nodes: int, error_probability: float) -> np.ndarray:
+    """``IidNoise.apply_noise`` (``flamingpy/noise/iid.py:37-50``): one ``rng.random()`` per node,
+    ``bit_val = int(draw < p)``.  The reference walks ``egraph.nodes`` in the insertion order of
+    its ``RHG_graph`` (a Python-set artefact, ``surface_code.py:186-226``); this restatement draws
+    in node-index order - same distribution, a different assignment of the stream to nodes - so
+    parity with the live reference is pinned on injected BITS (``trial_from_bits``)."""
+    return (rng.random(n_nodes) < error_probability).astype(np.uint8)
+
+
+def trial_from_bits(lat, bit_val, want_graph=True, want_paths=False) -> TrialResult:
+    """bits (one per lattice node, node-index order) -> uniform weights (``decoder.py:115-116``)
+    -> parity -> matching graph: the decoding front end for ``IidNoise`` realisations."""
+    bit_val = np.asarray(bit_val, np.uint8)
+    out = {}
+    for ec in lat.ec:
+        ct = lat.complexes[ec]
+        bits = bit_val[ct.qubits]
+        w = np.ones(ct.Q, np.float64)
+        par = stabilizer_parity(ct, bits)
+        rec = {"hom": np.zeros(ct.Q), "bits": bits, "frac": np.zeros(ct.Q), "weights": w, "parity": par}
+        if want_graph:
+            rec["graph"] = matching_graph(ct, w, par, want_paths=want_paths)
+        out[ec] = rec
+    return TrialResult(None, None, None, out)
+
+
+def correct_trial(lat, res: TrialResult) -> bool:
+    """``correct`` on a restated trial: decode every complex, all logical checks must pass."""
+    ok = True
+    for ec in lat.ec:
+        rec = res.per_complex[ec]
+        good, _ = decode_complex(lat.complexes[ec], rec["weights"], rec["bits"], rec.get("graph"))
+        ok = ok and good
+    return ok
+
+
 class TrialChain:
     """A reused ``CVLayer`` + the body of ``ec_mc_trial`` (``simulations.py:46-59``):
     same NumPy RNG call order as the reference, so with the same seed it sees
