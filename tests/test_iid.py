@@ -196,3 +196,33 @@ def test_iid_monte_carlo_failure_rate(case):
     sigma = np.sqrt(p_ref * (1 - p_ref) * (1 / n + 1 / case["trials"]))
     print(case, "got", p_got, "ref", p_ref, "z", (p_got - p_ref) / sigma)
     assert abs(p_got - p_ref) < 3.29 * sigma + 0.15 * p_ref
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("d,ec,b,p", [(13, "both", "periodic", 0.03), (13, "primal", "open", 0.04), (21, "primal", "open", 0.02)])
+def test_run_bits_full_size_against_c_oracle(d, ec, b, p):
+    """Full-size lattices: the C oracle has no bit-level entry, so the same bits are fed to it as
+    homodyne outcomes (p-quadrature = bit * sqrt(pi), all other draws zero: GKP binning returns
+    exactly that bit) with uniform weights; every output of fpb_run_bits must equal its result,
+    with the search kernel and with the table gather."""
+    from oracle import c_oracle
+
+    lat = build_lattice(d, ec, b)
+    N, T = lat.N, 3
+    bit_val = (np.random.default_rng(17).random((T, N)) < p).astype(np.uint8)
+    x = np.zeros((T, 2 * N))
+    x[:, N:] = bit_val * np.sqrt(np.pi)
+    ref = c_oracle.run(lat, 0.09, 0, {"method": "uniform"}, x, np.ones((T, N), np.uint8))
+    qn = np.concatenate([lat.complexes[e].qubits for e in lat.ec])
+    assert np.array_equal(ref.bits, bit_val[:, qn])
+    for table in (False, True):
+        eng = _engine(lat)
+        if table:
+            eng.build_table()
+        batch = eng.run_bits(bit_val[:, qn])
+        for e in lat.ec:
+            cb, rb = batch.complexes[e], ref.complexes[e]
+            assert np.array_equal(cb.parity, rb.parity) and np.array_equal(cb.odd_ids, rb.odd_ids)
+            assert np.array_equal(cb.pair_len, rb.pair_len)
+            assert np.array_equal(cb.bnd_len, rb.bnd_len) and np.array_equal(cb.bnd_side, rb.bnd_side)
+        eng.close()
