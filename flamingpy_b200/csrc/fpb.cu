@@ -80,6 +80,7 @@ struct ComplexHost {
   DevBuf<double> pair_len, bnd_len;
   DevBuf<uint8_t> bnd_side;
   long long total_odd = 0, total_pairs = 0;
+  int max_odd = 0;  // largest odd count of the last batch
   DevBuf<double> tab_pair, tab_bnd;  // all-pairs table of the static-weight path
   DevBuf<uint8_t> tab_side;
 };
@@ -337,7 +338,7 @@ int ensure_batch(fpb_handle* h, long long T) {
   if ((rc = h->bits.ensure((size_t)T * h->bit_words))) return rc;
   if ((rc = h->item_off.ensure((size_t)T * h->ncx + 1))) return rc;
   if ((rc = h->counter.ensure(1))) return rc;
-  if ((rc = h->totals.ensure(2 * MAXC + 1))) return rc;
+  if ((rc = h->totals.ensure(3 * MAXC + 1))) return rc;
   for (int c = 0; c < h->ncx; ++c) {
     ComplexHost& cx = h->cx[c];
     if ((rc = cx.parity.ensure((size_t)T * cx.par_words))) return rc;
@@ -406,6 +407,7 @@ int post_syndrome(fpb_handle* h, long long T, int stage, int* launches) {
     ComplexHost& cx = h->cx[c];
     cx.total_odd = h->totals_host[c];
     cx.total_pairs = h->totals_host[MAXC + c];
+    cx.max_odd = (int)h->totals_host[2 * MAXC + 1 + c];
     if ((rc = cx.odd_ids.ensure((size_t)cx.total_odd + 1))) return rc;
     if ((rc = cx.bnd_len.ensure((size_t)cx.total_odd + 1))) return rc;
     if ((rc = cx.bnd_side.ensure((size_t)cx.total_odd + 1))) return rc;
@@ -513,7 +515,8 @@ int run_pipeline(fpb_handle* h, long long T, int stage, int source, uint64_t see
       for (int c = 0; c < h->ncx; ++c) {
         ComplexHost& cx = h->cx[c];
         if (cx.total_odd == 0) continue;
-        dim3 grid((unsigned)T, (unsigned)((cx.S + GATHER_ROWS - 1) / GATHER_ROWS));
+        // rows = odd cubes: no CTA beyond the largest odd count of the batch
+        dim3 grid((unsigned)T, (unsigned)((cx.max_odd + GATHER_ROWS - 1) / GATHER_ROWS));
         k_gather<<<grid, GATHER_ROWS * 32, (size_t)cx.S * 2, st>>>(make_dev(cx), cx.tab_pair.p,
                                                                   cx.n_low > 0 ? cx.tab_bnd.p : nullptr, cx.tab_side.p);
         ++launches;
@@ -597,10 +600,10 @@ int fpb_create(const fpb_config* cfg, fpb_handle** out) {
     if (cudaEventCreate(&ev) != cudaSuccess) return bail(fail(FPB_ERR_CUDA, "event creation failed"));
   for (auto& ev : h->mark)
     if (cudaEventCreate(&ev) != cudaSuccess) return bail(fail(FPB_ERR_CUDA, "event creation failed"));
-  if (cudaHostAlloc(&h->totals_host, (2 * MAXC + 1) * sizeof(long long), cudaHostAllocMapped) != cudaSuccess ||
+  if (cudaHostAlloc(&h->totals_host, (3 * MAXC + 1) * sizeof(long long), cudaHostAllocMapped) != cudaSuccess ||
       cudaHostGetDevicePointer(&h->totals_map, h->totals_host, 0) != cudaSuccess)
     return bail(fail(FPB_ERR_CUDA, "mapped pinned allocation failed"));
-  memset(h->totals_host, 0, (2 * MAXC + 1) * sizeof(long long));
+  memset(h->totals_host, 0, (3 * MAXC + 1) * sizeof(long long));
   if (cudaHostAlloc(&h->static_flag_host, sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
       cudaHostGetDevicePointer(&h->static_flag_map, h->static_flag_host, 0) != cudaSuccess)
     return bail(fail(FPB_ERR_CUDA, "mapped pinned allocation failed"));

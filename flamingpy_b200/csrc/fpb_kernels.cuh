@@ -335,13 +335,17 @@ __device__ __forceinline__ int n_tasks_of(int K, int has_boundary) {
 __global__ void __launch_bounds__(1024) k_scan(ScanParams p, int T) {
   __shared__ long long wsum[32];
   __shared__ long long carry_s;
+  __shared__ int kmax_s;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   // three scans per complex (odd, pairs) and one over (trial, complex) items
   for (int which = 0; which < 2 * p.n_complex + 1; ++which) {
     const bool items = which == 2 * p.n_complex;
     const int c = which >> 1;
     const int n = items ? T * p.n_complex : T;
-    if (threadIdx.x == 0) carry_s = 0;
+    if (threadIdx.x == 0) {
+      carry_s = 0;
+      kmax_s = 0;
+    }
     __syncthreads();
     for (int i0 = 0; i0 < n; i0 += blockDim.x) {
       const int i = i0 + threadIdx.x;
@@ -354,6 +358,7 @@ __global__ void __launch_bounds__(1024) k_scan(ScanParams p, int T) {
         } else {
           const long long K = p.cx[c].odd_count[i];
           v = (which & 1) ? K * (K - 1) / 2 : K;
+          if (!(which & 1)) atomicMax(&kmax_s, (int)K);
         }
       }
       long long inc = v;
@@ -389,7 +394,7 @@ __global__ void __launch_bounds__(1024) k_scan(ScanParams p, int T) {
       const long long tot = carry_s;
       if (items) { p.item_off[n] = (int)tot; p.totals[2 * MAXC] = tot; }
       else if (which & 1) { p.cx[c].pair_off[n] = tot; p.totals[MAXC + c] = tot; }
-      else { p.cx[c].odd_off[n] = tot; p.totals[c] = tot; }
+      else { p.cx[c].odd_off[n] = tot; p.totals[c] = tot; p.totals[2 * MAXC + 1 + c] = kmax_s; }
     }
     __syncthreads();
   }
