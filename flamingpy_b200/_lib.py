@@ -20,7 +20,7 @@ STATE_SILENT, STATE_GKP, STATE_P = 0, 1, 2
 STAGE_NOISE, STAGE_SYNDROME, STAGE_GRAPH = 1, 2, 3
 
 LIB_NAME = "libfpb.so"
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
+LIB_PATH = os.environ.get("FPB_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 
 _i32p = C.POINTER(C.c_int32)
 _u16p = C.POINTER(C.c_uint16)
