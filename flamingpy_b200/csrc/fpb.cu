@@ -867,6 +867,7 @@ int fpb_build_table(fpb_handle* h) {
   CK(cudaStreamSynchronize(st));
   h->use_table = true;
   h->T = 0;  // the pseudo-trial is not a result
+  h->last_stage = 0;
   return FPB_OK;
 }
 
