@@ -60,6 +60,17 @@ def _p(a, typ):
     return a.ctypes.data_as(typ) if a is not None else None
 
 
+def default_threads() -> int:
+    """Host cores this process may use for matching: its CPU affinity, shared evenly between the
+    ranks of a one-process-per-GPU job on this node (``LOCAL_WORLD_SIZE``, set by torchrun)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:  # pragma: no cover
+        n = os.cpu_count() or 1
+    local = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
+    return max(1, n // local)
+
+
 def solve(K: int, pair_len: np.ndarray, bnd_len: Optional[np.ndarray]):
     """Matched queries [(u, v)] with v == -1 for "to its connector" (one matching graph)."""
     if K == 0:
@@ -100,7 +111,7 @@ def solve_batch(odd_count: np.ndarray, pair_len: np.ndarray, bnd_len: Optional[n
     pl = np.ascontiguousarray(pair_len, np.float64)
     bl = None if (bnd_len is None or len(bnd_len) == 0) else np.ascontiguousarray(bnd_len, np.float64)
     if threads <= 0:
-        threads = os.cpu_count() or 1
+        threads = default_threads()
     rc = lib.fpb_mwpm_batch(T, _p(oc, _i32p), _p(pl, _f64p), _p(bl, _f64p), _p(q_off, _i64p), _p(src, _i32p),
                             _p(dst, _i32p), _p(nq, _i32p), threads)
     if rc != 0:
