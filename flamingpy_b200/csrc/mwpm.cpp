@@ -559,8 +559,8 @@ int solve_one_sparse(int K, const double* pair_len, const double* bnd_len, int* 
     y.assign(n, INT64_MIN);
     vmate.assign(n, -1);
     for (int k = 0; k < sb.n_edges(); ++k) {
-      y[sb.eu[k]] = std::max(y[sb.eu[k]], sb.ew[k]);
-      y[sb.ev[k]] = std::max(y[sb.ev[k]], sb.ew[k]);
+      y[sb.E[k].u] = std::max(y[sb.E[k].u], sb.E[k].w);
+      y[sb.E[k].v] = std::max(y[sb.E[k].v], sb.E[k].w);
     }
     for (int u = 0; u < n; ++u)
       if (y[u] == INT64_MIN) return false;
@@ -696,7 +696,7 @@ int solve_one_sparse(int K, const double* pair_len, const double* bnd_len, int* 
     } else {
       // too many doublings: start over on the enlarged graph
       wshift = 0;
-      for (int k = 0; k < sb.n_edges(); ++k) sb.ew[k] = wt(sb.eu[k], sb.ev[k]);
+      for (int k = 0; k < sb.n_edges(); ++k) sb.E[k].w = wt(sb.E[k].u, sb.E[k].v);
       for (size_t i = 0; i < viol.size(); ++i) sb.add_edge(viol[i].u, viol[i].v, wt(viol[i].u, viol[i].v));
       sb.build_adjacency();
       if (!cold_start()) return -100;

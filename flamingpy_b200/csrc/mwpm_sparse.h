@@ -28,45 +28,50 @@ typedef long long ll;
 class SparseBlossom {
  public:
   int n = 0;
-  std::vector<int> eu, ev;
-  std::vector<ll> ew;
+  struct EdgeRec {  // one cache line holds four edges: endpoints and weight are read together
+    int u, v;
+    ll w;
+  };
+  std::vector<EdgeRec> E;
   std::vector<ll> dual;   // [0, n): vertices (2 x LP dual); [n, 2n): blossoms
   std::vector<int> mate;  // remote endpoint of the matched edge, -1 = free
   long long n_stages = 0, n_deltas = 0;
 
   void reset(int n_) {
     n = n_;
-    eu.clear(); ev.clear(); ew.clear();
+    E.clear();
     n_stages = n_deltas = 0;
   }
-  int n_edges() const { return (int)eu.size(); }
-  void add_edge(int u, int v, ll w) {
-    eu.push_back(u); ev.push_back(v); ew.push_back(w);
+  int n_edges() const { return (int)E.size(); }
+  void add_edge(int u, int v, ll w) { E.push_back(EdgeRec{u, v, w}); }
+  int endpoint(int p) const { return (p & 1) ? E[p >> 1].v : E[p >> 1].u; }
+  ll slack(int k) const {
+    const EdgeRec& e = E[k];
+    return dual[e.u] + dual[e.v] - 2 * e.w;
   }
-  int endpoint(int p) const { return (p & 1) ? ev[p >> 1] : eu[p >> 1]; }
-  ll slack(int k) const { return dual[eu[k]] + dual[ev[k]] - 2 * ew[k]; }
   int mate_vertex(int v) const { return mate[v] < 0 ? -1 : endpoint(mate[v]); }
 
   void build_adjacency() {
     const int ne = n_edges();
     adj_off.assign(n + 1, 0);
     for (int k = 0; k < ne; ++k) {
-      ++adj_off[eu[k] + 1];
-      ++adj_off[ev[k] + 1];
+      ++adj_off[E[k].u + 1];
+      ++adj_off[E[k].v + 1];
     }
     for (int v = 0; v < n; ++v) adj_off[v + 1] += adj_off[v];
     adj.resize(2 * (size_t)ne);
-    std::vector<int> fill(adj_off.begin(), adj_off.end() - 1);
+    fill_tmp.assign(adj_off.begin(), adj_off.end() - 1);
     for (int k = 0; k < ne; ++k) {
-      adj[fill[eu[k]]++] = 2 * k + 1;
-      adj[fill[ev[k]]++] = 2 * k;
+      adj[fill_tmp[E[k].u]++] = AdjRec{2 * k + 1, E[k].v, E[k].w};
+      adj[fill_tmp[E[k].v]++] = AdjRec{2 * k, E[k].u, E[k].w};
     }
   }
 
   bool is_bare(int v) const { return inblossom[v] == v; }  // top-level, not inside a blossom
   void double_all() {
     for (size_t i = 0; i < dual.size(); ++i) dual[i] *= 2;
-    for (size_t k = 0; k < ew.size(); ++k) ew[k] *= 2;
+    for (size_t k = 0; k < E.size(); ++k) E[k].w *= 2;
+    for (size_t i = 0; i < adj.size(); ++i) adj[i].wt *= 2;
   }
   // Dissolve the blossoms around v: a blossom's dual z moves onto its vertices (z / 2 each in LP
   // units), which keeps every inner edge's reduced cost, adds slack to the edges leaving it and
@@ -92,7 +97,7 @@ class SparseBlossom {
 
   template <class F>
   void for_neighbours(int u, F&& f) const {
-    for (int i = adj_off[u]; i < adj_off[u + 1]; ++i) f(endpoint(adj[i]), ew[adj[i] >> 1]);
+    for (int i = adj_off[u]; i < adj_off[u + 1]; ++i) f(adj[i].w, adj[i].wt);
   }
 
   // Start state: vertex duals y (feasible on every edge) and a matching on tight edges given as
@@ -105,9 +110,9 @@ class SparseBlossom {
     for (int v = 0; v < n; ++v) {
       if (vmate[v] < 0 || mate[v] >= 0) continue;
       for (int i = adj_off[v]; i < adj_off[v + 1]; ++i)
-        if (endpoint(adj[i]) == vmate[v]) {
-          mate[v] = adj[i];
-          mate[vmate[v]] = adj[i] ^ 1;
+        if (adj[i].w == vmate[v]) {
+          mate[v] = adj[i].p;
+          mate[vmate[v]] = adj[i].p ^ 1;
           break;
         }
     }
@@ -161,11 +166,12 @@ class SparseBlossom {
           const int v = queue.back();
           queue.pop_back();
           for (int ai = adj_off[v]; ai < adj_off[v + 1]; ++ai) {
-            const int p = adj[ai], k = p >> 1, w = endpoint(p);
+            const AdjRec& ar = adj[ai];  // the neighbour and the weight travel with the adjacency entry
+            const int p = ar.p, k = p >> 1, w = ar.w;
             if (inblossom[v] == inblossom[w]) continue;
             ll kslack = 0;
             if (!allow[k]) {
-              kslack = slack(k);
+              kslack = dual[v] + dual[w] - 2 * ar.wt;
               if (kslack <= 0) set_allow(k);
             }
             if (allow[k]) {
@@ -231,12 +237,12 @@ class SparseBlossom {
         }
         if (deltatype == 2) {
           set_allow(deltaedge);
-          int i = eu[deltaedge];
-          if (label[inblossom[i]] == 0) i = ev[deltaedge];
+          int i = E[deltaedge].u;
+          if (label[inblossom[i]] == 0) i = E[deltaedge].v;
           queue.push_back(i);
         } else if (deltatype == 3) {
           set_allow(deltaedge);
-          queue.push_back(eu[deltaedge]);
+          queue.push_back(E[deltaedge].u);
         } else {
           expand_blossom(deltablossom, false);
         }
@@ -271,7 +277,13 @@ class SparseBlossom {
   }
 
  private:
-  std::vector<int> adj_off, adj;
+  struct AdjRec {
+    int p;   // remote endpoint (2 * edge + side)
+    int w;   // the neighbour
+    ll wt;   // the edge weight
+  };
+  std::vector<int> adj_off, fill_tmp;
+  std::vector<AdjRec> adj;
   std::vector<int> label, labelend, inblossom, blossomparent, blossombase, bestedge;
   std::vector<std::vector<int>> childs, endps, bestedges;
   std::vector<char> has_bestedges, allow;
@@ -365,7 +377,7 @@ class SparseBlossom {
   std::vector<int> path;
 
   void add_blossom(int base, int k) {
-    int v = eu[k], w = ev[k];
+    int v = E[k].u, w = E[k].v;
     const int bb = inblossom[base];
     int bv = inblossom[v], bw = inblossom[w];
     const int b = unused.back();
@@ -405,8 +417,8 @@ class SparseBlossom {
     // least-slack edges from the new blossom to every neighbouring S-blossom
     touched.clear();
     auto consider = [&](int e) {
-      int j = ev[e];
-      if (inblossom[j] == b) j = eu[e];
+      int j = E[e].v;
+      if (inblossom[j] == b) j = E[e].u;
       const int bj = inblossom[j];
       if (bj != b && label[bj] == 1) {
         if (bestedgeto[bj] < 0) {
@@ -423,7 +435,7 @@ class SparseBlossom {
         for (size_t q = 0; q < bestedges[c].size(); ++q) consider(bestedges[c][q]);
       } else {
         leaves(c, [&](int x) {
-          for (int ai = adj_off[x]; ai < adj_off[x + 1]; ++ai) consider(adj[ai] >> 1);
+          for (int ai = adj_off[x]; ai < adj_off[x + 1]; ++ai) consider(adj[ai].p >> 1);
         });
       }
       if (c >= n) {
@@ -545,7 +557,7 @@ class SparseBlossom {
 
   void augment_matching(int k) {
     for (int side = 0; side < 2; ++side) {
-      int s = side ? ev[k] : eu[k];
+      int s = side ? E[k].v : E[k].u;
       int p = side ? 2 * k : 2 * k + 1;
       for (;;) {
         const int bs = inblossom[s];
