@@ -121,6 +121,7 @@ EXPORTS = {
     "fpb_destroy": (C.c_int, [C.c_void_p]),
     "fpb_run_injected": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "fpb_run_rng": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int64, C.c_int64, C.c_int]),
+    "fpb_knn": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]),
     "fpb_run_bits": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int]),
     "fpb_run_iid": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int64, C.c_int64, C.c_double, C.c_int]),
     "fpb_get_sizes": (C.c_int, [C.c_void_p, C.POINTER(Sizes)]),

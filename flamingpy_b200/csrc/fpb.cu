@@ -81,6 +81,7 @@ struct ComplexHost {
   DevBuf<uint8_t> bnd_side;
   long long total_odd = 0, total_pairs = 0;
   int max_odd = 0;  // largest odd count of the last batch
+  DevBuf<int> knn;  // candidate partners of the last fpb_knn call
   DevBuf<double> tab_pair, tab_bnd;  // all-pairs table of the static-weight path
   DevBuf<uint8_t> tab_side;
 };
@@ -671,7 +672,7 @@ int fpb_destroy(fpb_handle* h) {
     cudaFree(cx.low_cube); cudaFree(cx.low_slot); cudaFree(cx.high_cube); cudaFree(cx.high_slot);
     cx.parity.release(); cx.odd_count.release(); cx.odd_fixed.release(); cx.odd_ids.release();
     cx.odd_off.release(); cx.pair_off.release(); cx.pair_len.release(); cx.bnd_len.release();
-    cx.bnd_side.release(); cx.tab_pair.release(); cx.tab_bnd.release(); cx.tab_side.release();
+    cx.bnd_side.release(); cx.knn.release(); cx.tab_pair.release(); cx.tab_bnd.release(); cx.tab_side.release();
   }
   h->x.release(); h->hom.release(); h->weights.release(); h->state.release(); h->bits.release();
   h->flips.release(); h->item_off.release(); h->counter.release(); h->totals.release();
@@ -883,6 +884,38 @@ int fpb_elapsed_ms(fpb_handle* h, float* ms) {
   CK(cudaSetDevice(h->device));
   CK(cudaEventSynchronize(h->mark[1]));
   CK(cudaEventElapsedTime(ms, h->mark[0], h->mark[1]));
+  return FPB_OK;
+}
+
+int fpb_knn(fpb_handle* h, int complex_index, int k, int32_t* ids, int on_device) {
+  if (!h || !ids) return fail(FPB_ERR_ARG, "null argument");
+  if (complex_index < 0 || complex_index >= h->ncx) return fail(FPB_ERR_ARG, "bad complex index");
+  if (k < 1 || k > 64) return fail(FPB_ERR_ARG, "k must be in 1..64");
+  if (h->last_stage < FPB_STAGE_GRAPH) return fail(FPB_ERR_STATE, "fpb_knn needs a completed graph-stage run");
+  CK(cudaSetDevice(h->device));
+  ComplexHost& cx = h->cx[complex_index];
+  if (cx.total_odd == 0) return FPB_OK;
+  cudaStream_t st = h->stream;
+  int rc;
+  if ((rc = cx.knn.ensure((size_t)cx.total_odd * k))) return rc;
+  // one warp per odd cube; its row of cx.max_odd doubles lives in shared memory
+  const int row_cap = cx.max_odd > 0 ? cx.max_odd : 1;
+  int max_optin = 0;
+  CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+  int warps = (int)(((size_t)max_optin - 1024) / ((size_t)row_cap * sizeof(double)));
+  if (warps > 8) warps = 8;
+  if (warps < 1) return fail(FPB_ERR_UNSUPPORTED, "too many odd cubes in one trial for the candidate kernel");
+  const size_t smem = (size_t)warps * row_cap * sizeof(double);
+  CK(cudaFuncSetAttribute(k_knn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)h->T, (unsigned)((cx.max_odd + warps - 1) / warps));
+  k_knn<<<grid, warps * 32, smem, st>>>(make_dev(cx), k, row_cap, cx.knn.p);
+  CK(cudaGetLastError());
+  if (on_device) {
+    CK(cudaMemcpyAsync(ids, cx.knn.p, (size_t)cx.total_odd * k * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+  } else {
+    CK(cudaMemcpyAsync(ids, cx.knn.p, (size_t)cx.total_odd * k * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaStreamSynchronize(st));
   return FPB_OK;
 }
 

@@ -1604,6 +1604,63 @@ __global__ void k_iota_odd(ComplexDev c) {  // the "every cube is odd" pseudo-tr
   if (blockIdx.x == 0 && threadIdx.x == 0) c.odd_count[0] = c.S;
 }
 
+// ------------------------------------------------------------------------------------------
+// k_knn: candidate partners for the host matcher.  One warp per odd cube a of trial t: its row of
+// the reduced complete graph, min(d_ab, b_a + b_b) (decoders/mwpm/matching.py:144-173 folded into
+// the pair lengths, see csrc/mwpm.cpp), is staged in shared memory and the kn smallest entries are
+// extracted in kn rounds of a warp-wide lexicographic (length, index) minimum.  The host solver
+// starts from this sparse graph and proves optimality against the complete graph by pricing.
+// ------------------------------------------------------------------------------------------
+__global__ void k_knn(ComplexDev c, int kn, int row_cap, int* out /* [total_odd][kn] */) {
+  extern __shared__ double knn_rows[];  // [warps][row_cap]
+  const int t = blockIdx.x;
+  const int K = c.odd_count[t];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int a = blockIdx.y * nw + wid;
+  if (a >= K) return;
+  double* row = knn_rows + (size_t)wid * row_cap;
+  const long long poff = c.pair_off[t], ooff = c.odd_off[t];
+  const double* pl = c.pair_len + poff;
+  const bool bnd = c.n_low > 0;
+  const double ba = bnd ? c.bnd_len[ooff + a] : 0.0;
+  for (int b = lane; b < K; b += 32) {
+    double d = FPB_INF;
+    if (b < a) d = pl[(long long)b * K - (long long)b * (b + 1) / 2 + (a - b - 1)];
+    else if (b > a) d = pl[(long long)a * K - (long long)a * (a + 1) / 2 + (b - a - 1)];
+    if (bnd && b != a) d = fmin(d, ba + c.bnd_len[ooff + b]);
+    row[b] = d;
+  }
+  __syncwarp();
+  double pd = -1.0;
+  int pb = -1;
+  int* o = out + (ooff + a) * kn;
+  for (int r = 0; r < kn; ++r) {
+    double bd = FPB_INF;
+    int bb = 0x7fffffff;
+    for (int b = lane; b < K; b += 32) {
+      const double d = row[b];
+      const bool after = d > pd || (d == pd && b > pb);
+      const bool better = d < bd || (d == bd && b < bb);
+      if (b != a && after && better) {
+        bd = d;
+        bb = b;
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const double od = __shfl_xor_sync(0xffffffffu, bd, off);
+      const int ob = __shfl_xor_sync(0xffffffffu, bb, off);
+      if (od < bd || (od == bd && ob < bb)) {
+        bd = od;
+        bb = ob;
+      }
+    }
+    if (lane == 0) o[r] = bb == 0x7fffffff ? -1 : bb;
+    pd = bd;
+    pb = bb;
+  }
+}
+
 constexpr int GATHER_ROWS = 8;  // rows (= warps) per CTA
 
 __global__ void __launch_bounds__(GATHER_ROWS * 32) k_gather(ComplexDev c, const double* tab_pair,

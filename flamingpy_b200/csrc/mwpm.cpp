@@ -377,7 +377,8 @@ const int SPARSE_MIN_K = 48;
 // Same problem as solve_one, solved on a sparse candidate graph and proved optimal for the
 // complete graph by pricing (mwpm_sparse.h).  Returns -100 when the caller should fall back to
 // the dense solver (candidate graph without a perfect matching, or too many pricing rounds).
-int solve_one_sparse(int K, const double* pair_len, const double* bnd_len, int* out_src, int* out_dst, int knn) {
+int solve_one_sparse(int K, const double* pair_len, const double* bnd_len, int* out_src, int* out_dst, int knn,
+                     const int* cand = nullptr, int cand_k = 0) {
   using fpb_sparse::SparseBlossom;
   const int n = (bnd_len && (K & 1)) ? K + 1 : K;
   const long long t_begin = now_ns();
@@ -435,62 +436,80 @@ int solve_one_sparse(int K, const double* pair_len, const double* bnd_len, int* 
     const double w = pair_len[(size_t)((ll)u * K - (ll)u * (u + 1) / 2 + (v - u - 1))];
     return bnd_len ? std::min(w, bnd_len[u] + bnd_len[v]) : w;
   };
+  if (cand) {
+    // candidate partners computed on the GPU (fpb_knn): the first knn of each cube's list
+    const int take = std::min(knn, cand_k);
+    for (int u = 0; u < K; ++u)
+      for (int i = 0; i < take; ++i) {
+        const int v = cand[(size_t)u * cand_k + i];
+        if (v < 0 || v >= K || v == u) break;
+        const unsigned long long L = (unsigned long long)to_fixed((v < u ? reduced(v, u) : reduced(u, v)) * scale);
+        top[(size_t)u * cap2 + cnt[u]++] = (L << vbits) | (unsigned)v;
+      }
+    for (int u = 0; u < K; ++u)
+      if (cnt[u] == knn) {  // worst candidate = threshold, as the scan would have left it
+        unsigned long long worst = 0;
+        for (int i = 0; i < cnt[u]; ++i) worst = std::max(worst, top[(size_t)u * cap2 + i]);
+        thr[u] = worst;
+      }
+  } else {
   // Start every threshold at 1.3 x the median knn-th reduced length of a few sampled vertices:
-  // a vertex whose true knn-th length is larger ends the scan with fewer than knn offers and is
-  // redone exactly below; for all others the filter cannot drop one of their knn nearest.
-  auto gather_row = [&](int u, double* out) {  // reduced lengths from u to every v != u (v < K)
-    int c = 0;
-    for (int v = 0; v < u; ++v) out[c++] = reduced(v, u);
-    for (int v = u + 1; v < K; ++v) out[c++] = reduced(u, v);
-    return c;
-  };
-  if (K - 1 > 2 * knn) {
-    const int n_s = std::min(K, 16);
-    double d_s[16];
-    for (int i = 0; i < n_s; ++i) {
-      const int c = gather_row((int)((long long)i * K / n_s), wrow);
-      std::nth_element(wrow, wrow + (knn - 1), wrow + c);
-      d_s[i] = wrow[knn - 1];
-    }
-    std::nth_element(d_s, d_s + n_s / 2, d_s + n_s);
-    const double t0 = 1.3 * d_s[n_s / 2] + inv_scale;
-    for (int u = 0; u < K; ++u) thrd[u] = t0;
-  }
-  {
-    long long pos = 0;
-    for (int a = 0; a < K - 1; ++a) {
-      const int nb = K - 1 - a;
-      const double* row = pair_len + pos;
-      pos += nb;
-      if (bnd_len) {
-        const double ba = bnd_len[a];
-        const double* bb = bnd_len + a + 1;
-        for (int j = 0; j < nb; ++j) wrow[j] = std::min(row[j], ba + bb[j]);
-        row = wrow;
+    // a vertex whose true knn-th length is larger ends the scan with fewer than knn offers and is
+    // redone exactly below; for all others the filter cannot drop one of their knn nearest.
+    auto gather_row = [&](int u, double* out) {  // reduced lengths from u to every v != u (v < K)
+      int c = 0;
+      for (int v = 0; v < u; ++v) out[c++] = reduced(v, u);
+      for (int v = u + 1; v < K; ++v) out[c++] = reduced(u, v);
+      return c;
+    };
+    if (K - 1 > 2 * knn) {
+      const int n_s = std::min(K, 16);
+      double d_s[16];
+      for (int i = 0; i < n_s; ++i) {
+        const int c = gather_row((int)((long long)i * K / n_s), wrow);
+        std::nth_element(wrow, wrow + (knn - 1), wrow + c);
+        d_s[i] = wrow[knn - 1];
       }
-      const double ta = thrd[a];  // may go stale (too large) during the row: only costs exact checks
-      const double* tb = thrd + a + 1;
-      for (int j = 0; j < nb; ++j) flag[j] = (unsigned char)((row[j] < ta) | (row[j] < tb[j]));
-      for (int j = 0; j < nb; ++j) {
-        if (!flag[j]) continue;
-        const int b = a + 1 + j;
-        const unsigned long long L = (unsigned long long)to_fixed(row[j] * scale);
-        const unsigned long long kb = (L << vbits) | (unsigned)b, ka = (L << vbits) | (unsigned)a;
-        if (kb < thr[a]) offer(a, kb);
-        if (ka < thr[b]) offer(b, ka);
+      std::nth_element(d_s, d_s + n_s / 2, d_s + n_s);
+      const double t0 = 1.3 * d_s[n_s / 2] + inv_scale;
+      for (int u = 0; u < K; ++u) thrd[u] = t0;
+    }
+    {
+      long long pos = 0;
+      for (int a = 0; a < K - 1; ++a) {
+        const int nb = K - 1 - a;
+        const double* row = pair_len + pos;
+        pos += nb;
+        if (bnd_len) {
+          const double ba = bnd_len[a];
+          const double* bb = bnd_len + a + 1;
+          for (int j = 0; j < nb; ++j) wrow[j] = std::min(row[j], ba + bb[j]);
+          row = wrow;
+        }
+        const double ta = thrd[a];  // may go stale (too large) during the row: only costs exact checks
+        const double* tb = thrd + a + 1;
+        for (int j = 0; j < nb; ++j) flag[j] = (unsigned char)((row[j] < ta) | (row[j] < tb[j]));
+        for (int j = 0; j < nb; ++j) {
+          if (!flag[j]) continue;
+          const int b = a + 1 + j;
+          const unsigned long long L = (unsigned long long)to_fixed(row[j] * scale);
+          const unsigned long long kb = (L << vbits) | (unsigned)b, ka = (L << vbits) | (unsigned)a;
+          if (kb < thr[a]) offer(a, kb);
+          if (ka < thr[b]) offer(b, ka);
+        }
       }
     }
-  }
-  for (int u = 0; u < K; ++u) {
-    if (cnt[u] >= knn || cnt[u] >= K - 1) continue;
-    // fewer than knn partners under the starting threshold: select from the whole row
-    cnt[u] = 0;
-    thr[u] = ~0ull;
-    for (int v = 0; v < K; ++v) {
-      if (v == u) continue;
-      const unsigned long long L = (unsigned long long)to_fixed((v < u ? reduced(v, u) : reduced(u, v)) * scale);
-      const unsigned long long key = (L << vbits) | (unsigned)v;
-      if (key < thr[u]) offer(u, key);
+    for (int u = 0; u < K; ++u) {
+      if (cnt[u] >= knn || cnt[u] >= K - 1) continue;
+      // fewer than knn partners under the starting threshold: select from the whole row
+      cnt[u] = 0;
+      thr[u] = ~0ull;
+      for (int v = 0; v < K; ++v) {
+        if (v == u) continue;
+        const unsigned long long L = (unsigned long long)to_fixed((v < u ? reduced(v, u) : reduced(u, v)) * scale);
+        const unsigned long long key = (L << vbits) | (unsigned)v;
+        if (key < thr[u]) offer(u, key);
+      }
     }
   }
   std::vector<ll> dlen;
@@ -724,13 +743,16 @@ int solve_one_sparse(int K, const double* pair_len, const double* bnd_len, int* 
   return nq;
 }
 
-int solve_auto(int K, const double* pair_len, const double* bnd_len, int* out_src, int* out_dst) {
+int solve_auto(int K, const double* pair_len, const double* bnd_len, int* out_src, int* out_dst,
+               const int* cand = nullptr, int cand_k = 0) {
   const int mode = g_mode.load();
   if (K >= 4 && (bnd_len || !(K & 1)) && (mode == 2 || (mode == 0 && K >= SPARSE_MIN_K))) {
     // a candidate graph without a perfect matching (or one that needs too many pricing rounds)
     // is retried with four times the partners; with K - 1 partners it is the complete graph
     for (int knn = std::max(2, g_knn.load());; knn *= 4) {
-      const int r = solve_one_sparse(K, pair_len, bnd_len, out_src, out_dst, std::min(knn, K));
+      const bool use_cand = cand && knn <= cand_k;  // a denser retry needs the host's own scan
+      const int r = solve_one_sparse(K, pair_len, bnd_len, out_src, out_dst, std::min(knn, K), use_cand ? cand : nullptr,
+                                     cand_k);
       if (r != -100) return r;
       g_stats[1].fetch_add(1);
       if (knn >= K) break;
@@ -779,6 +801,29 @@ int fpb_mwpm_batch(int T, const int* odd_count, const double* pair_len, const do
     const int K = odd_count[t];
     const int r = solve_auto(K, pair_len + poff[t], bnd_len ? bnd_len + q_off[t] : nullptr, out_src + q_off[t],
                             out_dst + q_off[t]);
+    if (r < 0) bad |= 1;
+    n_queries[t] = r < 0 ? 0 : r;
+  }
+  return bad ? -1 : 0;
+}
+
+// Same as fpb_mwpm_batch with the candidate partners of every odd cube supplied (fpb_knn in fpb.h:
+// cand[q_off[t] + a][cand_k], indices into trial t's odd list, nearest first, -1 padded), which saves
+// the solver's own selection pass over the K(K-1)/2 lengths.  The result is the same exact optimum.
+int fpb_mwpm_batch_cand(int T, const int* odd_count, const double* pair_len, const double* bnd_len,
+                        const long long* q_off, const int* cand, int cand_k, int* out_src, int* out_dst,
+                        int* n_queries, int n_threads) {
+  std::vector<long long> poff((size_t)T + 1, 0);
+  for (int t = 0; t < T; ++t) poff[t + 1] = poff[t] + (long long)odd_count[t] * (odd_count[t] - 1) / 2;
+  int bad = 0;
+#ifdef _OPENMP
+  if (n_threads > 0) omp_set_num_threads(n_threads);
+#endif
+#pragma omp parallel for schedule(dynamic, 1) reduction(| : bad)
+  for (int t = 0; t < T; ++t) {
+    const int K = odd_count[t];
+    const int r = solve_auto(K, pair_len + poff[t], bnd_len ? bnd_len + q_off[t] : nullptr, out_src + q_off[t],
+                             out_dst + q_off[t], cand ? cand + q_off[t] * cand_k : nullptr, cand_k);
     if (r < 0) bad |= 1;
     n_queries[t] = r < 0 ? 0 : r;
   }

@@ -162,7 +162,13 @@ def decode_batch(code, eng, batch, backend="networkx"):
         if backend == "native":
             from . import mwpm_native
 
-            t_, s_, d_ = mwpm_native.solve_batch(cb.odd_count, cb.pair_len, cb.bnd_len if ct.has_boundary else None)
+            # large graphs: the device picks each cube's nearest partners, the host solver starts from
+            # that sparse graph (and still prices every pair, so the matching stays exact)
+            cand = None
+            if len(cb.odd_count) and int(cb.odd_count.max()) >= mwpm_native.SPARSE_MIN_K and batch.n_trials == eng.sizes().n_trials:
+                cand = eng.knn(ci, mwpm_native.CAND_K)
+            t_, s_, d_ = mwpm_native.solve_batch(cb.odd_count, cb.pair_len, cb.bnd_len if ct.has_boundary else None,
+                                                 cand=cand)
             trial.append(t_)
             cx.append(np.full(len(t_), ci, np.int32))
             src.append(s_)

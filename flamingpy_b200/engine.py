@@ -414,6 +414,18 @@ class TrialEngine:
         batch.timings = self.timings()
         return batch
 
+    def knn(self, complex_index: int, k: int = 12, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Candidate partners for the host matcher from the last graph-stage run: int32[sum K, k],
+        for every odd cube of every trial its ``k`` nearest other odd cubes of that trial (indices
+        into the trial's odd list, nearest first, -1 padded), computed on the device."""
+        s = self.sizes()
+        n = int(s.total_odd[complex_index])
+        if out is None or out.size < n * k:
+            out = np.empty(max(n * k, 1), np.int32)
+        if n:
+            _lib.check(self._lib.fpb_knn(self._h, complex_index, k, out.ctypes.data, 0))
+        return out[: n * k].reshape(n, k)
+
     def paths_toggle(self, trial, cx, src, dst) -> np.ndarray:
         """XOR-toggle the qubits on the shortest paths of the given (trial,
         complex, odd-index src, odd-index dst | -1) queries of the last run.

@@ -28,6 +28,9 @@ def load():
         lib.fpb_mwpm.argtypes = [C.c_int, _f64p, _f64p, _i32p, _i32p]
         lib.fpb_mwpm_batch.restype = C.c_int
         lib.fpb_mwpm_batch.argtypes = [C.c_int, _i32p, _f64p, _f64p, _i64p, _i32p, _i32p, _i32p, C.c_int]
+        lib.fpb_mwpm_batch_cand.restype = C.c_int
+        lib.fpb_mwpm_batch_cand.argtypes = [C.c_int, _i32p, _f64p, _f64p, _i64p, _i32p, C.c_int, _i32p, _i32p, _i32p,
+                                            C.c_int]
         lib.fpb_mwpm_max_threads.restype = C.c_int
         lib.fpb_mwpm_configure.restype = None
         lib.fpb_mwpm_configure.argtypes = [C.c_int, C.c_int]
@@ -38,6 +41,8 @@ def load():
 
 
 MODES = {"auto": 0, "dense": 1, "sparse": 2}
+SPARSE_MIN_K = 48  # graphs from this many odd cubes on go to the sparse solver (csrc/mwpm.cpp)
+CAND_K = 12        # candidate partners per cube requested from the device (= the solver's default knn)
 
 
 def configure(mode: str = "auto", knn: int = 0) -> None:
@@ -97,9 +102,11 @@ def min_weight_perfect_matching(K, pair_len, bnd_len):
     return mate
 
 
-def solve_batch(odd_count: np.ndarray, pair_len: np.ndarray, bnd_len: Optional[np.ndarray], threads: int = 0):
+def solve_batch(odd_count: np.ndarray, pair_len: np.ndarray, bnd_len: Optional[np.ndarray], threads: int = 0,
+                cand: Optional[np.ndarray] = None):
     """All trials of a batch at once (OpenMP over trials).  Returns (trial, src, dst) int32 arrays
-    of the matched queries, ready for ``TrialEngine.paths_toggle``."""
+    of the matched queries, ready for ``TrialEngine.paths_toggle``.  ``cand``: int32[sum K, k]
+    candidate partners from ``TrialEngine.knn`` (optional; the result is the same exact optimum)."""
     lib = load()
     T = len(odd_count)
     oc = np.ascontiguousarray(odd_count, np.int32)
@@ -112,8 +119,16 @@ def solve_batch(odd_count: np.ndarray, pair_len: np.ndarray, bnd_len: Optional[n
     bl = None if (bnd_len is None or len(bnd_len) == 0) else np.ascontiguousarray(bnd_len, np.float64)
     if threads <= 0:
         threads = default_threads()
-    rc = lib.fpb_mwpm_batch(T, _p(oc, _i32p), _p(pl, _f64p), _p(bl, _f64p), _p(q_off, _i64p), _p(src, _i32p),
-                            _p(dst, _i32p), _p(nq, _i32p), threads)
+    if cand is not None and len(cand):
+        cand = np.ascontiguousarray(cand, np.int32)
+        if cand.ndim != 2 or cand.shape[0] != total:
+            raise ValueError("cand must have one row per odd cube")
+        rc = lib.fpb_mwpm_batch_cand(T, _p(oc, _i32p), _p(pl, _f64p), _p(bl, _f64p), _p(q_off, _i64p),
+                                     _p(cand, _i32p), cand.shape[1], _p(src, _i32p), _p(dst, _i32p), _p(nq, _i32p),
+                                     threads)
+    else:
+        rc = lib.fpb_mwpm_batch(T, _p(oc, _i32p), _p(pl, _f64p), _p(bl, _f64p), _p(q_off, _i64p), _p(src, _i32p),
+                                _p(dst, _i32p), _p(nq, _i32p), threads)
     if rc != 0:
         raise ValueError("native matcher failed on at least one trial")
     keep = np.concatenate([np.arange(q_off[t], q_off[t] + nq[t]) for t in range(T)]) if T else np.empty(0, np.int64)

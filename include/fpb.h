@@ -204,6 +204,15 @@ int fpb_build_table(fpb_handle* h);
  * qubit ids crossed are XOR-toggled into flips [T][ceil(Qtot/32)] (bit-packed,
  * same layout as bits).  Replaces edge_path + the common_vertex loop of
  * mwpm_decoder (decoders/mwpm/algos.py:88-95). */
+/* Candidate partners for the host matcher, from the last graph-stage run: for every odd cube a of
+ * every trial of complex `complex_index`, the k nearest other odd cubes of the same trial in the
+ * matching graph (shortest-path length, or both boundary lengths if that is shorter - the pair
+ * weight of the reduced complete graph that stands for decoders/mwpm/matching.py:125-173), as
+ * indices into the trial's odd list, nearest first, ties by index, -1 padded.  ids: int32
+ * [total_odd][k] in the ragged order of odd_ids.  A matcher that starts from this sparse graph and
+ * prices the remaining pairs (fpb_mwpm.h) saves its own pass over the K(K-1)/2 lengths. */
+int fpb_knn(fpb_handle* h, int complex_index, int k, int32_t* ids, int on_device);
+
 int fpb_paths_toggle(fpb_handle* h, int64_t n_queries, const int32_t* trial, const int32_t* cx,
                      const int32_t* src, const int32_t* dst, uint32_t* flips_host);
 

@@ -31,6 +31,14 @@ int fpb_mwpm(int K, const double* pair_len, const double* bnd_len, int* out_src,
 int fpb_mwpm_batch(int T, const int* odd_count, const double* pair_len, const double* bnd_len,
                    const long long* q_off, int* out_src, int* out_dst, int* n_queries, int n_threads);
 
+/* fpb_mwpm_batch with candidate partners supplied by the GPU (fpb_knn in fpb.h): cand is int32
+ * [sum of odd_count][cand_k], row q_off[t] + a = the cand_k nearest partners of odd cube a of trial
+ * t (indices into that trial's odd list, nearest first, -1 padded); NULL = select on the host.  The
+ * candidates only seed the sparse solver; pricing against all K(K-1)/2 lengths keeps the result exact. */
+int fpb_mwpm_batch_cand(int T, const int* odd_count, const double* pair_len, const double* bnd_len,
+                        const long long* q_off, const int* cand, int cand_k, int* out_src, int* out_dst,
+                        int* n_queries, int n_threads);
+
 int fpb_mwpm_max_threads(void);
 
 /* mode 0: sparse candidate graph + pricing from 48 cubes on, dense O(n^3) below (default);

@@ -231,3 +231,52 @@ def test_fetch_decode_matches_full_fetch_and_pipelined_driver_is_batch_invariant
     finally:
         mwpm_native.configure("auto")
     assert len(set(counts)) == 1 and 0 < counts[0] < 500, counts
+
+
+@pytest.mark.parametrize("d,ec,b,ps", [(9, "primal", "open", 0.3), (7, "both", "periodic", 0.0), (3, "primal", "open", 0.25)])
+def test_device_candidate_lists_for_the_matcher(d, ec, b, ps):
+    """fpb_knn: per odd cube the k nearest partners in the reduced complete graph, nearest first,
+    ties by index, -1 padded - checked against NumPy on the fetched lengths; and the matcher seeded
+    with them returns matchings of exactly the weight it finds on its own."""
+    from flamingpy_b200 import mwpm_native
+    from tests.test_mwpm_native import total_weight
+
+    code = SurfaceCode(d, ec, b)
+    wo = {"method": "blueprint", "delta": 0.1}
+    eng = code.engine(0.1, ps, wo, mode="fresh")
+    T, kk = 7, 12
+    batch = eng.run_rng(21, 0, T)
+    for ci, e in enumerate(code.ec):
+        cb = batch.complexes[e]
+        has = code.lattice.complexes[e].has_boundary
+        cand = eng.knn(ci, kk)
+        assert cand.shape == (int(cb.odd_count.sum()), kk)
+        for t in range(T):
+            K = int(cb.odd_count[t])
+            rows = cand[cb.odd_off[t]:cb.odd_off[t + 1]]
+            if K == 0:
+                continue
+            full = np.full((K, K), np.inf)
+            iu = np.triu_indices(K, 1)
+            pl = cb.pairs(t)
+            full[iu] = np.minimum(pl, cb.boundary(t)[0][iu[0]] + cb.boundary(t)[0][iu[1]]) if has else pl
+            full = np.minimum(full, full.T)
+            for a in range(K):
+                want = sorted((full[a, v], v) for v in range(K) if v != a)[:kk]
+                got = rows[a][rows[a] >= 0]
+                assert len(got) == min(kk, K - 1) and np.all(rows[a][len(got):] == -1)
+                assert [v for _, v in want] == got.tolist()
+        try:
+            mwpm_native.configure("sparse", knn=kk)
+            bl = cb.bnd_len if has else None
+            plain = mwpm_native.solve_batch(cb.odd_count, cb.pair_len, bl, 2)
+            seeded = mwpm_native.solve_batch(cb.odd_count, cb.pair_len, bl, 2, cand=cand)
+        finally:
+            mwpm_native.configure("auto", knn=12)
+        for t in range(T):
+            K = int(cb.odd_count[t])
+            if K == 0 or (not has and K % 2):
+                continue
+            w = [total_weight(K, list(zip(r[1][r[0] == t].tolist(), r[2][r[0] == t].tolist())), cb.pairs(t),
+                              cb.boundary(t)[0] if has else None) for r in (plain, seeded)]
+            assert w[0] == pytest.approx(w[1], rel=1e-12, abs=1e-9)

@@ -142,3 +142,45 @@ def test_sparse_solver_on_oracle_matching_graphs():
             assert s["sparse_solves"] > 0 and s["retries"] <= s["sparse_solves"] // 4
     finally:
         mwpm_native.configure("auto", knn=12)
+
+
+def test_supplied_candidates_give_the_same_optimum():
+    """fpb_mwpm_batch_cand: candidate lists (here: the true nearest partners, then deliberately bad
+    ones) only seed the sparse solver; pricing keeps the total weight at the dense optimum."""
+    rng = np.random.default_rng(42)
+    Ks = [60, 75, 0, 52, 130]
+    graphs = [_random_graph(rng, k, 1 + (i % 3)) if k else (np.empty(0), np.empty(0)) for i, k in enumerate(Ks)]
+    pair = np.concatenate([g[0] for g in graphs])
+    bnd = np.concatenate([g[1] for g in graphs])
+    kk = 12
+
+    def lists(bad):
+        rows = []
+        for k, (pl, bl) in zip(Ks, graphs):
+            if not k:
+                continue
+            d = np.full((k, k), np.inf)
+            iu = np.triu_indices(k, 1)
+            d[iu] = np.minimum(pl, bl[iu[0]] + bl[iu[1]])
+            d = np.minimum(d, d.T)
+            order = np.argsort(d if not bad else -np.where(np.isinf(d), -1, d), axis=1, kind="stable")[:, :kk]
+            rows.append(order.astype(np.int32))
+        return np.concatenate(rows) if rows else np.empty((0, kk), np.int32)
+
+    try:
+        mwpm_native.configure("dense")
+        ref = mwpm_native.solve_batch(np.array(Ks, np.int32), pair, bnd, 2)
+        mwpm_native.configure("sparse", knn=12)
+        for bad in (False, True):
+            got = mwpm_native.solve_batch(np.array(Ks, np.int32), pair, bnd, 2, cand=lists(bad))
+            off_p = np.concatenate([[0], np.cumsum([k * (k - 1) // 2 for k in Ks])])
+            off_o = np.concatenate([[0], np.cumsum(Ks)])
+            for t, k in enumerate(Ks):
+                if not k:
+                    continue
+                pl, bl = pair[off_p[t]:off_p[t + 1]], bnd[off_o[t]:off_o[t + 1]]
+                w = [total_weight(k, list(zip(r[1][r[0] == t].tolist(), r[2][r[0] == t].tolist())), pl, bl)
+                     for r in (ref, got)]
+                assert w[1] == pytest.approx(w[0], rel=1e-12, abs=1e-9), (t, bad)
+    finally:
+        mwpm_native.configure("auto", knn=12)
