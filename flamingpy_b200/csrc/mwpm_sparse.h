@@ -143,8 +143,7 @@ class SparseBlossom {
   }
 
   // Stages: label every free vertex S, grow the alternating forest along tight edges, adjust the
-  // duals when it is stuck, until an augmenting path is found (plus whatever other tight
-  // augmenting paths the untouched trees still offer); repeat until none exists.
+  // duals when it is stuck, until one augmenting path is found; repeat until none exists.
   // Labels, least-slack records and allowed-edge flags are tracked in lists, so that a dual
   // adjustment and the clean-up of a stage cost the size of the forest, not of the graph.
   // Returns true when the matching is perfect.
@@ -152,8 +151,6 @@ class SparseBlossom {
     allow.assign(n_edges(), 0);
     upd_stamp.assign(2 * (size_t)n, 0);
     upd_t = 0;
-    root.assign(2 * (size_t)n, 0);
-    dead_stamp.assign((size_t)n, -1);
     lab_touched.clear();
     be_touched.clear();
     allow_touched.clear();
@@ -165,43 +162,35 @@ class SparseBlossom {
       ++n_stages;
       bool augmented = false;
       for (;;) {
-        // After the first augmentation of a stage the search goes on without dual changes: trees
-        // that were not touched are still valid, so further augmenting paths that are already
-        // tight are harvested too; the two trees an augmentation used are dead for the stage.
-        while (!queue.empty()) {
+        while (!queue.empty() && !augmented) {
           const int v = queue.back();
           queue.pop_back();
-          if (augmented && tree_dead(inblossom[v])) continue;
           for (int ai = adj_off[v]; ai < adj_off[v + 1]; ++ai) {
             const AdjRec& ar = adj[ai];  // the neighbour and the weight travel with the adjacency entry
             const int p = ar.p, k = p >> 1, w = ar.w;
             if (inblossom[v] == inblossom[w]) continue;
-            const int bw = inblossom[w];
-            if (augmented && label[bw] != 0 && tree_dead(bw)) continue;
             ll kslack = 0;
             if (!allow[k]) {
               kslack = dual[v] + dual[w] - 2 * ar.wt;
               if (kslack <= 0) set_allow(k);
             }
             if (allow[k]) {
-              if (label[bw] == 0) {
+              if (label[inblossom[w]] == 0) {
                 assign_label(w, 2, p ^ 1);
-              } else if (label[bw] == 1) {
+              } else if (label[inblossom[w]] == 1) {
                 const int base = scan_blossom(v, w);
                 if (base >= 0) {
                   add_blossom(base, k);
                 } else {
-                  const int r1 = root[inblossom[v]], r2 = root[bw];
                   augment_matching(k);
-                  dead_stamp[r1] = dead_stamp[r2] = n_stages;
                   augmented = true;
-                  break;  // v's tree is dead now
+                  break;
                 }
               } else if (label[w] == 0) {
                 set_label(w, 2);
                 labelend[w] = p ^ 1;
               }
-            } else if (label[bw] == 1) {
+            } else if (label[inblossom[w]] == 1) {
               const int b = inblossom[v];
               if (bestedge[b] < 0 || kslack < slack(bestedge[b])) set_bestedge(b, k);
             } else if (label[w] == 0) {
@@ -303,9 +292,6 @@ class SparseBlossom {
 
   std::vector<int> lab_touched, be_touched, allow_touched, upd_stamp;
   int upd_t = 0;
-  std::vector<int> root;        // per labelled top-level blossom: the free vertex its tree grew from
-  std::vector<ll> dead_stamp;   // root -> stage in which its tree was used by an augmentation
-  bool tree_dead(int b) const { return dead_stamp[root[b]] == n_stages; }
 
   static int wrap(int j, int len) { return j < 0 ? j + len : j; }
 
@@ -354,7 +340,6 @@ class SparseBlossom {
     set_label(w, t);
     set_label(b, t);
     labelend[w] = labelend[b] = p;
-    root[b] = p < 0 ? w : root[inblossom[endpoint(p)]];
     bestedge[w] = bestedge[b] = -1;
     if (t == 1) {
       leaves(b, [&](int v) { queue.push_back(v); });
@@ -424,7 +409,6 @@ class SparseBlossom {
     }
     set_label(b, 1);
     labelend[b] = labelend[bb];
-    root[b] = root[bb];
     dual[b] = 0;
     leaves(b, [&](int x) {
       if (label[inblossom[x]] == 2) queue.push_back(x);
@@ -510,7 +494,6 @@ class SparseBlossom {
       set_label(endpoint(p ^ 1), 2);
       set_label(bv, 2);
       labelend[endpoint(p ^ 1)] = labelend[bv] = p;
-      root[bv] = root[inblossom[endpoint(p)]];
       bestedge[bv] = -1;
       j += jstep;
       while (childs[b][wrap(j, len)] != entrychild) {
