@@ -112,8 +112,10 @@ def check_correction(code, sanity_check=False):
 def correct(code, decoder="MWPM", weight_options=None, sanity_check=False, decoder_opts=None, draw=False,
             drawing_opts=None):
     """``correct`` (``decoders/decoder.py:227-288``).  Returns True if error correction
-    succeeded.  ``decoder_opts["backend"]`` picks the host matcher ("networkx" by
-    default here: rustworkx / lemon are not installable offline)."""
+    succeeded.  ``decoder_opts["backend"]`` picks the host matcher: "networkx" (default here: it
+    reproduces the reference's networkx verdicts trial by trial, ties included) or "native"; the
+    reference's compiled backends "rustworkx" and "lemon" are not installable offline and map to
+    the native exact matcher (same total weight, possibly another choice among tied matchings)."""
     if decoder != "MWPM":
         raise NotImplementedError("only the MWPM decoder is on the accelerated path")
     if draw:
@@ -121,8 +123,8 @@ def correct(code, decoder="MWPM", weight_options=None, sanity_check=False, decod
     weight_options = dict(weight_options or {})
     opts = {"backend": "networkx"}
     opts.update(decoder_opts or {})
-    if opts["backend"] == "rustworkx":
-        opts["backend"] = "networkx"
+    if opts["backend"] in ("rustworkx", "retworkx", "lemon"):
+        opts["backend"] = "native"
     wo = {"method": "uniform", "integer": False, "multiplier": 1}
     wo.update(weight_options)
     eng, batch = _run_trial(code, wo, _lib.STAGE_GRAPH)

@@ -45,11 +45,11 @@ def solve_matching(K: int, pair_len: np.ndarray, bnd_len: Optional[np.ndarray], 
     Returns [(u, v)] over odd-cube indices, v == -1 for "matched to its connector"."""
     if K == 0:
         return []
-    if backend == "native":
+    if backend in ("native", "rustworkx", "retworkx", "lemon"):  # the compiled backends of the reference
         from . import mwpm_native
 
         mate = mwpm_native.min_weight_perfect_matching(K, pair_len, bnd_len)
-    elif backend in ("networkx", "rustworkx"):
+    elif backend == "networkx":
         import networkx as nx
 
         G = nx.Graph()
