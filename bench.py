@@ -371,8 +371,10 @@ def run_gpu_arm(args, cfg, lat):
     if rank == 0:
         peak, peak_src = load_peaks()
         kb = paths_kernel_bytes(lat, B * args.steps, tot_odd, tot_pairs)
-        if eng.uses_table:  # gather: reads one table entry and writes one length per pair / connector
-            kb = sum(4 * tot_odd[i] + 16 * tot_pairs[i] + (18 * tot_odd[i] if lat.complexes[e].has_boundary else 0)
+        if eng.uses_table:
+            # gather: one length written per pair / connector, the odd list read once.  The entries of
+            # the static all-pairs table come through L2 and count 0 like every static table
+            kb = sum(4 * tot_odd[i] + 8 * tot_pairs[i] + (9 * tot_odd[i] if lat.complexes[e].has_boundary else 0)
                      for i, e in enumerate(lat.ec))
         achieved = kb / (graph_ms * 1e-3) / 1e9 if graph_ms > 0 else 0.0
         pipe_b = algorithmic_bytes(lat, B * args.steps, tot_odd, tot_pairs)
@@ -399,7 +401,8 @@ def run_gpu_arm(args, cfg, lat):
                          "traffic": None if eng.uses_table else recorded_traffic(args.workload, args.mode, B),
                          "algorithmic_bytes_per_launch": kb / args.steps, "peak_source": peak_src,
                          "share_of_step": graph_ms / dev_ms if dev_ms else None,
-                         "note": ("static-weight table gather (HBM / L2 bound)" if eng.uses_table else
+                         "note": ("static-weight table gather: bound by the HBM writes of the lengths and the L2 reads of "
+                                  "the table entries (not counted)" if eng.uses_table else
                                   "k_paths is bound by shared-memory latency/issue, not HBM (DESIGN.md)"),
                          "pipeline_achieved": pipe_b / (dev_ms * 1e-3) / 1e9,
                          "pipeline_frac": pipe_b / (dev_ms * 1e-3) / 1e9 / peak},
