@@ -226,3 +226,18 @@ def test_run_bits_full_size_against_c_oracle(d, ec, b, p):
             assert np.array_equal(cb.pair_len, rb.pair_len)
             assert np.array_equal(cb.bnd_len, rb.bnd_len) and np.array_equal(cb.bnd_side, rb.bnd_side)
         eng.close()
+
+
+@pytest.mark.gpu
+def test_cli_runs_the_iid_arm(tmp_path):
+    """The reference's command line with -noise IidNoise: one CSV row with the reference's columns."""
+    from flamingpy_b200.simulations import main
+
+    f = tmp_path / "iid.csv"
+    errors = main(["-code_args", "{'distance': 3, 'ec': 'primal', 'boundaries': 'open'}", "-noise", "IidNoise",
+                   "-noise_args", "{'error_probability': 0.05}", "-decoder_args", "{'weight_opts': {'method': 'uniform'}}",
+                   "-trials", "300", "-fname", str(f)])
+    lines = f.read_text().strip().splitlines()
+    assert len(lines) == 2 and lines[0].startswith("code,distance,ec,boundaries,noise,error_probability,decoder,weight_opts,errors,trials")
+    row = lines[1].split(",")
+    assert row[0] == "SurfaceCode" and row[4] == "IidNoise" and 0 < errors < 300
