@@ -334,20 +334,32 @@ def run_gpu_arm(args, cfg, lat):
 
     lane_bufs = [alloc_bufs() for _ in engines]
 
-    def e2e_step(lane, i):
+    # A step streams its Be trials through the lanes in `chunks` sub-batches (host buffer slices), so
+    # that the only copies that cannot overlap a kernel are the first sub-batch's H2D and the last one's
+    # D2H (with whole steps as the pipeline unit that fill / drain is 11 % of a 5-step run)
+    if args.e2e_chunks > 0:
+        chunks = max(1, min(args.e2e_chunks, Be))
+    else:  # auto: sub-batches of at least ~3 ms of device work (launch + size round trips stay small), at most 8
+        ms_per_trial = dev_ms_max / max(1, B * args.steps)
+        chunks = max(1, min(8, int(Be * ms_per_trial / 3.0)))
+    bounds = [Be * c // chunks for c in range(chunks + 1)]
+
+    def e2e_chunk(lane, i, c):
         en = engines[lane]
-        en.run_injected(xs[i % n_sets], sts[i % n_sets], fetch=False)  # H2D inside
+        lo_, hi_ = bounds[c], bounds[c + 1]
+        nb = hi_ - lo_
+        en.run_injected(xs[i % n_sets][lo_:hi_], sts[i % n_sets][lo_:hi_], fetch=False)  # H2D inside
         s_ = en.fetch_into(lane_bufs[lane])  # D2H inside
-        return Be * (16 * Q + 4 * eng.bit_words) + sum(
-            Be * (4 * ((lat.complexes[e].S + 31) // 32) + 4) + 4 * int(s_.total_odd[j]) + 8 * int(s_.total_pairs[j])
+        return nb * (16 * Q + 4 * eng.bit_words) + sum(
+            nb * (4 * ((lat.complexes[e].S + 31) // 32) + 4) + 4 * int(s_.total_odd[j]) + 8 * int(s_.total_pairs[j])
             + (9 * int(s_.total_odd[j]) if lat.complexes[e].has_boundary else 0) for j, e in enumerate(lat.ec))
 
     def run_steps(first, count):
         done = [0] * len(engines)
 
         def work(lane):
-            for i in range(first + lane, first + count, len(engines)):
-                done[lane] += e2e_step(lane, i)
+            for g in range(first * chunks + lane, (first + count) * chunks, len(engines)):
+                done[lane] += e2e_chunk(lane, g // chunks, g % chunks)
 
         ths = [threading.Thread(target=work, args=(ln,)) for ln in range(len(engines))]
         for th in ths:
@@ -393,7 +405,8 @@ def run_gpu_arm(args, cfg, lat):
             "wall_ms_per_step": wall_ms_max / args.steps,
             "e2e": {"value": e2e_value, "unit": "trials/s", "h2d_bytes_per_step": h2d_per_step,
                     "d2h_bytes_per_step": d2h_bytes // max(1, args.steps), "trials_per_gpu_per_step": Be,
-                    "api": "TrialEngine.run_injected(host x, host labels) + fetch_into(pinned host buffers)",
+                    "chunks_per_step": chunks,
+                    "api": "TrialEngine.run_injected(host x, host labels) + fetch_into(pinned host buffers), per sub-batch",
                     "host_threads": len(engines)},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "k_gather" if eng.uses_table else "k_paths", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -434,6 +447,8 @@ def main():
                     help="compat = one reused CVLayer per chain like simulations.ec_monte_carlo; fresh = new layer per trial")
     ap.add_argument("--batch", type=int, default=2048, help="trials per GPU per step (device-resident arm)")
     ap.add_argument("--e2e-batch", type=int, default=512, help="trials per GPU per step (end-to-end arm)")
+    ap.add_argument("--e2e-chunks", type=int, default=0,
+                    help="sub-batches a step's trials are streamed in (end-to-end arm); 1 = whole steps, 0 = auto")
     ap.add_argument("--e2e-lanes", type=int, default=2, help="engines / host threads overlapping copies and kernels")
     ap.add_argument("--delta-step", type=float, default=0.0)
     ap.add_argument("--cpu-trials", type=int, default=0, help="CPU sample size in trials (0: 64 x cores for cpu_baseline, 32 x cores per step for --impl reference)")
