@@ -153,10 +153,10 @@ def correct(code, decoder="MWPM", weight_options=None, sanity_check=False, decod
     return bool(np.all(result))
 
 
-def decode_batch(code, eng, batch, backend="networkx"):
-    """Host matching + device path extraction for every trial of ``batch``.
-    Returns the recovery as uint8[T, Qtot] bit flips.  ``backend="native"`` solves all trials
-    with the C++ blossom matcher (OpenMP over trials); "networkx" is the reference's fallback."""
+def match_batch(code, eng, batch, backend="networkx", cands=None):
+    """Host matching of every trial of ``batch``: (trial, complex, src, dst) int32 arrays of the
+    matched queries (dst = -1: to the connector).  ``backend="native"`` solves all trials with the
+    C++ matcher (OpenMP over trials); ``cands`` = per-complex candidate lists (``candidates``)."""
     trial, cx, src, dst = [], [], [], []
     for ci, e in enumerate(code.ec):
         ct = code.lattice.complexes[e]
@@ -164,11 +164,7 @@ def decode_batch(code, eng, batch, backend="networkx"):
         if backend == "native":
             from . import mwpm_native
 
-            # large graphs: the device picks each cube's nearest partners, the host solver starts from
-            # that sparse graph (and still prices every pair, so the matching stays exact)
-            cand = None
-            if len(cb.odd_count) and int(cb.odd_count.max()) >= mwpm_native.SPARSE_MIN_K and batch.n_trials == eng.sizes().n_trials:
-                cand = eng.knn(ci, mwpm_native.CAND_K)
+            cand = cands[ci] if cands is not None else candidates(eng, batch, ci, e)
             t_, s_, d_ = mwpm_native.solve_batch(cb.odd_count, cb.pair_len, cb.bnd_len if ct.has_boundary else None,
                                                  cand=cand)
             trial.append(t_)
@@ -191,7 +187,25 @@ def decode_batch(code, eng, batch, backend="networkx"):
         src.append(np.array(ss, np.int32))
         dst.append(np.array(dd, np.int32))
     cat = lambda parts: np.concatenate(parts) if parts else np.empty(0, np.int32)  # noqa: E731
-    return eng.paths_toggle(cat(trial), cat(cx), cat(src), cat(dst))
+    return cat(trial), cat(cx), cat(src), cat(dst)
+
+
+def candidates(eng, batch, ci, e):
+    """Large graphs: the device picks each cube's nearest partners (``TrialEngine.knn``), the host
+    solver starts from that sparse graph and still prices every pair, so the matching stays exact.
+    Must be called while ``batch`` is the engine's last run; None for batches of small graphs."""
+    from . import mwpm_native
+
+    cb = batch.complexes[e]
+    if len(cb.odd_count) and int(cb.odd_count.max()) >= mwpm_native.SPARSE_MIN_K and batch.n_trials == eng.sizes().n_trials:
+        return eng.knn(ci, mwpm_native.CAND_K)
+    return None
+
+
+def decode_batch(code, eng, batch, backend="networkx"):
+    """Host matching + device path extraction for every trial of ``batch``.
+    Returns the recovery as uint8[T, Qtot] bit flips."""
+    return eng.paths_toggle(*match_batch(code, eng, batch, backend=backend))
 
 
 def logical_failures(code, batch, flips):

@@ -25,7 +25,7 @@ import numpy as np
 
 from . import _lib
 from .codes import SurfaceCode
-from .decoder import correct, decode_batch, logical_failures
+from .decoder import candidates, correct, logical_failures, match_batch
 from .noise import CVLayer, IidNoise
 
 int_time = int(str(datetime.now().timestamp()).replace(".", ""))
@@ -96,45 +96,83 @@ def ec_monte_carlo(trials, code_instance, noise_instance, decoder, decoder_args,
     if iid and not eng.uses_table:
         eng.build_table()  # uniform weights: every matching graph is a gather from one all-pairs table
     lo, hi = trial_range(trials, rank, size)
-    failures = 0
-    done = 0
-    t_dev = 0.0
-    # two engines alternate: while the host matches batch i (all cores) and extracts its paths, the
-    # other engine's GPU stage of batch i + 1 is already running on its own stream
-    engines = [eng]
-    starts = list(range(lo, hi, batch))
-    if len(starts) > 1:
-        engines.append(code.engine(n_delta, n_pswap, weight_opts, device=device, mode=mode, lane=1))
+    # Three stages on three threads, three engines in rotation: (1) device stage of batch k + fetch of
+    # what the decoder needs + candidate partners; (2) host matching of batch k - 1 on all cores;
+    # (3) correction paths of batch k - 2 on the device + logical check.  An engine starts its next
+    # batch only after stage 3 has released it (its last run is what paths_toggle works on).
+    import queue
     import threading
 
-    slots = {}
+    starts = list(range(lo, hi, batch))
+    n_eng = min(3, max(1, len(starts)))
+    engines = [eng] + [code.engine(n_delta, n_pswap, weight_opts, device=device, mode=mode, lane=i)
+                       for i in range(1, n_eng)]
     # pinned host buffers, one set per engine, reused by every batch and every later call
     lane_bufs = [e.__dict__.setdefault("_decode_bufs", {}) for e in engines]
+    free = [threading.Semaphore(1) for _ in engines]
+    q_graph, q_match = queue.Queue(maxsize=2), queue.Queue(maxsize=2)
+    state = {"failures": 0, "done": 0, "t_dev": 0.0, "error": None}
 
-    def produce(k):
-        first, lane = starts[k], k % len(engines)
-        if iid:
-            engines[lane].run_iid(seed, first, min(batch, hi - first), noise_instance.error_probability,
-                                  stage=_lib.STAGE_GRAPH, fetch=False)
+    def produce():
+        try:
+            for k, first in enumerate(starts):
+                lane = k % n_eng
+                free[lane].acquire()
+                if state["error"] is not None:
+                    break
+                en, n = engines[lane], min(batch, hi - first)
+                if iid:
+                    en.run_iid(seed, first, n, noise_instance.error_probability, stage=_lib.STAGE_GRAPH, fetch=False)
+                else:
+                    en.run_rng(seed, first, n, stage=_lib.STAGE_GRAPH, fetch=False)
+                b = en.fetch_decode(lane_bufs[lane])
+                cands = [candidates(en, b, ci, e) for ci, e in enumerate(code.ec)] if backend == "native" else None
+                q_graph.put((lane, b, cands))
+        except BaseException as exc:  # noqa: BLE001 - re-raised by the caller's thread
+            state["error"] = exc
+        q_graph.put(None)
+
+    def finish():
+        while True:
+            item = q_match.get()
+            if item is None:
+                return
+            lane, b, queries = item
+            try:
+                if state["error"] is None:
+                    flips = engines[lane].paths_toggle(*queries)
+                    state["failures"] += int(logical_failures(code, b, flips).sum())
+                    state["done"] += b.n_trials
+                    state["t_dev"] += b.timings["total_ms"]
+            except BaseException as exc:  # noqa: BLE001
+                state["error"] = exc
+            free[lane].release()
+
+    t_prod = threading.Thread(target=produce)
+    t_fin = threading.Thread(target=finish)
+    t_prod.start()
+    t_fin.start()
+    while True:
+        item = q_graph.get()
+        if item is None:
+            break
+        lane, b, cands = item
+        queries = None
+        try:
+            if state["error"] is None:
+                queries = match_batch(code, engines[lane], b, backend=backend, cands=cands)
+        except BaseException as exc:  # noqa: BLE001
+            state["error"] = exc
+        if queries is None:
+            free[lane].release()
         else:
-            engines[lane].run_rng(seed, first, min(batch, hi - first), stage=_lib.STAGE_GRAPH, fetch=False)
-        slots[k] = engines[lane].fetch_decode(lane_bufs[lane])
-
-    worker = None
-    if starts:
-        produce(0)
-    for k, first in enumerate(starts):
-        if k + 1 < len(starts):
-            worker = threading.Thread(target=produce, args=(k + 1,))
-            worker.start()
-        b = slots.pop(k)
-        t_dev += b.timings["total_ms"]
-        flips = decode_batch(code, engines[k % len(engines)], b, backend=backend)
-        failures += int(logical_failures(code, b, flips).sum())
-        done += b.n_trials
-        if worker is not None:
-            worker.join()
-            worker = None
+            q_match.put((lane, b, queries))
+    q_match.put(None)
+    t_prod.join()
+    t_fin.join()
+    if state["error"] is not None:
+        raise state["error"]
+    failures, done, t_dev = state["failures"], state["done"], state["t_dev"]
     counts = np.array([failures, done], np.int64)
     if dist is not None and size > 1:
         import torch

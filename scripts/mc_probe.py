@@ -13,7 +13,7 @@ for d, b, delta, n in [(9, "open", 0.08, 16384), (13, "open", 0.09, 8192), (13, 
         continue
     code = SurfaceCode(d, "primal", b); noise = CVLayer(code, delta=delta, p_swap=0)
     wo = {"weight_opts": {"method": "blueprint", "delta": delta}}
-    ec_monte_carlo(512, code, noise, "MWPM", wo, seed=1, mode="fresh", batch=256)  # warm-up: engines, pinned buffers
+    ec_monte_carlo(1024, code, noise, "MWPM", wo, seed=1, mode="fresh", batch=256)  # warm-up: engines, pinned buffers
     mwpm_native.stats(reset=True)
     t0 = time.perf_counter()
     e, st = ec_monte_carlo(n, code, noise, "MWPM", wo, seed=2, mode="fresh", batch=256, return_stats=True)
