@@ -107,8 +107,9 @@ def ec_monte_carlo(trials, code_instance, noise_instance, decoder, decoder_args,
     n_eng = min(3, max(1, len(starts)))
     engines = [eng] + [code.engine(n_delta, n_pswap, weight_opts, device=device, mode=mode, lane=i)
                        for i in range(1, n_eng)]
-    # pinned host buffers, one set per engine, reused by every batch and every later call
-    lane_bufs = [e.__dict__.setdefault("_decode_bufs", {}) for e in engines]
+    # pinned host buffers, one set per lane, kept on the code object: reused by every batch, every
+    # later call and every other noise / weight setting of a sweep (pinning memory is slow)
+    lane_bufs = [code.__dict__.setdefault("_decode_bufs", {}).setdefault((device, i), {}) for i in range(n_eng)]
     free = [threading.Semaphore(1) for _ in engines]
     q_graph, q_match = queue.Queue(maxsize=2), queue.Queue(maxsize=2)
     state = {"failures": 0, "done": 0, "t_dev": 0.0, "error": None}
