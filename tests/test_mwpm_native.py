@@ -184,3 +184,13 @@ def test_supplied_candidates_give_the_same_optimum():
                 assert w[1] == pytest.approx(w[0], rel=1e-12, abs=1e-9), (t, bad)
     finally:
         mwpm_native.configure("auto", knn=12)
+
+
+def test_matcher_threads_are_shared_between_local_ranks(monkeypatch):
+    import os
+
+    n = len(os.sched_getaffinity(0))
+    monkeypatch.delenv("LOCAL_WORLD_SIZE", raising=False)
+    assert mwpm_native.default_threads() == n
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "8")
+    assert mwpm_native.default_threads() == max(1, n // 8)
