@@ -530,17 +530,31 @@ int solve_one_sparse(int K, const double* pair_len, const double* bnd_len, int* 
   };
   const long long t_scan = now_ns();
   g_stats[4].fetch_add(t_scan - t_begin);
-  keys.clear();
+  (void)keys;
+  // cut every list back to its knn nearest, then emit each candidate edge once: the pair (u, v)
+  // comes from the smaller endpoint's list, or from the larger one's if the smaller does not list it
+  const unsigned long long vmask = (1ull << vbits) - 1;
   for (int u = 0; u < n; ++u) {
     unsigned long long* t = top + (size_t)u * cap2;
     if (cnt[u] > knn) {
       std::nth_element(t, t + (knn - 1), t + cnt[u]);
       cnt[u] = knn;
     }
+  }
+  auto lists = [&](int u, int v) {  // is v in u's list?
+    const unsigned long long* t = top + (size_t)u * cap2;
+    for (int i = 0; i < cnt[u]; ++i)
+      if ((int)(t[i] & vmask) == v) return true;
+    return false;
+  };
+  static thread_local SparseBlossom sb_tls;
+  SparseBlossom& sb = sb_tls;
+  sb.reset(n);
+  for (int u = 0; u < n; ++u) {
+    const unsigned long long* t = top + (size_t)u * cap2;
     for (int i = 0; i < cnt[u]; ++i) {
-      const int v = (int)(t[i] & ((1ull << vbits) - 1));
-      const unsigned long long lo = std::min(u, v), hi = std::max(u, v);
-      keys.push_back((lo << 32) | hi);
+      const int v = (int)(t[i] & vmask);
+      if (u < v || !lists(v, u)) sb.add_edge(std::min(u, v), std::max(u, v), -(ll)(2 * (t[i] >> vbits)));
     }
   }
   if (bnd_len) {
@@ -548,23 +562,16 @@ int solve_one_sparse(int K, const double* pair_len, const double* bnd_len, int* 
     // b_a + b_b whatever the pairing.  Nearest partners alone give that group a star (everyone
     // points at the few cubes closest to the boundary), which has no perfect matching; a chain
     // through the cubes in order of their boundary length lets neighbours in that order pair up.
-    std::vector<int> order(K);
+    static thread_local std::vector<int> order_tls;
+    order_tls.resize((size_t)K);
+    int* const order = order_tls.data();
     for (int a = 0; a < K; ++a) order[a] = a;
-    std::sort(order.begin(), order.end(), [&](int a, int b) { return bnd_len[a] < bnd_len[b] || (bnd_len[a] == bnd_len[b] && a < b); });
+    std::sort(order, order + K, [&](int a, int b) { return bnd_len[a] < bnd_len[b] || (bnd_len[a] == bnd_len[b] && a < b); });
     for (int i = 0; i < K; ++i)
       for (int j = 1; j <= 3 && i + j < K; ++j) {
-        const unsigned long long lo = std::min(order[i], order[i + j]), hi = std::max(order[i], order[i + j]);
-        keys.push_back((lo << 32) | hi);
+        const int a = std::min(order[i], order[i + j]), b2 = std::max(order[i], order[i + j]);
+        if (!lists(a, b2) && !lists(b2, a)) sb.add_edge(a, b2, wt(a, b2));
       }
-  }
-  std::sort(keys.begin(), keys.end());
-  keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
-  static thread_local SparseBlossom sb_tls;
-  SparseBlossom& sb = sb_tls;
-  sb.reset(n);
-  for (size_t i = 0; i < keys.size(); ++i) {
-    const int u = (int)(keys[i] >> 32), v = (int)(keys[i] & 0xffffffffu);
-    sb.add_edge(u, v, wt(u, v));
   }
   sb.build_adjacency();
   static thread_local std::vector<ll> y_tls;
