@@ -676,8 +676,13 @@ int solve_one_sparse(int K, const double* pair_len, const double* bnd_len, int* 
         const double du = duald[u] - margin;
         const double* dv = duald + u + 1;
         for (int j = 0; j < nb; ++j) flag[j] = (unsigned char)(du + dv[j] + c4 * row[j] < 0.0);
-        for (int j = 0; j < nb; ++j)
-          if (flag[j]) exact(u, u + 1 + j);
+        for (int j = 0; j < nb; j += 8) {  // flags are sparse: test eight at a time
+          unsigned long long eight;
+          std::memcpy(&eight, flag + j, 8);  // flag[] has 8 bytes of slack past K
+          if (!eight) continue;
+          for (int q = j; q < std::min(nb, j + 8); ++q)
+            if (flag[q]) exact(u, u + 1 + q);
+        }
       }
       if (n > K)
         for (int u = 0; u < K; ++u) exact(u, K);
