@@ -871,6 +871,16 @@ __global__ void __launch_bounds__(MAXT, MINB) k_paths(const __grid_constant__ Pa
 // slots are exchanged through a few shared words.  Control flow is identical in both warps.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void team_bar(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+// the pair's barrier with an OR of one predicate per thread folded in (bar.red)
+__device__ __forceinline__ bool team_bar_or(int id, bool pred) {
+  int r;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 q, %2, 0;\n\tbar.red.or.pred p, %1, 64, q;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(r)
+      : "r"(id), "r"((int)pred)
+      : "memory");
+  return r != 0;
+}
 
 struct TeamX {      // exchange words of one team (shared memory)
   int cnt[2];       // staged cubes per half
@@ -957,7 +967,6 @@ __device__ __forceinline__ void team_search(const CtaMem& cm, uint32_t cinfo_a, 
       const int n0 = tx->cnt[0], n1 = tx->cnt[1];
       const int nst = n0 + n1;
       // ---------------- relax: 64 staged cubes per round, 32 per warp, all six directions ----------------
-      int parity = 0;
       for (int cb = 0; cb < nst; cb += 64) {
         uint32_t ua[6], wa[6];
         double nd[6], old[6];
@@ -1017,11 +1026,7 @@ __device__ __forceinline__ void team_search(const CtaMem& cm, uint32_t cinfo_a, 
             mine |= lost;
             chk[d] = chk[d] && !(fin[d] < nd[d]);  // beaten by a smaller value: its owner files the cube
           }
-          mine = __any_sync(0xffffffffu, mine);
-          if (lane == 0) tx->redo[parity][half] = mine;
-          team_bar(bar_id);  // (c) re-stores visible; exchange the redo flags
-          redo = tx->redo[parity][0] | tx->redo[parity][1];
-          parity ^= 1;
+          redo = team_bar_or(bar_id, mine);  // (c) re-stores visible; did either warp lose a store?
         } while (redo);
         // after the last round every surviving candidate saw its own value in place: it owns the
         // target's final distance and files the cube under that distance's bucket
@@ -1192,6 +1197,18 @@ struct TeamXW {
 };
 template <int W>
 __device__ __forceinline__ void teamw_bar(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(32 * W) : "memory"); }
+// barrier over the team that also ORs one predicate of every thread (one instruction instead of
+// flag store + barrier + flag loads)
+template <int W>
+__device__ __forceinline__ bool teamw_bar_or(int id, bool pred) {
+  int r;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 q, %2, 0;\n\tbar.red.or.pred p, %1, %3, q;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(r)
+      : "r"(id), "r"((int)pred), "n"(32 * W)
+      : "memory");
+  return r != 0;
+}
 
 template <int NCHW, int W>
 __device__ __forceinline__ void teamw_search(const CtaMem& cm, const WarpMem& wm, const DirTab& dt, int S, double step,
@@ -1267,7 +1284,6 @@ __device__ __forceinline__ void teamw_search(const CtaMem& cm, const WarpMem& wm
         if (lane >= o) my_end += y;
       }
       const int nst = __shfl_sync(0xffffffffu, my_end, W - 1);
-      int parity = 0;
       for (int cb = 0; cb < nst; cb += 32 * W) {
         uint32_t ua[6], wa[6];
         double nd[6], old[6];
@@ -1332,11 +1348,7 @@ __device__ __forceinline__ void teamw_search(const CtaMem& cm, const WarpMem& wm
             mine |= lost;
             chk[d] = chk[d] && !(fin[d] < nd[d]);
           }
-          mine = __any_sync(0xffffffffu, mine);
-          if (lane == 0) tx->redo[parity][widx] = mine;
-          teamw_bar<W>(bar_id);  // (c) re-stores visible; exchange the redo flags
-          redo = __any_sync(0xffffffffu, lane < W && tx->redo[parity][lane < W ? lane : 0] != 0);
-          parity ^= 1;
+          redo = teamw_bar_or<W>(bar_id, mine);  // (c) re-stores visible; any store lost anywhere in the team?
         } while (redo);
 #pragma unroll
         for (int d = 0; d < 6; ++d) {
