@@ -247,7 +247,7 @@ def run_gpu_arm(args, cfg, lat):
         if use_dist:
             dist.barrier()
         torch.cuda.synchronize()
-        eng._lib.fpb_synchronize(eng._h)
+        eng.synchronize()
 
     def first_trial(step):  # contiguous block per (step, rank): independent of the GPU count
         return (step * world + rank) * B

@@ -9,7 +9,6 @@ back NumPy arrays.  The reference-compatible classes in ``codes.py``,
 
 from __future__ import annotations
 
-import ctypes as C
 from dataclasses import dataclass
 from typing import Dict, List, Optional
 
@@ -19,64 +18,47 @@ from . import _lib
 from .lattice import LatticeTables
 
 
-def _ptr(a: np.ndarray, typ):
-    return a.ctypes.data_as(typ)
-
-
-def build_config(lat: LatticeTables, delta: float, p_swap: float, wo: dict, mode: str = "compat",
-                 chain_len: int = 0, device: int = 0, delta_step: float = 0.0):
-    """Fill an ``fpb_config`` (include/fpb.h) from lattice tables and options.
-    Returns (config, keep-alive list of arrays, qubit offsets per complex, Qtot)."""
-    keepalive = []
-
-    def keep(a, dtype):
-        a = np.ascontiguousarray(a, dtype=dtype)
-        keepalive.append(a)
-        return a
-
-    cfg = _lib.Config()
-    cfg.abi_version = _lib.FPB_ABI_VERSION
-    cfg.device = device
-    cfg.n_nodes = lat.N
-    cfg.adj_indptr = _ptr(keep(lat.adj_indptr, np.int32), _lib._i32p)
-    cfg.adj_indices = _ptr(keep(lat.adj_indices, np.int32), _lib._i32p)
-    cfg.adj_vals = _ptr(keep(lat.adj_vals, np.int8), _lib._i8p)
-    cfg.n_complex = len(lat.ec)
+def config_dict(lat: LatticeTables, delta: float, p_swap: float, wo: dict, mode: str = "compat",
+                chain_len: int = 0, device: int = 0, delta_step: float = 0.0, length_mode: int = _lib.LENGTH_FLOAT):
+    """The fields of ``fpb_config`` (include/fpb.h) by name, from lattice tables and options -
+    what ``_lib.open_handle`` (pybind11 ``fpbpy.Handle`` or ctypes) takes.
+    Returns (config dict, qubit offsets per complex, Qtot)."""
+    complexes = []
     q_off = {}
     off = 0
-    for i, ec in enumerate(lat.ec):
+    for ec in lat.ec:
         ct = lat.complexes[ec]
-        d = cfg.complex_[i]
-        d.n_cubes = ct.S
-        d.n_qubits = ct.Q
-        d.qubit_node = _ptr(keep(ct.qubits, np.int32), _lib._i32p)
-        d.cube_qubit = _ptr(keep(ct.cube_qubit, np.int32), _lib._i32p)
-        d.ninfo = _ptr(keep(ct.ninfo, np.uint16), _lib._u16p)
-        d.sbase = _ptr(keep(ct.sbase, np.int32), _lib._i32p)
-        for j, v in enumerate(np.asarray(ct.d_off, np.int32).ravel()):
-            d.d_off[j] = int(v)
-        for j, v in enumerate(np.asarray(ct.s_off, np.int32).ravel()):
-            d.s_off[j] = int(v)
-        d.n_slots = ct.n_slots
-        d.slot_qubit = _ptr(keep(ct.slot_qubit, np.int32), _lib._i32p)
-        d.n_low = len(ct.low_seed_cube)
-        d.low_cube = _ptr(keep(ct.low_seed_cube, np.int32), _lib._i32p)
-        d.low_slot = _ptr(keep(ct.low_seed_slot, np.int32), _lib._i32p)
-        d.n_high = len(ct.high_seed_cube)
-        d.high_cube = _ptr(keep(ct.high_seed_cube, np.int32), _lib._i32p)
-        d.high_slot = _ptr(keep(ct.high_seed_slot, np.int32), _lib._i32p)
+        complexes.append({
+            "n_cubes": ct.S, "n_qubits": ct.Q, "n_slots": ct.n_slots,
+            "qubit_node": np.ascontiguousarray(ct.qubits, np.int32),
+            "cube_qubit": np.ascontiguousarray(ct.cube_qubit, np.int32).ravel(),
+            "ninfo": np.ascontiguousarray(ct.ninfo, np.uint16),
+            "sbase": np.ascontiguousarray(ct.sbase, np.int32),
+            "d_off": np.ascontiguousarray(ct.d_off, np.int32).ravel(),
+            "s_off": np.ascontiguousarray(ct.s_off, np.int32).ravel(),
+            "slot_qubit": np.ascontiguousarray(ct.slot_qubit, np.int32),
+            "low_cube": np.ascontiguousarray(ct.low_seed_cube, np.int32),
+            "low_slot": np.ascontiguousarray(ct.low_seed_slot, np.int32),
+            "high_cube": np.ascontiguousarray(ct.high_seed_cube, np.int32),
+            "high_slot": np.ascontiguousarray(ct.high_seed_slot, np.int32),
+        })
         q_off[ec] = off
         off += ct.Q
-    cfg.delta = float(delta)
-    cfg.p_swap = float(p_swap or 0.0)
-    cfg.weight_method = _lib.WEIGHT_BLUEPRINT if wo["method"] == "blueprint" else _lib.WEIGHT_UNIFORM
-    cfg.weight_delta = float(wo.get("delta") or delta)
-    cfg.weight_integer = int(bool(wo.get("integer", False)))
-    cfg.weight_multiplier = float(wo.get("multiplier", 1))
-    cfg.label_mode = _lib.MODE_FRESH if mode == "fresh" else _lib.MODE_COMPAT
-    cfg.chain_len = int(chain_len)
-    cfg.delta_step = float(delta_step)
-    return cfg, keepalive, q_off, off
+    cfg = {
+        "device": int(device), "n_nodes": lat.N,
+        "adj_indptr": np.ascontiguousarray(lat.adj_indptr, np.int32),
+        "adj_indices": np.ascontiguousarray(lat.adj_indices, np.int32),
+        "adj_vals": np.ascontiguousarray(lat.adj_vals, np.int8),
+        "complexes": complexes,
+        "delta": float(delta), "p_swap": float(p_swap or 0.0),
+        "weight_method": _lib.WEIGHT_BLUEPRINT if wo["method"] == "blueprint" else _lib.WEIGHT_UNIFORM,
+        "weight_delta": float(wo.get("delta") or delta),
+        "weight_integer": int(bool(wo.get("integer", False))),
+        "weight_multiplier": float(wo.get("multiplier", 1)),
+        "label_mode": _lib.MODE_FRESH if mode == "fresh" else _lib.MODE_COMPAT,
+        "chain_len": int(chain_len), "delta_step": float(delta_step), "length_mode": int(length_mode),
+    }
+    return cfg, q_off, off
 
 
 @dataclass
@@ -132,9 +114,8 @@ class TrialEngine:
         chain_len: int = 0,
         device: int = 0,
         delta_step: float = 0.0,
+        lengths: str = "float",
     ):
-        lib = _lib.load()
-        self._lib = lib
         self.lat = lat
         self.delta = float(delta)
         self.p_swap = float(p_swap or 0.0)
@@ -148,19 +129,21 @@ class TrialEngine:
         self.mode = mode
         self.device = device
         self.ec = list(lat.ec)
-        cfg, self._keep, self.q_off, self.Qtot = build_config(
-            lat, self.delta, self.p_swap, wo, mode, chain_len, device, delta_step)
+        if lengths not in ("float", "rustworkx"):
+            raise ValueError("lengths must be 'float' (networkx path sums) or 'rustworkx' (sum of int(weight))")
+        self.lengths = lengths
+        cfg, self.q_off, self.Qtot = config_dict(
+            lat, self.delta, self.p_swap, wo, mode, chain_len, device, delta_step,
+            _lib.LENGTH_RX_TRUNC if lengths == "rustworkx" else _lib.LENGTH_FLOAT)
         self.bit_words = (self.Qtot + 31) // 32
-        handle = C.c_void_p()
-        _lib.check(lib.fpb_create(C.byref(cfg), C.byref(handle)))
-        self._h = handle
-        self._keep = []
+        self._h = _lib.open_handle(cfg)  # pybind11 fpbpy.Handle, or ctypes when the module is absent
+        self.binding = _lib.binding_name()
         self.uses_table = False
 
     # ------------------------------------------------------------------ lifecycle
     def close(self):
-        if getattr(self, "_h", None):
-            self._lib.fpb_destroy(self._h)
+        if getattr(self, "_h", None) is not None:
+            self._h.close()
             self._h = None
 
     def __del__(self):
@@ -180,13 +163,13 @@ class TrialEngine:
         if state.shape != (x.shape[0], self.lat.N):
             raise ValueError(f"state must have shape [T, {self.lat.N}]")
         T = x.shape[0]
-        _lib.check(self._lib.fpb_run_injected(self._h, T, x.ctypes.data, state.ctypes.data, 0, stage))
+        self._h.run_injected(x, state, stage)
         return self.fetch(stage) if fetch else TrialBatch(T, stage, timings=self.timings())
 
     def run_rng(self, seed: int, first_trial: int, n_trials: int, stage: int = _lib.STAGE_GRAPH,
                 fetch: bool = True, want_draws: bool = False) -> TrialBatch:
         """Run trials ``[first_trial, first_trial + n_trials)`` of the Philox stream ``seed``."""
-        _lib.check(self._lib.fpb_run_rng(self._h, seed & (2**64 - 1), first_trial, n_trials, stage))
+        self._h.run_rng(seed & (2**64 - 1), first_trial, n_trials, stage)
         return self.fetch(stage, want_draws=want_draws) if fetch else TrialBatch(
             n_trials, stage, timings=self.timings())
 
@@ -205,45 +188,43 @@ class TrialEngine:
             raise ValueError(f"packed bits must have shape (n_trials, {self.bit_words})")
         bits = np.ascontiguousarray(bits)
         n_trials = bits.shape[0]
-        _lib.check(self._lib.fpb_run_bits(self._h, n_trials, bits.ctypes.data, 0, stage))
+        self._h.run_bits(bits, stage)
         return self.fetch(stage) if fetch else TrialBatch(n_trials, stage, timings=self.timings())
 
     def run_iid(self, seed: int, first_trial: int, n_trials: int, p_err: float, stage: int = _lib.STAGE_GRAPH,
                 fetch: bool = True) -> TrialBatch:
         """Trials ``[first_trial, first_trial + n_trials)`` of i.i.d. Z errors with probability
         ``p_err`` per qubit, drawn on the device (Philox stream ``seed``).  Needs uniform weights."""
-        _lib.check(self._lib.fpb_run_iid(self._h, seed & (2**64 - 1), first_trial, n_trials, float(p_err), stage))
+        self._h.run_iid(seed & (2**64 - 1), first_trial, n_trials, float(p_err), stage)
         return self.fetch(stage) if fetch else TrialBatch(n_trials, stage, timings=self.timings())
 
-    def sizes(self) -> _lib.Sizes:
-        s = _lib.Sizes()
-        _lib.check(self._lib.fpb_get_sizes(self._h, C.byref(s)))
-        return s
+    def sizes(self) -> _lib.SizesView:
+        return _lib.SizesView(self._h.sizes())
 
     def timings(self) -> dict:
-        t = _lib.Timings()
-        _lib.check(self._lib.fpb_get_timings(self._h, C.byref(t)))
-        return {name: getattr(t, name) for name, _ in _lib.Timings._fields_}
+        return dict(self._h.timings())
+
+    def synchronize(self):
+        """Wait for everything queued on the handle's stream."""
+        self._h.synchronize()
 
     def build_table(self):
         """Precompute the all-pairs distance table for trial-independent weights (uniform, or
         blueprint with ``p_swap == 1``); later graph-stage runs gather from it."""
-        _lib.check(self._lib.fpb_build_table(self._h))
+        self._h.build_table()
         self.uses_table = True
 
     def mark(self, which: int):
         """Record timing mark 0 / 1 on the handle's stream."""
-        _lib.check(self._lib.fpb_mark(self._h, which))
+        self._h.mark(which)
 
     def elapsed_ms(self) -> float:
-        ms = C.c_float()
-        _lib.check(self._lib.fpb_elapsed_ms(self._h, C.byref(ms)))
-        return float(ms.value)
+        return float(self._h.elapsed_ms())
 
-    def device_outputs(self) -> _lib.Outputs:
-        o = _lib.Outputs()
-        _lib.check(self._lib.fpb_device_outputs(self._h, C.byref(o)))
-        return o
+    def device_outputs(self) -> dict:
+        """Raw device addresses of the last run's result buffers (``fpb_device_outputs``), keyed
+        like ``fetch_into``'s buffers."""
+        return dict(self._h.device_outputs())
 
     def device_tensors(self) -> dict:
         """Zero-copy ``torch`` views of the last run's result buffers on the GPU (valid until the
@@ -260,22 +241,21 @@ class TrialEngine:
                 self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False),
                                                  "version": 2, "strides": None}
 
-        def view(ptr, shape, typestr):
-            addr = C.cast(ptr, C.c_void_p).value
+        def view(addr, shape, typestr):
             if not addr or 0 in shape:
                 return None
             return torch.as_tensor(_View(addr, shape, typestr), device=torch.device("cuda", self.device))
 
-        out = {"hom": view(o.hom, (T, self.Qtot), "<f8"), "weights": view(o.weights, (T, self.Qtot), "<f8"),
-               "bits": view(o.bits, (T, self.bit_words), "<i4")}
+        out = {"hom": view(o["hom"], (T, self.Qtot), "<f8"), "weights": view(o["weights"], (T, self.Qtot), "<f8"),
+               "bits": view(o["bits"], (T, self.bit_words), "<i4")}
         for i, ec in enumerate(self.ec):
             ct = self.lat.complexes[ec]
             out[ec] = {
-                "parity": view(o.parity[i], (T, (ct.S + 31) // 32), "<i4"),
-                "odd_count": view(o.odd_count[i], (T,), "<i4"),
-                "odd_ids": view(o.odd_ids[i], (int(s.total_odd[i]),), "<i4"),
-                "pair_len": view(o.pair_len[i], (int(s.total_pairs[i]),), "<f8"),
-                "bnd_len": view(o.bnd_len[i], (int(s.total_odd[i]),), "<f8"),
+                "parity": view(o[f"parity{i}"], (T, (ct.S + 31) // 32), "<i4"),
+                "odd_count": view(o[f"odd_count{i}"], (T,), "<i4"),
+                "odd_ids": view(o[f"odd_ids{i}"], (int(s.total_odd[i]),), "<i4"),
+                "pair_len": view(o[f"pair_len{i}"], (int(s.total_pairs[i]),), "<f8"),
+                "bnd_len": view(o[f"bnd_len{i}"], (int(s.total_odd[i]),), "<f8"),
             }
         return out
 
@@ -284,92 +264,53 @@ class TrialEngine:
         s = self.sizes()
         T = int(s.n_trials)
         N, Q = self.lat.N, self.Qtot
-        out = _lib.Outputs()
+        bufs = {}
         batch = TrialBatch(T, stage)
-        packed_bits = None
         if want_noise:
-            batch.hom = np.empty((T, Q), np.float64)
-            batch.weights = np.empty((T, Q), np.float64)
-            packed_bits = np.empty((T, self.bit_words), np.uint32)
-            out.hom = _ptr(batch.hom, _lib._f64p)
-            out.weights = _ptr(batch.weights, _lib._f64p)
-            out.bits = _ptr(packed_bits, _lib._u32p)
+            batch.hom = bufs["hom"] = np.empty((T, Q), np.float64)
+            batch.weights = bufs["weights"] = np.empty((T, Q), np.float64)
+            bufs["bits"] = np.empty((T, self.bit_words), np.uint32)
         if want_draws:
-            batch.state = np.empty((T, N), np.uint8)
-            batch.x = np.empty((T, 2 * N), np.float64)
-            out.state = _ptr(batch.state, _lib._u8p)
-            out.x = _ptr(batch.x, _lib._f64p)
-        packed_par: List[Optional[np.ndarray]] = []
+            batch.state = bufs["state"] = np.empty((T, N), np.uint8)
+            batch.x = bufs["x"] = np.empty((T, 2 * N), np.float64)
         batch.complexes = {}
         for i, ec in enumerate(self.ec):
             ct = self.lat.complexes[ec]
             cb = ComplexBatch()
-            pp = None
             if stage >= _lib.STAGE_SYNDROME:
-                pw = (ct.S + 31) // 32
-                pp = np.empty((T, pw), np.uint32)
-                cb.odd_count = np.empty(T, np.int32)
-                cb.odd_ids = np.empty(int(s.total_odd[i]), np.int32)
-                out.parity[i] = _ptr(pp, _lib._u32p)
-                out.odd_count[i] = _ptr(cb.odd_count, _lib._i32p)
-                out.odd_ids[i] = _ptr(cb.odd_ids, _lib._i32p)
+                bufs[f"parity{i}"] = np.empty((T, (ct.S + 31) // 32), np.uint32)
+                cb.odd_count = bufs[f"odd_count{i}"] = np.empty(T, np.int32)
+                cb.odd_ids = bufs[f"odd_ids{i}"] = np.empty(int(s.total_odd[i]), np.int32)
             if stage >= _lib.STAGE_GRAPH:
-                cb.pair_len = np.empty(int(s.total_pairs[i]), np.float64)
-                out.pair_len[i] = _ptr(cb.pair_len, _lib._f64p)
+                cb.pair_len = bufs[f"pair_len{i}"] = np.empty(int(s.total_pairs[i]), np.float64)
                 if ct.has_boundary:
-                    cb.bnd_len = np.empty(int(s.total_odd[i]), np.float64)
-                    cb.bnd_side = np.empty(int(s.total_odd[i]), np.uint8)
-                    out.bnd_len[i] = _ptr(cb.bnd_len, _lib._f64p)
-                    out.bnd_side[i] = _ptr(cb.bnd_side, _lib._u8p)
+                    cb.bnd_len = bufs[f"bnd_len{i}"] = np.empty(int(s.total_odd[i]), np.float64)
+                    cb.bnd_side = bufs[f"bnd_side{i}"] = np.empty(int(s.total_odd[i]), np.uint8)
                 else:
                     cb.bnd_len = np.empty(0, np.float64)
                     cb.bnd_side = np.empty(0, np.uint8)
-            packed_par.append(pp)
             batch.complexes[ec] = cb
-        _lib.check(self._lib.fpb_fetch(self._h, C.byref(out), 0))
-        if packed_bits is not None:
-            batch.bits = unpack_bits(packed_bits, Q)
+        self._h.fetch_into(bufs)
+        if want_noise:
+            batch.bits = unpack_bits(bufs["bits"], Q)
         for i, ec in enumerate(self.ec):
             cb = batch.complexes[ec]
-            if packed_par[i] is not None:
-                cb.parity = unpack_bits(packed_par[i], self.lat.complexes[ec].S)
+            if stage >= _lib.STAGE_SYNDROME:
+                cb.parity = unpack_bits(bufs[f"parity{i}"], self.lat.complexes[ec].S)
                 K = cb.odd_count.astype(np.int64)
                 cb.odd_off = np.concatenate([[0], np.cumsum(K)]).astype(np.int64)
                 cb.pair_off = np.concatenate([[0], np.cumsum(K * (K - 1) // 2)]).astype(np.int64)
         batch.timings = self.timings()
         return batch
 
-    def fetch_into(self, bufs: dict) -> _lib.Sizes:
+    def fetch_into(self, bufs: dict) -> _lib.SizesView:
         """Copy the last run's results into caller-owned (e.g. pinned) NumPy
         buffers without allocating: keys ``hom``, ``weights``, ``bits`` (packed
         uint32) and per complex index ``i``: ``parity{i}`` (packed), ``odd_count{i}``,
         ``odd_ids{i}``, ``pair_len{i}``, ``bnd_len{i}``, ``bnd_side{i}``.  Buffers must be
         at least as large as the sizes returned by ``sizes()``."""
         s = self.sizes()
-        T = int(s.n_trials)
-        out = _lib.Outputs()
-
-        def need(key, n, typ):
-            a = bufs.get(key)
-            if a is None:
-                return None
-            if a.size < n:
-                raise ValueError(f"buffer {key!r} too small: {a.size} < {n}")
-            return _ptr(a, typ)
-
-        out.hom = need("hom", T * self.Qtot, _lib._f64p)
-        out.weights = need("weights", T * self.Qtot, _lib._f64p)
-        out.bits = need("bits", T * self.bit_words, _lib._u32p)
-        for i, ec in enumerate(self.ec):
-            ct = self.lat.complexes[ec]
-            out.parity[i] = need(f"parity{i}", T * ((ct.S + 31) // 32), _lib._u32p)
-            out.odd_count[i] = need(f"odd_count{i}", T, _lib._i32p)
-            out.odd_ids[i] = need(f"odd_ids{i}", int(s.total_odd[i]), _lib._i32p)
-            out.pair_len[i] = need(f"pair_len{i}", int(s.total_pairs[i]), _lib._f64p)
-            if ct.has_boundary:
-                out.bnd_len[i] = need(f"bnd_len{i}", int(s.total_odd[i]), _lib._f64p)
-                out.bnd_side[i] = need(f"bnd_side{i}", int(s.total_odd[i]), _lib._u8p)
-        _lib.check(self._lib.fpb_fetch(self._h, C.byref(out), 0))
+        self._h.fetch_into({k: v for k, v in bufs.items() if isinstance(v, np.ndarray)})
         return s
 
     def fetch_decode(self, bufs: Optional[dict] = None) -> "TrialBatch":
@@ -423,7 +364,7 @@ class TrialEngine:
         if out is None or out.size < n * k:
             out = np.empty(max(n * k, 1), np.int32)
         if n:
-            _lib.check(self._lib.fpb_knn(self._h, complex_index, k, out.ctypes.data, 0))
+            self._h.knn(complex_index, k, out)
         return out[: n * k].reshape(n, k)
 
     def paths_toggle(self, trial, cx, src, dst) -> np.ndarray:
@@ -436,11 +377,8 @@ class TrialEngine:
         cx = np.ascontiguousarray(cx, np.int32)
         src = np.ascontiguousarray(src, np.int32)
         dst = np.ascontiguousarray(dst, np.int32)
-        n = len(trial)
         flips = np.zeros((T, self.bit_words), np.uint32)
-        _lib.check(self._lib.fpb_paths_toggle(
-            self._h, n, _ptr(trial, _lib._i32p), _ptr(cx, _lib._i32p), _ptr(src, _lib._i32p),
-            _ptr(dst, _lib._i32p), _ptr(flips, _lib._u32p)))
+        self._h.paths_toggle(trial, cx, src, dst, flips)
         return unpack_bits(flips, self.Qtot)
 
 

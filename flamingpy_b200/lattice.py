@@ -144,6 +144,106 @@ def _polarity_sign(p1: np.ndarray, p2: np.ndarray) -> np.ndarray:
     return np.where(src % 2 == 0, 1, -1).astype(np.int8)
 
 
+def _reference_node_order(dims, btypes):
+    """First-insertion rank of every lattice node in the reference's ``RHG_graph``
+    (``surface_code.py:172-243``).  The reference fills its graph while iterating a Python *set*
+    of primal vertices, so the order is a property of CPython's tuple hashing; it is re-derived
+    here with real sets.  Only the size-2 periodic case needs it (``_double_edge_keep``)."""
+    import itertools as it
+
+    d = [int(v) for v in dims]
+    rng = [range(d[a] - (1 if btypes[a] == "primal" else 0)) for a in range(3)]
+    faces = ((0, 1, 1), (1, 0, 1), (1, 1, 0), (2, 1, 1), (1, 2, 1), (1, 1, 2))
+    primal_vertices = {(2 * i + f[0], 2 * j + f[1], 2 * k + f[2]) for (i, j, k) in it.product(*rng) for f in faces}
+
+    def outside(p):
+        for a in range(3):
+            if btypes[a] == "dual" and p[a] in (0, 2 * d[a]):
+                return True
+            if btypes[a] == "periodic" and p[a] == 2 * d[a]:
+                return True
+        return False
+
+    def four_neighbours(p):
+        x, y, z = p
+        if z % 2:
+            if x % 2:
+                return [(x, y, z - 1), (x - 1, y, z), (x, y, z + 1), (x + 1, y, z)]
+            return [(x, y, z - 1), (x, y + 1, z), (x, y, z + 1), (x, y - 1, z)]
+        return [(x, y - 1, z), (x - 1, y, z), (x, y + 1, z), (x + 1, y, z)]
+
+    rank = {}
+    for v in primal_vertices:
+        if outside(v):
+            continue
+        for nb in four_neighbours(v):
+            if outside(nb):
+                continue
+            rank.setdefault(v, len(rank))
+            rank.setdefault(nb, len(rank))
+            for a in range(3):
+                if btypes[a] == "periodic" and nb[a] == 0:
+                    other = list(nb)
+                    other[a] = 2 * d[a] - 1
+                    rank.setdefault(tuple(other), len(rank))
+    return rank
+
+
+def _double_edge_keep(ec, dims, btypes, cidx, start, pairs):
+    """Which of the two qubits shared by a doubly-connected cube pair the reference keeps as the
+    edge's ``common_vertex``: ``(set(stab1.coords()) & set(stab2.coords())).pop()``
+    (``stabilizer_graph.py:295-298``) - whatever CPython's set iteration yields.  Reproduced by
+    running the same set operations on the same coordinate tuples in the same insertion orders
+    (``surface_code.py:413-451``; networkx ``subgraph`` keeps ``set(nodes)``).
+    ``pairs``: iterable of (cube1 < cube2).  Returns {(cube1, cube2): kept coordinate tuple}."""
+    d = [int(v) for v in dims]
+    rank = _reference_node_order(dims, btypes)
+    n_graph = len(rank)
+    periodic_axes = [a for a in range(3) if btypes[a] == "periodic"]
+    cache = {}
+
+    def coords_of(s):
+        if s in cache:
+            return cache[s]
+        i, j, k = (int(v) for v in (cidx[s] + start))
+        if ec == "primal":
+            body = [(2 * i, 2 * j + 1, 2 * k + 1), (2 * i + 1, 2 * j, 2 * k + 1), (2 * i + 1, 2 * j + 1, 2 * k),
+                    (2 * i + 2, 2 * j + 1, 2 * k + 1), (2 * i + 1, 2 * j + 2, 2 * k + 1), (2 * i + 1, 2 * j + 1, 2 * k + 2)]
+        else:
+            body = [(2 * i + 1, 2 * j + 2, 2 * k + 2), (2 * i + 2, 2 * j + 1, 2 * k + 2), (2 * i + 2, 2 * j + 2, 2 * k + 1),
+                    (2 * i + 3, 2 * j + 2, 2 * k + 2), (2 * i + 2, 2 * j + 3, 2 * k + 2), (2 * i + 2, 2 * j + 2, 2 * k + 3)]
+        members = set(body)
+        found = set()
+        for p in sorted((p for p in members if p in rank), key=rank.get):  # intersection iterates the graph
+            found.add(p)
+        actual = list(found)
+        if len(actual) < 6:
+            for a in periodic_axes:
+                if ec == "dual":
+                    p = list(body[3 + a])
+                    if p[a] == 1:
+                        p[a] = 2 * d[a] - 1
+                        actual.append(tuple(p))
+                else:
+                    p = list(body[a])
+                    if p[a] == 2 * d[a] - 2:
+                        p[a] = 0
+                        actual.append(tuple(p))
+        shown = set(p for p in actual if p in rank)
+        if 2 * len(shown) < n_graph:
+            out = [p for p in shown]
+        else:
+            out = sorted(shown, key=rank.get)
+        cache[s] = out
+        return out
+
+    keep = {}
+    for s1, s2 in pairs:
+        common = set(coords_of(s1)) & set(coords_of(s2))
+        keep[(s1, s2)] = common.pop()
+    return keep
+
+
 def build_lattice(
     distance,
     ec="primal",
@@ -351,6 +451,24 @@ def _build_complex(ec, dims, btypes, bound_str, coords, lookup) -> ComplexTables
     if standard and not (S > 0 and counts.max() <= 2 and dangling == bset):
         if not (min(dims) <= 2 and per.any()):  # d=2 periodic: cubes share two faces
             raise AssertionError("lattice invariant violated: dangling qubits != boundary points")
+
+    # size-2 periodic axes: the two cubes of such an axis share two qubits, but the reference's
+    # stabilizer graph holds one edge per cube pair (stabilizer_graph.py:295-298) - the other
+    # qubit still counts for the parities, it just is no edge
+    for a in range(3):
+        if per[a] and n_cubes[a] == 2:
+            first = np.nonzero(cidx[:, a] == 0)[0]
+            pairs = [(int(c), int(c + strides[a])) for c in first]
+            keep = _double_edge_keep(ec, dims, btypes, cidx, start, pairs)
+            for c, c2 in pairs:
+                inner, seam = face_node[c, 2 * a + 1], face_node[c, 2 * a]
+                kept = tuple(int(v) for v in keep[(c, c2)])
+                if kept == tuple(int(v) for v in coords[inner]):
+                    nbr[c, 2 * a] = nbr[c2, 2 * a + 1] = NBR_NONE
+                elif kept == tuple(int(v) for v in coords[seam]):
+                    nbr[c, 2 * a + 1] = nbr[c2, 2 * a] = NBR_NONE
+                else:
+                    raise AssertionError("double edge: kept qubit is neither shared face")
 
     # face kinds
     ninfo = np.zeros(S, np.uint16)

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define FPB_ABI_VERSION 1
+#define FPB_ABI_VERSION 2
 #define FPB_MAX_COMPLEX 2
 
 /* error codes */
@@ -48,6 +48,12 @@ extern "C" {
 #define FPB_STATE_SILENT 0
 #define FPB_STATE_GKP 1
 #define FPB_STATE_P 2
+
+/* what a path "length" is (fpb_config.length_mode) */
+#define FPB_LENGTH_FLOAT 0    /* sum of the float weights along the shortest path: the networkx backend
+                                 (codes/graphs/stabilizer_graph.py:405-410) */
+#define FPB_LENGTH_RX_TRUNC 1 /* sum of int(weight) along the float-shortest path: what the reference's default
+                                 rustworkx backend reports (stabilizer_graph.py:486-500, _path_weight) */
 
 /* stages to run */
 #define FPB_STAGE_NOISE 1    /* homodyne values, bits, weights */
@@ -99,6 +105,9 @@ typedef struct fpb_config {
   int32_t label_mode;   /* FPB_MODE_* (device RNG only) */
   int64_t chain_len;    /* trials per reused-layer chain in compat mode; <=0: one chain */
   double delta_step;    /* shortest-path bucket width in units of the trial's mean weight; <=0: default (2.0) */
+  int32_t length_mode;  /* FPB_LENGTH_* */
+  int32_t reserved_i[7]; /* must be 0 */
+  double reserved_d[4];  /* must be 0 */
 } fpb_config;
 
 typedef struct fpb_handle fpb_handle;
@@ -198,12 +207,6 @@ int fpb_elapsed_ms(fpb_handle* h, float* ms);
  * a later injected run whose labels are not all "p" fails with FPB_ERR_STATE. */
 int fpb_build_table(fpb_handle* h);
 
-/* Correction paths for matched pairs of the last run.  Query i asks, in trial
- * trial[i] and complex cx[i], for the shortest path from odd cube src[i] to
- * odd cube dst[i] (dst >= 0), or to its nearer connector (dst == -1).  The local
- * qubit ids crossed are XOR-toggled into flips [T][ceil(Qtot/32)] (bit-packed,
- * same layout as bits).  Replaces edge_path + the common_vertex loop of
- * mwpm_decoder (decoders/mwpm/algos.py:88-95). */
 /* Candidate partners for the host matcher, from the last graph-stage run: for every odd cube a of
  * every trial of complex `complex_index`, the k nearest other odd cubes of the same trial in the
  * matching graph (shortest-path length, or both boundary lengths if that is shorter - the pair
@@ -213,6 +216,12 @@ int fpb_build_table(fpb_handle* h);
  * prices the remaining pairs (fpb_mwpm.h) saves its own pass over the K(K-1)/2 lengths. */
 int fpb_knn(fpb_handle* h, int complex_index, int k, int32_t* ids, int on_device);
 
+/* Correction paths for matched pairs of the last run.  Query i asks, in trial
+ * trial[i] and complex cx[i], for the shortest path from odd cube src[i] to
+ * odd cube dst[i] (dst >= 0), or to its nearer connector (dst == -1).  The local
+ * qubit ids crossed are XOR-toggled into flips [T][ceil(Qtot/32)] (bit-packed,
+ * same layout as bits).  Replaces edge_path + the common_vertex loop of
+ * mwpm_decoder (decoders/mwpm/algos.py:88-95). */
 int fpb_paths_toggle(fpb_handle* h, int64_t n_queries, const int32_t* trial, const int32_t* cx,
                      const int32_t* src, const int32_t* dst, uint32_t* flips_host);
 

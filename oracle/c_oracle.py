@@ -15,7 +15,7 @@ import subprocess
 import numpy as np
 
 from flamingpy_b200 import _lib
-from flamingpy_b200.engine import ComplexBatch, TrialBatch, build_config
+from flamingpy_b200.engine import ComplexBatch, TrialBatch, config_dict
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libfpb_oracle.so")
@@ -83,7 +83,8 @@ def run(lat, delta, p_swap, weight_opts, x, state, stage=_lib.STAGE_GRAPH, n_thr
     lib = load()
     wo = {"method": "uniform", "integer": False, "multiplier": 1}
     wo.update(weight_opts or {})
-    cfg, keep, q_off, Qtot = build_config(lat, delta, p_swap, wo)
+    cfg_d, q_off, Qtot = config_dict(lat, delta, p_swap, wo)
+    cfg, keep = _lib.ctypes_config(cfg_d)
     x = np.ascontiguousarray(x, np.float64)
     state = np.ascontiguousarray(state, np.uint8)
     T = x.shape[0]

@@ -35,6 +35,9 @@ CASES = [
      {"method": "blueprint", "delta": 0.09, "integer": True, "multiplier": 100}, 6, 109),
     ("d234_open_primal_ps01", (2, 3, 4), "primal", "open", 0.12, 0.1, {"method": "blueprint", "delta": 0.12}, 6, 110),
     ("d7_open_primal_ps0", 7, "primal", "open", 0.105, 0, {"method": "blueprint", "delta": 0.105}, 3, 111),
+    # size-2 periodic axes (two cubes share two qubits, the reference keeps one edge per pair)
+    ("d2_periodic_both_ps0", 2, "both", "periodic", 0.12, 0, {"method": "blueprint", "delta": 0.12}, 8, 112),
+    ("d223_toric_dual_ps025", (2, 2, 3), "dual", "toric", 0.12, 0.25, {"method": "blueprint", "delta": 0.12}, 6, 113),
 ]
 
 
@@ -78,5 +81,9 @@ def generate(case):
 
 
 if __name__ == "__main__":
+    import sys
+
     for c in CASES:
+        if len(sys.argv) > 1 and c[0] not in sys.argv[1:]:
+            continue  # regenerate only the named sets
         print("wrote", generate(c))

@@ -27,6 +27,11 @@ CASES = [
     (3, "primal", "open", 0.09, 0.25,
      {"method": "blueprint", "delta": 0.09, "integer": True, "multiplier": 100}, 3),
     ((2, 3, 4), "primal", "open", 0.12, 0.1, {"method": "blueprint", "delta": 0.12}, 3),
+    # size-2 periodic axes: two cubes share two qubits, one edge kept (stabilizer_graph.py:295-298)
+    (2, "primal", "periodic", 0.12, 0, {"method": "blueprint", "delta": 0.12}, 4),
+    (2, "dual", "periodic", 0.12, 0.25, {"method": "blueprint", "delta": 0.12}, 4),
+    ((2, 2, 3), "dual", "toric", 0.12, 0.25, {"method": "blueprint", "delta": 0.12}, 4),
+    ((3, 2, 4), "primal", "periodic", 0.1, 0, {"method": "blueprint", "delta": 0.1}, 3),
 ]
 
 
