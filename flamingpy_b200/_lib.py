@@ -133,6 +133,8 @@ EXPORTS = {
     "fpb_run_rng": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int64, C.c_int64, C.c_int]),
     "fpb_knn": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]),
     "fpb_run_bits": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int]),
+    "fpb_run_weighted": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "fpb_paths_list": (C.c_int, [C.c_void_p, C.c_int64, _i32p, _i32p, _i32p, _i32p, C.c_int32, _i32p, _i32p]),
     "fpb_run_iid": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int64, C.c_int64, C.c_double, C.c_int]),
     "fpb_get_sizes": (C.c_int, [C.c_void_p, C.POINTER(Sizes)]),
     "fpb_fetch": (C.c_int, [C.c_void_p, C.POINTER(Outputs), C.c_int]),
@@ -293,6 +295,9 @@ class CtypesHandle:
     def run_bits(self, bits, stage=STAGE_GRAPH):
         check(self._lib.fpb_run_bits(self._h, bits.shape[0], bits.ctypes.data, 0, stage))
 
+    def run_weighted(self, weights, bits, stage=STAGE_GRAPH):
+        check(self._lib.fpb_run_weighted(self._h, weights.shape[0], weights.ctypes.data, bits.ctypes.data, 0, stage))
+
     def run_iid(self, seed, first_trial, n_trials, p_err, stage=STAGE_GRAPH):
         check(self._lib.fpb_run_iid(self._h, seed, first_trial, n_trials, float(p_err), stage))
 
@@ -379,6 +384,17 @@ class CtypesHandle:
         p = lambda a: a.ctypes.data_as(_i32p)  # noqa: E731
         check(self._lib.fpb_paths_toggle(self._h, len(trial), p(trial), p(cx), p(src), p(dst),
                                          flips.ctypes.data_as(_u32p)))
+
+
+    def paths_list(self, trial, cx, src, dst, max_len):
+        import numpy as np
+
+        n = len(trial)
+        qubits = np.empty((n, max_len), np.int32)
+        length = np.empty(n, np.int32)
+        p = lambda a: a.ctypes.data_as(_i32p)  # noqa: E731
+        check(self._lib.fpb_paths_list(self._h, n, p(trial), p(cx), p(src), p(dst), max_len, p(qubits), p(length)))
+        return qubits, length
 
 
 _fpbpy = None

@@ -214,6 +214,26 @@ class StabilizerGraphView:
     def assign_weights(self, code):
         """Edge weights are read straight from the qubit weights by the kernels."""
 
+    def edge_data(self, node1, node2):
+        """``{"common_vertex": coords, "weight": w}`` of a stabilizer-graph edge
+        (``stabilizer_graph.py:72-88,289-302,321-329``): between two adjacent cubes the shared
+        syndrome qubit, between a cube and a boundary point the point itself."""
+        code, ct = self._code, self._code.lattice.complexes[self.ec]
+        g = code.graph
+        if isinstance(node1, Stabilizer) and isinstance(node2, Stabilizer):
+            faces = np.nonzero(ct.nbr[node1.index] == node2.index)[0]
+            if node1.ec != self.ec or node2.ec != self.ec or len(faces) == 0:
+                raise KeyError((node1, node2))
+            node = int(ct.qubits[ct.cube_qubit[node1.index, faces[0]]])
+        else:
+            stab, point = (node1, node2) if isinstance(node1, Stabilizer) else (node2, node1)
+            node = g.to_indices.get(tuple(point)) if not isinstance(point, str) else None
+            if not isinstance(stab, Stabilizer) or node is None or node not in stab._nodes or (
+                    node not in ct.low_points and node not in ct.high_points):
+                raise KeyError((node1, node2))
+        weight = None if g.weight is None or np.isnan(g.weight[node]) else g.weight[node]
+        return {"common_vertex": g.to_points[node], "weight": weight}
+
 
 class SurfaceCode:
     """``SurfaceCode(distance, ec="primal", boundaries="open", polarity=None, backend="b200")``."""
@@ -267,6 +287,44 @@ class SurfaceCode:
     def alternating_polarity(self, edge):  # pragma: no cover - convenience
         raise NotImplementedError
 
+    def q_offset(self, ec):
+        """Column of the first syndrome qubit of complex ``ec`` in the engine's qubit order."""
+        off = 0
+        for e in self.ec:
+            if e == ec:
+                return off
+            off += self.lattice.complexes[e].Q
+        raise KeyError(ec)
+
+    def qubit_cubes(self, ec):
+        """int32[Q, 2]: the one or two cubes of complex ``ec`` that contain each of its syndrome
+        qubits (a boundary point lies in one cube: both entries equal)."""
+        cache = self.__dict__.setdefault("_qubit_cubes", {})
+        if ec not in cache:
+            ct = self.lattice.complexes[ec]
+            qc = np.full((ct.Q, 2), -1, np.int32)
+            for f in range(6):
+                q = ct.cube_qubit[:, f]
+                for c in np.nonzero(q >= 0)[0]:
+                    col = 0 if qc[q[c], 0] in (-1, c) else 1
+                    qc[q[c], col] = c
+            qc[qc[:, 1] < 0, 1] = qc[qc[:, 1] < 0, 0]
+            cache[ec] = qc
+        return cache[ec]
+
+    def release_engines(self):
+        """Close every cached engine (device buffers, streams).  Sweeps over noise / weight
+        parameters call this after each point: the cache is keyed by those parameters and would
+        otherwise hold every point's batch buffers until the code object dies."""
+        for eng in self._engines.values():
+            eng.close()
+        self._engines.clear()
+
+    def graph_engine(self, device=0):
+        """The engine that builds matching graphs from the ``weight`` / ``bit_val`` node attributes
+        (``fpb_run_weighted``); its own handle, never switched to the static-weight table."""
+        return self.engine(1.0, 0.0, {"method": "uniform"}, device=device, lane="weighted")
+
     # ------------------------------------------------------------------ engine cache
     def engine(self, delta, p_swap, weight_opts=None, device=0, mode="compat", lane=0):
         """The ``TrialEngine`` for these noise / weight options (created once).  ``lane`` > 0
@@ -278,7 +336,7 @@ class SurfaceCode:
         eng = self._engines.get(key)
         if eng is None:
             eng = TrialEngine(self.lattice, delta, p_swap, wo, mode=mode, device=device)
-            if lane and self.engine(delta, p_swap, weight_opts, device, mode).uses_table:
+            if lane and lane != "weighted" and self.engine(delta, p_swap, weight_opts, device, mode).uses_table:
                 eng.build_table()
             self._engines[key] = eng
         return eng

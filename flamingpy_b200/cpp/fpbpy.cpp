@@ -189,6 +189,20 @@ class Handle {
     }
     check(rc);
   }
+  void run_weighted(carray<double> weights, carray<uint32_t> bits, int stage) {
+    if (weights.ndim() != 2 || bits.ndim() != 2 || weights.shape(0) != bits.shape(0) ||
+        weights.shape(1) != (py::ssize_t)qtot_ || bits.shape(1) != (py::ssize_t)bit_words_)
+      throw std::runtime_error("weights must be float64[T, Qtot] and bits uint32[T, bit_words]");
+    const int64_t T = weights.shape(0);
+    const double* wp = weights.data();
+    const uint32_t* bp = bits.data();
+    int rc;
+    {
+      py::gil_scoped_release release;
+      rc = fpb_run_weighted(h(), T, wp, bp, 0, stage);
+    }
+    check(rc);
+  }
   void run_iid(uint64_t seed, int64_t first_trial, int64_t n_trials, double p_err, int stage) {
     int rc;
     {
@@ -363,6 +377,25 @@ class Handle {
     check(rc);
   }
 
+  // ordered correction paths: (qubits int32[n, max_len], lengths int32[n]) - freshly owned arrays
+  py::tuple paths_list(carray<int32_t> trial, carray<int32_t> cx, carray<int32_t> src, carray<int32_t> dst,
+                       int max_len) {
+    const int64_t n = trial.size();
+    if (cx.size() != n || src.size() != n || dst.size() != n) throw std::runtime_error("query arrays differ in length");
+    if (max_len < 1) throw std::runtime_error("max_len must be positive");
+    py::array_t<int32_t> qubits({(py::ssize_t)n, (py::ssize_t)max_len});
+    py::array_t<int32_t> length((py::ssize_t)n);
+    const int32_t *tp = trial.data(), *cp = cx.data(), *sp = src.data(), *dp = dst.data();
+    int32_t *qp = qubits.mutable_data(), *lp = length.mutable_data();
+    int rc;
+    {
+      py::gil_scoped_release release;
+      rc = fpb_paths_list(h(), n, tp, cp, sp, dp, max_len, qp, lp);
+    }
+    check(rc);
+    return py::make_tuple(qubits, length);
+  }
+
  private:
   fpb_handle* h_ = nullptr;
   size_t n_nodes_ = 0, qtot_ = 0, bit_words_ = 0;
@@ -393,6 +426,7 @@ PYBIND11_MODULE(fpbpy, m) {
       .def("run_rng", &Handle::run_rng, py::arg("seed"), py::arg("first_trial"), py::arg("n_trials"),
            py::arg("stage") = FPB_STAGE_GRAPH)
       .def("run_bits", &Handle::run_bits, py::arg("bits"), py::arg("stage") = FPB_STAGE_GRAPH)
+      .def("run_weighted", &Handle::run_weighted, py::arg("weights"), py::arg("bits"), py::arg("stage") = FPB_STAGE_GRAPH)
       .def("run_iid", &Handle::run_iid, py::arg("seed"), py::arg("first_trial"), py::arg("n_trials"), py::arg("p_err"),
            py::arg("stage") = FPB_STAGE_GRAPH)
       .def("sizes", &Handle::sizes)
@@ -405,5 +439,6 @@ PYBIND11_MODULE(fpbpy, m) {
       .def("mark", &Handle::mark)
       .def("elapsed_ms", &Handle::elapsed_ms)
       .def("knn", &Handle::knn, py::arg("complex_index"), py::arg("k"), py::arg("out"))
-      .def("paths_toggle", &Handle::paths_toggle);
+      .def("paths_toggle", &Handle::paths_toggle)
+      .def("paths_list", &Handle::paths_list);
 }

@@ -105,7 +105,7 @@ struct fpb_handle {
   DevBuf<double> x, hom, weights;
   DevBuf<uint8_t> state;
   DevBuf<uint32_t> bits, flips;
-  DevBuf<int> item_off, counter, q_trial, q_cx, q_src, q_dst;
+  DevBuf<int> item_off, counter, q_trial, q_cx, q_src, q_dst, path_qubits, path_len;
   DevBuf<long long> totals;
   long long* totals_host = nullptr;  // pinned + mapped: kernels write it directly (no copy-engine hop)
   long long* totals_map = nullptr;   // device alias of totals_host
@@ -276,7 +276,9 @@ int configure_paths(fpb_handle* h) {
       if (teams > 8) teams = 8;
       if (h->paths_team && teams <= h->warps) continue;  // the shared-weights variant already holds as many
       const size_t need = cta_b + (size_t)teams * warp_b;
-      CK(cudaFuncSetAttribute(tf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+      // the attribute is per function and process-wide: always the full opt-in room, so that a handle with
+      // a smaller lattice in the same template bucket cannot lower another live handle's limit
+      CK(cudaFuncSetAttribute(tf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)room));
       int resident = 0;
       CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, tf, teams * 64, need));
       if (resident < 1) continue;
@@ -311,7 +313,8 @@ int configure_paths(fpb_handle* h) {
         if (teams > 16 / W) teams = 16 / W;
         if (teams >= 1) {
           const size_t need = (size_t)teams * warp_b;
-          CK(cudaFuncSetAttribute(tf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+          CK(cudaFuncSetAttribute(tf, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)((size_t)max_optin - fattr.sharedSizeBytes)));
           int resident = 0;
           CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, tf, teams * W * 32, need));
           if (resident >= 1) {
@@ -421,7 +424,7 @@ int post_syndrome(fpb_handle* h, long long T, int stage, int* launches) {
 }
 
 // source of a batch: injected draws + labels, Philox draws + labels, injected bits, Philox i.i.d. bits
-enum { SRC_INJECTED = 0, SRC_GEN = 1, SRC_BITS = 2, SRC_IID = 3 };
+enum { SRC_INJECTED = 0, SRC_GEN = 1, SRC_BITS = 2, SRC_IID = 3, SRC_WEIGHTED = 4 };
 
 int run_pipeline(fpb_handle* h, long long T, int stage, int source, uint64_t seed, long long first_trial,
                  double p_err = 0.0) {
@@ -474,7 +477,10 @@ int run_pipeline(fpb_handle* h, long long T, int stage, int source, uint64_t see
     ++launches;
   }
   CK(cudaEventRecord(h->ev[1], st));
-  if (source == SRC_BITS || source == SRC_IID) {
+  if (source == SRC_WEIGHTED) {
+    // weights and bits were given: nothing to compute before the syndrome
+    CK(cudaMemsetAsync(h->hom.p, 0, (size_t)T * h->Qtot * sizeof(double), st));
+  } else if (source == SRC_BITS || source == SRC_IID) {
     // bits-only trials: no homodyne outcomes; every syndrome qubit carries the uniform weight 1
     const long long nw = T * (long long)h->Qtot;
     const long long blocks = (nw + 255) / 256, cap = (long long)h->sm_count * 32;
@@ -676,6 +682,7 @@ int fpb_destroy(fpb_handle* h) {
   }
   h->x.release(); h->hom.release(); h->weights.release(); h->state.release(); h->bits.release();
   h->flips.release(); h->item_off.release(); h->counter.release(); h->totals.release();
+  h->path_qubits.release(); h->path_len.release();
   h->q_trial.release(); h->q_cx.release(); h->q_src.release(); h->q_dst.release(); h->wscratch.release();
   if (h->totals_host) cudaFreeHost(h->totals_host);
   if (h->static_flag_host) cudaFreeHost(h->static_flag_host);
@@ -728,6 +735,21 @@ int fpb_run_bits(fpb_handle* h, int64_t n_trials, const uint32_t* bits, int on_d
                      on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
   h->have_rng = false;
   return run_pipeline(h, n_trials, stage, SRC_BITS, 0, 0);
+}
+
+int fpb_run_weighted(fpb_handle* h, int64_t n_trials, const double* weights, const uint32_t* bits, int on_device,
+                     int stage) {
+  if (!h || !weights || !bits) return fail(FPB_ERR_ARG, "null argument");
+  if (stage < FPB_STAGE_SYNDROME) return fail(FPB_ERR_ARG, "a weights + bits run starts at the syndrome stage");
+  if (h->use_table) return fail(FPB_ERR_STATE, "the static-weight table is in use: given weights would be ignored");
+  CK(cudaSetDevice(h->device));
+  int rc = ensure_batch(h, n_trials);
+  if (rc) return rc;
+  const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  CK(cudaMemcpyAsync(h->weights.p, weights, (size_t)n_trials * h->Qtot * sizeof(double), kind, h->stream));
+  CK(cudaMemcpyAsync(h->bits.p, bits, (size_t)n_trials * h->bit_words * sizeof(uint32_t), kind, h->stream));
+  h->have_rng = false;
+  return run_pipeline(h, n_trials, stage, SRC_WEIGHTED, 0, 0);
 }
 
 int fpb_run_iid(fpb_handle* h, uint64_t seed, int64_t first_trial, int64_t n_trials, double p_err, int stage) {
@@ -906,7 +928,7 @@ int fpb_knn(fpb_handle* h, int complex_index, int k, int32_t* ids, int on_device
   if (warps > 8) warps = 8;
   if (warps < 1) return fail(FPB_ERR_UNSUPPORTED, "too many odd cubes in one trial for the candidate kernel");
   const size_t smem = (size_t)warps * row_cap * sizeof(double);
-  CK(cudaFuncSetAttribute(k_knn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cudaFuncSetAttribute(k_knn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - 1024));
   dim3 grid((unsigned)h->T, (unsigned)((cx.max_odd + warps - 1) / warps));
   k_knn<<<grid, warps * 32, smem, st>>>(make_dev(cx), k, row_cap, cx.knn.p);
   CK(cudaGetLastError());
@@ -919,16 +941,19 @@ int fpb_knn(fpb_handle* h, int complex_index, int k, int32_t* ids, int on_device
   return FPB_OK;
 }
 
-int fpb_paths_toggle(fpb_handle* h, int64_t n_queries, const int32_t* trial, const int32_t* cx_id,
-                     const int32_t* src, const int32_t* dst, uint32_t* flips_host) {
-  if (!h || !flips_host) return fail(FPB_ERR_ARG, "null argument");
-  if (h->last_stage < FPB_STAGE_GRAPH) return fail(FPB_ERR_STATE, "fpb_paths_toggle needs a completed graph-stage run");
+// fpb_paths_toggle (flips_host) and fpb_paths_list (qubits_host / length_host) share the query machinery
+static int run_path_queries(fpb_handle* h, int64_t n_queries, const int32_t* trial, const int32_t* cx_id,
+                            const int32_t* src, const int32_t* dst, uint32_t* flips_host, int max_len,
+                            int32_t* qubits_host, int32_t* length_host) {
+  if (h->last_stage < FPB_STAGE_GRAPH) return fail(FPB_ERR_STATE, "path queries need a completed graph-stage run");
   CK(cudaSetDevice(h->device));
   cudaStream_t st = h->stream;
   int rc;
   const size_t nflip = (size_t)h->T * h->bit_words;
-  if ((rc = h->flips.ensure(nflip))) return rc;
-  CK(cudaMemsetAsync(h->flips.p, 0, nflip * sizeof(uint32_t), st));
+  if (flips_host) {
+    if ((rc = h->flips.ensure(nflip))) return rc;
+    CK(cudaMemsetAsync(h->flips.p, 0, nflip * sizeof(uint32_t), st));
+  }
   if (n_queries > 0) {
     if (!trial || !cx_id || !src || !dst) return fail(FPB_ERR_ARG, "null query array");
     // validate on the host: indices must address odd cubes of the last run
@@ -962,6 +987,11 @@ int fpb_paths_toggle(fpb_handle* h, int64_t n_queries, const int32_t* trial, con
     pp.n_queries = (int)n_queries;
     pp.q_trial = h->q_trial.p; pp.q_cx = h->q_cx.p; pp.q_src = h->q_src.p; pp.q_dst = h->q_dst.p;
     pp.flips = h->flips.p; pp.bit_words = h->bit_words;
+    if (qubits_host) {
+      if ((rc = h->path_qubits.ensure((size_t)n_queries * max_len))) return rc;
+      if ((rc = h->path_len.ensure((size_t)n_queries))) return rc;
+      pp.path_qubits = h->path_qubits.p; pp.path_len = h->path_len.p; pp.path_cap = max_len;
+    }
     int max_optin = 0;
     CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
     const bool wg = h->paths_wg;
@@ -971,7 +1001,12 @@ int fpb_paths_toggle(fpb_handle* h, int64_t n_queries, const int32_t* trial, con
     if (warps > 8) warps = 8;
     const size_t smem = (size_t)warps * per_warp;
     toggle_fn tfn = pick_toggle_kernel(h->S_max, wg);
-    CK(cudaFuncSetAttribute(tfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+      cudaFuncAttributes fattr;
+      CK(cudaFuncGetAttributes(&fattr, tfn));
+      CK(cudaFuncSetAttribute(tfn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)((size_t)max_optin - fattr.sharedSizeBytes)));
+    }
     long long grid = (n_queries + warps - 1) / warps;
     const long long cap = (long long)h->sm_count * 4;
     if (grid > cap) grid = cap;
@@ -981,10 +1016,27 @@ int fpb_paths_toggle(fpb_handle* h, int64_t n_queries, const int32_t* trial, con
     }
     tfn<<<(unsigned)grid, warps * 32, smem, st>>>(pp);
     CK(cudaGetLastError());
+    if (qubits_host) {
+      CK(cudaMemcpyAsync(qubits_host, h->path_qubits.p, (size_t)n_queries * max_len * sizeof(int), cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(length_host, h->path_len.p, (size_t)n_queries * sizeof(int), cudaMemcpyDeviceToHost, st));
+    }
   }
-  CK(cudaMemcpyAsync(flips_host, h->flips.p, nflip * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  if (flips_host) CK(cudaMemcpyAsync(flips_host, h->flips.p, nflip * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   return FPB_OK;
+}
+
+int fpb_paths_toggle(fpb_handle* h, int64_t n_queries, const int32_t* trial, const int32_t* cx_id,
+                     const int32_t* src, const int32_t* dst, uint32_t* flips_host) {
+  if (!h || !flips_host) return fail(FPB_ERR_ARG, "null argument");
+  return run_path_queries(h, n_queries, trial, cx_id, src, dst, flips_host, 0, nullptr, nullptr);
+}
+
+int fpb_paths_list(fpb_handle* h, int64_t n_queries, const int32_t* trial, const int32_t* cx_id, const int32_t* src,
+                   const int32_t* dst, int32_t max_len, int32_t* qubits, int32_t* length) {
+  if (!h || !qubits || !length) return fail(FPB_ERR_ARG, "null argument");
+  if (max_len < 1) return fail(FPB_ERR_ARG, "max_len must be positive");
+  return run_path_queries(h, n_queries, trial, cx_id, src, dst, nullptr, max_len, qubits, length);
 }
 
 }  // extern "C"

@@ -431,6 +431,9 @@ struct PathsParams {
   const int* q_dst;
   uint32_t* flips;            // [T][bit_words]
   int bit_words;
+  int* path_qubits;           // fpb_paths_list: [n_queries][path_cap] local qubit ids in walk order (else nullptr)
+  int* path_len;              // [n_queries]
+  int path_cap;
   double* wscratch;           // [grid][slots_max] slot-ordered weights (global-weights variant only)
 };
 
@@ -1540,6 +1543,7 @@ __global__ void __launch_bounds__(256) k_path_toggle(const __grid_constant__ Pat
     const int src = odd[p.q_src[qi]];
     const bool pair_query = p.q_dst[qi] >= 0;
     uint32_t* flips = p.flips + (long long)t * p.bit_words;
+    int* plist = p.path_qubits ? p.path_qubits + (long long)qi * p.path_cap : nullptr;
     warp_clear(wm, S, lane);
     int walk_from, stop, side = 0;
     uint32_t present = 0;
@@ -1559,6 +1563,17 @@ __global__ void __launch_bounds__(256) k_path_toggle(const __grid_constant__ Pat
     __syncwarp();
     if (lane == 0) {
       int u = walk_from;
+      int steps = 0;
+      // one crossed qubit: XOR-toggle it (fpb_paths_toggle) or append it to the query's list (fpb_paths_list)
+      auto cross = [&](int local_q) {
+        if (plist) {
+          if (steps < p.path_cap) plist[steps] = local_q;
+          ++steps;
+        } else {
+          const int g = c.qoff + local_q;
+          atomicXor(&flips[g >> 5], 1u << (g & 31));
+        }
+      };
       for (int guard = 0; guard < S + 2; ++guard) {
         const int din = wm.pred[u];
         if (din == 6) break;  // reached the source cube
@@ -1569,8 +1584,7 @@ __global__ void __launch_bounds__(256) k_path_toggle(const __grid_constant__ Pat
           const int* slots = side ? c.high_slot : c.low_slot;
           for (int i = 0; i < n; ++i)
             if (cubes[i] == u) {
-              const int g = c.qoff + c.slot_qubit[slots[i]];
-              atomicXor(&flips[g >> 5], 1u << (g & 31));
+              cross(c.slot_qubit[slots[i]]);
               break;
             }
           break;
@@ -1581,10 +1595,10 @@ __global__ void __launch_bounds__(256) k_path_toggle(const __grid_constant__ Pat
         const int v = u + (kb ? dt.dwrap[back] : dt.dreg[back]);
         const uint32_t kf = (c.ninfo[v] >> (2 * din)) & 3u;
         const int slot = c.sbase[v] + (kf ? dt.swrap[din] : dt.sreg[din]);
-        const int g = c.qoff + c.slot_qubit[slot];
-        atomicXor(&flips[g >> 5], 1u << (g & 31));
+        cross(c.slot_qubit[slot]);
         u = v;
       }
+      if (plist) p.path_len[qi] = steps <= p.path_cap ? steps : -1;
     }
     __syncwarp();
   }

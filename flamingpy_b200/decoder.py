@@ -61,13 +61,43 @@ def assign_weights(code, decoder="MWPM", **kwargs):
     return eng
 
 
-def build_match_graph(code, ec, matching_backend="networkx", weight_options=None):
-    """``build_match_graph`` (``decoders/mwpm/algos.py:23-47``): the matching graph of the
-    current noise realisation, built on the GPU."""
-    wo = {"method": "uniform", "integer": False, "multiplier": 1}
-    wo.update(weight_options or {})
-    eng, batch = _run_trial(code, wo, _lib.STAGE_GRAPH)
-    return GpuMatchingGraph.from_batch(code, ec, eng, batch, 0, backend=matching_backend)
+def build_match_graph(code, ec, matching_backend="native", weight_options=None):
+    """``build_match_graph(code, ec, matching_backend)`` (``decoders/mwpm/algos.py:23-47``): the
+    matching graph of the code's current ``weight`` / ``bit_val`` attributes, built on the GPU.
+
+    ``matching_backend``: a string picks the host matcher of ``GpuMatchingGraph`` ("native";
+    "networkx"; the reference's compiled backends "rustworkx" / "lemon" map to the native one), or -
+    like in the reference - any class deriving from the ``MatchingGraph`` contract with an
+    ``(ec, code)`` constructor, e.g. ``GpuMatchingGraph`` itself.  ``weight_options`` (not in the
+    reference's signature) runs ``assign_weights`` first; without it the weights must already be
+    on the code, as in the reference's ``correct`` (``decoder.py:270-273``)."""
+    if weight_options is not None:
+        assign_weights(code, "MWPM", **weight_options)
+    if isinstance(matching_backend, str):
+        backend = "native" if matching_backend in ("rustworkx", "retworkx", "lemon") else matching_backend
+        if backend not in ("native", "networkx"):
+            raise ValueError(f"unknown matching backend {matching_backend!r}")
+        return GpuMatchingGraph(ec, code, backend=backend)
+    return matching_backend(ec, code)
+
+
+def mwpm_decoder(code, ec, backend="native", draw=False, drawing_opts=None):
+    """``mwpm_decoder`` (``decoders/mwpm/algos.py:50-96``): build the matching graph, solve the
+    matching, and return the set of qubits (coordinates) whose bit values the recovery flips -
+    the XOR of the ``common_vertex`` of every edge on every matched path."""
+    if draw:
+        raise NotImplementedError("drawing is out of scope for the accelerated path")
+    stab_graph = getattr(code, ec + "_stab_graph")
+    matching_graph = build_match_graph(code, ec, backend)
+    virtual = set(matching_graph.virtual_points)
+    qubits_to_flip = set()
+    for match in matching_graph.min_weight_perfect_matching():
+        if match[0] in virtual and match[1] in virtual:
+            continue
+        path = matching_graph.edge_path(match)
+        for a, b in zip(path[:-1], path[1:]):
+            qubits_to_flip ^= {stab_graph.edge_data(a, b)["common_vertex"]}
+    return qubits_to_flip
 
 
 def recovery(qubits_to_flip, code, ec, sanity_check=False):
@@ -112,16 +142,17 @@ def check_correction(code, sanity_check=False):
 def correct(code, decoder="MWPM", weight_options=None, sanity_check=False, decoder_opts=None, draw=False,
             drawing_opts=None):
     """``correct`` (``decoders/decoder.py:227-288``).  Returns True if error correction
-    succeeded.  ``decoder_opts["backend"]`` picks the host matcher: "networkx" (default here: it
-    reproduces the reference's networkx verdicts trial by trial, ties included) or "native"; the
-    reference's compiled backends "rustworkx" and "lemon" are not installable offline and map to
-    the native exact matcher (same total weight, possibly another choice among tied matchings)."""
+    succeeded.  ``decoder_opts["backend"]`` picks the host matcher.  The default is the compiled one
+    ("native": exact C++ blossom matcher), like the reference's default is its compiled backend
+    (``decoder.py:277``); the reference's "rustworkx" and "lemon" are not installable offline and
+    map to it (same total weight, possibly another choice among tied matchings).  "networkx"
+    reproduces the reference's networkx verdicts trial by trial, ties included, and is slow."""
     if decoder != "MWPM":
         raise NotImplementedError("only the MWPM decoder is on the accelerated path")
     if draw:
         raise NotImplementedError("drawing is out of scope for the accelerated path")
     weight_options = dict(weight_options or {})
-    opts = {"backend": "networkx"}
+    opts = {"backend": "native"}
     opts.update(decoder_opts or {})
     if opts["backend"] in ("rustworkx", "retworkx", "lemon"):
         opts["backend"] = "native"
@@ -153,7 +184,7 @@ def correct(code, decoder="MWPM", weight_options=None, sanity_check=False, decod
     return bool(np.all(result))
 
 
-def match_batch(code, eng, batch, backend="networkx", cands=None):
+def match_batch(code, eng, batch, backend="native", cands=None):
     """Host matching of every trial of ``batch``: (trial, complex, src, dst) int32 arrays of the
     matched queries (dst = -1: to the connector).  ``backend="native"`` solves all trials with the
     C++ matcher (OpenMP over trials); ``cands`` = per-complex candidate lists (``candidates``)."""
@@ -202,7 +233,7 @@ def candidates(eng, batch, ci, e):
     return None
 
 
-def decode_batch(code, eng, batch, backend="networkx"):
+def decode_batch(code, eng, batch, backend="native"):
     """Host matching + device path extraction for every trial of ``batch``.
     Returns the recovery as uint8[T, Qtot] bit flips."""
     return eng.paths_toggle(*match_batch(code, eng, batch, backend=backend))

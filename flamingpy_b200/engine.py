@@ -139,6 +139,7 @@ class TrialEngine:
         self._h = _lib.open_handle(cfg)  # pybind11 fpbpy.Handle, or ctypes when the module is absent
         self.binding = _lib.binding_name()
         self.uses_table = False
+        self.run_id = 0  # bumped by every run: consumers of "the last run" check it
 
     # ------------------------------------------------------------------ lifecycle
     def close(self):
@@ -163,20 +164,20 @@ class TrialEngine:
         if state.shape != (x.shape[0], self.lat.N):
             raise ValueError(f"state must have shape [T, {self.lat.N}]")
         T = x.shape[0]
+        self.run_id += 1
         self._h.run_injected(x, state, stage)
         return self.fetch(stage) if fetch else TrialBatch(T, stage, timings=self.timings())
 
     def run_rng(self, seed: int, first_trial: int, n_trials: int, stage: int = _lib.STAGE_GRAPH,
                 fetch: bool = True, want_draws: bool = False) -> TrialBatch:
         """Run trials ``[first_trial, first_trial + n_trials)`` of the Philox stream ``seed``."""
+        self.run_id += 1
         self._h.run_rng(seed & (2**64 - 1), first_trial, n_trials, stage)
         return self.fetch(stage, want_draws=want_draws) if fetch else TrialBatch(
             n_trials, stage, timings=self.timings())
 
-    def run_bits(self, bits, stage: int = _lib.STAGE_GRAPH, fetch: bool = True) -> TrialBatch:
-        """Trials given directly as bit values of the syndrome qubits - the i.i.d. Pauli-noise model
-        (``flamingpy/noise/iid.py``) or any other bit-level sampler.  ``bits``: uint8[T, Qtot] (0/1)
-        or already packed uint32[T, bit_words] (LSB first).  Needs uniform weights."""
+    def _packed_bits(self, bits) -> np.ndarray:
+        """uint8[T, Qtot] (0/1) or already packed uint32[T, bit_words] -> packed, C-contiguous."""
         bits = np.asarray(bits)
         if bits.dtype != np.uint32:
             if bits.ndim != 2 or bits.shape[1] != self.Qtot:
@@ -186,15 +187,37 @@ class TrialEngine:
             bits = np.packbits(pad, axis=1, bitorder="little").view(np.uint32)
         if bits.ndim != 2 or bits.shape[1] != self.bit_words:
             raise ValueError(f"packed bits must have shape (n_trials, {self.bit_words})")
-        bits = np.ascontiguousarray(bits)
+        return np.ascontiguousarray(bits)
+
+    def run_bits(self, bits, stage: int = _lib.STAGE_GRAPH, fetch: bool = True) -> TrialBatch:
+        """Trials given directly as bit values of the syndrome qubits - the i.i.d. Pauli-noise model
+        (``flamingpy/noise/iid.py``) or any other bit-level sampler.  ``bits``: uint8[T, Qtot] (0/1)
+        or already packed uint32[T, bit_words] (LSB first).  Needs uniform weights."""
+        bits = self._packed_bits(bits)
         n_trials = bits.shape[0]
+        self.run_id += 1
         self._h.run_bits(bits, stage)
         return self.fetch(stage) if fetch else TrialBatch(n_trials, stage, timings=self.timings())
+
+    def run_weighted(self, weights, bits, stage: int = _lib.STAGE_GRAPH, fetch: bool = True) -> TrialBatch:
+        """Trials given as the node attributes the reference's matching-graph builder reads: the
+        ``weight`` (float64[T, Qtot]) and ``bit_val`` (uint8[T, Qtot], or packed uint32[T, bit_words])
+        of every syndrome qubit, whatever produced them (``mwpm/matching.py:97-173``)."""
+        weights = np.ascontiguousarray(weights, np.float64)
+        if weights.ndim != 2 or weights.shape[1] != self.Qtot:
+            raise ValueError(f"weights must have shape (n_trials, {self.Qtot})")
+        bits = self._packed_bits(bits)
+        if bits.shape[0] != weights.shape[0]:
+            raise ValueError("weights and bits differ in the number of trials")
+        self.run_id += 1
+        self._h.run_weighted(weights, bits, stage)
+        return self.fetch(stage) if fetch else TrialBatch(weights.shape[0], stage, timings=self.timings())
 
     def run_iid(self, seed: int, first_trial: int, n_trials: int, p_err: float, stage: int = _lib.STAGE_GRAPH,
                 fetch: bool = True) -> TrialBatch:
         """Trials ``[first_trial, first_trial + n_trials)`` of i.i.d. Z errors with probability
         ``p_err`` per qubit, drawn on the device (Philox stream ``seed``).  Needs uniform weights."""
+        self.run_id += 1
         self._h.run_iid(seed & (2**64 - 1), first_trial, n_trials, float(p_err), stage)
         return self.fetch(stage) if fetch else TrialBatch(n_trials, stage, timings=self.timings())
 
@@ -366,6 +389,22 @@ class TrialEngine:
         if n:
             self._h.knn(complex_index, k, out)
         return out[: n * k].reshape(n, k)
+
+    def paths_list(self, trial, cx, src, dst, max_len: int = 0):
+        """Ordered correction paths of the given queries (same arguments as ``paths_toggle``):
+        a list with one int32 array per query holding the local qubit ids crossed (qubit order of the
+        query's complex), walking from ``dst`` back to ``src``, or from ``src`` out to its nearer
+        connector (``dst == -1``, last entry = the boundary qubit)."""
+        trial = np.ascontiguousarray(trial, np.int32)
+        cx = np.ascontiguousarray(cx, np.int32)
+        src = np.ascontiguousarray(src, np.int32)
+        dst = np.ascontiguousarray(dst, np.int32)
+        if max_len <= 0:
+            max_len = max(self.lat.complexes[e].S for e in self.ec) + 1  # a simple path visits a cube once
+        qubits, length = self._h.paths_list(trial, cx, src, dst, int(max_len))
+        if np.any(length < 0):
+            raise ValueError("a path is longer than max_len")
+        return [qubits[i, : length[i]].copy() for i in range(len(trial))]
 
     def paths_toggle(self, trial, cx, src, dst) -> np.ndarray:
         """XOR-toggle the qubits on the shortest paths of the given (trial,

@@ -40,7 +40,7 @@ def dense_inverse_weights(K: int, pair_len: np.ndarray, bnd_len: Optional[np.nda
     return A
 
 
-def solve_matching(K: int, pair_len: np.ndarray, bnd_len: Optional[np.ndarray], backend="networkx"):
+def solve_matching(K: int, pair_len: np.ndarray, bnd_len: Optional[np.ndarray], backend="native"):
     """Minimum-weight perfect matching of one matching graph on the host.
     Returns [(u, v)] over odd-cube indices, v == -1 for "matched to its connector"."""
     if K == 0:
@@ -81,25 +81,76 @@ def solve_matching(K: int, pair_len: np.ndarray, bnd_len: Optional[np.ndarray], 
 
 
 class GpuMatchingGraph:
-    """Reference ``MatchingGraph`` interface over GPU-built lengths."""
+    """The reference's ``MatchingGraph`` plug-in contract (``decoders/mwpm/matching.py:36-173``) over
+    GPU-built lengths.
 
-    def __init__(self, ec, code=None):
+    ``GpuMatchingGraph(ec, code)`` builds itself from the code's current realisation exactly like
+    the reference's backends do (``MatchingGraph.__init__`` -> ``with_edges_from``): it reads the
+    ``weight`` and ``bit_val`` node attributes that the noise model and ``assign_weights`` left on
+    ``code.graph`` and runs parity -> odd cubes -> shortest paths on the device
+    (``fpb_run_weighted``).  So the class can be handed to ``build_match_graph(code, ec, <class>)``
+    (``mwpm/algos.py:29-47``), and ``mwpm_decoder``'s loop over ``edge_path`` /
+    ``stab_graph.edge_data(...)["common_vertex"]`` (``algos.py:88-95``) runs unchanged on it.
+
+    Nodes are the odd ``Stabilizer`` objects and, with boundary points, one virtual node
+    ``(boundary point, i)`` per odd cube (``matching.py:159-168``); virtual-virtual edges weigh 0.
+    """
+
+    backend = "native"  # host matcher used by min_weight_perfect_matching ("native" | "networkx")
+
+    def __init__(self, ec, code=None, backend=None):
         self.ec = ec
         self.code = code
         self.virtual_points: List = []
         self.K = 0
         self._pair = np.empty(0)
         self._bnd = None
+        self._side = None
         self._extra = {}
-        self._backend = "networkx"
         self._stabs = []
+        self._index = {}
+        self._eng = None
+        self._rerun = None
+        if backend is not None:
+            self.backend = backend if isinstance(backend, str) else "native"
+        if code is not None:
+            self.with_edges_from(code, ec)
+
+    # -- construction --------------------------------------------------------------------
+    def with_edges_from(self, code, ec):
+        """``MatchingGraph.with_edges_from`` (``matching.py:97-123``) for the code's current
+        ``weight`` / ``bit_val`` attributes."""
+        g = code.graph
+        if g.weight is None or g.bit_val is None:
+            raise ValueError("no weights / bit values on the code: apply a noise model and assign_weights first")
+        qn = np.concatenate([code.lattice.complexes[e].qubits for e in code.ec])
+        w = np.array(g.weight[qn], np.float64)
+        b = np.array(g.bit_val[qn])
+        ct = code.lattice.complexes[ec]
+        sl = slice(code.q_offset(ec), code.q_offset(ec) + ct.Q)
+        if np.isnan(w[sl]).any() or (b[sl] < 0).any():
+            raise ValueError(f"syndrome qubits of the {ec} complex lack a weight or a bit value")
+        w = np.where(np.isnan(w), 1.0, w)  # other complexes: not part of this graph
+        b = (b > 0).astype(np.uint8)
+        eng = code.graph_engine()
+        batch = eng.run_weighted(w[None, :], b[None, :])
+        self._populate(code, ec, eng, batch, 0)
+        self._rerun = (w, b)
+        return self
 
     @classmethod
-    def from_batch(cls, code, ec, eng, batch, t, backend="networkx"):
-        self = cls(ec, code)
+    def from_batch(cls, code, ec, eng, batch, t, backend="native"):
+        """Trial ``t`` of a batch the engine has just run (the batched drivers' shortcut)."""
+        self = cls(ec, None, backend=backend)
+        self.code = code
+        self._populate(code, ec, eng, batch, t)
+        return self
+
+    def _populate(self, code, ec, eng, batch, t):
+        self.code = code
         ct = code.lattice.complexes[ec]
         cb = batch.complexes[ec]
-        self._eng, self._t, self._ci = eng, t, code.ec.index(ec)
+        self._eng, self._t, self._ci, self._run_id = eng, t, code.ec.index(ec), eng.run_id
         odd = cb.odd(t)
         self.K = len(odd)
         self._odd = odd
@@ -107,13 +158,24 @@ class GpuMatchingGraph:
         self._stabs = [stabs[int(c)] for c in odd]
         self._index = {s: i for i, s in enumerate(self._stabs)}
         self._pair = cb.pairs(t)
+        self.virtual_points = []
+        self._bnd = self._side = None
         if ct.has_boundary and self.K:
-            self._bnd, side = cb.boundary(t)
-            sg = getattr(code, ec + "_stab_graph")
-            self.virtual_points = [(("low", "high")[int(s)], i) for i, s in enumerate(side)]
+            self._bnd, self._side = cb.boundary(t)
+            # the virtual node of cube i is named after the boundary point its connector path ends in
+            self._conn = eng.paths_list([t] * self.K, [self._ci] * self.K, list(range(self.K)), [-1] * self.K)
+            g = code.graph
+            self.virtual_points = [(g.to_points[int(ct.qubits[p[-1]])], i) for i, p in enumerate(self._conn)]
             self._index.update({vp: self.K + i for i, vp in enumerate(self.virtual_points)})
-        self._backend = backend if isinstance(backend, str) else "networkx"
-        return self
+
+    def _engine(self):
+        """The engine with this graph's realisation as its last run (re-run if it moved on)."""
+        if self._eng.run_id != self._run_id:
+            if self._rerun is None:
+                raise RuntimeError("the engine has run another batch since this graph was built")
+            self._eng.run_weighted(self._rerun[0][None, :], self._rerun[1][None, :], fetch=False)
+            self._run_id, self._t = self._eng.run_id, 0
+        return self._eng
 
     # -- MatchingGraph interface ------------------------------------------------------
     def add_edge(self, edge, weight, path=()):
@@ -128,29 +190,52 @@ class GpuMatchingGraph:
         i, j = sorted(self._ij(edge))
         K = self.K
         if j < K:
-            return float(self._pair[tri_index(i, j, K)])
-        if i >= K:
+            w = float(self._pair[tri_index(i, j, K)])
+        elif i >= K:
             return 0
-        if j == K + i:
-            return float(self._bnd[i])
-        raise KeyError(edge)
+        elif j == K + i:
+            w = float(self._bnd[i])
+        else:
+            raise KeyError(edge)
+        return int(w) if self._eng is not None and self._eng.lengths == "rustworkx" else w
 
     def edge_path(self, edge):
-        """Syndrome qubits (coordinates) crossed by the correction of this edge."""
+        """The path of stabilizer-graph nodes behind a matching-graph edge, in the form
+        ``mwpm_decoder`` consumes (``algos.py:88-95``): ``[stab1, ..., stab2]`` between two odd
+        cubes, ``[boundary point, cube, ..., cube_i]`` for cube ``i`` and its virtual node
+        (``matching.py:157-160``: the connector path without 'low' / 'high'), ``[]`` between two
+        virtual nodes."""
         if frozenset(edge) in self._extra:
             return self._extra[frozenset(edge)][1]
         i, j = sorted(self._ij(edge))
         if i >= self.K:
             return []
-        dst = j if j < self.K else -1
-        flips = self._eng.paths_toggle([self._t], [self._ci], [i], [dst])[self._t]
-        ct = self.code.lattice.complexes[self.ec]
-        off = self._eng.q_off[self.ec]
-        g = self.code.graph
-        return [g.to_points[int(ct.qubits[q])] for q in np.nonzero(flips[off : off + ct.Q])[0]]
+        code, ct = self.code, self.code.lattice.complexes[self.ec]
+        stabs = getattr(code, self.ec + "_stabilizers")
+        other = code.qubit_cubes(self.ec)
+        if j >= self.K:
+            if j != self.K + i:
+                raise KeyError(edge)
+            qs = self._conn[i]
+            cube, nodes = int(self._odd[i]), []
+            for q in qs[:-1]:
+                nodes.append(stabs[cube])
+                a, b = other[q]
+                cube = int(b if a == cube else a)
+            nodes.append(stabs[cube])
+            nodes.append(code.graph.to_points[int(ct.qubits[qs[-1]])])
+            return nodes[::-1]
+        qs = self._engine().paths_list([self._t], [self._ci], [i], [j])[0]
+        cube, nodes = int(self._odd[j]), []
+        for q in qs:
+            nodes.append(stabs[cube])
+            a, b = other[q]
+            cube = int(b if a == cube else a)
+        nodes.append(stabs[cube])
+        return nodes[::-1]
 
     def min_weight_perfect_matching(self):
-        pairs = solve_matching(self.K, self._pair, self._bnd, backend=self._backend)
+        pairs = solve_matching(self.K, self._pair, self._bnd, backend=self.backend)
         out = []
         used = set()
         for u, v in pairs:

@@ -62,9 +62,11 @@ def ec_monte_carlo(trials, code_instance, noise_instance, decoder, decoder_args,
     """Run ``trials`` Monte-Carlo trials of the complete error-correction procedure and
     return the number of logical errors.
 
-    ``world_comm`` / ``mpi_rank`` / ``mpi_size`` are accepted for signature
-    compatibility; with ``torch.distributed`` initialised the trial range is split
-    over its ranks instead and the counts are all-reduced.
+    Trial split: with ``torch.distributed`` initialised, over its ranks with one ``all_reduce`` of
+    the counts (one process per GPU; NCCL).  Otherwise, if an mpi4py-style ``world_comm`` is given
+    with ``mpi_size > 1``, over the MPI ranks with ``world_comm.allreduce`` (the reference's
+    ``Reduce``, ``simulations.py:98-110``; every rank gets the total).  Without either, ``mpi_rank``
+    / ``mpi_size`` are ignored and this process runs all ``trials``.
     """
     if decoder != "MWPM":
         raise NotImplementedError("only the MWPM decoder is on the accelerated path")
@@ -78,8 +80,15 @@ def ec_monte_carlo(trials, code_instance, noise_instance, decoder, decoder_args,
         n_delta, n_pswap, mode = 1.0, 0.0, "fresh"  # engine parameters that bit-level trials never read
     else:
         n_delta, n_pswap = noise_instance.delta, noise_instance.p_swap
+        if not n_pswap and len(np.atleast_1d(noise_instance.states.get("p", []))):
+            # the device Philox path draws labels from p_swap only: a layer with hand-picked
+            # p-squeezed nodes would silently run as all-GKP
+            raise NotImplementedError(
+                "ec_monte_carlo does not batch a CVLayer built with explicit states={'p': [...]}: "
+                "use p_swap, or loop ec_mc_trial (apply_noise + correct) for such a layer")
     dist, rank, size = _dist_info()
-    if dist is None and mpi_size > 1:
+    use_mpi = dist is None and world_comm is not None and mpi_size > 1
+    if use_mpi:
         rank, size = mpi_rank, mpi_size
     if device is None:
         device = 0
@@ -182,10 +191,37 @@ def ec_monte_carlo(trials, code_instance, noise_instance, decoder, decoder_args,
         tc = torch.tensor(counts, dtype=torch.int64, device=dev)
         dist.all_reduce(tc, op=dist.ReduceOp.SUM)
         counts = tc.cpu().numpy()
+    elif use_mpi:
+        counts = np.array(world_comm.allreduce([int(failures), int(done)]) if hasattr(world_comm, "allreduce")
+                          else [failures, done], np.int64).reshape(-1, 2).sum(axis=0)
+    if int(counts[1]) != trials and (dist is not None or use_mpi or size == 1):
+        raise RuntimeError(f"trial accounting: {int(counts[1])} trials completed, {trials} requested")
     errors = int(counts[0])
     if return_stats:
         return errors, {"trials_done": int(counts[1]), "device_ms": t_dev, "rank": rank, "world_size": size}
     return errors
+
+
+def write_csv_row(file_name, code_name, code_args, noise_name, noise_args, decoder, decoder_args, errors, trials,
+                  seconds, mpi_size):
+    """Append one result row in the reference's CSV format (``simulations.py:151-194``, pinned
+    by its ``tests/frontend/test_simulations.py:124-174``): columns ``code``, the code argument names,
+    ``noise``, the noise argument names, ``decoder``, the decoder argument names, then ``errors,
+    trials, current_time, simulation_time, mpi_size``; the header is written when the file is new."""
+    import csv
+    import os
+
+    header = (["code"] + list(code_args) + ["noise"] + list(noise_args) + ["decoder"] + list(decoder_args)
+              + ["errors", "trials", "current_time", "simulation_time", "mpi_size"])
+    row = ([code_name] + list(code_args.values()) + [noise_name] + list(noise_args.values()) + [decoder]
+           + list(decoder_args.values())
+           + [int(errors), int(trials), datetime.now().time().strftime("%H:%M:%S"), "%f" % seconds, int(mpi_size)])
+    new_file = not os.path.exists(file_name)
+    with open(file_name, "a", newline="", encoding="utf8") as f:
+        w = csv.writer(f, lineterminator="\n")  # quotes the weight_opts dict, which contains commas
+        if new_file:
+            w.writerow(header)
+        w.writerow(row)
 
 
 def run_ec_simulation(trials, code, code_args, noise, noise_args, decoder, decoder_args, fname=None, **mc_kwargs):
@@ -199,36 +235,8 @@ def run_ec_simulation(trials, code, code_args, noise, noise_args, decoder, decod
                             **mc_kwargs)
     stop = perf_counter()
     if rank == 0:
-        file_name = fname or "./sims_results.csv"
-        try:
-            file = open(file_name, "x", newline="", encoding="utf8")
-            file.write("code,")
-            for key in code_args:
-                file.write("%s," % (key))
-            file.write("noise,")
-            for key in noise_args:
-                file.write("%s," % (key))
-            file.write("decoder,")
-            for key in decoder_args:
-                file.write("%s," % (key))
-            file.write("errors,trials,current_time,simulation_time,mpi_size\n")
-        except FileExistsError:
-            file = open(file_name, "a", newline="", encoding="utf8")
-        file.write("%s," % (code.__name__))
-        for value in code_args.values():
-            file.write("%s," % (value))
-        file.write("%s," % (noise.__name__))
-        for value in noise_args.values():
-            file.write("%s," % (value))
-        file.write("%s," % (decoder))
-        for key, value in decoder_args.items():
-            if key == "weight_opts":
-                file.write('"%s",' % (value))
-            else:
-                file.write("%s," % (value))
-        current_time = datetime.now().time().strftime("%H:%M:%S")
-        file.write("%i,%i,%s,%f,%i\n" % (errors, trials, current_time, (stop - start), size))
-        file.close()
+        write_csv_row(fname or "./sims_results.csv", code.__name__, code_args, noise.__name__, noise_args, decoder,
+                      decoder_args, errors, trials, stop - start, size)
     return errors
 
 

@@ -27,7 +27,7 @@ COLUMNS = ["code", "distance", "ec", "boundaries", "noise", "delta", "p_swap", "
            "trials", "current_time", "simulation_time", "mpi_size", "mode", "gpus", "device_trials_per_s"]
 
 
-def sweep(distances, deltas, trials, p_swap=0.0, boundaries="open", ec="primal", mode="compat", fname=None,
+def sweep(distances, deltas, trials, p_swap=0.0, boundaries="open", ec="primal", mode="fresh", fname=None,
           graph_only=False, seed=20261019, batch=1024, backend="native"):
     _, rank, size = _dist_info()
     rows = []
@@ -54,6 +54,7 @@ def sweep(distances, deltas, trials, p_swap=0.0, boundaries="open", ec="primal",
             row = ["SurfaceCode", d, ec, boundaries, "CVLayer", delta, p_swap, "MWPM", '"%s"' % wo, errors, trials,
                    time.strftime("%H:%M:%S"), "%f" % dt, size, mode, size, "%.1f" % rate]
             rows.append(row)
+            code.release_engines()  # a finished (delta, weights) point frees its device buffers
             if rank == 0 and fname:
                 new = not os.path.exists(fname)
                 with open(fname, "a", encoding="utf8") as f:
@@ -71,7 +72,9 @@ def main(argv=None):
     ap.add_argument("-p_swap", type=float, default=0.0)
     ap.add_argument("-boundaries", type=str, default="open")
     ap.add_argument("-ec", type=str, default="primal")
-    ap.add_argument("-mode", type=str, default="compat")
+    ap.add_argument("-mode", type=str, default="fresh",
+                    help="fresh (default): a new CVLayer per trial - what a threshold estimate needs; compat: the "
+                         "reference's reused-layer carry-over (with p_swap=0 every second trial is noise-free)")
     ap.add_argument("-fname", type=str, default=None)
     ap.add_argument("-graph_only", action="store_true")
     ap.add_argument("-batch", type=int, default=1024)

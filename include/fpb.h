@@ -186,6 +186,15 @@ int fpb_run_rng(fpb_handle* h, uint64_t seed, int64_t first_trial, int64_t n_tri
 int fpb_run_bits(fpb_handle* h, int64_t n_trials, const uint32_t* bits, int on_device, int stage);
 int fpb_run_iid(fpb_handle* h, uint64_t seed, int64_t first_trial, int64_t n_trials, double p_err, int stage);
 
+/* Trials given as the two node attributes the reference's matching-graph builder reads
+ * (decoders/mwpm/matching.py:97-173 through codes/graphs/stabilizer_graph.py:304-329): the
+ * `weight` of every syndrome qubit, [n_trials][Qtot] doubles, and its `bit_val`,
+ * [n_trials][bit_words] packed like fpb_outputs.bits.  Runs parity -> odd cubes -> matching graph
+ * (stage >= FPB_STAGE_SYNDROME) whatever noise model and weight assignment produced them;
+ * `hom` reads back as zeros. */
+int fpb_run_weighted(fpb_handle* h, int64_t n_trials, const double* weights, const uint32_t* bits, int on_device,
+                     int stage);
+
 int fpb_get_sizes(fpb_handle* h, fpb_sizes* out);
 /* Copy results of the last run into caller buffers (host if on_device == 0). */
 int fpb_fetch(fpb_handle* h, const fpb_outputs* dst, int on_device);
@@ -224,6 +233,15 @@ int fpb_knn(fpb_handle* h, int complex_index, int k, int32_t* ids, int on_device
  * mwpm_decoder (decoders/mwpm/algos.py:88-95). */
 int fpb_paths_toggle(fpb_handle* h, int64_t n_queries, const int32_t* trial, const int32_t* cx,
                      const int32_t* src, const int32_t* dst, uint32_t* flips_host);
+
+/* The same queries as fpb_paths_toggle, answered as ordered paths: for query i the local qubit
+ * ids (qubit order of the query's complex) crossed by the shortest path, walking from dst back to
+ * src (dst >= 0), or from src to its nearer connector (dst == -1; the last entry is the boundary
+ * qubit), into qubits[i * max_len ...], and the number of qubits into length[i] (-1 if the path has
+ * more than max_len qubits).  Together with the cube-qubit incidence this is
+ * MatchingGraph.edge_path (decoders/mwpm/matching.py:71-74; consumed by algos.py:88-95). */
+int fpb_paths_list(fpb_handle* h, int64_t n_queries, const int32_t* trial, const int32_t* cx, const int32_t* src,
+                   const int32_t* dst, int32_t max_len, int32_t* qubits, int32_t* length);
 
 #ifdef __cplusplus
 }

@@ -56,6 +56,33 @@ def test_create_fails_loudly_without_gpu():
         TrialEngine(build_lattice(3, "primal", "open"), 0.09, 0.25)
 
 
+def test_pybind_module_is_the_default_binding(monkeypatch):
+    """flamingpy_b200.cpp.fpbpy (the reference's native-plugin pattern, lemonpy.cpp:50-84) imports,
+    carries the header's ABI version and every Handle method the engine calls, and is what
+    ``open_handle`` uses; without a device its constructor fails like the ctypes path."""
+    import torch
+
+    fpbpy = _lib.pybind_module()
+    assert fpbpy is not None and fpbpy.abi_version() == _lib.FPB_ABI_VERSION
+    assert _lib.binding_name() == "pybind11"
+    monkeypatch.setenv("FPB_BINDING", "ctypes")
+    assert _lib.binding_name() == "ctypes"
+    monkeypatch.delenv("FPB_BINDING")
+    methods = {n for n in dir(_lib.CtypesHandle) if not n.startswith("_")}
+    assert methods <= set(dir(fpbpy.Handle)), methods - set(dir(fpbpy.Handle))
+    if not torch.cuda.is_available():
+        from flamingpy_b200.engine import config_dict
+        from flamingpy_b200.lattice import build_lattice
+
+        cfg, _, _ = config_dict(build_lattice(3, "primal", "open"), 0.09, 0.25, {"method": "uniform"})
+        with pytest.raises(_lib.FpbError, match="no usable CUDA device"):
+            fpbpy.Handle(cfg)
+        with pytest.raises(_lib.FpbError, match="no usable CUDA device"):
+            _lib.CtypesHandle(cfg)
+        with pytest.raises((RuntimeError, KeyError)):
+            fpbpy.Handle({"n_nodes": 3})
+
+
 def test_product_never_imports_oracle():
     pkg = os.path.join(ROOT, "flamingpy_b200")
     for dirpath, _, files in os.walk(pkg):
