@@ -169,6 +169,22 @@ paths_fn pick_paths_kernel(int S, bool wg, int* max_warps) {
 }
 // two-warp-team variant (shared-memory lattices with more than 1024 cubes): NCH2 = chunks per warp
 paths_fn pick_team_kernel(int S, bool wg) {
+  // FPB_TEAM_RM=1: residue-major bucket bytes + stride-dealt rounds + lean verify (team_search_rm).  Measured on
+  // B200 (profiles/r2_k_paths_rm_experiment.md): 45 % fewer bank-conflict replays and 10 % fewer instructions,
+  // but 5-20 % slower than the round-1 search on every lattice - the kernel is bound by the dependent
+  // latency of a round at 16 warps per SM, not by the shared-memory pipe - so it stays opt-in.
+  static const bool rm = getenv("FPB_TEAM_RM") != nullptr;
+  if (rm) {
+    const int rows = paths_bkt_row(S);  // chunks to scan; 64 lanes x NCHT (odd) chunks each
+    if (wg) {
+      if (rows <= 64 * 3) return k_paths_team<3, 2, 512, 1, true, true>;
+      if (rows <= 64 * 5) return k_paths_team<5, 2, 512, 1, true, true>;
+      return k_paths_team<9, 2, 512, 1, true, true>;
+    }
+    if (rows <= 64 * 3) return k_paths_team<3, 2, 512, 1, false, true>;
+    if (rows <= 64 * 5) return k_paths_team<5, 2, 512, 1, false, true>;
+    return k_paths_team<9, 2, 512, 1, false, true>;
+  }
   if (wg) {
     if (S <= 4096) return k_paths_team<4, 2, 512, 1, true>;
     return k_paths_team<8, 2, 512, 1, true>;

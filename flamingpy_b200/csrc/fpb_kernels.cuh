@@ -446,6 +446,7 @@ struct WarpMem {
   uint8_t* bkt;     // [ceil16(S)] ring slot of the cube's pending entry, 0xFF none; 16-byte aligned
   uint16_t* stage;  // [STAGE_CAP]
   uint8_t* pred;    // [S] incoming direction (path-toggle kernel only)
+  int sb;           // 0: bkt[c] is cube c's byte; > 0: residue-major rows, byte (c & 15) * sb + (c >> 4)
 };
 
 struct CtaMem {
@@ -465,8 +466,12 @@ __host__ __device__ inline size_t paths_cta_bytes(int S_max, int slots_max) {
 }
 // staging-list entries per search: the wide-team kernels of very large lattices stage more cubes per scan
 __host__ __device__ inline int paths_stage_entries(int S_max) { return S_max > 6144 ? 4 * STAGE_CAP : STAGE_CAP; }
+// bucket bytes of one search: room for the residue-major layout of the team kernel (16 rows of
+// paths_bkt_row(S) bytes, one row per cube index mod 16; >= the linear layout's align16(S))
+__host__ __device__ inline int paths_bkt_row(int S) { return (((S + 15) >> 4) + 15) & ~15; }
+__host__ __device__ inline size_t paths_bkt_bytes(int S_max) { return (size_t)16 * paths_bkt_row(S_max); }
 __host__ __device__ inline size_t paths_warp_bytes(int S_max, bool pred) {
-  return align16((size_t)S_max * 8) + align16((size_t)S_max) + align16((size_t)paths_stage_entries(S_max) * 2) +
+  return align16((size_t)S_max * 8) + paths_bkt_bytes(S_max) + align16((size_t)paths_stage_entries(S_max) * 2) +
          (pred ? align16((size_t)S_max) : 0);
 }
 
@@ -475,7 +480,8 @@ __host__ __device__ inline size_t paths_warp_bytes(int S_max, bool pred) {
 __device__ __forceinline__ WarpMem carve_warp(unsigned char* wp, int S_max, bool pred) {
   WarpMem wm;
   wm.dist = (double*)wp; wp += align16((size_t)S_max * 8);
-  wm.bkt = (uint8_t*)wp; wp += align16((size_t)S_max);
+  wm.bkt = (uint8_t*)wp; wp += paths_bkt_bytes(S_max);
+  wm.sb = 0;
   wm.stage = (uint16_t*)wp; wp += align16((size_t)paths_stage_entries(S_max) * 2);
   wm.pred = pred ? (uint8_t*)wp : nullptr;
   return wm;
@@ -509,7 +515,7 @@ __device__ __forceinline__ uint32_t seed_cube(const WarpMem& wm, int c, double d
   wm.dist[c] = d0;
   int bi = bucket_of(d0, inv);
   bi = bi < NRING - 1 ? bi : NRING - 1;
-  wm.bkt[c] = (uint8_t)bi;
+  wm.bkt[wm.sb ? (c & 15) * wm.sb + (c >> 4) : c] = (uint8_t)bi;
   if (wm.pred) wm.pred[c] = pred_code;
   return 1u << bi;
 }
@@ -1051,7 +1057,205 @@ __device__ __forceinline__ void team_search(const CtaMem& cm, uint32_t cinfo_a, 
   }
 }
 
-template <int NCH2, int NV, int MAXT, int MINB, bool WG>
+// ------------------------------------------------------------------------------------------
+// team_search_rm: the two-warp search with (1) the bucket bytes in residue-major order and the
+// staged cubes dealt to the lanes of a round at a stride, and (2) a verify round that only
+// re-checks what it re-stored.
+//
+// (1) ncu on the round-1 kernel: 47 % of its shared-memory wavefronts were bank-conflict replays
+// of the random 8-byte gathers (3.7 wavefronts per 21-lane load where 1.5 would do).  A 64-bit
+// access is conflict-free when its lanes' addresses fall into different bank pairs, i.e. when the
+// cubes of a half-warp differ mod 16 - and every neighbour gather (a uniform index offset per
+// direction) and every weight gather (slot = 3 * cube + const, 3 coprime to 16) then is, too.  So
+// byte row r of the bucket array holds the cubes with index = r (mod 16): the scan emits each warp's
+// cubes sorted by residue, and warp-round rho (of 2R per pass) deals entry k * 2R + rho - a stride
+// sample through both warps' lists with about two cubes of every residue - to lane (k & 1) * 16 + k / 2.
+// (2) After the stores of a round (barrier b) every improving candidate re-reads its target once.
+// It either sees its own value (it owns the target for now and files it), a smaller one (beaten:
+// done), or a larger one (its store was overwritten: it re-stores and must look again next pass).
+// Memory only moves down across passes, so a candidate that did not re-store has nothing left to
+// lose: later passes load for the re-storers only (round 1 spent 27 % of its wavefronts re-loading
+// every candidate 2.25 times per round).  A later, smaller owner files after an earlier one (the
+// passes are barrier-separated), so the bucket byte ends up being that of the final distance.
+// ------------------------------------------------------------------------------------------
+template <int NCHT, bool WG>
+__device__ __forceinline__ void team_search_rm(const CtaMem& cm, uint32_t cinfo_a, const WarpMem& wm, const DirTab& dt,
+                                               int S, double step, uint32_t present, int lane, int half, int bar_id,
+                                               volatile TeamX* tx) {
+  const double inv = 1.0 / step;
+  const int SB = wm.sb;                 // bytes per residue row = 16-byte chunks in the whole array
+  const uint32_t dist_a = smem_addr(wm.dist), bkt_a = smem_addr(wm.bkt);
+  const uint32_t stage_a = smem_addr(wm.stage) + (uint32_t)half * STAGE_CAP;  // own half of the staging list
+  const uint32_t stage0_a = smem_addr(wm.stage), stage1_a = stage0_a + STAGE_CAP;
+  const uint32_t wslot_a = WG ? 0u : smem_addr(cm.wslot);
+  constexpr int HCAP = STAGE_CAP / 2;
+  // this lane's chunks are consecutive (list order = byte order = residue order); NCHT is odd, so
+  // the lanes' 16-byte loads fall into distinct bank quads
+  const int ch0 = (half * 32 + lane) * NCHT;
+  int cube0[NCHT];  // cube of byte 0 of each chunk: (column << 4) | row
+  {
+    const uint32_t cr = (uint32_t)SB >> 4;          // chunks per row
+    const uint32_t rcp = 0xffffffffu / cr + 1u;     // ch / cr == umulhi(ch, rcp) for ch < 65536
+#pragma unroll
+    for (int j = 0; j < NCHT; ++j) {
+      const uint32_t ch = (uint32_t)(ch0 + j);
+      const uint32_t row = __umulhi(ch, rcp);
+      const uint32_t col = (ch - row * cr) << 4;
+      cube0[j] = (int)((col << 4) | row);
+    }
+  }
+  int cur = 0;
+  while (present) {
+    {
+      const uint32_t rot = __funnelshift_r(present, present, cur & (NRING - 1));
+      cur += __ffs(rot) - 1;
+    }
+    const int r = cur & (NRING - 1);
+    const int far = cur + NRING - 1;
+    while ((present >> r) & 1u) {
+      present &= ~(1u << r);
+      // ---------------- scan (this warp's chunks): stage cubes filed under slot r ----------------
+      uint32_t masks[NCHT];
+      int cnt = 0;
+      const uint32_t r4 = (uint32_t)r * 0x01010101u;
+#pragma unroll
+      for (int j = 0; j < NCHT; ++j) {
+        const int ch = ch0 + j;
+        uint32_t m = 0;
+        if (ch < SB) {
+          uint4 q = lds_v4(bkt_a + (ch << 4));
+          const uint32_t z0 = eq_bytes(q.x, r4), z1 = eq_bytes(q.y, r4), z2 = eq_bytes(q.z, r4), z3 = eq_bytes(q.w, r4);
+          m = movemask4(z0) | (movemask4(z1) << 4) | (movemask4(z2) << 8) | (movemask4(z3) << 12);
+          if (m) {
+            q.x |= (z0 >> 7) * 0xffu;
+            q.y |= (z1 >> 7) * 0xffu;
+            q.z |= (z2 >> 7) * 0xffu;
+            q.w |= (z3 >> 7) * 0xffu;
+            sts_v4(bkt_a + (ch << 4), q);
+          }
+        }
+        masks[j] = m;
+        cnt += __popc(m);
+      }
+      int incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+      }
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      int pos = incl - cnt;
+      uint32_t lp = 0;  // slots this lane filed cubes under
+#pragma unroll
+      for (int j = 0; j < NCHT; ++j) {
+        uint32_t m = masks[j];
+        while (m) {
+          const int bit = __ffs(m) - 1;
+          m &= m - 1;
+          if (pos < HCAP) sts_u16(stage_a + 2 * pos, cube0[j] + (bit << 4));
+          else sts_u8(bkt_a + ((ch0 + j) << 4) + bit, r);  // staging half full: leave it filed for the next scan
+          ++pos;
+        }
+      }
+      if (total > HCAP) lp |= 1u << r;
+      if (lane == 0) tx->cnt[half] = total < HCAP ? total : HCAP;
+      team_bar(bar_id);  // (a) both halves of the staging list are complete
+      const int n0 = tx->cnt[0], n1 = tx->cnt[1];
+      const int nst = n0 + n1;
+      // ---------------- relax: W warp-rounds, entry k * W + rho of the lists goes to round rho ----------------
+      // a 64-bit access is served one half-warp at a time: the 16 lanes of a half-warp take every second
+      // entry of the stride sample, so that each half-warp holds (about) one cube of every residue
+      const int W = (nst + 31) >> 5;
+      const int deal = (((lane & 15) << 1) | (lane >> 4)) * W;
+      for (int rho = half; rho < ((W + 1) & ~1); rho += 2) {
+        // W odd: the last round is warp 0's alone; warp 1 only takes part in its barriers
+        const bool live = rho < W;
+        uint32_t ua[6], fa[6], fs[6];
+        double nd[6];
+        bool chk[6];  // stored in the last pass: must see what became of it
+#pragma unroll
+        for (int d = 0; d < 6; ++d) chk[d] = false;
+        if (live) {
+          uint32_t wa[6];
+          double old[6];
+          bool imp[6];
+          const int idx = deal + rho;
+          const bool valid = idx < nst;
+          const uint32_t sa = idx < n0 ? stage0_a + 2 * idx : stage1_a + 2 * (idx - n0);
+          const int v = valid ? (int)lds_u16(sa) : 0;
+          const uint32_t va = dist_a + 8u * v;
+          const double dv = lds_f64(va);
+          const int bt = bucket_of(dv, inv);
+          if (valid && bt > cur) {  // a parked cube: move it towards its real bucket
+            const int s2 = (bt < far ? bt : far) & (NRING - 1);
+            sts_u8(bkt_a + (v & 15) * SB + (v >> 4), s2);
+            lp |= 1u << s2;
+          }
+          const bool act = valid && bt <= cur;
+          uint32_t ci = 0xaaau;  // inactive lanes: every face "none"
+          if (act) ci = WG ? ((uint32_t)cm.ninfo[v] | ((uint32_t)cm.sbase[v] << 16)) : lds_u32(cinfo_a + 4u * v);
+          const uint32_t sb = WG ? (ci >> 16) : wslot_a + 8u * (ci >> 16);  // slot index (WG) or shared address
+#pragma unroll
+          for (int d = 0; d < 6; ++d) {
+            const uint32_t kind = (ci >> (2 * d)) & 3u;
+            const bool a = kind < 2u;
+            ua[d] = va + 8 * (kind ? dt.dwrap[d] : dt.dreg[d]);
+            wa[d] = sb + (WG ? 1 : 8) * (kind ? dt.swrap[d] : dt.sreg[d]);
+            old[d] = a ? lds_f64(ua[d]) : 0.0;
+            imp[d] = a && old[d] > dv;
+          }
+#pragma unroll
+          for (int d = 0; d < 6; ++d) {
+            nd[d] = imp[d] ? dv + (WG ? cm.wslot[wa[d]] : lds_f64(wa[d])) : 0.0;
+            imp[d] = imp[d] && nd[d] < old[d];
+          }
+#pragma unroll
+          for (int d = 0; d < 6; ++d)
+            if (imp[d]) sts_f64(ua[d], nd[d]);
+          // where an improved target is filed: byte address and ring slot of its new distance
+#pragma unroll
+          for (int d = 0; d < 6; ++d) {
+            const int bi = bucket_of(nd[d], inv);
+            fs[d] = (uint32_t)((bi < far ? bi : far) & (NRING - 1));
+            const uint32_t ui = (ua[d] - dist_a) >> 3;
+            fa[d] = bkt_a + (ui & 15u) * (uint32_t)SB + (ui >> 4);
+            chk[d] = imp[d];
+          }
+        }
+        team_bar(bar_id);  // (b) all stores of the round, from both warps, precede the verify loads
+        bool redo;
+        do {
+          bool mine = false;
+          const bool any = chk[0] | chk[1] | chk[2] | chk[3] | chk[4] | chk[5];
+          if (__any_sync(0xffffffffu, any)) {
+            double fin[6];
+#pragma unroll
+            for (int d = 0; d < 6; ++d) fin[d] = chk[d] ? lds_f64(ua[d]) : 0.0;
+#pragma unroll
+            for (int d = 0; d < 6; ++d) {
+              const bool lost = chk[d] && fin[d] > nd[d];
+              const bool own = chk[d] && fin[d] == nd[d];  // in place: it files the target (a later, smaller owner re-files)
+              if (lost) sts_f64(ua[d], nd[d]);
+              if (own) sts_u8(fa[d], fs[d]);
+              lp |= own ? (1u << fs[d]) : 0u;
+              mine |= lost;
+              chk[d] = lost;
+            }
+          }
+          redo = team_bar_or(bar_id, mine);  // (c) re-stores and bytes visible; did either warp re-store?
+        } while (redo);
+      }
+      lp = __reduce_or_sync(0xffffffffu, lp);
+      if (lane == 0) tx->lp[half] = (int)lp;
+      team_bar(bar_id);  // (d) filed slots exchanged, bucket bytes visible to the next scan
+      present |= (uint32_t)tx->lp[0] | (uint32_t)tx->lp[1];
+    }
+  }
+}
+
+// RM: residue-major bucket bytes + stride-dealt rounds + lean verify (team_search_rm; NCH2 is then the
+// odd number of consecutive 16-byte chunks per lane, 64 * NCH2 >= paths_bkt_row(S_max))
+template <int NCH2, int NV, int MAXT, int MINB, bool WG, bool RM = false>
 __global__ void __launch_bounds__(MAXT, MINB) k_paths_team(const __grid_constant__ PathsParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ int item_s;
@@ -1075,7 +1279,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_paths_team(const __grid_constant
   CtaMem cm;
   cm.wslot = wslot; cm.ninfo = nullptr; cm.sbase = nullptr;
   const uint32_t cinfo_a = WG ? 0u : smem_addr(cinfo_s);
-  const WarpMem wm = carve_warp(ptr + (size_t)team * paths_warp_bytes(p.S_max, false), p.S_max, false);
+  WarpMem wm = carve_warp(ptr + (size_t)team * paths_warp_bytes(p.S_max, false), p.S_max, false);
   DirTab dt = load_dirtab(p.cx[0]);
 
   int staged_tc = -1, staged_c = -1;
@@ -1097,6 +1301,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_paths_team(const __grid_constant
     const ComplexDev& c = p.cx[ci];
     const int chunk = item - p.item_off[tc];
     const int S = c.S;
+    wm.sb = RM ? paths_bkt_row(S) : 0;
 
     if (staged_c != ci) {
       if (WG) {
@@ -1144,7 +1349,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_paths_team(const __grid_constant
         // clear the shared state, half each
         for (int v = half * 32 + lane; v < S; v += 64) wm.dist[v] = FPB_INF;
         {
-          const int n16 = (S + 15) >> 4;
+          const int n16 = RM ? wm.sb : (S + 15) >> 4;
           uint4* b4 = reinterpret_cast<uint4*>(wm.bkt);
           for (int i = half * 32 + lane; i < n16; i += 64) b4[i] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
         }
@@ -1164,7 +1369,8 @@ __global__ void __launch_bounds__(MAXT, MINB) k_paths_team(const __grid_constant
         team_bar(bar_id);
         present = (uint32_t)tx->lp[0];
         team_bar(bar_id);  // lp[0] is rewritten inside the search
-        team_search<NCH2, NV, WG>(cm, cinfo_a, wm, dt, S, step, present, lane, half, bar_id, tx);
+        if (RM) team_search_rm<NCH2, WG>(cm, cinfo_a, wm, dt, S, step, present, lane, half, bar_id, tx);
+        else team_search<NCH2, NV, WG>(cm, cinfo_a, wm, dt, S, step, present, lane, half, bar_id, tx);
         if (pair_task) {
           const long long row = poff + (long long)task * K - (long long)task * (task + 1) / 2;
           for (int b = task + 1 + half * 32 + lane; b < K; b += 64) c.pair_len[row + (b - task - 1)] = wm.dist[odd[b]];
