@@ -78,7 +78,8 @@ class Config(C.Structure):
         ("chain_len", C.c_int64),
         ("delta_step", C.c_double),
         ("length_mode", C.c_int32),
-        ("reserved_i", C.c_int32 * 7),
+        ("reserve_sms", C.c_int32),
+        ("reserved_i", C.c_int32 * 6),
         ("reserved_d", C.c_double * 4),
     ]
 
@@ -135,6 +136,11 @@ EXPORTS = {
     "fpb_run_bits": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int]),
     "fpb_run_weighted": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "fpb_paths_list": (C.c_int, [C.c_void_p, C.c_int64, _i32p, _i32p, _i32p, _i32p, C.c_int32, _i32p, _i32p]),
+    "fpb_knn_len": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fpb_pairs_at": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, _i32p, _i32p, _i32p, _f64p]),
+    "fpb_pairs_of_trial": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, _f64p, C.c_int64]),
+    "fpb_price": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int64), _i32p, C.POINTER(C.c_int64), _f64p, _i32p, _u8p,
+                            C.c_int64, _i32p, _i32p, _i32p, _f64p, C.POINTER(C.c_int64)]),
     "fpb_run_iid": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int64, C.c_int64, C.c_double, C.c_int]),
     "fpb_get_sizes": (C.c_int, [C.c_void_p, C.POINTER(Sizes)]),
     "fpb_fetch": (C.c_int, [C.c_void_p, C.POINTER(Outputs), C.c_int]),
@@ -253,6 +259,7 @@ def ctypes_config(cfg: dict):
     c.chain_len = int(cfg.get("chain_len", 0))
     c.delta_step = float(cfg.get("delta_step", 0.0))
     c.length_mode = int(cfg.get("length_mode", LENGTH_FLOAT))
+    c.reserve_sms = int(cfg.get("reserve_sms", 0))
     return c, keep
 
 
@@ -385,6 +392,53 @@ class CtypesHandle:
         check(self._lib.fpb_paths_toggle(self._h, len(trial), p(trial), p(cx), p(src), p(dst),
                                          flips.ctypes.data_as(_u32p)))
 
+
+    def knn_len(self, complex_index, k):
+        import numpy as np
+
+        s = self.sizes()
+        n = s["total_odd"][complex_index]
+        ids = np.empty((n, k), np.int32)
+        lens = np.empty((n, k), np.float64)
+        wmax = np.empty(s["n_trials"], np.float64)
+        check(self._lib.fpb_knn_len(self._h, complex_index, k, ids.ctypes.data, lens.ctypes.data, wmax.ctypes.data))
+        return ids, lens, wmax
+
+    def pairs_at(self, complex_index, trial, a, b):
+        import numpy as np
+
+        out = np.empty(len(trial), np.float64)
+        p = lambda x: x.ctypes.data_as(_i32p)  # noqa: E731
+        check(self._lib.fpb_pairs_at(self._h, complex_index, len(trial), p(trial), p(a), p(b),
+                                     out.ctypes.data_as(_f64p)))
+        return out
+
+    def pairs_of_trial(self, complex_index, trial, n_pairs):
+        import numpy as np
+
+        out = np.empty(n_pairs, np.float64)
+        check(self._lib.fpb_pairs_of_trial(self._h, complex_index, trial, out.ctypes.data_as(_f64p), n_pairs))
+        return out
+
+    def price(self, complex_index, y, top, ztop, scale, wshift, active, cap=65536):
+        import numpy as np
+
+        f = lambda x: x.ctypes.data_as(_f64p)  # noqa: E731
+        i64 = C.POINTER(C.c_int64)
+        topp = top.ctypes.data_as(_i32p) if top is not None else None
+        ztp = ztop.ctypes.data_as(i64) if top is not None else None
+        while True:
+            vt, va, vb = (np.empty(cap, np.int32) for _ in range(3))
+            vl = np.empty(cap, np.float64)
+            found = C.c_int64()
+            check(self._lib.fpb_price(self._h, complex_index, y.ctypes.data_as(i64), topp, ztp, f(scale),
+                                      wshift.ctypes.data_as(_i32p), active.ctypes.data_as(_u8p), cap,
+                                      vt.ctypes.data_as(_i32p), va.ctypes.data_as(_i32p), vb.ctypes.data_as(_i32p),
+                                      f(vl), C.byref(found)))
+            n = int(found.value)
+            if n <= cap:
+                return vt[:n], va[:n], vb[:n], vl[:n]
+            cap = n + n // 8 + 64
 
     def paths_list(self, trial, cx, src, dst, max_len):
         import numpy as np

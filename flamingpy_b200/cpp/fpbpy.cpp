@@ -127,6 +127,7 @@ class Handle {
     cfg.chain_len = get_or<int64_t>(c, "chain_len", 0);
     cfg.delta_step = get_or<double>(c, "delta_step", 0.0);
     cfg.length_mode = get_or<int>(c, "length_mode", FPB_LENGTH_FLOAT);
+    cfg.reserve_sms = get_or<int>(c, "reserve_sms", 0);
     check(fpb_create(&cfg, &h_));
     n_nodes_ = cfg.n_nodes;
     ncx_ = cfg.n_complex;
@@ -357,6 +358,97 @@ class Handle {
     check(rc);
   }
 
+  // sparse hand-off: candidates with reduced lengths, (ids int32[n, k], lens float64[n, k], wmax float64[T])
+  py::tuple knn_len(int complex_index, int k) {
+    fpb_sizes s;
+    check(fpb_get_sizes(h(), &s));
+    if (complex_index < 0 || complex_index >= s.n_complex) throw std::runtime_error("bad complex index");
+    const py::ssize_t n = (py::ssize_t)s.total_odd[complex_index];
+    py::array_t<int32_t> ids({n, (py::ssize_t)k});
+    py::array_t<double> lens({n, (py::ssize_t)k});
+    py::array_t<double> wmax((py::ssize_t)s.n_trials);
+    int32_t* ip = ids.mutable_data();
+    double *lp = lens.mutable_data(), *wp = wmax.mutable_data();
+    int rc;
+    {
+      py::gil_scoped_release release;
+      rc = fpb_knn_len(h(), complex_index, k, ip, lp, wp);
+    }
+    check(rc);
+    return py::make_tuple(ids, lens, wmax);
+  }
+  py::array_t<double> pairs_at(int complex_index, carray<int32_t> trial, carray<int32_t> a, carray<int32_t> b) {
+    const int64_t n = trial.size();
+    if (a.size() != n || b.size() != n) throw std::runtime_error("pair arrays differ in length");
+    py::array_t<double> out((py::ssize_t)n);
+    const int32_t *tp = trial.data(), *ap = a.data(), *bp = b.data();
+    double* op = out.mutable_data();
+    int rc;
+    {
+      py::gil_scoped_release release;
+      rc = fpb_pairs_at(h(), complex_index, n, tp, ap, bp, op);
+    }
+    check(rc);
+    return out;
+  }
+  // device-side pricing: (trial, a, b, reduced length) of every pair violating the vertex-dual test
+  py::array_t<double> pairs_of_trial(int complex_index, int64_t trial, int64_t n_pairs) {
+    py::array_t<double> out((py::ssize_t)n_pairs);
+    double* op = out.mutable_data();
+    int rc;
+    {
+      py::gil_scoped_release release;
+      rc = fpb_pairs_of_trial(h(), complex_index, trial, op, n_pairs);
+    }
+    check(rc);
+    return out;
+  }
+  py::tuple price(int complex_index, carray<int64_t> y, py::object top_o, py::object ztop_o, carray<double> scale,
+                  carray<int32_t> wshift, carray<uint8_t> active, int64_t cap) {
+    carray<int32_t> top;
+    carray<int64_t> ztop;
+    const bool have_top = !top_o.is_none();
+    if (have_top) {
+      top = carray<int32_t>::ensure(top_o);
+      ztop = carray<int64_t>::ensure(ztop_o);
+      if (!top || !ztop || top.size() < y.size() || ztop.size() < y.size())
+        throw std::runtime_error("price: top / ztop need one entry per vertex dual");
+    }
+    fpb_sizes s;
+    check(fpb_get_sizes(h(), &s));
+    if (complex_index < 0 || complex_index >= s.n_complex) throw std::runtime_error("bad complex index");
+    if (y.size() < s.total_odd[complex_index] || scale.size() < s.n_trials || wshift.size() < s.n_trials ||
+        active.size() < s.n_trials)
+      throw std::runtime_error("price: y needs total_odd entries, scale / wshift / active one per trial");
+    const int64_t* yp = y.data();
+    const int32_t* topp = have_top ? top.data() : nullptr;
+    const int64_t* ztp = have_top ? ztop.data() : nullptr;
+    const double* cp = scale.data();
+    const int32_t* mp = wshift.data();
+    const uint8_t* ap = active.data();
+    for (;;) {
+      py::array_t<int32_t> vt((py::ssize_t)cap), va((py::ssize_t)cap), vb((py::ssize_t)cap);
+      py::array_t<double> vl((py::ssize_t)cap);
+      int32_t *tp = vt.mutable_data(), *up = va.mutable_data(), *wp = vb.mutable_data();
+      double* lp = vl.mutable_data();
+      int64_t found = 0;
+      int rc;
+      {
+        py::gil_scoped_release release;
+        rc = fpb_price(h(), complex_index, yp, topp, ztp, cp, mp, ap, cap, tp, up, wp, lp, &found);
+      }
+      check(rc);
+      if (found <= cap) {
+        vt.resize({(py::ssize_t)found});
+        va.resize({(py::ssize_t)found});
+        vb.resize({(py::ssize_t)found});
+        vl.resize({(py::ssize_t)found});
+        return py::make_tuple(vt, va, vb, vl);
+      }
+      cap = found + found / 8 + 64;  // not enough room: once more with what was needed
+    }
+  }
+
   // correction paths of matched pairs: XOR-toggles the crossed qubits into flips uint32[T, bit_words]
   void paths_toggle(carray<int32_t> trial, carray<int32_t> cx, carray<int32_t> src, carray<int32_t> dst,
                     py::array flips) {
@@ -439,6 +531,12 @@ PYBIND11_MODULE(fpbpy, m) {
       .def("mark", &Handle::mark)
       .def("elapsed_ms", &Handle::elapsed_ms)
       .def("knn", &Handle::knn, py::arg("complex_index"), py::arg("k"), py::arg("out"))
+      .def("knn_len", &Handle::knn_len, py::arg("complex_index"), py::arg("k"))
+      .def("pairs_at", &Handle::pairs_at)
+      .def("pairs_of_trial", &Handle::pairs_of_trial)
+      .def("price", &Handle::price, py::arg("complex_index"), py::arg("y"), py::arg("top"), py::arg("ztop"),
+           py::arg("scale"), py::arg("wshift"),
+           py::arg("active"), py::arg("cap") = 65536)
       .def("paths_toggle", &Handle::paths_toggle)
       .def("paths_list", &Handle::paths_list);
 }

@@ -82,6 +82,7 @@ struct ComplexHost {
   long long total_odd = 0, total_pairs = 0;
   int max_odd = 0;  // largest odd count of the last batch
   DevBuf<int> knn;  // candidate partners of the last fpb_knn call
+  DevBuf<double> knn_len;
   DevBuf<double> tab_pair, tab_bnd;  // all-pairs table of the static-weight path
   DevBuf<uint8_t> tab_side;
 };
@@ -94,7 +95,7 @@ struct fpb_handle {
   int N = 0, Qtot = 0, bit_words = 0, ncx = 0;
   int S_max = 0, slots_max = 0;
   double delta = 0, p_swap = 0, weight_delta = 0, weight_multiplier = 1, step_factor = 1;
-  int weight_method = 0, weight_integer = 0, label_mode = 0;
+  int weight_method = 0, weight_integer = 0, label_mode = 0, reserve_sms = 0;
   long long chain_len = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -107,6 +108,13 @@ struct fpb_handle {
   DevBuf<uint32_t> bits, flips;
   DevBuf<int> item_off, counter, q_trial, q_cx, q_src, q_dst, path_qubits, path_len;
   DevBuf<long long> totals;
+  // sparse hand-off (fpb_knn_len / fpb_pairs_at / fpb_price)
+  DevBuf<unsigned long long> trial_wmax, price_n;
+  DevBuf<long long> price_y;
+  DevBuf<double> price_c, pair_out;
+  DevBuf<int> price_ws, price_top;
+  DevBuf<uint8_t> price_active;
+  DevBuf<int> price_idx;
   long long* totals_host = nullptr;  // pinned + mapped: kernels write it directly (no copy-engine hop)
   long long* totals_map = nullptr;   // device alias of totals_host
   long long T = 0;
@@ -386,7 +394,7 @@ int launch_paths(fpb_handle* h, long long T, int* launches) {
   pp.counter = h->counter.p;
   for (int c = 0; c < h->ncx; ++c) pp.cx[c] = make_dev(h->cx[c]);
   CK(cudaMemsetAsync(h->counter.p, 0, sizeof(int), st));
-  long long grid = (long long)h->sm_count * h->ctas_per_sm;
+  long long grid = (long long)(h->sm_count - h->reserve_sms) * h->ctas_per_sm;
   if (grid > total_items) grid = total_items;
   if (h->paths_wg) {
     int rc2 = h->wscratch.ensure((size_t)grid * h->slots_max);
@@ -617,6 +625,8 @@ int fpb_create(const fpb_config* cfg, fpb_handle** out) {
   h->weight_multiplier = cfg->weight_multiplier != 0 ? cfg->weight_multiplier : 1.0;
   h->label_mode = cfg->label_mode;
   h->chain_len = cfg->chain_len;
+  h->reserve_sms = cfg->reserve_sms < 0 ? 0 : cfg->reserve_sms;
+  if (h->reserve_sms >= h->sm_count) h->reserve_sms = h->sm_count - 1;
   h->step_factor = cfg->delta_step > 0 ? cfg->delta_step : 2.0;
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(FPB_ERR_CUDA, "stream creation failed"));
   for (auto& ev : h->ev)
@@ -694,11 +704,13 @@ int fpb_destroy(fpb_handle* h) {
     cudaFree(cx.low_cube); cudaFree(cx.low_slot); cudaFree(cx.high_cube); cudaFree(cx.high_slot);
     cx.parity.release(); cx.odd_count.release(); cx.odd_fixed.release(); cx.odd_ids.release();
     cx.odd_off.release(); cx.pair_off.release(); cx.pair_len.release(); cx.bnd_len.release();
-    cx.bnd_side.release(); cx.knn.release(); cx.tab_pair.release(); cx.tab_bnd.release(); cx.tab_side.release();
+    cx.bnd_side.release(); cx.knn.release(); cx.knn_len.release(); cx.tab_pair.release(); cx.tab_bnd.release(); cx.tab_side.release();
   }
   h->x.release(); h->hom.release(); h->weights.release(); h->state.release(); h->bits.release();
   h->flips.release(); h->item_off.release(); h->counter.release(); h->totals.release();
   h->path_qubits.release(); h->path_len.release();
+  h->trial_wmax.release(); h->price_n.release(); h->price_y.release(); h->price_c.release(); h->price_ws.release(); h->price_top.release();
+  h->pair_out.release(); h->price_active.release(); h->price_idx.release();
   h->q_trial.release(); h->q_cx.release(); h->q_src.release(); h->q_dst.release(); h->wscratch.release();
   if (h->totals_host) cudaFreeHost(h->totals_host);
   if (h->static_flag_host) cudaFreeHost(h->static_flag_host);
@@ -925,35 +937,163 @@ int fpb_elapsed_ms(fpb_handle* h, float* ms) {
   return FPB_OK;
 }
 
-int fpb_knn(fpb_handle* h, int complex_index, int k, int32_t* ids, int on_device) {
+static int run_knn(fpb_handle* h, int complex_index, int k, int32_t* ids, double* lens, double* wmax, int on_device) {
   if (!h || !ids) return fail(FPB_ERR_ARG, "null argument");
   if (complex_index < 0 || complex_index >= h->ncx) return fail(FPB_ERR_ARG, "bad complex index");
   if (k < 1 || k > 64) return fail(FPB_ERR_ARG, "k must be in 1..64");
   if (h->last_stage < FPB_STAGE_GRAPH) return fail(FPB_ERR_STATE, "fpb_knn needs a completed graph-stage run");
   CK(cudaSetDevice(h->device));
   ComplexHost& cx = h->cx[complex_index];
-  if (cx.total_odd == 0) return FPB_OK;
   cudaStream_t st = h->stream;
   int rc;
-  if ((rc = cx.knn.ensure((size_t)cx.total_odd * k))) return rc;
-  // one warp per odd cube; its row of cx.max_odd doubles lives in shared memory
-  const int row_cap = cx.max_odd > 0 ? cx.max_odd : 1;
-  int max_optin = 0;
-  CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
-  int warps = (int)(((size_t)max_optin - 1024) / ((size_t)row_cap * sizeof(double)));
-  if (warps > 8) warps = 8;
-  if (warps < 1) return fail(FPB_ERR_UNSUPPORTED, "too many odd cubes in one trial for the candidate kernel");
-  const size_t smem = (size_t)warps * row_cap * sizeof(double);
-  CK(cudaFuncSetAttribute(k_knn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - 1024));
-  dim3 grid((unsigned)h->T, (unsigned)((cx.max_odd + warps - 1) / warps));
-  k_knn<<<grid, warps * 32, smem, st>>>(make_dev(cx), k, row_cap, cx.knn.p);
-  CK(cudaGetLastError());
-  if (on_device) {
-    CK(cudaMemcpyAsync(ids, cx.knn.p, (size_t)cx.total_odd * k * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
-  } else {
-    CK(cudaMemcpyAsync(ids, cx.knn.p, (size_t)cx.total_odd * k * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (wmax) {
+    if ((rc = h->trial_wmax.ensure((size_t)h->T))) return rc;
+    CK(cudaMemsetAsync(h->trial_wmax.p, 0, (size_t)h->T * sizeof(unsigned long long), st));
   }
+  if (cx.total_odd > 0) {
+    if ((rc = cx.knn.ensure((size_t)cx.total_odd * k))) return rc;
+    if (lens && (rc = cx.knn_len.ensure((size_t)cx.total_odd * k))) return rc;
+    // one warp per odd cube; its row of cx.max_odd doubles lives in shared memory
+    const int row_cap = cx.max_odd > 0 ? cx.max_odd : 1;
+    int max_optin = 0;
+    CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+    int warps = (int)(((size_t)max_optin - 1024) / ((size_t)row_cap * sizeof(double)));
+    if (warps > 8) warps = 8;
+    if (warps < 1) return fail(FPB_ERR_UNSUPPORTED, "too many odd cubes in one trial for the candidate kernel");
+    const size_t smem = (size_t)warps * row_cap * sizeof(double);
+    CK(cudaFuncSetAttribute(k_knn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - 1024));
+    dim3 grid((unsigned)h->T, (unsigned)((cx.max_odd + warps - 1) / warps));
+    k_knn<<<grid, warps * 32, smem, st>>>(make_dev(cx), k, row_cap, cx.knn.p, lens ? cx.knn_len.p : nullptr,
+                                          wmax ? h->trial_wmax.p : nullptr);
+    CK(cudaGetLastError());
+    const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    CK(cudaMemcpyAsync(ids, cx.knn.p, (size_t)cx.total_odd * k * sizeof(int32_t), kind, st));
+    if (lens) CK(cudaMemcpyAsync(lens, cx.knn_len.p, (size_t)cx.total_odd * k * sizeof(double), kind, st));
+  }
+  if (wmax)  // the bits of a non-negative double, written by atomicMax
+    CK(cudaMemcpyAsync(wmax, h->trial_wmax.p, (size_t)h->T * sizeof(double), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  return FPB_OK;
+}
+
+int fpb_knn(fpb_handle* h, int complex_index, int k, int32_t* ids, int on_device) {
+  return run_knn(h, complex_index, k, ids, nullptr, nullptr, on_device);
+}
+
+int fpb_knn_len(fpb_handle* h, int complex_index, int k, int32_t* ids, double* lens, double* wmax) {
+  if (!lens || !wmax) return fail(FPB_ERR_ARG, "null argument");
+  return run_knn(h, complex_index, k, ids, lens, wmax, 0);
+}
+
+int fpb_pairs_at(fpb_handle* h, int complex_index, int64_t n, const int32_t* trial, const int32_t* a, const int32_t* b,
+                 double* out) {
+  if (!h || (n > 0 && (!trial || !a || !b || !out))) return fail(FPB_ERR_ARG, "null argument");
+  if (complex_index < 0 || complex_index >= h->ncx) return fail(FPB_ERR_ARG, "bad complex index");
+  if (h->last_stage < FPB_STAGE_GRAPH) return fail(FPB_ERR_STATE, "fpb_pairs_at needs a completed graph-stage run");
+  if (n <= 0) return FPB_OK;
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  ComplexHost& cx = h->cx[complex_index];
+  // validate on the host against the odd counts of the last run
+  std::vector<int> counts((size_t)h->T);
+  CK(cudaMemcpyAsync(counts.data(), cx.odd_count.p, (size_t)h->T * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  for (int64_t i = 0; i < n; ++i) {
+    if (trial[i] < 0 || trial[i] >= h->T) return fail(FPB_ERR_ARG, "pair trial out of range");
+    const int K = counts[trial[i]];
+    if (a[i] < 0 || a[i] >= K || b[i] < 0 || b[i] >= K) return fail(FPB_ERR_ARG, "pair endpoint out of range");
+  }
+  int rc;
+  if ((rc = h->q_trial.ensure((size_t)n))) return rc;
+  if ((rc = h->q_src.ensure((size_t)n))) return rc;
+  if ((rc = h->q_dst.ensure((size_t)n))) return rc;
+  if ((rc = h->pair_out.ensure((size_t)n))) return rc;
+  CK(cudaMemcpyAsync(h->q_trial.p, trial, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(h->q_src.p, a, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(h->q_dst.p, b, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
+  const long long blocks = (n + 255) / 256, cap = (long long)h->sm_count * 8;
+  k_pairs_at<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(make_dev(cx), n, h->q_trial.p, h->q_src.p,
+                                                                     h->q_dst.p, h->pair_out.p);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, h->pair_out.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return FPB_OK;
+}
+
+int fpb_pairs_of_trial(fpb_handle* h, int complex_index, int64_t trial, double* out, int64_t cap) {
+  if (!h || !out) return fail(FPB_ERR_ARG, "null argument");
+  if (complex_index < 0 || complex_index >= h->ncx) return fail(FPB_ERR_ARG, "bad complex index");
+  if (h->last_stage < FPB_STAGE_GRAPH) return fail(FPB_ERR_STATE, "fpb_pairs_of_trial needs a completed graph-stage run");
+  if (trial < 0 || trial >= h->T) return fail(FPB_ERR_ARG, "trial out of range");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  ComplexHost& cx = h->cx[complex_index];
+  long long off[2];
+  CK(cudaMemcpyAsync(off, cx.pair_off.p + trial, 2 * sizeof(long long), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  const long long n = off[1] - off[0];
+  if (n > cap) return fail(FPB_ERR_ARG, "output buffer smaller than K(K-1)/2");
+  if (n > 0) CK(cudaMemcpyAsync(out, cx.pair_len.p + off[0], (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return FPB_OK;
+}
+
+int fpb_price(fpb_handle* h, int complex_index, const int64_t* y, const int32_t* top, const int64_t* ztop,
+              const double* scale, const int32_t* wshift, const uint8_t* active, int64_t cap, int32_t* out_trial, int32_t* out_a, int32_t* out_b, double* out_len,
+              int64_t* n_out) {
+  if (!h || !y || !scale || !wshift || !active || !n_out) return fail(FPB_ERR_ARG, "null argument");
+  if (cap > 0 && (!out_trial || !out_a || !out_b || !out_len)) return fail(FPB_ERR_ARG, "null output array");
+  if (complex_index < 0 || complex_index >= h->ncx) return fail(FPB_ERR_ARG, "bad complex index");
+  if (h->last_stage < FPB_STAGE_GRAPH) return fail(FPB_ERR_STATE, "fpb_price needs a completed graph-stage run");
+  *n_out = 0;
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  ComplexHost& cx = h->cx[complex_index];
+  if (cx.total_odd == 0) return FPB_OK;
+  if (cap < 0) cap = 0;
+  int rc;
+  const size_t T = (size_t)h->T;
+  if ((top != nullptr) != (ztop != nullptr)) return fail(FPB_ERR_ARG, "top and ztop come together");
+  if ((rc = h->price_y.ensure(2 * (size_t)cx.total_odd))) return rc;
+  if ((rc = h->price_top.ensure((size_t)cx.total_odd))) return rc;
+  if ((rc = h->price_c.ensure(T))) return rc;
+  if ((rc = h->price_ws.ensure(T))) return rc;
+  if ((rc = h->price_active.ensure(T))) return rc;
+  if ((rc = h->price_idx.ensure(3 * (size_t)cap + 1))) return rc;
+  if ((rc = h->pair_out.ensure((size_t)cap + 1))) return rc;
+  if ((rc = h->price_n.ensure(1))) return rc;
+  CK(cudaMemcpyAsync(h->price_y.p, y, (size_t)cx.total_odd * sizeof(long long), cudaMemcpyHostToDevice, st));
+  if (top) {
+    CK(cudaMemcpyAsync(h->price_y.p + cx.total_odd, ztop, (size_t)cx.total_odd * sizeof(long long), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->price_top.p, top, (size_t)cx.total_odd * sizeof(int), cudaMemcpyHostToDevice, st));
+  }
+  CK(cudaMemcpyAsync(h->price_c.p, scale, T * sizeof(double), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(h->price_ws.p, wshift, T * sizeof(int), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(h->price_active.p, active, T, cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(h->price_n.p, 0, sizeof(unsigned long long), st));
+  PriceParams pp;
+  pp.top = top ? h->price_top.p : nullptr; pp.ztop = h->price_y.p + cx.total_odd;
+  pp.y = h->price_y.p; pp.scale = h->price_c.p; pp.wshift = h->price_ws.p; pp.active = h->price_active.p;
+  pp.cap = cap;
+  pp.out_trial = h->price_idx.p; pp.out_a = h->price_idx.p + cap; pp.out_b = h->price_idx.p + 2 * cap;
+  pp.out_len = h->pair_out.p; pp.n_out = h->price_n.p;
+  int rows = (cx.max_odd + PRICE_ROWS - 1) / PRICE_ROWS;
+  if (rows < 1) rows = 1;
+  if (rows > 64) rows = 64;
+  k_price<<<dim3((unsigned)T, (unsigned)rows), PRICE_ROWS * 32, 0, st>>>(make_dev(cx), pp);
+  CK(cudaGetLastError());
+  unsigned long long found = 0;
+  CK(cudaMemcpyAsync(&found, h->price_n.p, sizeof found, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  *n_out = (int64_t)found;
+  const size_t take = (size_t)(found < (unsigned long long)cap ? found : (unsigned long long)cap);
+  if (take > 0) {
+    CK(cudaMemcpyAsync(out_trial, pp.out_trial, take * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(out_a, pp.out_a, take * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(out_b, pp.out_b, take * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(out_len, pp.out_len, take * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
   return FPB_OK;
 }
 

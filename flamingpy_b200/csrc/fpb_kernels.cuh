@@ -1843,7 +1843,9 @@ __global__ void k_iota_odd(ComplexDev c) {  // the "every cube is odd" pseudo-tr
 // extracted in kn rounds of a warp-wide lexicographic (length, index) minimum.  The host solver
 // starts from this sparse graph and proves optimality against the complete graph by pricing.
 // ------------------------------------------------------------------------------------------
-__global__ void k_knn(ComplexDev c, int kn, int row_cap, int* out /* [total_odd][kn] */) {
+__global__ void k_knn(ComplexDev c, int kn, int row_cap, int* out /* [total_odd][kn] */,
+                      double* out_len /* [total_odd][kn] reduced lengths, or nullptr */,
+                      unsigned long long* trial_wmax /* [T] bits of the largest reduced length / 2 x boundary length, or nullptr */) {
   extern __shared__ double knn_rows[];  // [warps][row_cap]
   const int t = blockIdx.x;
   const int K = c.odd_count[t];
@@ -1855,12 +1857,19 @@ __global__ void k_knn(ComplexDev c, int kn, int row_cap, int* out /* [total_odd]
   const double* pl = c.pair_len + poff;
   const bool bnd = c.n_low > 0;
   const double ba = bnd ? c.bnd_len[ooff + a] : 0.0;
+  double rmax = 2.0 * ba;
   for (int b = lane; b < K; b += 32) {
     double d = FPB_INF;
     if (b < a) d = pl[(long long)b * K - (long long)b * (b + 1) / 2 + (a - b - 1)];
     else if (b > a) d = pl[(long long)a * K - (long long)a * (a + 1) / 2 + (b - a - 1)];
     if (bnd && b != a) d = fmin(d, ba + c.bnd_len[ooff + b]);
     row[b] = d;
+    if (b != a) rmax = fmax(rmax, d);
+  }
+  if (trial_wmax) {  // non-negative doubles order like their bit patterns
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) rmax = fmax(rmax, __shfl_xor_sync(0xffffffffu, rmax, off));
+    if (lane == 0) atomicMax(&trial_wmax[t], (unsigned long long)__double_as_longlong(rmax));
   }
   __syncwarp();
   double pd = -1.0;
@@ -1887,9 +1896,85 @@ __global__ void k_knn(ComplexDev c, int kn, int row_cap, int* out /* [total_odd]
         bb = ob;
       }
     }
-    if (lane == 0) o[r] = bb == 0x7fffffff ? -1 : bb;
+    if (lane == 0) {
+      o[r] = bb == 0x7fffffff ? -1 : bb;
+      if (out_len) out_len[(ooff + a) * kn + r] = bd;
+    }
     pd = bd;
     pb = bb;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Sparse hand-off to the host matcher: the triangle of lengths stays in HBM.  k_pairs_at returns the
+// lengths of requested pairs; k_price tests every pair of the active trials against the matcher's
+// vertex duals in the matcher's own integer arithmetic, y_a + y_b + ((4 * fixed(w_ab * scale_t)) <<
+// wshift_t) < 0 with w_ab the reduced length min(d_ab, b_a + b_b) and fixed(v) = (long long)(v + 0.5)
+// (csrc/mwpm.cpp: to_fixed, wt), and appends the violators - the pricing pass of csrc/mwpm.cpp moved
+// to where the lengths are.  Exact, so tight pairs (slack 0: every two cubes that end at their
+// connectors) are not reported.  Blossom duals are non-negative and only add slack, so the vertex
+// test never misses a violated edge; the host adds them when it re-checks the returned pairs.
+// ------------------------------------------------------------------------------------------
+__global__ void k_pairs_at(ComplexDev c, long long n, const int* trial, const int* qa, const int* qb, double* out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int t = trial[i];
+    const long long K = c.odd_count[t];
+    const long long a = min(qa[i], qb[i]), b = max(qa[i], qb[i]);
+    out[i] = (a == b) ? 0.0 : c.pair_len[c.pair_off[t] + a * K - a * (a + 1) / 2 + (b - a - 1)];
+  }
+}
+
+constexpr int PRICE_ROWS = 8;  // rows (= warps) per CTA
+
+struct PriceParams {
+  const long long* y;          // [total_odd] vertex duals of the host matcher
+  const int* top;              // [total_odd] top-level blossom of each vertex (-1: none), or nullptr
+  const long long* ztop;       // [total_odd] 2 x the dual of that blossom
+  const double* scale;         // [T] fixed-point scale of the trial's lengths (a power of two)
+  const int* wshift;           // [T] doublings applied to the trial's weights and duals
+  const uint8_t* active;       // [T] trials to price
+  long long cap;
+  int* out_trial;
+  int* out_a;
+  int* out_b;
+  double* out_len;             // reduced length of the violating pair
+  unsigned long long* n_out;   // appended entries (may exceed cap: the caller retries with more room)
+};
+
+__global__ void __launch_bounds__(PRICE_ROWS * 32) k_price(ComplexDev c, PriceParams p) {
+  const int t = blockIdx.x;
+  if (!p.active[t]) return;
+  const int K = c.odd_count[t];
+  const int lane = threadIdx.x & 31;
+  const long long poff = c.pair_off[t], ooff = c.odd_off[t];
+  const bool bnd = c.n_low > 0;
+  const double scale = p.scale[t];
+  const int wshift = p.wshift[t] + 2;  // 4 * fixed << wshift
+  const long long* y = p.y + ooff;
+  const int* top = p.top ? p.top + ooff : nullptr;
+  const long long* ztop = p.top ? p.ztop + ooff : nullptr;
+  for (int a = blockIdx.y * PRICE_ROWS + (threadIdx.x >> 5); a < K - 1; a += gridDim.y * PRICE_ROWS) {
+    const double* row = c.pair_len + poff + ((long long)a * K - (long long)a * (a + 1) / 2 - a - 1);
+    const long long ya = y[a];
+    const int ta = top ? top[a] : -1;
+    const long long za = ta >= 0 ? ztop[a] : 0;
+    const double ba = bnd ? c.bnd_len[ooff + a] : 0.0;
+    for (int b = a + 1 + lane; b < K; b += 32) {
+      double w = row[b];
+      if (bnd) w = fmin(w, ba + c.bnd_len[ooff + b]);
+      // two vertices of one top-level blossom: its dual is part of their slack (a lower bound of
+      // the sum over all their common blossoms, so still no violated pair is missed)
+      const long long zc = (ta >= 0 && top[b] == ta) ? za : 0;
+      if (ya + y[b] + zc + (__double2ll_rz(w * scale + 0.5) << wshift) < 0) {
+        const unsigned long long pos = atomicAdd(p.n_out, 1ull);
+        if ((long long)pos < p.cap) {
+          p.out_trial[pos] = t;
+          p.out_a[pos] = a;
+          p.out_b[pos] = b;
+          p.out_len[pos] = w;
+        }
+      }
+    }
   }
 }
 

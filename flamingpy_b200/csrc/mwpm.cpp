@@ -22,6 +22,7 @@
 #include <cstring>
 #include <atomic>
 #include <chrono>
+#include <mutex>
 #include <queue>
 #include <vector>
 
@@ -773,6 +774,310 @@ int solve_auto(int K, const double* pair_len, const double* bnd_len, int* out_sr
   return solve_one(K, pair_len, bnd_len, out_src, out_dst);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Sparse hand-off (include/fpb_mwpm.h, fpb_mwpm_sparse_*): the same sparse-candidate-graph +
+// pricing solver as solve_one_sparse, for a whole batch of trials whose K(K-1)/2 lengths stay on
+// the GPU.  A job sees only the candidate lists with their reduced lengths (fpb_knn_len), the
+// lengths of the few pairs it asks for (chain edges; every pair of a small graph: fpb_pairs_at) and
+// the pairs the device-side pricing pass flags under its duals (fpb_price).  The solver state of
+// every trial is kept across the pricing rounds of the batch, so a violated edge costs the same
+// warm restart as in solve_one_sparse.
+// ---------------------------------------------------------------------------------------------
+struct SparseJob {
+  enum State { EMPTY, DENSE_WAIT, NEED_START, NEED_SOLVE, PRICING, DONE, FAILED };
+  State state = EMPTY;
+  int K = 0, n = 0, wshift = 0, rounds = 0, knn = 0;
+  bool bnd = false;
+  double scale = 0, wmax = 0;
+  std::vector<double> blen;   // boundary lengths
+  std::vector<ll> dlen;       // fixed-point boundary lengths (edges to the dummy vertex K)
+  fpb_sparse::SparseBlossom sb;
+  std::vector<ll> w0;         // matcher weight of every edge of sb.E at wshift = 0
+  std::vector<double> elen;   // reduced length of every edge of sb.E (dummy edges: boundary length)
+  std::vector<ll> y;
+  std::vector<int> vmate;
+  std::vector<int> req_a, req_b;  // pairs whose lengths were asked for
+  struct Viol { ll s; int u, v; double len; };
+  std::vector<Viol> pending;  // violated edges to the dummy vertex, found on the host
+  std::vector<int> res_src, res_dst;
+  int error = 0;
+
+  ll fixed_w(double len) const { return -(2 * to_fixed(len * scale)); }
+  ll wt_now(ll base) const { return base * ((ll)1 << wshift); }
+  void add_edge(int u, int v, double len) {
+    const ll b = (v >= K) ? -(2 * dlen[u]) : fixed_w(len);
+    sb.add_edge(u, v, wt_now(b));
+    w0.push_back(b);
+    elen.push_back(len);
+  }
+
+  void init(int K_, const int* cand, const double* cand_len, int cand_k, const double* bnd_len, double wmax_, int knn_) {
+    // jobs are recycled between batches (their vectors keep their capacity): reset every field
+    state = EMPTY;
+    n = wshift = rounds = error = 0;
+    scale = 0;
+    blen.clear(); dlen.clear(); w0.clear(); elen.clear(); req_a.clear(); req_b.clear(); pending.clear();
+    res_src.clear(); res_dst.clear();
+    K = K_;
+    bnd = bnd_len != nullptr;
+    knn = knn_;
+    wmax = wmax_;
+    if (K == 0) { state = DONE; return; }
+    if (!bnd && (K & 1)) { state = FAILED; error = -1; return; }
+    n = (bnd && (K & 1)) ? K + 1 : K;
+    if (bnd) blen.assign(bnd_len, bnd_len + K);
+    if (K < SPARSE_MIN_K || K < 4) {  // small graph: ask for every pair and solve it densely
+      for (int a = 0; a < K - 1; ++a)
+        for (int b = a + 1; b < K; ++b) { req_a.push_back(a); req_b.push_back(b); }
+      state = DENSE_WAIT;
+      return;
+    }
+    if (!(wmax < 1e15)) { state = FAILED; error = -2; return; }
+    int shift = 32;
+    while (shift > 0 && std::ldexp(wmax + 1.0, shift) * (double)(n + 2) > 1e17) --shift;
+    scale = std::ldexp(1.0, shift);
+    sb.reset(n);
+    w0.clear();
+    elen.clear();
+    if (n > K) {
+      dlen.resize(K);
+      for (int a = 0; a < K; ++a) dlen[a] = to_fixed(blen[a] * scale);
+    }
+    // candidate edges, each pair once: from the smaller endpoint's list, or from the larger one's if the
+    // smaller does not list it (as in solve_one_sparse)
+    const int take = std::min(knn, cand_k);
+    std::vector<double> worst(K, 0.0);
+    auto lists = [&](int u, int v) {  // is v among the first `take` candidates of u?
+      const int* c = cand + (size_t)u * cand_k;
+      for (int i = 0; i < take; ++i) {
+        if (c[i] == v) return true;
+        if (c[i] < 0) break;
+      }
+      return false;
+    };
+    for (int u = 0; u < K; ++u)
+      for (int i = 0; i < take; ++i) {
+        const int v = cand[(size_t)u * cand_k + i];
+        if (v < 0 || v >= K || v == u) break;
+        const double len = cand_len[(size_t)u * cand_k + i];
+        worst[u] = std::max(worst[u], len);
+        if (u < v || !lists(v, u)) add_edge(std::min(u, v), std::max(u, v), len);
+      }
+    auto listed = [&](int a, int b) { return lists(a, b) || lists(b, a); };
+    if (n > K) {
+      // dummy vertex: the cubes nearest to the boundary, and every cube whose boundary length beats
+      // its worst candidate
+      std::vector<int> order(K);
+      for (int a = 0; a < K; ++a) order[a] = a;
+      std::sort(order.begin(), order.end(), [&](int a, int b) { return blen[a] < blen[b] || (blen[a] == blen[b] && a < b); });
+      std::vector<char> in(K, 0);
+      for (int i = 0; i < std::min(K, knn); ++i) in[order[i]] = 1;
+      for (int a = 0; a < K; ++a)
+        if (blen[a] < worst[a]) in[a] = 1;
+      for (int a = 0; a < K; ++a)
+        if (in[a]) add_edge(a, K, blen[a]);
+    }
+    if (bnd) {
+      // chain through the cubes in order of boundary length (see solve_one_sparse): ask for the lengths
+      std::vector<int> order(K);
+      for (int a = 0; a < K; ++a) order[a] = a;
+      std::sort(order.begin(), order.end(), [&](int a, int b) { return blen[a] < blen[b] || (blen[a] == blen[b] && a < b); });
+      for (int i = 0; i < K; ++i)
+        for (int j = 1; j <= 3 && i + j < K; ++j) {
+          const int a = std::min(order[i], order[i + j]), b2 = std::max(order[i], order[i + j]);
+          if (!listed(a, b2)) { req_a.push_back(a); req_b.push_back(b2); }
+        }
+    }
+    state = NEED_START;
+  }
+
+  // lengths of the requested pairs have arrived
+  void start(const double* req_len) {
+    if (state == DENSE_WAIT) {
+      std::vector<double> tri(req_len, req_len + req_a.size());
+      res_src.resize(K);
+      res_dst.resize(K);
+      const int r = solve_one(K, tri.data(), bnd ? blen.data() : nullptr, res_src.data(), res_dst.data());
+      if (r < 0) { state = FAILED; error = r; return; }
+      res_src.resize(r);
+      res_dst.resize(r);
+      state = DONE;
+      return;
+    }
+    if (state != NEED_START) return;
+    for (size_t i = 0; i < req_a.size(); ++i) {
+      const int a = req_a[i], b = req_b[i];
+      add_edge(a, b, bnd ? std::min(req_len[i], blen[a] + blen[b]) : req_len[i]);
+    }
+    sb.build_adjacency();
+    state = cold_start() ? NEED_SOLVE : FAILED;
+    if (state == FAILED) error = -100;
+  }
+
+  bool cold_start() {  // as in solve_one_sparse
+    y.assign(n, INT64_MIN);
+    vmate.assign(n, -1);
+    for (int k = 0; k < sb.n_edges(); ++k) {
+      y[sb.E[k].u] = std::max(y[sb.E[k].u], sb.E[k].w);
+      y[sb.E[k].v] = std::max(y[sb.E[k].v], sb.E[k].w);
+    }
+    for (int u = 0; u < n; ++u)
+      if (y[u] == INT64_MIN) return false;
+    for (int u = 0; u < n; ++u) {
+      if (vmate[u] >= 0) continue;
+      ll smin = INT64_MAX;
+      int pick = -1;
+      sb.for_neighbours(u, [&](int v, ll w) {
+        const ll sl = y[u] + y[v] - 2 * w;
+        if (sl < smin || (sl == smin && pick >= 0 && vmate[pick] >= 0 && vmate[v] < 0)) {
+          smin = sl;
+          pick = v;
+        }
+      });
+      y[u] -= smin;
+      if (vmate[pick] < 0) {
+        vmate[u] = pick;
+        vmate[pick] = u;
+      }
+    }
+    for (int u = 0; u < n; ++u) {
+      if (vmate[u] >= 0) continue;
+      bool found = false;
+      sb.for_neighbours(u, [&](int v, ll w) {
+        if (found || vmate[v] < 0 || y[u] + y[v] != 2 * w) return;
+        const int v2 = vmate[v];
+        int x = -1;
+        sb.for_neighbours(v2, [&](int c, ll w2) {
+          if (x < 0 && c != u && vmate[c] < 0 && y[v2] + y[c] == 2 * w2) x = c;
+        });
+        if (x >= 0) {
+          vmate[u] = v; vmate[v] = u;
+          vmate[v2] = x; vmate[x] = v2;
+          found = true;
+        }
+      });
+    }
+    sb.start(y, vmate);
+    return true;
+  }
+
+  // one solve; on success the duals for the device-side pricing pass: an edge of reduced length w is
+  // violated iff y_u + y_v + ((4 * to_fixed(w * scale)) << wshift) + blossom duals < 0
+  void solve(ll* y_out, int* top_out, ll* ztop_out, double* scale_out, int* wshift_out) {
+    if (state != NEED_SOLVE) return;
+    if (!sb.solve()) { state = FAILED; error = -100; return; }
+    for (int v = 0; v < K; ++v) y_out[v] = sb.dual[v];
+    if (top_out)
+      for (int v = 0; v < K; ++v) {
+        const int b = sb.top_blossom(v);
+        top_out[v] = b >= n ? b : -1;
+        ztop_out[v] = b >= n ? 2 * sb.dual[b] : 0;
+      }
+    *scale_out = scale;
+    *wshift_out = wshift;
+    pending.clear();
+    if (n > K)
+      for (int u = 0; u < K; ++u) {
+        ll sl = sb.dual[u] + sb.dual[K] - 2 * wt_now(-(2 * dlen[u]));
+        if (sl < 0) {
+          sl += sb.common_blossom_dual(u, K);
+          if (sl < 0) pending.push_back(Viol{sl, u, K, blen[u]});
+        }
+      }
+    state = PRICING;
+  }
+
+  // pairs the pricing pass flagged for this trial (u < v < K, reduced lengths); returns true if the
+  // job needs another solve
+  bool apply(const int* vu, const int* vv, const double* vlen, size_t cnt, int max_rounds) {
+    if (state != PRICING) return false;
+    std::vector<Viol> viol(pending);
+    for (size_t i = 0; i < cnt; ++i) {
+      const int u = vu[i], v = vv[i];
+      ll sl = sb.dual[u] + sb.dual[v] - 2 * wt_now(fixed_w(vlen[i]));
+      if (sl < 0) {
+        sl += sb.common_blossom_dual(u, v);
+        if (sl < 0) viol.push_back(Viol{sl, u, v, vlen[i]});
+      }
+    }
+    if (viol.empty()) {
+      finish();
+      return false;
+    }
+    if (++rounds > max_rounds) { state = FAILED; error = -100; return false; }  // the caller solves it from the full triangle
+    g_stats[2].fetch_add(1);
+    const size_t cap = (size_t)4 * n;
+    if (viol.size() > cap) {
+      std::nth_element(viol.begin(), viol.begin() + cap, viol.end(), [](const Viol& a, const Viol& b) { return a.s < b.s; });
+      viol.resize(cap);
+    }
+    g_stats[3].fetch_add((long long)viol.size());
+    auto wt = [&](const Viol& e) { return wt_now(e.v >= K ? -(2 * dlen[e.u]) : fixed_w(e.len)); };
+    if (wshift < 6) {  // warm restart, as in solve_one_sparse
+      sb.double_all();
+      ++wshift;
+      std::vector<int> marked;
+      for (size_t i = 0; i < viol.size(); ++i) {
+        const int u = viol[i].u, v = viol[i].v;
+        if (sb.dual[u] + sb.dual[v] - 2 * wt(viol[i]) + sb.common_blossom_dual(u, v) >= 0) continue;
+        const int x = sb.is_bare(u) ? u : (sb.is_bare(v) ? v : u);
+        sb.make_bare(x);
+        const ll rc = sb.dual[u] + sb.dual[v] - 2 * wt(viol[i]) + sb.common_blossom_dual(u, v);
+        if (rc >= 0) continue;
+        sb.dual[x] -= rc;
+        marked.push_back(x);
+      }
+      for (size_t i = 0; i < viol.size(); ++i) add_edge(viol[i].u, viol[i].v, viol[i].len);
+      sb.build_adjacency();
+      for (size_t i = 0; i < marked.size(); ++i) sb.unmatch(marked[i]);
+      state = NEED_SOLVE;
+    } else {  // too many doublings: start over on the enlarged graph
+      wshift = 0;
+      for (int k = 0; k < sb.n_edges(); ++k) sb.E[k].w = w0[k];
+      for (size_t i = 0; i < viol.size(); ++i) add_edge(viol[i].u, viol[i].v, viol[i].len);
+      sb.build_adjacency();
+      state = cold_start() ? NEED_SOLVE : FAILED;
+      if (state == FAILED) error = -100;
+    }
+    return state == NEED_SOLVE;
+  }
+
+  void finish() {
+    res_src.clear();
+    res_dst.clear();
+    for (int a = 0; a < K; ++a) {
+      const int b = sb.mate_vertex(a);
+      if (b < 0) { state = FAILED; error = -3; return; }
+      if (b >= K) {
+        res_src.push_back(a);
+        res_dst.push_back(-1);
+      } else if (a < b) {
+        const double len = elen[sb.mate[a] >> 1];
+        if (bnd && !(len < blen[a] + blen[b])) {  // the pair weighs b_a + b_b: both end at their connector
+          res_src.push_back(a); res_dst.push_back(-1);
+          res_src.push_back(b); res_dst.push_back(-1);
+        } else {
+          res_src.push_back(a);
+          res_dst.push_back(b);
+        }
+      }
+    }
+    state = DONE;
+  }
+};
+
+struct SparseBatch {
+  int T = 0, threads = 0;
+  std::vector<long long> q_off;  // [T + 1]
+  std::vector<long long> req_off;  // [T + 1] offsets of each trial's requests
+  std::vector<SparseJob> jobs;   // grows to the largest batch seen; only the first T are in use
+};
+// finished batches are kept for reuse: a job owns some thirty vectors (the solver's forests, blossom
+// lists, adjacency), and allocating them afresh for every trial costs more than the pricing pass saves
+std::mutex g_pool_mutex;
+std::vector<SparseBatch*> g_pool;
+
 }  // namespace
 
 extern "C" {
@@ -840,6 +1145,146 @@ int fpb_mwpm_batch_cand(int T, const int* odd_count, const double* pair_len, con
     n_queries[t] = r < 0 ? 0 : r;
   }
   return bad ? -1 : 0;
+}
+
+// ---- sparse hand-off (see SparseJob above and include/fpb_mwpm.h) ----
+void* fpb_mwpm_sparse_begin(int T, const int* odd_count, const long long* q_off, const int* cand,
+                            const double* cand_len, int cand_k, const double* bnd_len, const double* wmax,
+                            int n_threads) {
+  SparseBatch* B = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    if (!g_pool.empty()) {
+      B = g_pool.back();
+      g_pool.pop_back();
+    }
+  }
+  if (!B) B = new SparseBatch();
+  B->T = T;
+  B->threads = n_threads;
+  B->q_off.assign(q_off, q_off + T + 1);
+  if ((int)B->jobs.size() < T) B->jobs.resize((size_t)T);
+  const int knn = std::max(2, g_knn.load());
+#ifdef _OPENMP
+  if (n_threads > 0) omp_set_num_threads(n_threads);
+#endif
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int t = 0; t < T; ++t)
+    B->jobs[t].init(odd_count[t], cand + q_off[t] * cand_k, cand_len + q_off[t] * cand_k, cand_k,
+                    bnd_len ? bnd_len + q_off[t] : nullptr, wmax[t], knn);
+  B->req_off.assign((size_t)T + 1, 0);
+  for (int t = 0; t < T; ++t) B->req_off[t + 1] = B->req_off[t] + (long long)B->jobs[t].req_a.size();
+  return B;
+}
+
+long long fpb_mwpm_sparse_requests(void* ctx, int* trial, int* a, int* b, long long cap) {
+  SparseBatch* B = static_cast<SparseBatch*>(ctx);
+  const long long total = B->req_off[B->T];
+  if (cap < total || !trial || !a || !b) return total;
+  for (int t = 0; t < B->T; ++t) {
+    const SparseJob& J = B->jobs[t];
+    long long o = B->req_off[t];
+    for (size_t i = 0; i < J.req_a.size(); ++i, ++o) {
+      trial[o] = t;
+      a[o] = J.req_a[i];
+      b[o] = J.req_b[i];
+    }
+  }
+  return total;
+}
+
+int fpb_mwpm_sparse_start(void* ctx, const double* req_len) {
+  SparseBatch* B = static_cast<SparseBatch*>(ctx);
+#ifdef _OPENMP
+  if (B->threads > 0) omp_set_num_threads(B->threads);
+#endif
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int t = 0; t < B->T; ++t) B->jobs[t].start(req_len ? req_len + B->req_off[t] : nullptr);
+  return 0;
+}
+
+// Solve every job that needs it; y [sum K], scale / wshift / active [T] receive what fpb_price takes.
+// Returns the number of jobs awaiting a pricing pass.
+int fpb_mwpm_sparse_solve(void* ctx, long long* y, int* top, long long* ztop, double* scale, int* wshift,
+                          unsigned char* active) {
+  SparseBatch* B = static_cast<SparseBatch*>(ctx);
+  int n_active = 0;
+#ifdef _OPENMP
+  if (B->threads > 0) omp_set_num_threads(B->threads);
+#endif
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : n_active)
+  for (int t = 0; t < B->T; ++t) {
+    SparseJob& J = B->jobs[t];
+    active[t] = 0;
+    if (J.state == SparseJob::NEED_SOLVE) {
+      g_stats[0].fetch_add(J.rounds == 0 ? 1 : 0);
+      J.solve(y + B->q_off[t], top ? top + B->q_off[t] : nullptr, ztop ? ztop + B->q_off[t] : nullptr, scale + t,
+              wshift + t);
+    }
+    if (J.state == SparseJob::PRICING) {
+      active[t] = 1;
+      ++n_active;
+    }
+  }
+  return n_active;
+}
+
+// The flagged pairs of fpb_price (any order).  Returns the number of jobs that need another solve.
+int fpb_mwpm_sparse_apply(void* ctx, long long n, const int* vt, const int* va, const int* vb, const double* vlen,
+                          int max_rounds) {
+  SparseBatch* B = static_cast<SparseBatch*>(ctx);
+  // bucket the pairs by trial
+  std::vector<long long> off((size_t)B->T + 1, 0);
+  for (long long i = 0; i < n; ++i) ++off[vt[i] + 1];
+  for (int t = 0; t < B->T; ++t) off[t + 1] += off[t];
+  std::vector<int> ua((size_t)n), ub((size_t)n);
+  std::vector<double> ul((size_t)n);
+  {
+    std::vector<long long> fill(off.begin(), off.end() - 1);
+    for (long long i = 0; i < n; ++i) {
+      const long long o = fill[vt[i]]++;
+      ua[o] = va[i];
+      ub[o] = vb[i];
+      ul[o] = vlen[i];
+    }
+  }
+  int again = 0;
+#ifdef _OPENMP
+  if (B->threads > 0) omp_set_num_threads(B->threads);
+#endif
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : again)
+  for (int t = 0; t < B->T; ++t)
+    if (B->jobs[t].apply(ua.data() + off[t], ub.data() + off[t], ul.data() + off[t], (size_t)(off[t + 1] - off[t]),
+                         max_rounds > 0 ? max_rounds : 40))
+      ++again;
+  return again;
+}
+
+// Queries of every finished trial (layout of fpb_mwpm_batch); failed [T] flags the trials the caller
+// must solve from the full triangle instead (no perfect matching in the candidate graph, ...).
+int fpb_mwpm_sparse_finish(void* ctx, int* out_src, int* out_dst, int* n_queries, unsigned char* failed) {
+  SparseBatch* B = static_cast<SparseBatch*>(ctx);
+  int n_failed = 0;
+  for (int t = 0; t < B->T; ++t) {
+    const SparseJob& J = B->jobs[t];
+    failed[t] = J.state != SparseJob::DONE;
+    n_queries[t] = 0;
+    if (failed[t]) {
+      ++n_failed;
+      continue;
+    }
+    n_queries[t] = (int)J.res_src.size();
+    std::copy(J.res_src.begin(), J.res_src.end(), out_src + B->q_off[t]);
+    std::copy(J.res_dst.begin(), J.res_dst.end(), out_dst + B->q_off[t]);
+  }
+  return n_failed;
+}
+
+void fpb_mwpm_sparse_free(void* ctx) {
+  if (!ctx) return;
+  std::lock_guard<std::mutex> lock(g_pool_mutex);
+  if (g_pool.size() < 8) g_pool.push_back(static_cast<SparseBatch*>(ctx));
+  else delete static_cast<SparseBatch*>(ctx);
 }
 
 int fpb_mwpm_max_threads(void) {

@@ -68,6 +68,7 @@ class SparseBlossom {
   }
 
   bool is_bare(int v) const { return inblossom[v] == v; }  // top-level, not inside a blossom
+  int top_blossom(int v) const { return inblossom[v]; }    // v itself, or the outermost blossom around it (>= n)
   void double_all() {
     for (size_t i = 0; i < dual.size(); ++i) dual[i] *= 2;
     for (size_t k = 0; k < E.size(); ++k) E[k].w *= 2;

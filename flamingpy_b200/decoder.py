@@ -184,14 +184,32 @@ def correct(code, decoder="MWPM", weight_options=None, sanity_check=False, decod
     return bool(np.all(result))
 
 
-def match_batch(code, eng, batch, backend="native", cands=None):
+def match_batch(code, eng, batch, backend="native", cands=None, handoff="full", stats=None):
     """Host matching of every trial of ``batch``: (trial, complex, src, dst) int32 arrays of the
     matched queries (dst = -1: to the connector).  ``backend="native"`` solves all trials with the
-    C++ matcher (OpenMP over trials); ``cands`` = per-complex candidate lists (``candidates``)."""
+    C++ matcher (OpenMP over trials); ``cands`` = per-complex candidate lists (``candidates``).
+    ``handoff="sparse"`` (native backend only): the pair lengths stay on the device - the matcher
+    gets candidate lists with lengths and prices the complete graph through ``TrialEngine.price``
+    (``mwpm_native.solve_batch_sparse``); ``batch`` must be the engine's last run and ``cands`` then
+    holds per complex the ``TrialEngine.knn_len`` triple (or None: fetched here)."""
     trial, cx, src, dst = [], [], [], []
     for ci, e in enumerate(code.ec):
         ct = code.lattice.complexes[e]
         cb = batch.complexes[e]
+        if backend == "native" and handoff == "sparse":
+            from . import mwpm_native
+
+            st = {} if stats is not None else None
+            t_, s_, d_ = mwpm_native.solve_batch_sparse(eng, ci, cb.odd_count, cb.bnd_len if ct.has_boundary else None,
+                                                        stats=st, knn=cands[ci] if cands is not None else None)
+            if stats is not None:
+                for k, v in st.items():
+                    stats[k] = stats.get(k, 0) + v
+            trial.append(t_)
+            cx.append(np.full(len(t_), ci, np.int32))
+            src.append(s_)
+            dst.append(d_)
+            continue
         if backend == "native":
             from . import mwpm_native
 

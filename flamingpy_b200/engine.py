@@ -19,7 +19,8 @@ from .lattice import LatticeTables
 
 
 def config_dict(lat: LatticeTables, delta: float, p_swap: float, wo: dict, mode: str = "compat",
-                chain_len: int = 0, device: int = 0, delta_step: float = 0.0, length_mode: int = _lib.LENGTH_FLOAT):
+                chain_len: int = 0, device: int = 0, delta_step: float = 0.0, length_mode: int = _lib.LENGTH_FLOAT,
+                reserve_sms: int = 0):
     """The fields of ``fpb_config`` (include/fpb.h) by name, from lattice tables and options -
     what ``_lib.open_handle`` (pybind11 ``fpbpy.Handle`` or ctypes) takes.
     Returns (config dict, qubit offsets per complex, Qtot)."""
@@ -57,6 +58,7 @@ def config_dict(lat: LatticeTables, delta: float, p_swap: float, wo: dict, mode:
         "weight_multiplier": float(wo.get("multiplier", 1)),
         "label_mode": _lib.MODE_FRESH if mode == "fresh" else _lib.MODE_COMPAT,
         "chain_len": int(chain_len), "delta_step": float(delta_step), "length_mode": int(length_mode),
+        "reserve_sms": int(reserve_sms),
     }
     return cfg, q_off, off
 
@@ -115,6 +117,7 @@ class TrialEngine:
         device: int = 0,
         delta_step: float = 0.0,
         lengths: str = "float",
+        reserve_sms: int = 0,
     ):
         self.lat = lat
         self.delta = float(delta)
@@ -134,7 +137,7 @@ class TrialEngine:
         self.lengths = lengths
         cfg, self.q_off, self.Qtot = config_dict(
             lat, self.delta, self.p_swap, wo, mode, chain_len, device, delta_step,
-            _lib.LENGTH_RX_TRUNC if lengths == "rustworkx" else _lib.LENGTH_FLOAT)
+            _lib.LENGTH_RX_TRUNC if lengths == "rustworkx" else _lib.LENGTH_FLOAT, reserve_sms)
         self.bit_words = (self.Qtot + 31) // 32
         self._h = _lib.open_handle(cfg)  # pybind11 fpbpy.Handle, or ctypes when the module is absent
         self.binding = _lib.binding_name()
@@ -336,10 +339,11 @@ class TrialEngine:
         self._h.fetch_into({k: v for k, v in bufs.items() if isinstance(v, np.ndarray)})
         return s
 
-    def fetch_decode(self, bufs: Optional[dict] = None) -> "TrialBatch":
+    def fetch_decode(self, bufs: Optional[dict] = None, want_pairs: bool = True) -> "TrialBatch":
         """What the host decoder needs of the last run - bits, odd counts, pair and boundary
         lengths - copied into reusable pinned buffers (``bufs``, grown on demand and owned by
-        the caller; the returned arrays are views into them, valid until the next call)."""
+        the caller; the returned arrays are views into them, valid until the next call).
+        ``want_pairs=False`` (sparse hand-off) leaves the K(K-1)/2 pair lengths on the device."""
         import torch
 
         bufs = {} if bufs is None else bufs
@@ -358,10 +362,12 @@ class TrialEngine:
         room("bits", T * self.bit_words, torch.int32)
         for i, ec in enumerate(self.ec):
             room(f"odd_count{i}", T, torch.int32)
-            room(f"pair_len{i}", int(s.total_pairs[i]), torch.float64)
+            if want_pairs:
+                room(f"pair_len{i}", int(s.total_pairs[i]), torch.float64)
             if self.lat.complexes[ec].has_boundary:
                 room(f"bnd_len{i}", int(s.total_odd[i]), torch.float64)
-        self.fetch_into({k: v for k, v in bufs.items() if not k.startswith("_keep_")})
+        self.fetch_into({k: v for k, v in bufs.items()
+                         if not k.startswith("_keep_") and (want_pairs or not k.startswith("pair_len"))})
         batch = TrialBatch(T, _lib.STAGE_GRAPH)
         batch.bits = unpack_bits(bufs["bits"][: T * self.bit_words].reshape(T, self.bit_words), self.Qtot)
         batch.complexes = {}
@@ -371,7 +377,7 @@ class TrialEngine:
             k64 = cb.odd_count.astype(np.int64)
             cb.odd_off = np.concatenate([[0], np.cumsum(k64)])
             cb.pair_off = np.concatenate([[0], np.cumsum(k64 * (k64 - 1) // 2)])
-            cb.pair_len = bufs[f"pair_len{i}"][: int(s.total_pairs[i])]
+            cb.pair_len = bufs[f"pair_len{i}"][: int(s.total_pairs[i])] if want_pairs else None
             cb.bnd_len = (bufs[f"bnd_len{i}"][: int(s.total_odd[i])] if self.lat.complexes[ec].has_boundary
                           else np.empty(0, np.float64))
             batch.complexes[ec] = cb
@@ -389,6 +395,32 @@ class TrialEngine:
         if n:
             self._h.knn(complex_index, k, out)
         return out[: n * k].reshape(n, k)
+
+    # -- sparse hand-off to the host matcher (fpb_knn_len / fpb_pairs_at / fpb_price) ----------------
+    def knn_len(self, complex_index: int, k: int = 12):
+        """Candidate partners with their reduced weights ``min(d_ab, b_a + b_b)``: (ids int32[sum K, k],
+        lens float64[sum K, k], wmax float64[T]).  The K(K-1)/2 lengths stay on the device."""
+        return self._h.knn_len(int(complex_index), int(k))
+
+    def pairs_at(self, complex_index: int, trial, a, b) -> np.ndarray:
+        """Shortest-path lengths of the requested pairs (trial, odd index a, odd index b) of the last run."""
+        c = lambda x: np.ascontiguousarray(x, np.int32)  # noqa: E731
+        return self._h.pairs_at(int(complex_index), c(trial), c(a), c(b))
+
+    def pairs_of_trial(self, complex_index: int, trial: int, K: int) -> np.ndarray:
+        """The packed triangle of all K(K-1)/2 lengths of one trial of the last run."""
+        return self._h.pairs_of_trial(int(complex_index), int(trial), int(K) * (int(K) - 1) // 2)
+
+    def price(self, complex_index: int, y, scale, wshift, active, cap: int = 65536, top=None, ztop=None):
+        """Pricing of the complete graph under the matcher's vertex duals on the device, in the
+        matcher's integer arithmetic: the pairs with ``y_a + y_b + ((4 * int64(w_ab * scale_t + 0.5)) <<
+        wshift_t) < 0`` as (trial, a, b, w_ab) arrays.  ``top`` / ``ztop``: each vertex's outermost
+        blossom (-1: none) and twice its dual, added for two vertices of one blossom."""
+        if top is not None:
+            top, ztop = np.ascontiguousarray(top, np.int32), np.ascontiguousarray(ztop, np.int64)
+        return self._h.price(int(complex_index), np.ascontiguousarray(y, np.int64), top, ztop,
+                             np.ascontiguousarray(scale, np.float64), np.ascontiguousarray(wshift, np.int32),
+                             np.ascontiguousarray(active, np.uint8), int(cap))
 
     def paths_list(self, trial, cx, src, dst, max_len: int = 0):
         """Ordered correction paths of the given queries (same arguments as ``paths_toggle``):

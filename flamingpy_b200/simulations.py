@@ -58,9 +58,17 @@ def trial_range(trials: int, rank: int, size: int):
 
 def ec_monte_carlo(trials, code_instance, noise_instance, decoder, decoder_args, world_comm=None, mpi_rank=0,
                    mpi_size=1, *, seed=None, batch=1024, mode="compat", backend="native", device=None,
-                   return_stats=False):
+                   return_stats=False, handoff=None):
     """Run ``trials`` Monte-Carlo trials of the complete error-correction procedure and
     return the number of logical errors.
+
+    ``handoff``: how the matching graphs reach the host matcher.  "full" (default): every length is
+    copied to the host (the contract outputs of ``fpb_fetch``).  "sparse" (native matcher only): the
+    K(K-1)/2 lengths stay in HBM, the matcher receives candidate partners with lengths and prices the
+    complete graph on the device (``fpb_knn_len`` / ``fpb_pairs_at`` / ``fpb_price``) - the same exact
+    optimum for ~7 % of the bytes over the bus.  On one B200 with 16 host cores both are bound by the
+    matcher's stages (d=13 periodic: 8.6 k trials/s full, 7.1 k sparse, whose pricing rounds are
+    batch-synchronous); sparse is for hosts where the copy bandwidth is the scarce resource.
 
     Trial split: with ``torch.distributed`` initialised, over its ranks with one ``all_reduce`` of
     the counts (one process per GPU; NCCL).  Otherwise, if an mpi4py-style ``world_comm`` is given
@@ -100,8 +108,15 @@ def ec_monte_carlo(trials, code_instance, noise_instance, decoder, decoder_args,
         except ImportError:  # pragma: no cover
             pass
     seed = int_time if seed is None else int(seed)
+    if handoff is None:
+        handoff = "full"
+    if handoff not in ("sparse", "full") or (handoff == "sparse" and backend != "native"):
+        raise ValueError("handoff must be 'sparse' (native matcher only) or 'full'")
     code = code_instance
-    eng = code.engine(n_delta, n_pswap, weight_opts, device=device, mode=mode)
+    # sparse hand-off: the matcher's pricing kernels run while the next batch's persistent shortest-path
+    # kernel holds the SMs; leaving it a few SMs short costs the graph stage ~3 % and the matcher no wait
+    rsv = 4 if handoff == "sparse" else 0
+    eng = code.engine(n_delta, n_pswap, weight_opts, device=device, mode=mode, reserve_sms=rsv)
     if iid and not eng.uses_table:
         eng.build_table()  # uniform weights: every matching graph is a gather from one all-pairs table
     lo, hi = trial_range(trials, rank, size)
@@ -114,14 +129,14 @@ def ec_monte_carlo(trials, code_instance, noise_instance, decoder, decoder_args,
 
     starts = list(range(lo, hi, batch))
     n_eng = min(3, max(1, len(starts)))
-    engines = [eng] + [code.engine(n_delta, n_pswap, weight_opts, device=device, mode=mode, lane=i)
+    engines = [eng] + [code.engine(n_delta, n_pswap, weight_opts, device=device, mode=mode, lane=i, reserve_sms=rsv)
                        for i in range(1, n_eng)]
     # pinned host buffers, one set per lane, kept on the code object: reused by every batch, every
     # later call and every other noise / weight setting of a sweep (pinning memory is slow)
     lane_bufs = [code.__dict__.setdefault("_decode_bufs", {}).setdefault((device, i), {}) for i in range(n_eng)]
     free = [threading.Semaphore(1) for _ in engines]
     q_graph, q_match = queue.Queue(maxsize=2), queue.Queue(maxsize=2)
-    state = {"failures": 0, "done": 0, "t_dev": 0.0, "error": None}
+    state = {"failures": 0, "done": 0, "t_dev": 0.0, "error": None, "match": {}}
 
     def produce():
         try:
@@ -135,8 +150,15 @@ def ec_monte_carlo(trials, code_instance, noise_instance, decoder, decoder_args,
                     en.run_iid(seed, first, n, noise_instance.error_probability, stage=_lib.STAGE_GRAPH, fetch=False)
                 else:
                     en.run_rng(seed, first, n, stage=_lib.STAGE_GRAPH, fetch=False)
-                b = en.fetch_decode(lane_bufs[lane])
-                cands = [candidates(en, b, ci, e) for ci, e in enumerate(code.ec)] if backend == "native" else None
+                b = en.fetch_decode(lane_bufs[lane], want_pairs=handoff == "full")
+                if backend != "native":
+                    cands = None
+                elif handoff == "full":
+                    cands = [candidates(en, b, ci, e) for ci, e in enumerate(code.ec)]
+                else:  # candidates with lengths: what the sparse hand-off starts from
+                    from . import mwpm_native
+
+                    cands = [en.knn_len(ci, mwpm_native.CAND_K) for ci in range(len(code.ec))]
                 q_graph.put((lane, b, cands))
         except BaseException as exc:  # noqa: BLE001 - re-raised by the caller's thread
             state["error"] = exc
@@ -170,7 +192,8 @@ def ec_monte_carlo(trials, code_instance, noise_instance, decoder, decoder_args,
         queries = None
         try:
             if state["error"] is None:
-                queries = match_batch(code, engines[lane], b, backend=backend, cands=cands)
+                queries = match_batch(code, engines[lane], b, backend=backend, cands=cands, handoff=handoff,
+                                      stats=state["match"])
         except BaseException as exc:  # noqa: BLE001
             state["error"] = exc
         if queries is None:
@@ -198,7 +221,8 @@ def ec_monte_carlo(trials, code_instance, noise_instance, decoder, decoder_args,
         raise RuntimeError(f"trial accounting: {int(counts[1])} trials completed, {trials} requested")
     errors = int(counts[0])
     if return_stats:
-        return errors, {"trials_done": int(counts[1]), "device_ms": t_dev, "rank": rank, "world_size": size}
+        return errors, {"trials_done": int(counts[1]), "device_ms": t_dev, "rank": rank, "world_size": size,
+                        "handoff": handoff, **state["match"]}
     return errors
 
 

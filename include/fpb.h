@@ -106,7 +106,9 @@ typedef struct fpb_config {
   int64_t chain_len;    /* trials per reused-layer chain in compat mode; <=0: one chain */
   double delta_step;    /* shortest-path bucket width in units of the trial's mean weight; <=0: default (2.0) */
   int32_t length_mode;  /* FPB_LENGTH_* */
-  int32_t reserved_i[7]; /* must be 0 */
+  int32_t reserve_sms;  /* SMs the persistent shortest-path kernel leaves free, so that short kernels of other
+                           handles (fpb_price, fpb_knn_len of the previous batch) need not wait for its end */
+  int32_t reserved_i[6]; /* must be 0 */
   double reserved_d[4];  /* must be 0 */
 } fpb_config;
 
@@ -224,6 +226,36 @@ int fpb_build_table(fpb_handle* h);
  * [total_odd][k] in the ragged order of odd_ids.  A matcher that starts from this sparse graph and
  * prices the remaining pairs (fpb_mwpm.h) saves its own pass over the K(K-1)/2 lengths. */
 int fpb_knn(fpb_handle* h, int complex_index, int k, int32_t* ids, int on_device);
+
+/* The sparse hand-off to a host matcher: the K(K-1)/2 lengths stay in HBM and only what the matcher
+ * touches crosses the bus (1.5 MB per d=13 trial otherwise).  All three calls refer to the last
+ * graph-stage run and to the reduced pair weight w_ab = min(d_ab, b_a + b_b) (without boundary points:
+ * d_ab) that stands for decoders/mwpm/matching.py:125-173 in csrc/mwpm.cpp.
+ *
+ * fpb_knn_len: fpb_knn plus the reduced weights of the candidates, lens [total_odd][k] (inf padded), and
+ *   per trial the largest reduced weight / twice the largest boundary length, wmax [n_trials] (the
+ *   matcher's fixed-point scale).
+ * fpb_pairs_at: the shortest-path lengths d_ab of n requested pairs (trial, a, b), a, b indices into the
+ *   trial's odd list.
+ * fpb_price: pricing of the complete graph under the matcher's duals, in the matcher's integer
+ *   arithmetic (fpb_mwpm.h).  y [total_odd] are its vertex duals (ragged like odd_ids), scale / wshift
+ *   [n_trials] the fixed-point scale (a power of two) and the number of doublings of each trial's
+ *   weights, active [n_trials] selects the trials; every pair with
+ *   y_a + y_b + ((4 * (int64)(w_ab * scale + 0.5)) << wshift) < 0 is appended to (out_trial, out_a,
+ *   out_b, out_len = w_ab), at most `cap` entries; *n_out receives the number found (> cap: call again
+ *   with more room).  Blossom duals only add slack, so no violated edge is missed; optionally
+ *   top / ztop [total_odd] (both or neither) name each vertex's outermost blossom (-1: none) and
+ *   twice its dual, which is added for two vertices of the same blossom - a lower bound of their
+ *   true blossom term that spares the host most of the pairs it would clear anyway.
+ * fpb_pairs_of_trial: all K(K-1)/2 lengths of one trial (the packed triangle of fpb_outputs.pair_len),
+ *   for the rare graph a sparse solver gives up on. */
+int fpb_knn_len(fpb_handle* h, int complex_index, int k, int32_t* ids, double* lens, double* wmax);
+int fpb_pairs_at(fpb_handle* h, int complex_index, int64_t n, const int32_t* trial, const int32_t* a, const int32_t* b,
+                 double* out);
+int fpb_pairs_of_trial(fpb_handle* h, int complex_index, int64_t trial, double* out, int64_t cap);
+int fpb_price(fpb_handle* h, int complex_index, const int64_t* y, const int32_t* top, const int64_t* ztop,
+              const double* scale, const int32_t* wshift, const uint8_t* active, int64_t cap, int32_t* out_trial, int32_t* out_a, int32_t* out_b, double* out_len,
+              int64_t* n_out);
 
 /* Correction paths for matched pairs of the last run.  Query i asks, in trial
  * trial[i] and complex cx[i], for the shortest path from odd cube src[i] to

@@ -39,6 +39,35 @@ int fpb_mwpm_batch_cand(int T, const int* odd_count, const double* pair_len, con
                         const long long* q_off, const int* cand, int cand_k, int* out_src, int* out_dst,
                         int* n_queries, int n_threads);
 
+/* Sparse hand-off: the same exact solver for a batch whose K(K-1)/2 lengths stay on the GPU.  The
+ * caller feeds each step from libfpb.so (fpb.h):
+ *   ctx = fpb_mwpm_sparse_begin(T, odd_count, q_off, cand, cand_len, cand_k, bnd_len, wmax, threads)
+ *           cand / cand_len / wmax from fpb_knn_len; bnd_len [sum K] or NULL; q_off as in fpb_mwpm_batch
+ *   n   = fpb_mwpm_sparse_requests(ctx, trial, a, b, cap)   pairs whose lengths the jobs need (chain edges
+ *           between cubes of neighbouring boundary length; every pair of a graph below 48 cubes); returns
+ *           the count, fills the arrays when cap >= count
+ *   fpb_mwpm_sparse_start(ctx, req_len)                      req_len [n] from fpb_pairs_at
+ *   loop: fpb_mwpm_sparse_solve(ctx, y, top, ztop, scale, wshift, active)  -> number of trials awaiting pricing (0: done);
+ *           top / ztop [sum K] (or NULL): outermost blossom of each vertex and twice its dual, for fpb_price
+ *         fpb_mwpm_sparse_apply(ctx, n, vt, va, vb, vlen, max_rounds)   the pairs fpb_price flagged; a trial still
+ *           violated after max_rounds (<= 0: 40) warm restarts is given up (reported by finish)
+ *   fpb_mwpm_sparse_finish(ctx, out_src, out_dst, n_queries, failed)   queries in the layout of fpb_mwpm_batch;
+ *           failed [T] marks trials to be solved from their full triangle instead (returns their number)
+ *   fpb_mwpm_sparse_free(ctx)
+ * Exactness: a trial is finished only when no pair of the complete graph violates dual feasibility
+ * (exact integer vertex-dual test on the device, re-check with blossom duals here), as in fpb_mwpm. */
+void* fpb_mwpm_sparse_begin(int T, const int* odd_count, const long long* q_off, const int* cand,
+                            const double* cand_len, int cand_k, const double* bnd_len, const double* wmax,
+                            int n_threads);
+long long fpb_mwpm_sparse_requests(void* ctx, int* trial, int* a, int* b, long long cap);
+int fpb_mwpm_sparse_start(void* ctx, const double* req_len);
+int fpb_mwpm_sparse_solve(void* ctx, long long* y, int* top, long long* ztop, double* scale, int* wshift,
+                          unsigned char* active);
+int fpb_mwpm_sparse_apply(void* ctx, long long n, const int* vt, const int* va, const int* vb, const double* vlen,
+                          int max_rounds);
+int fpb_mwpm_sparse_finish(void* ctx, int* out_src, int* out_dst, int* n_queries, unsigned char* failed);
+void fpb_mwpm_sparse_free(void* ctx);
+
 int fpb_mwpm_max_threads(void);
 
 /* mode 0: sparse candidate graph + pricing from 48 cubes on, dense O(n^3) below (default);

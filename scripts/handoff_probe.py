@@ -1,0 +1,28 @@
+"""Complete EC trials per second through ec_monte_carlo with the full-fetch and the sparse hand-off
+(developer tool)."""
+import sys, time, argparse
+sys.path.insert(0, ".")
+from flamingpy_b200.codes import SurfaceCode
+from flamingpy_b200.noise import CVLayer
+from flamingpy_b200.simulations import ec_monte_carlo
+from flamingpy_b200 import mwpm_native
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--d", type=int, default=13)
+ap.add_argument("--ec", default="primal")
+ap.add_argument("--bound", default="periodic")
+ap.add_argument("--delta", type=float, default=0.09)
+ap.add_argument("--trials", type=int, default=4096)
+ap.add_argument("--batch", type=int, default=512)
+ap.add_argument("--mode", default="fresh")
+a = ap.parse_args()
+code = SurfaceCode(a.d, a.ec, a.bound)
+noise = CVLayer(code, delta=a.delta, p_swap=0)
+args = {"weight_opts": {"method": "blueprint", "delta": a.delta}}
+for handoff in ("full", "sparse", "full", "sparse"):
+    mwpm_native.stats(reset=True)
+    t0 = time.perf_counter()
+    f, st = ec_monte_carlo(a.trials, code, noise, "MWPM", args, seed=5, batch=a.batch, mode=a.mode, handoff=handoff,
+                           return_stats=True)
+    dt = time.perf_counter() - t0
+    print(f"d={a.d} {a.ec} {a.bound} {handoff:6s}: {a.trials/dt:9.0f} trials/s  failures {f}  {st}  {mwpm_native.stats()}", flush=True)

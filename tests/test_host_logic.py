@@ -37,7 +37,9 @@ def test_matcher_library_exports_every_declared_symbol():
     header = open(os.path.join(ROOT, "include", "fpb_mwpm.h")).read()
     declared = set(re.findall(r"\b(fpb_mwpm[a-z_]*)\s*\(", header))
     assert {"fpb_mwpm", "fpb_mwpm_batch", "fpb_mwpm_batch_cand", "fpb_mwpm_configure", "fpb_mwpm_stats",
-            "fpb_mwpm_max_threads"} == declared
+            "fpb_mwpm_max_threads", "fpb_mwpm_sparse_begin", "fpb_mwpm_sparse_requests", "fpb_mwpm_sparse_start",
+            "fpb_mwpm_sparse_solve", "fpb_mwpm_sparse_apply", "fpb_mwpm_sparse_finish",
+            "fpb_mwpm_sparse_free"} == declared
     lib = ctypes.CDLL(mwpm_native.LIB_PATH)
     for name in declared:
         assert hasattr(lib, name), name
