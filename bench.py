@@ -170,18 +170,26 @@ def host_inputs(lat, cfg, n_trials, seed, fresh):
 
 
 def time_cpu_port(lat, cfg, n_trials, fresh, threads=0, seed=SEED):
-    """Time oracle/fpb_oracle.c (the CPU restatement of the reference path) on `n_trials`
-    host-sampled trials, sampling included.  Returns (seconds, threads used)."""
+    """Time oracle/fpb_oracle.c (the CPU restatement of the reference path) on `n_trials` trials whose
+    draws and labels are already in host memory - the same starting point as the B200 arm's `e2e`
+    (host sampling is outside the timed region in both arms).  Returns (seconds, threads used)."""
     from oracle import c_oracle  # checker / baseline leg only
 
     c_oracle.load()
     if threads <= 0:
         threads = os.cpu_count() or 1  # explicit: torchrun exports OMP_NUM_THREADS=1
-    t0 = time.perf_counter()
     x, st = host_inputs(lat, cfg, n_trials, seed, fresh)
+    t0 = time.perf_counter()
     c_oracle.run(lat, cfg["delta"], cfg["p_swap"], cfg["weight_opts"], x, st, n_threads=threads, copy_out=False)
     dt = time.perf_counter() - t0
     return dt, threads
+
+
+def workload_config(args, cfg):
+    """The `config` object: the workload and nothing else, identical in both arms."""
+    return {"workload": args.workload, **{k: v for k, v in cfg.items() if k != "weight_opts"},
+            "weights": cfg["weight_opts"]["method"], "mode": args.mode,
+            "span": "noise->weights->syndrome->matching graph (MWPM excluded)"}
 
 
 def run_reference_arm(args, cfg, lat):
@@ -204,13 +212,11 @@ def run_reference_arm(args, cfg, lat):
         "unit": "trials/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t_tot / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, **{k: v for k, v in cfg.items() if k != "weight_opts"},
-                   "weights": cfg["weight_opts"]["method"], "mode": args.mode,
-                   "span": "noise->weights->syndrome->matching graph (MWPM excluded)"},
+        "config": workload_config(args, cfg),
         "cpu_baseline": {"value": value, "unit": "trials/s", "cores": threads, "kind": "port",
                          "sample": f"{per_step} trials/step x {args.steps} steps, oracle/fpb_oracle.c (C + OpenMP "
                                    f"restatement of the reference path; the Python reference itself cannot run on "
-                                   f"this box), host NumPy sampling included"},
+                                   f"this box), draws and labels pre-sampled in host memory (as for the B200 arm's e2e)"},
         "e2e": {"value": value, "unit": "trials/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -316,9 +322,15 @@ def run_gpu_arm(args, cfg, lat):
     eng.run_injected(xs[0], sts[0], fetch=False)
     sz = eng.sizes()
 
-    def alloc_bufs():
-        bufs = {"hom": pin((Be * Q,), torch.float64), "weights": pin((Be * Q,), torch.float64),
-                "bits": pin((Be * eng.bit_words,), torch.int32).view(np.uint32)}
+    KNN = 12  # candidate partners per odd cube in the sparse hand-off (mwpm_native.CAND_K)
+
+    def alloc_bufs(product):
+        # "sparse": what the host matcher and the logical check need - bits, parities, odd lists, boundary
+        # lengths and each cube's nearest partners with lengths; hom / weights / the K(K-1)/2 pair lengths stay
+        # in HBM (the correction-path stage reads them there).  "contract": every output of fpb_fetch.
+        bufs = {"bits": pin((Be * eng.bit_words,), torch.int32).view(np.uint32)}
+        if product == "contract":
+            bufs.update(hom=pin((Be * Q,), torch.float64), weights=pin((Be * Q,), torch.float64))
         for i, e in enumerate(lat.ec):
             ct = lat.complexes[e]
             mo = int(sz.total_odd[i] * 1.25) + 1024
@@ -326,13 +338,18 @@ def run_gpu_arm(args, cfg, lat):
             bufs[f"parity{i}"] = pin((Be * ((ct.S + 31) // 32),), torch.int32).view(np.uint32)
             bufs[f"odd_count{i}"] = pin((Be,), torch.int32)
             bufs[f"odd_ids{i}"] = pin((mo,), torch.int32)
-            bufs[f"pair_len{i}"] = pin((mp,), torch.float64)
+            if product == "contract":
+                bufs[f"pair_len{i}"] = pin((mp,), torch.float64)
+            else:
+                bufs[f"_knn_ids{i}"] = pin((mo * KNN,), torch.int32)
+                bufs[f"_knn_len{i}"] = pin((mo * KNN,), torch.float64)
+                bufs[f"_wmax{i}"] = pin((Be,), torch.float64)
             if ct.has_boundary:
                 bufs[f"bnd_len{i}"] = pin((mo,), torch.float64)
                 bufs[f"bnd_side{i}"] = pin((mo,), torch.uint8)
         return bufs
 
-    lane_bufs = [alloc_bufs() for _ in engines]
+    lane_bufs = {prod: [alloc_bufs(prod) for _ in engines] for prod in ("sparse", "contract")}
 
     # A step streams its Be trials through the lanes in `chunks` sub-batches (host buffer slices), so
     # that the only copies that cannot overlap a kernel are the first sub-batch's H2D and the last one's
@@ -344,22 +361,29 @@ def run_gpu_arm(args, cfg, lat):
         chunks = max(1, min(8, int(Be * ms_per_trial / 3.0)))
     bounds = [Be * c // chunks for c in range(chunks + 1)]
 
-    def e2e_chunk(lane, i, c):
+    def e2e_chunk(product, lane, i, c):
         en = engines[lane]
+        bufs = lane_bufs[product][lane]
         lo_, hi_ = bounds[c], bounds[c + 1]
         nb = hi_ - lo_
         en.run_injected(xs[i % n_sets][lo_:hi_], sts[i % n_sets][lo_:hi_], fetch=False)  # H2D inside
-        s_ = en.fetch_into(lane_bufs[lane])  # D2H inside
-        return nb * (16 * Q + 4 * eng.bit_words) + sum(
-            nb * (4 * ((lat.complexes[e].S + 31) // 32) + 4) + 4 * int(s_.total_odd[j]) + 8 * int(s_.total_pairs[j])
-            + (9 * int(s_.total_odd[j]) if lat.complexes[e].has_boundary else 0) for j, e in enumerate(lat.ec))
+        s_ = en.fetch_into({k: v for k, v in bufs.items() if not k.startswith("_")})  # D2H inside
+        per_cx = lambda j, e: (nb * (4 * ((lat.complexes[e].S + 31) // 32) + 4) + 4 * int(s_.total_odd[j])  # noqa: E731
+                               + (9 * int(s_.total_odd[j]) if lat.complexes[e].has_boundary else 0))
+        if product == "contract":
+            return nb * (16 * Q + 4 * eng.bit_words) + sum(per_cx(j, e) + 8 * int(s_.total_pairs[j])
+                                                           for j, e in enumerate(lat.ec))
+        for j in range(len(lat.ec)):  # candidates with lengths, D2H inside
+            en.knn_len_into(j, KNN, bufs[f"_knn_ids{j}"], bufs[f"_knn_len{j}"], bufs[f"_wmax{j}"])
+        return nb * 4 * eng.bit_words + sum(per_cx(j, e) + 12 * KNN * int(s_.total_odd[j]) + 8 * nb
+                                            for j, e in enumerate(lat.ec))
 
-    def run_steps(first, count):
+    def run_steps(product, first, count):
         done = [0] * len(engines)
 
         def work(lane):
             for g in range(first * chunks + lane, (first + count) * chunks, len(engines)):
-                done[lane] += e2e_chunk(lane, g // chunks, g % chunks)
+                done[lane] += e2e_chunk(product, lane, g // chunks, g % chunks)
 
         ths = [threading.Thread(target=work, args=(ln,)) for ln in range(len(engines))]
         for th in ths:
@@ -368,17 +392,75 @@ def run_gpu_arm(args, cfg, lat):
             th.join()
         return sum(done)
 
-    run_steps(0, max(len(engines), args.warmup))
-    barrier()
-    t0 = time.perf_counter()
-    d2h_bytes = run_steps(args.warmup, args.steps)
-    barrier()
-    e2e_wall = time.perf_counter() - t0
-    e2e_t = torch.tensor([e2e_wall], dtype=torch.float64, device="cuda")
-    if use_dist:
-        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_value = Be * args.steps * world / float(e2e_t.item())
+    def time_e2e(product):
+        run_steps(product, 0, max(len(engines), args.warmup))
+        barrier()
+        t0 = time.perf_counter()
+        nbytes = run_steps(product, args.warmup, args.steps)
+        barrier()
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if use_dist:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return Be * args.steps * world / float(t.item()), nbytes // max(1, args.steps)
+
+    e2e_value, d2h_bytes = time_e2e("sparse")
+    e2e_contract, d2h_contract = time_e2e("contract")
     h2d_per_step = Be * (2 * N * 8 + N)
+
+    # ---------------- the other label mode, device-resident (compat halves the noisy trials) ----------------
+    other = "fresh" if args.mode == "compat" else "compat"
+    eng_o = TrialEngine(lat, cfg["delta"], cfg["p_swap"], cfg["weight_opts"], mode=other, device=local,
+                        delta_step=args.delta_step)
+    if eng.uses_table:
+        eng_o.build_table()
+    n_o = max(2, min(args.steps, 5))
+    eng_o.run_rng(SEED, first_trial(0), B, fetch=False)
+    barrier()
+    o_ms = 0.0
+    for s_i in range(n_o):
+        eng_o.mark(0)
+        eng_o.run_rng(SEED, first_trial(1 + s_i), B, fetch=False)
+        eng_o.mark(1)
+        o_ms += eng_o.elapsed_ms()
+    eng_o.close()
+    o_t = torch.tensor([o_ms], dtype=torch.float64, device="cuda")
+    if use_dist:
+        dist.all_reduce(o_t, op=dist.ReduceOp.MAX)
+    other_value = B * n_o * world / (float(o_t.item()) * 1e-3)
+
+    # ---------------- complete EC trials through the public API (`e2e_full`) ----------------
+    # simulations.ec_monte_carlo: device stage + host matcher on this rank's share of the host cores +
+    # correction paths + logical check, the reference's Monte-Carlo loop (simulations.py:62-116)
+    e2e_full = None
+    if not args.no_e2e_full:
+        from flamingpy_b200.codes import SurfaceCode
+        from flamingpy_b200.noise import CVLayer
+        from flamingpy_b200.simulations import ec_monte_carlo
+
+        for en in engines[1:]:
+            en.close()
+        engines = engines[:1]
+        code = SurfaceCode(cfg["distance"], cfg["ec"], cfg["boundaries"])
+        noise = CVLayer(code, delta=cfg["delta"], p_swap=cfg["p_swap"])
+        dargs = {"weight_opts": cfg["weight_opts"]}
+        n_full = args.full_trials * world  # ec_monte_carlo splits the global count over the ranks
+        ec_monte_carlo(min(n_full, 512 * world), code, noise, "MWPM", dargs, seed=SEED, batch=args.full_batch, mode=args.mode)
+        barrier()
+        t0 = time.perf_counter()
+        fails, st_full = ec_monte_carlo(n_full, code, noise, "MWPM", dargs, seed=SEED + 1, batch=args.full_batch,
+                                        mode=args.mode, return_stats=True)
+        barrier()
+        f_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if use_dist:
+            dist.all_reduce(f_t, op=dist.ReduceOp.MAX)
+        from flamingpy_b200 import mwpm_native
+
+        e2e_full = {"value": n_full / float(f_t.item()), "unit": "trials/s", "trials": n_full, "failures": int(fails),
+                    "api": "simulations.ec_monte_carlo(trials, SurfaceCode, CVLayer, 'MWPM', weight_opts): complete "
+                           "error-correction trials incl. host MWPM, correction paths and logical check",
+                    "handoff": st_full["handoff"], "matcher_threads_per_rank": mwpm_native.default_threads(),
+                    "batch": args.full_batch}
+        code.release_engines()
 
     if rank == 0:
         peak, peak_src = load_peaks()
@@ -395,19 +477,31 @@ def run_gpu_arm(args, cfg, lat):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, **{k: v for k, v in cfg.items() if k != "weight_opts"},
-                       "weights": cfg["weight_opts"]["method"], "mode": args.mode,
-                       "trials_per_gpu_per_step": B, "rng": "Philox4x32-10 keyed by (seed, global trial, node)",
-                       "span": "noise->weights->syndrome->matching graph (MWPM excluded)",
-                       "l2": "per-step inputs and outputs exceed L2 (%.0f MB written per step)" % (
-                           pipe_b / args.steps / 1e6),
-                       "odd_cubes_per_trial": sum(tot_odd) / max(1, B * args.steps)},
+            "config": workload_config(args, cfg),
+            "run": {"trials_per_gpu_per_step": B, "rng": "Philox4x32-10 keyed by (seed, global trial, node)",
+                    "l2": "per-step inputs and outputs exceed L2 (%.0f MB written per step)" % (
+                        pipe_b / args.steps / 1e6),
+                    "odd_cubes_per_trial": sum(tot_odd) / max(1, B * args.steps),
+                    "binding": eng.binding,
+                    "host_sampling": "outside the timed region in both arms (draws and labels start in host memory)"},
+            "value_other_mode": {"mode": other, "value": other_value, "unit": "trials/s",
+                                 "note": "compat = the reference's reused-CVLayer behaviour: with p_swap = 0 every "
+                                         "second trial of a chain is noise-free; fresh = a new layer per trial"},
             "wall_ms_per_step": wall_ms_max / args.steps,
             "e2e": {"value": e2e_value, "unit": "trials/s", "h2d_bytes_per_step": h2d_per_step,
-                    "d2h_bytes_per_step": d2h_bytes // max(1, args.steps), "trials_per_gpu_per_step": Be,
+                    "d2h_bytes_per_step": d2h_bytes, "trials_per_gpu_per_step": Be,
                     "chunks_per_step": chunks,
-                    "api": "TrialEngine.run_injected(host x, host labels) + fetch_into(pinned host buffers), per sub-batch",
-                    "host_threads": len(engines)},
+                    "handoff": "sparse: per odd cube its %d nearest partners with lengths (fpb_knn_len) + odd lists, "
+                               "boundary lengths, bits, parities; hom / weights / the K(K-1)/2 lengths stay in HBM for "
+                               "fpb_price / fpb_pairs_at / fpb_paths_toggle" % KNN,
+                    "api": "TrialEngine.run_injected(host x, host labels) + fetch_into + knn_len_into(pinned host "
+                           "buffers), per sub-batch",
+                    "host_threads": n_lanes},
+            "e2e_contract": {"value": e2e_contract, "unit": "trials/s", "h2d_bytes_per_step": h2d_per_step,
+                             "d2h_bytes_per_step": d2h_contract,
+                             "handoff": "full: every output of fpb_fetch incl. hom, weights and all pair lengths "
+                                        "(round 1's e2e definition)"},
+            "e2e_full": e2e_full,
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "k_gather" if eng.uses_table else "k_paths", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak,
@@ -428,7 +522,7 @@ def run_gpu_arm(args, cfg, lat):
             line["cpu_baseline"] = {
                 "value": n_cpu / dt, "unit": "trials/s", "cores": threads, "kind": "port",
                 "sample": f"{n_cpu} trials of the same workload, oracle/fpb_oracle.c (C + OpenMP restatement of "
-                          f"the reference path), host NumPy sampling included, {dt:.1f} s"}
+                          f"the reference path), draws and labels pre-sampled in host memory, {dt:.1f} s"}
         print(json.dumps(line), flush=True)
     for en in engines:
         en.close()
@@ -453,6 +547,9 @@ def main():
     ap.add_argument("--delta-step", type=float, default=0.0)
     ap.add_argument("--cpu-trials", type=int, default=0, help="CPU sample size in trials (0: 64 x cores for cpu_baseline, 32 x cores per step for --impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e-full", action="store_true", help="skip the complete-EC-trial measurement (ec_monte_carlo)")
+    ap.add_argument("--full-trials", type=int, default=32768, help="complete EC trials per GPU for e2e_full")
+    ap.add_argument("--full-batch", type=int, default=512)
     ap.add_argument("--no-table", action="store_true", help="static-weight workloads: search instead of the table gather")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":

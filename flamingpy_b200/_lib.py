@@ -404,6 +404,13 @@ class CtypesHandle:
         check(self._lib.fpb_knn_len(self._h, complex_index, k, ids.ctypes.data, lens.ctypes.data, wmax.ctypes.data))
         return ids, lens, wmax
 
+    def knn_len_into(self, complex_index, k, ids, lens, wmax):
+        s = self.sizes()
+        need = s["total_odd"][complex_index] * k
+        if ids.size < need or lens.size < need or wmax.size < s["n_trials"]:
+            raise FpbError("knn_len_into: buffers too small")
+        check(self._lib.fpb_knn_len(self._h, complex_index, k, ids.ctypes.data, lens.ctypes.data, wmax.ctypes.data))
+
     def pairs_at(self, complex_index, trial, a, b):
         import numpy as np
 

@@ -377,6 +377,28 @@ class Handle {
     check(rc);
     return py::make_tuple(ids, lens, wmax);
   }
+  // the same into caller-owned (e.g. pinned) arrays: ids int32 / lens float64 with >= total_odd * k
+  // entries, wmax float64 with >= n_trials entries
+  void knn_len_into(int complex_index, int k, py::array ids, py::array lens, py::array wmax) {
+    fpb_sizes s;
+    check(fpb_get_sizes(h(), &s));
+    if (complex_index < 0 || complex_index >= s.n_complex) throw std::runtime_error("bad complex index");
+    const int64_t need = s.total_odd[complex_index] * (int64_t)k;
+    auto ok = [](const py::array& a, size_t item, int64_t n) {
+      return (a.flags() & py::array::c_style) && a.writeable() && (size_t)a.itemsize() == item && (int64_t)a.size() >= n;
+    };
+    if (!ok(ids, 4, need) || !ok(lens, 8, need) || !ok(wmax, 8, s.n_trials))
+      throw std::runtime_error("knn_len_into: buffers must be writable, C-contiguous and large enough");
+    int32_t* ip = static_cast<int32_t*>(ids.mutable_data());
+    double* lp = static_cast<double*>(lens.mutable_data());
+    double* wp = static_cast<double*>(wmax.mutable_data());
+    int rc;
+    {
+      py::gil_scoped_release release;
+      rc = fpb_knn_len(h(), complex_index, k, ip, lp, wp);
+    }
+    check(rc);
+  }
   py::array_t<double> pairs_at(int complex_index, carray<int32_t> trial, carray<int32_t> a, carray<int32_t> b) {
     const int64_t n = trial.size();
     if (a.size() != n || b.size() != n) throw std::runtime_error("pair arrays differ in length");
@@ -532,6 +554,7 @@ PYBIND11_MODULE(fpbpy, m) {
       .def("elapsed_ms", &Handle::elapsed_ms)
       .def("knn", &Handle::knn, py::arg("complex_index"), py::arg("k"), py::arg("out"))
       .def("knn_len", &Handle::knn_len, py::arg("complex_index"), py::arg("k"))
+      .def("knn_len_into", &Handle::knn_len_into)
       .def("pairs_at", &Handle::pairs_at)
       .def("pairs_of_trial", &Handle::pairs_of_trial)
       .def("price", &Handle::price, py::arg("complex_index"), py::arg("y"), py::arg("top"), py::arg("ztop"),

@@ -402,6 +402,10 @@ class TrialEngine:
         lens float64[sum K, k], wmax float64[T]).  The K(K-1)/2 lengths stay on the device."""
         return self._h.knn_len(int(complex_index), int(k))
 
+    def knn_len_into(self, complex_index: int, k: int, ids: np.ndarray, lens: np.ndarray, wmax: np.ndarray):
+        """``knn_len`` into caller-owned (e.g. pinned) buffers: no allocation, direct D2H copies."""
+        self._h.knn_len_into(int(complex_index), int(k), ids, lens, wmax)
+
     def pairs_at(self, complex_index: int, trial, a, b) -> np.ndarray:
         """Shortest-path lengths of the requested pairs (trial, odd index a, odd index b) of the last run."""
         c = lambda x: np.ascontiguousarray(x, np.int32)  # noqa: E731
