@@ -141,6 +141,10 @@ EXPORTS = {
     "fpb_pairs_of_trial": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, _f64p, C.c_int64]),
     "fpb_price": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int64), _i32p, C.POINTER(C.c_int64), _f64p, _i32p, _u8p,
                             C.c_int64, _i32p, _i32p, _i32p, _f64p, C.POINTER(C.c_int64)]),
+    "fpb_set_macro": (C.c_int, [C.c_void_p, _i32p, _i8p]),
+    "fpb_run_macro_injected": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "fpb_run_macro_rng": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int64, C.c_int64, C.c_int]),
+    "fpb_fetch_macro": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "fpb_run_iid": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int64, C.c_int64, C.c_double, C.c_int]),
     "fpb_get_sizes": (C.c_int, [C.c_void_p, C.POINTER(Sizes)]),
     "fpb_fetch": (C.c_int, [C.c_void_p, C.POINTER(Outputs), C.c_int]),
@@ -304,6 +308,25 @@ class CtypesHandle:
 
     def run_weighted(self, weights, bits, stage=STAGE_GRAPH):
         check(self._lib.fpb_run_weighted(self._h, weights.shape[0], weights.ctypes.data, bits.ctypes.data, 0, stage))
+
+    def set_macro(self, partner, sign):
+        check(self._lib.fpb_set_macro(self._h, partner.ctypes.data_as(_i32p), sign.ctypes.data_as(_i8p)))
+
+    def run_macro_injected(self, state, mean, z, stage=STAGE_GRAPH):
+        check(self._lib.fpb_run_macro_injected(self._h, state.shape[0], state.ctypes.data, mean.ctypes.data,
+                                               z.ctypes.data, 0, stage))
+
+    def run_macro_rng(self, seed, first_trial, n_trials, stage=STAGE_GRAPH):
+        check(self._lib.fpb_run_macro_rng(self._h, seed, first_trial, n_trials, stage))
+
+    def fetch_macro(self):
+        import numpy as np
+
+        T = self.sizes()["n_trials"]
+        rs, bv = np.empty((T, self._n_nodes), np.uint8), np.empty((T, self._n_nodes), np.uint8)
+        pp, oc = np.empty((T, self._n_nodes), np.float64), np.empty((T, self._n_nodes), np.float64)
+        check(self._lib.fpb_fetch_macro(self._h, rs.ctypes.data, bv.ctypes.data, pp.ctypes.data, oc.ctypes.data, 0))
+        return rs, bv, pp, oc
 
     def run_iid(self, seed, first_trial, n_trials, p_err, stage=STAGE_GRAPH):
         check(self._lib.fpb_run_iid(self._h, seed, first_trial, n_trials, float(p_err), stage))

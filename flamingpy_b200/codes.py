@@ -43,7 +43,8 @@ class _NodeData:
             if g.state is None:
                 raise KeyError(key)
             return _STATE_NAMES[int(g.state[i])]
-        arr = {"hom_val_p": g.hom_val_p, "bit_val": g.bit_val, "weight": g.weight}.get(key)
+        arr = {"hom_val_p": g.hom_val_p, "bit_val": g.bit_val, "weight": g.weight,
+               "p_phase_cond": g.p_phase_cond}.get(key)
         if arr is None or (key != "bit_val" and np.isnan(arr[i])) or (key == "bit_val" and arr[i] < 0):
             raise KeyError(key)
         return int(arr[i]) if key == "bit_val" else arr[i]
@@ -62,8 +63,10 @@ class _NodeData:
         elif key == "bit_val":
             g._ensure_arrays()
             g.bit_val[i] = int(value)
-        elif key in ("hom_val_p", "weight"):
+        elif key in ("hom_val_p", "weight", "p_phase_cond"):
             g._ensure_arrays()
+            if key == "p_phase_cond" and g.p_phase_cond is None:
+                g.p_phase_cond = np.full(g.lattice.N, np.nan)
             getattr(g, key)[i] = value
         else:
             raise KeyError(key)
@@ -104,6 +107,7 @@ class LatticeGraph:
         self.hom_val_p = None
         self.bit_val = None
         self.weight = None
+        self.p_phase_cond = None  # CVMacroLayer: conditional phase error probability of the reduced nodes
 
     def _ensure_arrays(self):
         N = self.lattice.N

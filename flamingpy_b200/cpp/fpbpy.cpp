@@ -204,6 +204,53 @@ class Handle {
     }
     check(rc);
   }
+  // ---- macronode layer (fpb_set_macro / fpb_run_macro_* / fpb_fetch_macro) ----
+  void set_macro(carray<int32_t> partner, carray<int8_t> sign) {
+    if (partner.size() != 4 * (py::ssize_t)n_nodes_ || sign.size() != 4 * (py::ssize_t)n_nodes_)
+      throw std::runtime_error("partner and sign need 4 N entries");
+    check(fpb_set_macro(h(), partner.data(), sign.data()));
+  }
+  void run_macro_injected(carray<uint8_t> state, carray<float> mean, carray<double> z, int stage) {
+    const py::ssize_t M = 4 * (py::ssize_t)n_nodes_;
+    if (state.ndim() != 2 || mean.ndim() != 2 || z.ndim() != 2 || state.shape(1) != M || mean.shape(1) != M ||
+        z.shape(1) != M || mean.shape(0) != state.shape(0) || z.shape(0) != state.shape(0))
+      throw std::runtime_error("state uint8[T, 4N], mean float32[T, 4N] and z float64[T, 4N] expected");
+    const int64_t T = state.shape(0);
+    const uint8_t* sp = state.data();
+    const float* mp = mean.data();
+    const double* zp = z.data();
+    int rc;
+    {
+      py::gil_scoped_release release;
+      rc = fpb_run_macro_injected(h(), T, sp, mp, zp, 0, stage);
+    }
+    check(rc);
+  }
+  void run_macro_rng(uint64_t seed, int64_t first_trial, int64_t n_trials, int stage) {
+    int rc;
+    {
+      py::gil_scoped_release release;
+      rc = fpb_run_macro_rng(h(), seed, first_trial, n_trials, stage);
+    }
+    check(rc);
+  }
+  // reduced lattice of the last macronode run: freshly owned (red_state, bit_val, p_phase_cond, outcome), each [T, N]
+  py::tuple fetch_macro() {
+    fpb_sizes s;
+    check(fpb_get_sizes(h(), &s));
+    const py::ssize_t T = (py::ssize_t)s.n_trials, N = (py::ssize_t)n_nodes_;
+    py::array_t<uint8_t> rs({T, N}), bv({T, N});
+    py::array_t<double> pp({T, N}), oc({T, N});
+    uint8_t *rp = rs.mutable_data(), *bp = bv.mutable_data();
+    double *ppp = pp.mutable_data(), *op = oc.mutable_data();
+    int rc;
+    {
+      py::gil_scoped_release release;
+      rc = fpb_fetch_macro(h(), rp, bp, ppp, op, 0);
+    }
+    check(rc);
+    return py::make_tuple(rs, bv, pp, oc);
+  }
   void run_iid(uint64_t seed, int64_t first_trial, int64_t n_trials, double p_err, int stage) {
     int rc;
     {
@@ -541,6 +588,12 @@ PYBIND11_MODULE(fpbpy, m) {
            py::arg("stage") = FPB_STAGE_GRAPH)
       .def("run_bits", &Handle::run_bits, py::arg("bits"), py::arg("stage") = FPB_STAGE_GRAPH)
       .def("run_weighted", &Handle::run_weighted, py::arg("weights"), py::arg("bits"), py::arg("stage") = FPB_STAGE_GRAPH)
+      .def("set_macro", &Handle::set_macro)
+      .def("run_macro_injected", &Handle::run_macro_injected, py::arg("state"), py::arg("mean"), py::arg("z"),
+           py::arg("stage") = FPB_STAGE_GRAPH)
+      .def("run_macro_rng", &Handle::run_macro_rng, py::arg("seed"), py::arg("first_trial"), py::arg("n_trials"),
+           py::arg("stage") = FPB_STAGE_GRAPH)
+      .def("fetch_macro", &Handle::fetch_macro)
       .def("run_iid", &Handle::run_iid, py::arg("seed"), py::arg("first_trial"), py::arg("n_trials"), py::arg("p_err"),
            py::arg("stage") = FPB_STAGE_GRAPH)
       .def("sizes", &Handle::sizes)

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "fpb_kernels.cuh"
+#include "fpb_macro.cuh"
 
 using namespace fpb;
 
@@ -108,6 +109,13 @@ struct fpb_handle {
   DevBuf<uint32_t> bits, flips;
   DevBuf<int> item_off, counter, q_trial, q_cx, q_src, q_dst, path_qubits, path_len;
   DevBuf<long long> totals;
+  // macronode layer (fpb_set_macro / fpb_run_macro_*)
+  int* macro_partner = nullptr;
+  int8_t* macro_sign = nullptr;
+  DevBuf<uint8_t> m_state, m_body, m_red_state, m_bit_val;
+  DevBuf<float> m_mean;
+  DevBuf<double> m_z, m_val, m_p_phase, m_outcome;
+  bool last_macro = false;
   // sparse hand-off (fpb_knn_len / fpb_pairs_at / fpb_price)
   DevBuf<unsigned long long> trial_wmax, price_n;
   DevBuf<long long> price_y;
@@ -448,7 +456,7 @@ int post_syndrome(fpb_handle* h, long long T, int stage, int* launches) {
 }
 
 // source of a batch: injected draws + labels, Philox draws + labels, injected bits, Philox i.i.d. bits
-enum { SRC_INJECTED = 0, SRC_GEN = 1, SRC_BITS = 2, SRC_IID = 3, SRC_WEIGHTED = 4 };
+enum { SRC_INJECTED = 0, SRC_GEN = 1, SRC_BITS = 2, SRC_IID = 3, SRC_WEIGHTED = 4, SRC_MACRO = 5, SRC_MACRO_GEN = 6 };
 
 int run_pipeline(fpb_handle* h, long long T, int stage, int source, uint64_t seed, long long first_trial,
                  double p_err = 0.0) {
@@ -500,8 +508,45 @@ int run_pipeline(fpb_handle* h, long long T, int stage, int source, uint64_t see
     k_iid<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(g, T);
     ++launches;
   }
+  const bool macro = source == SRC_MACRO || source == SRC_MACRO_GEN;
+  h->last_macro = macro;
+  if (source == SRC_MACRO_GEN) {
+    MacroGenParams g;
+    g.M = 4 * h->N;
+    g.seed_lo = (uint32_t)seed; g.seed_hi = (uint32_t)(seed >> 32);
+    g.first_trial = first_trial; g.chain_len = h->chain_len;
+    g.fresh = h->label_mode == FPB_MODE_FRESH;
+    g.p_swap = h->p_swap;
+    const double th = h->p_swap * 4294967296.0;
+    g.p_thresh = th >= 4294967295.0 ? 0xffffffffu : (uint32_t)th;
+    g.state = h->m_state.p; g.mean = h->m_mean.p; g.z = h->m_z.p;
+    const long long total = T * 4ll * h->N, blocks = (total + 255) / 256, cap = (long long)h->sm_count * 32;
+    k_macro_gen<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(g, T);
+    ++launches;
+  }
   CK(cudaEventRecord(h->ev[1], st));
-  if (source == SRC_WEIGHTED) {
+  if (macro) {
+    MacroParams mp;
+    mp.N = h->N; mp.partner = h->macro_partner; mp.sign = h->macro_sign;
+    mp.sd = (float)pow(h->delta / 2.0, 0.5);
+    mp.delta = h->delta;
+    mp.state = h->m_state.p; mp.mean = h->m_mean.p; mp.z = h->m_z.p;
+    mp.body = h->m_body.p; mp.val = h->m_val.p;
+    mp.red_state = h->m_red_state.p; mp.bit_val = h->m_bit_val.p; mp.p_phase = h->m_p_phase.p; mp.outcome = h->m_outcome.p;
+    const long long total = T * (long long)h->N, cap = (long long)h->sm_count * 32;
+    const long long b256 = (total + 255) / 256, b128 = (total + 127) / 128;
+    k_macro_measure<<<(unsigned)(b256 < cap ? b256 : cap), 256, 0, st>>>(mp, T);
+    k_macro_reduce<<<(unsigned)(b128 < 2 * cap ? b128 : 2 * cap), 128, 0, st>>>(mp, T);
+    MacroWeightParams wp;
+    wp.N = h->N; wp.Qtot = h->Qtot; wp.bit_words = h->bit_words;
+    wp.adj_indptr = h->adj_indptr; wp.adj_indices = h->adj_indices; wp.qubit_node = h->qubit_node;
+    wp.method = h->weight_method; wp.integer = h->weight_integer; wp.multiplier = h->weight_multiplier;
+    wp.red_state = h->m_red_state.p; wp.bit_val = h->m_bit_val.p; wp.p_phase = h->m_p_phase.p; wp.outcome = h->m_outcome.p;
+    wp.hom = h->hom.p; wp.weights = h->weights.p; wp.bits = h->bits.p;
+    const long long bpt = (h->Qtot + 255) / 256;
+    k_macro_weights<<<(unsigned)(bpt * T), 256, 0, st>>>(wp);
+    launches += 3;
+  } else if (source == SRC_WEIGHTED) {
     // weights and bits were given: nothing to compute before the syndrome
     CK(cudaMemsetAsync(h->hom.p, 0, (size_t)T * h->Qtot * sizeof(double), st));
   } else if (source == SRC_BITS || source == SRC_IID) {
@@ -709,6 +754,9 @@ int fpb_destroy(fpb_handle* h) {
   h->x.release(); h->hom.release(); h->weights.release(); h->state.release(); h->bits.release();
   h->flips.release(); h->item_off.release(); h->counter.release(); h->totals.release();
   h->path_qubits.release(); h->path_len.release();
+  cudaFree(h->macro_partner); cudaFree(h->macro_sign);
+  h->m_state.release(); h->m_body.release(); h->m_red_state.release(); h->m_bit_val.release(); h->m_mean.release();
+  h->m_z.release(); h->m_val.release(); h->m_p_phase.release(); h->m_outcome.release();
   h->trial_wmax.release(); h->price_n.release(); h->price_y.release(); h->price_c.release(); h->price_ws.release(); h->price_top.release();
   h->pair_out.release(); h->price_active.release(); h->price_idx.release();
   h->q_trial.release(); h->q_cx.release(); h->q_src.release(); h->q_dst.release(); h->wscratch.release();
@@ -778,6 +826,83 @@ int fpb_run_weighted(fpb_handle* h, int64_t n_trials, const double* weights, con
   CK(cudaMemcpyAsync(h->bits.p, bits, (size_t)n_trials * h->bit_words * sizeof(uint32_t), kind, h->stream));
   h->have_rng = false;
   return run_pipeline(h, n_trials, stage, SRC_WEIGHTED, 0, 0);
+}
+
+static int ensure_macro(fpb_handle* h, long long T) {
+  if (!h->macro_partner) return fail(FPB_ERR_STATE, "no macronode tables: call fpb_set_macro first");
+  if (h->use_table) return fail(FPB_ERR_STATE, "the static-weight table is in use: macronode weights are trial-dependent");
+  int rc;
+  const size_t M = (size_t)T * 4 * h->N, Nn = (size_t)T * h->N;
+  if ((rc = h->m_state.ensure(M))) return rc;
+  if ((rc = h->m_mean.ensure(M))) return rc;
+  if ((rc = h->m_z.ensure(M))) return rc;
+  if ((rc = h->m_body.ensure(M))) return rc;
+  if ((rc = h->m_val.ensure(M))) return rc;
+  if ((rc = h->m_red_state.ensure(Nn))) return rc;
+  if ((rc = h->m_bit_val.ensure(Nn))) return rc;
+  if ((rc = h->m_p_phase.ensure(Nn))) return rc;
+  if ((rc = h->m_outcome.ensure(Nn))) return rc;
+  return FPB_OK;
+}
+
+int fpb_set_macro(fpb_handle* h, const int32_t* partner, const int8_t* sign) {
+  if (!h || !partner || !sign) return fail(FPB_ERR_ARG, "null argument");
+  CK(cudaSetDevice(h->device));
+  const int M = 4 * h->N;
+  for (int i = 0; i < M; ++i) {
+    if (partner[i] < -1 || partner[i] >= M) return fail(FPB_ERR_ARG, "macronode partner out of range");
+    if (partner[i] >= 0 && (partner[partner[i]] != i || partner[i] / 4 == i / 4))
+      return fail(FPB_ERR_ARG, "macronode partners must pair micronodes of different macronodes");
+  }
+  if (h->macro_partner) cudaFree(h->macro_partner);
+  if (h->macro_sign) cudaFree(h->macro_sign);
+  h->macro_partner = nullptr; h->macro_sign = nullptr;
+  int rc;
+  if ((rc = upload(partner, (size_t)M, &h->macro_partner))) return rc;
+  if ((rc = upload(sign, (size_t)M, &h->macro_sign))) return rc;
+  return FPB_OK;
+}
+
+int fpb_run_macro_injected(fpb_handle* h, int64_t n_trials, const uint8_t* state, const float* mean, const double* z,
+                           int on_device, int stage) {
+  if (!h || !state || !mean || !z) return fail(FPB_ERR_ARG, "null argument");
+  CK(cudaSetDevice(h->device));
+  int rc = ensure_batch(h, n_trials);
+  if (rc) return rc;
+  if ((rc = ensure_macro(h, n_trials))) return rc;
+  const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  const size_t M = (size_t)n_trials * 4 * h->N;
+  CK(cudaMemcpyAsync(h->m_state.p, state, M, kind, h->stream));
+  CK(cudaMemcpyAsync(h->m_mean.p, mean, M * sizeof(float), kind, h->stream));
+  CK(cudaMemcpyAsync(h->m_z.p, z, M * sizeof(double), kind, h->stream));
+  h->have_rng = false;
+  return run_pipeline(h, n_trials, stage, SRC_MACRO, 0, 0);
+}
+
+int fpb_run_macro_rng(fpb_handle* h, uint64_t seed, int64_t first_trial, int64_t n_trials, int stage) {
+  if (!h) return fail(FPB_ERR_ARG, "null handle");
+  if (first_trial < 0) return fail(FPB_ERR_ARG, "first_trial must be >= 0");
+  CK(cudaSetDevice(h->device));
+  int rc = ensure_batch(h, n_trials);
+  if (rc) return rc;
+  if ((rc = ensure_macro(h, n_trials))) return rc;
+  h->have_rng = true;
+  return run_pipeline(h, n_trials, stage, SRC_MACRO_GEN, seed, first_trial);
+}
+
+int fpb_fetch_macro(fpb_handle* h, uint8_t* red_state, uint8_t* bit_val, double* p_phase_cond, double* outcome,
+                    int on_device) {
+  if (!h) return fail(FPB_ERR_ARG, "null handle");
+  if (h->T <= 0 || !h->last_macro) return fail(FPB_ERR_STATE, "the last run was not a macronode run");
+  CK(cudaSetDevice(h->device));
+  const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  const size_t n = (size_t)h->T * h->N;
+  if (red_state) CK(cudaMemcpyAsync(red_state, h->m_red_state.p, n, kind, h->stream));
+  if (bit_val) CK(cudaMemcpyAsync(bit_val, h->m_bit_val.p, n, kind, h->stream));
+  if (p_phase_cond) CK(cudaMemcpyAsync(p_phase_cond, h->m_p_phase.p, n * sizeof(double), kind, h->stream));
+  if (outcome) CK(cudaMemcpyAsync(outcome, h->m_outcome.p, n * sizeof(double), kind, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return FPB_OK;
 }
 
 int fpb_run_iid(fpb_handle* h, uint64_t seed, int64_t first_trial, int64_t n_trials, double p_err, int stage) {

@@ -46,6 +46,9 @@ __host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t 
 constexpr uint32_t SLOT_QUADRATURE = 0;  // 128 bits -> one Box-Muller pair (q, p)
 constexpr uint32_t SLOT_LABEL = 1;       // 32 bits  -> Bernoulli(p_swap)
 constexpr uint32_t SLOT_IID = 2;         // 53 bits  -> Bernoulli(p_err) of the i.i.d. noise model
+// macronode layer: the "node" of the counter is the micronode index
+constexpr uint32_t SLOT_MACRO_LABEL = 3;  // 32 bits  -> Bernoulli(p_swap) per micronode
+constexpr uint32_t SLOT_MACRO_DRAW = 4;   // 53 bits -> initial mean (uniform or bit), 64 bits -> measurement normal
 
 // uniform in (0, 1) from 53 random bits (never 0, never 1)
 __host__ __device__ __forceinline__ double u01_53(uint32_t hi, uint32_t lo) {

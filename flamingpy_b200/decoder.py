@@ -28,6 +28,18 @@ def _run_trial(code, wo, stage):
     CVLayer realisations are (x, state, delta, p_swap); bit-level ones (IidNoise) are
     ("bits", bit values of all nodes) and need uniform weights."""
     trial = _require_trial(code)
+    if isinstance(trial[0], str) and trial[0] == "macro":
+        # CVMacroLayer realisation: (labels, initial means, normals) of the micronodes; blueprint weights
+        # come from the reduced nodes' p_phase_cond (decoder.py:67-68)
+        if wo.get("method") == "blueprint" and not wo.get("prob_precomputed"):
+            raise ValueError("CVMacroLayer leaves no homodyne values on the reduced lattice: use weight_options "
+                             "{'method': 'blueprint', 'prob_precomputed': True} (or 'uniform')")
+        (state, mean, z), delta, p_swap = trial[1], trial[2], trial[3]
+        eng = code.engine(delta, p_swap, wo)
+        eng.run_macro_injected(state[None, :], mean[None, :], z[None, :], stage=stage)
+        return eng, eng.fetch(stage)
+    if wo.get("prob_precomputed"):
+        raise ValueError("prob_precomputed weights need the p_phase_cond attribute that CVMacroLayer computes")
     if isinstance(trial[0], str) and trial[0] == "bits":
         if wo.get("method", "uniform") != "uniform":
             raise ValueError("IidNoise has no homodyne outcomes: use weight_options {'method': 'uniform'}")
@@ -46,9 +58,6 @@ def assign_weights(code, decoder="MWPM", **kwargs):
         raise NotImplementedError("only the MWPM decoder is on the accelerated path")
     wo = {"method": "uniform", "integer": False, "multiplier": 1}
     wo.update(kwargs)
-    if wo.get("prob_precomputed"):
-        raise NotImplementedError("prob_precomputed weights belong to CVMacroLayer (out of scope, SURVEY.md 8f)")
-    wo.pop("prob_precomputed", None)
     eng, batch = _run_trial(code, wo, _lib.STAGE_NOISE)
     g = code.graph
     g._ensure_arrays()
@@ -159,7 +168,7 @@ def correct(code, decoder="MWPM", weight_options=None, sanity_check=False, decod
     wo = {"method": "uniform", "integer": False, "multiplier": 1}
     wo.update(weight_options)
     eng, batch = _run_trial(code, wo, _lib.STAGE_GRAPH)
-    is_cv = not isinstance(code._trial[0], str)
+    is_cv = not isinstance(code._trial[0], str)  # CVLayer: homodyne values exist on the lattice
     g = code.graph
     g._ensure_arrays()
     off = 0

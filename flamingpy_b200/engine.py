@@ -216,6 +216,46 @@ class TrialEngine:
         self._h.run_weighted(weights, bits, stage)
         return self.fetch(stage) if fetch else TrialBatch(weights.shape[0], stage, timings=self.timings())
 
+    # -- macronode layer (CVMacroLayer) ------------------------------------------------------------
+    def _ensure_macro(self):
+        if not getattr(self, "_macro_ready", False):
+            from .lattice import macro_tables
+
+            partner, sign = macro_tables(self.lat)
+            self._h.set_macro(np.ascontiguousarray(partner, np.int32), np.ascontiguousarray(sign, np.int8))
+            self._macro_ready = True
+
+    def run_macro_injected(self, state, mean, z, stage: int = _lib.STAGE_GRAPH) -> dict:
+        """``CVMacroLayer`` trials on injected draws: ``state`` uint8[T, 4N] micronode labels, ``mean``
+        float32[T, 4N] initial q means, ``z`` float64[T, 4N] standard normals (stars, then planets) -
+        see ``noise.MacroSampler``.  Returns the reduced lattice (``fetch_macro``); the usual outputs
+        (weights from the precomputed probabilities, bits, parities, matching graph) follow from
+        ``fetch``."""
+        self._ensure_macro()
+        state = np.ascontiguousarray(state, np.uint8)
+        mean = np.ascontiguousarray(mean, np.float32)
+        z = np.ascontiguousarray(z, np.float64)
+        M = 4 * self.lat.N
+        if state.ndim != 2 or state.shape[1] != M or mean.shape != state.shape or z.shape != state.shape:
+            raise ValueError(f"state, mean and z must have shape [T, {M}]")
+        self.run_id += 1
+        self._h.run_macro_injected(state, mean, z, stage)
+        return self.fetch_macro()
+
+    def run_macro_rng(self, seed: int, first_trial: int, n_trials: int, stage: int = _lib.STAGE_GRAPH,
+                      fetch: bool = True):
+        """``CVMacroLayer`` trials ``[first_trial, first_trial + n_trials)`` of the Philox stream ``seed``."""
+        self._ensure_macro()
+        self.run_id += 1
+        self._h.run_macro_rng(seed & (2**64 - 1), first_trial, n_trials, stage)
+        return self.fetch(stage) if fetch else TrialBatch(n_trials, stage, timings=self.timings())
+
+    def fetch_macro(self) -> dict:
+        """Reduced lattice of the last macronode run, each [T, N]: ``red_state`` (1 GKP, 2 p),
+        ``bit_val``, ``p_phase_cond``, ``outcome`` (effective homodyne value)."""
+        rs, bv, pp, oc = self._h.fetch_macro()
+        return {"red_state": rs, "bit_val": bv, "p_phase_cond": pp, "outcome": oc}
+
     def run_iid(self, seed: int, first_trial: int, n_trials: int, p_err: float, stage: int = _lib.STAGE_GRAPH,
                 fetch: bool = True) -> TrialBatch:
         """Trials ``[first_trial, first_trial + n_trials)`` of i.i.d. Z errors with probability

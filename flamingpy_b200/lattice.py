@@ -144,11 +144,15 @@ def _polarity_sign(p1: np.ndarray, p2: np.ndarray) -> np.ndarray:
     return np.where(src % 2 == 0, 1, -1).astype(np.int8)
 
 
-def _reference_node_order(dims, btypes):
-    """First-insertion rank of every lattice node in the reference's ``RHG_graph``
-    (``surface_code.py:172-243``).  The reference fills its graph while iterating a Python *set*
-    of primal vertices, so the order is a property of CPython's tuple hashing; it is re-derived
-    here with real sets.  Only the size-2 periodic case needs it (``_double_edge_keep``)."""
+def _reference_graph_order(dims, btypes):
+    """Insertion order of the reference's ``RHG_graph`` (``surface_code.py:172-243``): the rank of
+    every node and, per node, its neighbours in the order their edges were added.  The reference fills
+    its graph while iterating a Python *set* of primal vertices, so these orders are a property of
+    CPython's tuple hashing; they are re-derived here with real sets.  Two things depend on them: which
+    of the two qubits shared by a size-2 periodic cube pair becomes the edge (``_double_edge_keep``),
+    and the order of the micronodes inside each macronode of ``CVMacroLayer`` (``macro_tables``).
+    Returns (rank: {node: int}, nbrs: {node: [neighbour, ...]}, seam: set of frozenset edges that
+    cross a periodic boundary)."""
     import itertools as it
 
     d = [int(v) for v in dims]
@@ -172,21 +176,79 @@ def _reference_node_order(dims, btypes):
             return [(x, y, z - 1), (x, y + 1, z), (x, y, z + 1), (x, y - 1, z)]
         return [(x, y - 1, z), (x - 1, y, z), (x, y + 1, z), (x + 1, y, z)]
 
-    rank = {}
+    rank, nbrs, seam = {}, {}, set()
+
+    def node(p):
+        if p not in rank:
+            rank[p] = len(rank)
+            nbrs[p] = []
+
+    def edge(u, v):
+        if v not in nbrs[u]:
+            nbrs[u].append(v)
+        if u not in nbrs[v]:
+            nbrs[v].append(u)
+
     for v in primal_vertices:
         if outside(v):
             continue
         for nb in four_neighbours(v):
             if outside(nb):
                 continue
-            rank.setdefault(v, len(rank))
-            rank.setdefault(nb, len(rank))
+            node(v)
+            node(nb)
+            edge(v, nb)
             for a in range(3):
                 if btypes[a] == "periodic" and nb[a] == 0:
                     other = list(nb)
                     other[a] = 2 * d[a] - 1
-                    rank.setdefault(tuple(other), len(rank))
-    return rank
+                    other = tuple(other)
+                    node(other)
+                    edge(nb, other)
+                    seam.add(frozenset((nb, other)))
+    return rank, nbrs, seam
+
+
+def _reference_node_order(dims, btypes):
+    return _reference_graph_order(dims, btypes)[0]
+
+
+def macro_tables(lat: "LatticeTables"):
+    """Static tables of the macronode lattice of ``CVMacroLayer`` (``noise/cv.py:367-375``,
+    ``codes/graphs/egraph.py:26-103,133-155``): every node of the canonical lattice becomes a
+    macronode of exactly four micronodes, one per incident edge (each edge a two-micronode
+    'dumbbell') plus padding micronodes without a partner at the boundary.  Micronode ``4 * i + j``
+    is the ``j``-th micronode of canonical node ``i`` in the reference's order - the order in which
+    the edges at that node come up in ``can_graph.edges`` (insertion order of ``RHG_graph``, see
+    ``_reference_graph_order``), then the padding.  Returns (partner int32[4N]: the micronode at the
+    other end of the dumbbell or -1, sign int8[4N]: the edge's polarity weight)."""
+    rank, nbrs, _ = _reference_graph_order(lat.dims, lat.boundaries)
+    index = lat.coord_index()
+    if set(rank) != set(index):
+        raise AssertionError("reference graph order: node set differs from the lattice tables")
+    N = lat.N
+    slots = [[] for _ in range(N)]  # per canonical node: the canonical neighbour behind each micronode
+    seen = set()
+    for n in sorted(rank, key=rank.get):  # networkx EdgeView: nodes in insertion order, skip seen ends
+        for nb in nbrs[n]:
+            if nb not in seen:
+                slots[index[n]].append(index[nb])
+                slots[index[nb]].append(index[n])
+        seen.add(n)
+    partner = np.full(4 * N, -1, np.int32)
+    sign = np.zeros(4 * N, np.int8)
+    # polarity weights of the canonical edges
+    weight = {}
+    for i in range(N):
+        for e in range(lat.adj_indptr[i], lat.adj_indptr[i + 1]):
+            weight[(i, int(lat.adj_indices[e]))] = int(lat.adj_vals[e])
+    for i in range(N):
+        if len(slots[i]) > 4:
+            raise AssertionError("a lattice node with more than four neighbours")
+        for j, nb in enumerate(slots[i]):
+            partner[4 * i + j] = 4 * nb + slots[nb].index(i)
+            sign[4 * i + j] = weight[(i, nb)]
+    return partner, sign
 
 
 def _double_edge_keep(ec, dims, btypes, cidx, start, pairs):

@@ -189,6 +189,114 @@ class CVLayer:
         return self.states.get("GKP")
 
 
+class MacroSampler:
+    """The random draws of ``CVMacroLayer.apply_noise`` on a (reused) layer, in the reference's RNG
+    call order (``noise/cv.py:375-403``), for the 4N micronodes of the macronode lattice:
+
+    1. labels as in ``LabelSampler`` (``cv.py:121-140,306-321``), over the micronodes;
+    2. the initial q means of the two-step sampling (``cv.py:323-349``): ``rng.random(n_p) * 2 sqrt(pi)``
+       for the p-squeezed micronodes in the order ``rng.choice`` returned them, then
+       ``rng.integers(0, 2, n_gkp) * sqrt(pi)`` for the GKP micronodes in the order of the reference's
+       ``list(set(range(N)) - set(used))`` - a Python-set order, reproduced with a real set - both
+       stored as float32; micronodes in neither set (reused layer) keep mean 0;
+    3. standard normals for the N star p-measurements, then the 3N planet q-measurements
+       (``rng.normal(means, covs)`` is ``means + covs * standard_normal`` element by element).
+    """
+
+    def __init__(self, n_micro: int, p_swap, fresh: bool = False):
+        self.M = int(n_micro)
+        self.p_swap = p_swap
+        self.fresh = fresh
+        self._prev_gkp = np.empty(0, dtype=int)
+
+    def next(self, rng):
+        """Returns (state uint8[M], mean32 float32[M], z float64[M])."""
+        M = self.M
+        if self.p_swap:
+            if self.p_swap == 1:
+                p_inds = np.arange(M)
+            else:
+                num_p = rng.binomial(M, self.p_swap)
+                p_inds = rng.choice(range(M), size=int(np.floor(num_p)), replace=False)
+        else:
+            p_inds = np.empty(0, dtype=int)
+        used = np.concatenate([p_inds, np.empty(0, dtype=int) if self.fresh else self._prev_gkp])
+        gkp_inds = np.array(list(set(range(M)) - set(used)), dtype=int)
+        self._prev_gkp = gkp_inds
+        state = np.zeros(M, np.uint8)
+        state[gkp_inds] = 1
+        state[p_inds] = 2
+        mean = np.zeros(M, np.float32)
+        if len(p_inds):
+            mean[p_inds] = rng.random(size=len(p_inds)) * (2 * np.sqrt(np.pi))
+        if len(gkp_inds):
+            mean[gkp_inds] = rng.integers(0, 2, size=len(gkp_inds)) * np.sqrt(np.pi)
+        z = np.concatenate([rng.standard_normal(M // 4), rng.standard_normal(M - M // 4)])
+        return state, mean, z
+
+
+class CVMacroLayer:
+    """Reference-compatible macronode noise layer (``flamingpy/noise/cv.py:352-625``; the reference
+    CLI's default noise model, ``simulations.py:224``).
+
+    ``CVMacroLayer(code, *, delta, p_swap=None)``; ``apply_noise(rng)`` draws the micronode labels,
+    initial means and measurement noise on the host in the reference's RNG call order, and the GPU
+    entangles the dumbbells, applies the four-splitter of every macronode, measures stars in p and
+    planets in q and reduces each macronode to the canonical lattice: ``state``, ``bit_val`` and
+    ``p_phase_cond`` of every node of ``code.graph``.  Decode with
+    ``weight_options={"method": "blueprint", "prob_precomputed": True}`` (``decoder.py:67-68``).
+    """
+
+    def __init__(self, code, *, delta, bs_network=None, **kwargs):
+        from .codes import SurfaceCode
+
+        if not isinstance(code, SurfaceCode):
+            raise TypeError("CVMacroLayer needs a flamingpy_b200.codes.SurfaceCode")
+        if bs_network is not None:
+            raise NotImplementedError("only the standard four-splitter (cv/ops.py:104-127) is implemented")
+        if kwargs.get("states") is not None and len(kwargs["states"].get("p", [])):
+            raise NotImplementedError("CVMacroLayer with hand-picked p-squeezed micronodes: use p_swap")
+        if kwargs.get("translator") is not None:
+            raise NotImplementedError("the GPU path implements the standard GKP binner only")
+        self.code = code
+        self.reduced_graph = code.graph
+        self.delta = delta
+        self.p_swap = kwargs.get("p_swap")
+        self._N = 4 * len(code.graph)  # micronodes
+        self._sampler = MacroSampler(self._N, self.p_swap)
+        self.states = {"p": np.empty(0, dtype=int)}
+
+    def apply_noise(self, rng=None):
+        from . import _lib
+
+        rng = np.random.default_rng() if rng is None else rng
+        state, mean, z = self._sampler.next(rng)
+        self.states = {"p": np.nonzero(state == 2)[0], "GKP": np.nonzero(state == 1)[0]}
+        code = self.code
+        code._trial = ("macro", (state, mean, z), self.delta, self.p_swap)
+        eng = code.engine(self.delta, self.p_swap, {"method": "blueprint", "prob_precomputed": True})
+        red = eng.run_macro_injected(state[None, :], mean[None, :], z[None, :], stage=_lib.STAGE_NOISE)
+        g = self.reduced_graph
+        g._ensure_arrays()
+        g.state = red["red_state"][0].copy()
+        g.bit_val[:] = red["bit_val"][0]
+        g.p_phase_cond = red["p_phase_cond"][0].copy()
+        g.hom_val_p[:] = np.nan  # the reduced lattice carries no homodyne values (cv.py:622-625)
+
+    def bit_values(self, inds=None):
+        inds = range(len(self.code.graph)) if inds is None else inds
+        b = self.reduced_graph.bit_val
+        return [None if (b is None or b[i] < 0) else int(b[i]) for i in inds]
+
+    @property
+    def p_inds(self):
+        return self.states.get("p")
+
+    @property
+    def gkp_inds(self):
+        return self.states.get("GKP")
+
+
 class IidNoise:
     """Reference-compatible i.i.d. Z-error model (``flamingpy/noise/iid.py:19-50``):
     ``IidNoise(code, error_probability).apply_noise(rng)`` sets ``bit_val = int(rng.random() < p)``

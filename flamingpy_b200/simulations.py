@@ -26,7 +26,7 @@ import numpy as np
 from . import _lib
 from .codes import SurfaceCode
 from .decoder import candidates, correct, logical_failures, match_batch
-from .noise import CVLayer, IidNoise
+from .noise import CVLayer, CVMacroLayer, IidNoise
 
 int_time = int(str(datetime.now().timestamp()).replace(".", ""))
 
@@ -78,17 +78,23 @@ def ec_monte_carlo(trials, code_instance, noise_instance, decoder, decoder_args,
     """
     if decoder != "MWPM":
         raise NotImplementedError("only the MWPM decoder is on the accelerated path")
-    if not isinstance(noise_instance, (CVLayer, IidNoise)):
-        raise NotImplementedError("the batched driver accelerates CVLayer and IidNoise")
+    if not isinstance(noise_instance, (CVLayer, CVMacroLayer, IidNoise)):
+        raise NotImplementedError("the batched driver accelerates CVLayer, CVMacroLayer and IidNoise")
     weight_opts = dict(decoder_args.get("weight_opts") or {})
     iid = isinstance(noise_instance, IidNoise)
+    macro = isinstance(noise_instance, CVMacroLayer)
+    if macro and weight_opts.get("method", "uniform") == "blueprint" and not weight_opts.get("prob_precomputed"):
+        raise ValueError("CVMacroLayer leaves no homodyne values on the reduced lattice: use weight_opts "
+                         "{'method': 'blueprint', 'prob_precomputed': True} (or 'uniform')")
+    if not macro and weight_opts.get("prob_precomputed"):
+        raise ValueError("prob_precomputed weights need the p_phase_cond attribute that CVMacroLayer computes")
     if iid:
         if weight_opts.get("method", "uniform") != "uniform":
             raise ValueError("IidNoise has no homodyne outcomes: use weight_opts {'method': 'uniform'}")
         n_delta, n_pswap, mode = 1.0, 0.0, "fresh"  # engine parameters that bit-level trials never read
     else:
         n_delta, n_pswap = noise_instance.delta, noise_instance.p_swap
-        if not n_pswap and len(np.atleast_1d(noise_instance.states.get("p", []))):
+        if not macro and not n_pswap and len(np.atleast_1d(noise_instance.states.get("p", []))):
             # the device Philox path draws labels from p_swap only: a layer with hand-picked
             # p-squeezed nodes would silently run as all-GKP
             raise NotImplementedError(
@@ -148,6 +154,8 @@ def ec_monte_carlo(trials, code_instance, noise_instance, decoder, decoder_args,
                 en, n = engines[lane], min(batch, hi - first)
                 if iid:
                     en.run_iid(seed, first, n, noise_instance.error_probability, stage=_lib.STAGE_GRAPH, fetch=False)
+                elif macro:
+                    en.run_macro_rng(seed, first, n, stage=_lib.STAGE_GRAPH, fetch=False)
                 else:
                     en.run_rng(seed, first, n, stage=_lib.STAGE_GRAPH, fetch=False)
                 b = en.fetch_decode(lane_bufs[lane], want_pairs=handoff == "full")
@@ -281,7 +289,7 @@ def main(argv=None):
         dec = "MWPM"
     else:
         raise ValueError(f"Decoder {args.decoder} is either invalid or not yet implemented.")
-    classes = {"SurfaceCode": SurfaceCode, "CVLayer": CVLayer, "IidNoise": IidNoise}
+    classes = {"SurfaceCode": SurfaceCode, "CVLayer": CVLayer, "CVMacroLayer": CVMacroLayer, "IidNoise": IidNoise}
     return run_ec_simulation(args.trials, classes[args.code], l_eval(args.code_args), classes[args.noise],
                              l_eval(args.noise_args), dec, l_eval(args.decoder_args), fname=args.fname,
                              mode=args.mode)

@@ -197,6 +197,30 @@ int fpb_run_iid(fpb_handle* h, uint64_t seed, int64_t first_trial, int64_t n_tri
 int fpb_run_weighted(fpb_handle* h, int64_t n_trials, const double* weights, const uint32_t* bits, int on_device,
                      int stage);
 
+/* Macronode noise layer, CVMacroLayer (flamingpy/noise/cv.py:352-625; the reference CLI's default noise,
+ * simulations.py:224).  Every lattice node is a macronode of four micronodes (micronode 4 i + j of node i),
+ * one per incident edge plus partner-less padding (codes/graphs/egraph.py:26-103).
+ *
+ * fpb_set_macro: the macronode lattice - partner [4N] = micronode at the other end of each edge 'dumbbell'
+ *   (-1: padding), sign [4N] = that edge's weight (+-1 polarity).  Replaces EGraph.macronize + the
+ *   adjacency matrix of CVMacroLayer.__init__ (cv.py:367-375).
+ * fpb_run_macro_injected: trials on caller-supplied draws - state [T][4N] micronode labels (FPB_STATE_*),
+ *   mean [T][4N] float32 initial q means of the two-step sampling (cv.py:323-349), z [T][4N] standard normals
+ *   of the N star p-measurements then the 3N planet q-measurements (cv.py:474-489) - through CZ gates,
+ *   four-splitters (cv/ops.py:104-127), homodyne measurement and the reduction of every macronode to the
+ *   canonical lattice (cv.py:548-625), then the weights of assign_weights(prob_precomputed=True)
+ *   (decoders/decoder.py:58-93; uniform weights if the handle says so), parities and matching graph.
+ *   fpb_outputs.hom holds the effective homodyne value of each syndrome qubit.
+ * fpb_run_macro_rng: the same with labels, means and normals from the Philox stream of (seed; trial, micronode).
+ * fpb_fetch_macro: per lattice node [T][N] the reduced state label (FPB_STATE_GKP / FPB_STATE_P), bit_val,
+ *   p_phase_cond and effective homodyne value of the last macronode run (any pointer may be NULL). */
+int fpb_set_macro(fpb_handle* h, const int32_t* partner, const int8_t* sign);
+int fpb_run_macro_injected(fpb_handle* h, int64_t n_trials, const uint8_t* state, const float* mean, const double* z,
+                           int on_device, int stage);
+int fpb_run_macro_rng(fpb_handle* h, uint64_t seed, int64_t first_trial, int64_t n_trials, int stage);
+int fpb_fetch_macro(fpb_handle* h, uint8_t* red_state, uint8_t* bit_val, double* p_phase_cond, double* outcome,
+                    int on_device);
+
 int fpb_get_sizes(fpb_handle* h, fpb_sizes* out);
 /* Copy results of the last run into caller buffers (host if on_device == 0). */
 int fpb_fetch(fpb_handle* h, const fpb_outputs* dst, int on_device);

@@ -31,9 +31,13 @@ def load():
             mod.__version__ = "0.0-stub"
             sys.modules[name] = mod
     sym = sys.modules["thewalrus.symplectic"]
-    if not hasattr(sym, "expand"):
-        sym.expand = None
-        sym.beam_splitter = None
+    if getattr(sym, "expand", None) is None:
+        # thewalrus is not installed here.  The reference uses two of its functions, for the fixed
+        # four-splitter of CVMacroLayer only (cv/ops.py:104-127); both have short closed forms
+        # (thewalrus.symplectic, "xxpp" ordering), restated here so that the unmodified reference
+        # class runs: a lossless two-mode beamsplitter and the embedding of a symplectic into N modes.
+        sym.beam_splitter = _beam_splitter
+        sym.expand = _expand
     sys.modules["thewalrus"].symplectic = sym
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)
@@ -44,6 +48,32 @@ def load():
         import flamingpy.noise  # noqa: F401
         import flamingpy.decoders.decoder  # noqa: F401
     return sys.modules["flamingpy"]
+
+
+def _beam_splitter(theta, phi):
+    """Symplectic of the beamsplitter U = [[cos t, -e^{-i phi} sin t], [e^{i phi} sin t, cos t]] in
+    (q1, q2, p1, p2) ordering: [[Re U, -Im U], [Im U, Re U]]."""
+    import numpy as np
+
+    ct, st = np.cos(theta), np.sin(theta)
+    eip = np.cos(phi) + 1j * np.sin(phi)
+    U = np.array([[ct, -np.conj(eip) * st], [eip * st, ct]])
+    X, Y = U.real, U.imag
+    return np.block([[X, -Y], [Y, X]])
+
+
+def _expand(S, modes, N):
+    """Embed the symplectic S of len(modes) modes into N modes (identity elsewhere), xxpp ordering."""
+    import numpy as np
+
+    M = len(S) // 2
+    S2 = np.identity(2 * N, dtype=S.dtype)
+    w = np.array([modes]) if isinstance(modes, int) else np.array(modes)
+    S2[w.reshape(-1, 1), w.reshape(1, -1)] = S[:M, :M].copy()
+    S2[(w + N).reshape(-1, 1), (w + N).reshape(1, -1)] = S[M:, M:].copy()
+    S2[w.reshape(-1, 1), (w + N).reshape(1, -1)] = S[:M, M:].copy()
+    S2[(w + N).reshape(-1, 1), w.reshape(1, -1)] = S[M:, :M].copy()
+    return S2
 
 
 def make_code(distance, ec="primal", boundaries="open", polarity=None):

@@ -458,3 +458,136 @@ class TrialChain:
             good, _ = decode_complex(ct, rec["weights"], rec["bits"], rec.get("graph"))
             ok = ok and good
         return ok
+
+
+# --------------------------------------------------------------------------------------
+# f4: CVMacroLayer (noise/cv.py:352-625) - macronode lattice reduced to the canonical lattice
+# --------------------------------------------------------------------------------------
+# q- and p-block of the four-splitter (cv/ops.py:104-127: beamsplitters on modes (1,0), (3,2), (2,0),
+# (3,1), cast to float32); every entry is exactly +-1/2
+SPLITTER = np.array([[1, 1, 1, 1], [-1, 1, -1, 1], [-1, -1, 1, 1], [1, -1, -1, 1]], np.float32) * np.float32(0.5)
+
+
+def z_err_cond_hom(var, val):
+    """``Z_err_cond(var, val, use_hom_val=True)`` (``cv/gkp.py:116-133``): the sums run over the whole
+    homodyne value, the numerator over the odd (even) multiples of sqrt(pi) if the value bins to 0 (1)."""
+    val = np.asarray(val, np.float64)
+    bit, _ = gkp_binner(val)
+    factor = 1 - bit.astype(np.int64)
+    sq = np.sqrt(np.pi)
+    num = np.zeros_like(val)
+    den = np.zeros_like(val)
+    for k in range(-10, 10):
+        num = num + np.exp(-((val - (2 * k + factor) * sq) ** 2) / var)
+        den = den + np.exp(-((val - k * sq) ** 2) / var)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return np.where(den != 0, num / den, 0.0)
+
+
+def macro_trial_from_draws(lat, partner, sign, state, mean32, z, delta):
+    """One ``CVMacroLayer.apply_noise`` (``noise/cv.py:375-403``) from its random draws.
+
+    ``state`` uint8[4N]: micronode labels (2 = p-squeezed, anything else reads "GKP");
+    ``mean32`` float32[4N]: the initial q means of the two-step sampling (``cv.py:323-349``);
+    ``z`` float64[4N]: standard normals, the N star p-measurements then the 3N planet q-measurements
+    in the reference's order (``cv.py:474-489``).  Returns per canonical node: reduced state label
+    (2 = p), bit value, conditional phase error probability and the effective homodyne value."""
+    N = lat.N
+    M = 4 * N
+    state = np.asarray(state)
+    is_p = state == 2
+    # CZ gates on the float32 means: p_i += sign * q_partner (ops.py:65,84; every micronode has <= 1 partner)
+    q = np.asarray(mean32, np.float32)
+    p = np.where(partner >= 0, sign.astype(np.float32) * q[np.maximum(partner, 0)], np.float32(0)).astype(np.float32)
+    # stars first: GKP micronodes in index order, then the p-squeezed ones (cv.py:529-546)
+    lab = is_p.reshape(N, 4)
+    perm = np.argsort(lab, axis=1, kind="stable")  # False (GKP) before True (p), stable
+    idx = (4 * np.arange(N)[:, None] + perm)  # micronode index at body position k = 0..3
+    body = np.empty(M, np.int64)
+    body[idx.ravel()] = np.tile(np.arange(1, 5), N)
+    # four-splitter in float32, summed pairwise like NumPy's float32 matrix-vector product
+    xq = q[idx]
+    xp = p[idx]
+
+    def split(x):
+        t = SPLITTER[None, :, :] * x[:, None, :]  # [N, 4 out, 4 in]; products are exact
+        return ((t[:, :, 0] + t[:, :, 1]) + (t[:, :, 2] + t[:, :, 3])).astype(np.float32)
+
+    nq, np_ = split(xq), split(xp)
+    sd = np.float32((delta / 2) ** 0.5)
+    z = np.asarray(z, np.float64)
+    star_p = np_[:, 0].astype(np.float64) + np.float64(sd) * z[:N]
+    planet_q = nq[:, 1:].astype(np.float64) + np.float64(sd) * z[N:].reshape(N, 3)
+    hq = np.zeros((N, 5))  # [macronode][body index] q outcome of the planets (cv.py:447-465)
+    hq[:, 2:] = planet_q
+    red_p = is_p[idx[:, 0]]  # reduced label = label of the star (cv.py:417-420)
+    bit_val = np.zeros(N, np.uint8)
+    p_err_out = np.zeros(N)
+    outcome_out = np.zeros(N)
+    for j in range(N):  # cv.py:566-625
+        outcome = 2 * star_p[j]
+        num_p = 0
+        z_gkp = []
+        for k in range(4):
+            u = idx[j, k]
+            nb = partner[u]
+            if nb < 0:
+                continue
+            nbody = body[nb]
+            m = hq[nb // 4]
+            zval = 0.0 if nbody == 1 else (m[2] - m[4] if nbody == 2 else (m[3] - m[4] if nbody == 3 else m[2] + m[3]))
+            if is_p[nb]:
+                num_p += 1
+                outcome -= zval
+            else:
+                z_gkp.append(zval)
+        p_err = 0.0
+        for zval in z_gkp:
+            p_err += float(z_err_cond_hom(2 * delta, np.float64(zval)))
+        p_err += float(z_err_cond_hom(2 * (2 + num_p) * delta, np.float64(outcome)))
+        p_err = max(min(p_err, 0.5), 0)
+        bits = int(gkp_binner(np.array([outcome]))[0][0])
+        for zval in z_gkp:
+            bits += int(gkp_binner(np.array([zval]))[0][0])
+        bit_val[j] = bits % 2
+        p_err_out[j] = p_err
+        outcome_out[j] = outcome
+    return {"red_state": np.where(red_p, 2, 1).astype(np.uint8), "bit_val": bit_val, "p_phase_cond": p_err_out,
+            "outcome": outcome_out}
+
+
+def macro_weights(lat, red_state, p_phase_cond, weight_opts):
+    """``assign_weights(..., prob_precomputed=True)`` (``decoders/decoder.py:58-93``) for all nodes."""
+    wo = {"method": "uniform", "integer": False, "multiplier": 1}
+    wo.update(weight_opts or {})
+    N = lat.N
+    if wo["method"] == "uniform":
+        return np.ones(N)
+    pc = p_neighbour_count(lat, red_state)
+    err = np.minimum(np.asarray(p_phase_cond, np.float64), 0.5)
+    err = np.where(err == 0, FLOAT_MIN, err)
+    table = np.array([0, 0, 1 / 4, 1 / 3, 2 / 5])
+    err = np.where(pc <= 1, err, table[np.minimum(pc, 4)])
+    if wo.get("integer"):
+        return np.array([float(round(-wo["multiplier"] * math.log(e))) for e in err])
+    return -np.log(err)
+
+
+def macro_trial(lat, partner, sign, state, mean32, z, delta, weight_opts, want_graph=True) -> "TrialResult":
+    """A complete macronode trial in the shape of ``trial_from_draws``: reduction, precomputed-
+    probability weights, parities and matching graph per complex."""
+    red = macro_trial_from_draws(lat, partner, sign, state, mean32, z, delta)
+    w_nodes = macro_weights(lat, red["red_state"], red["p_phase_cond"], weight_opts)
+    per = {}
+    for ec in lat.ec:
+        ct = lat.complexes[ec]
+        w = w_nodes[ct.qubits]
+        bits = red["bit_val"][ct.qubits]
+        parity = stabilizer_parity(ct, bits)
+        rec = {"hom": red["outcome"][ct.qubits], "bits": bits, "weights": w, "parity": parity}
+        if want_graph:
+            rec["graph"] = matching_graph(ct, w, parity)
+        per[ec] = rec
+    res = TrialResult(state=red["red_state"], x=None, hom_all=red["outcome"], per_complex=per)
+    res.macro = red
+    return res

@@ -11,7 +11,24 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 def golden_files():
     """CVLayer chains (oracle/gen_golden.py); the iid_*.npz files of the i.i.d. arm have their own
     layout and tests (tests/test_iid.py)."""
-    return sorted(p for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")) if not os.path.basename(p).startswith("iid_"))
+    return sorted(p for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
+                  if not os.path.basename(p).startswith(("iid_", "macro_")))
+
+
+def macro_files():
+    """CVMacroLayer chains (oracle/gen_golden_macro.py)."""
+    return sorted(glob.glob(os.path.join(GOLDEN_DIR, "macro_*.npz")))
+
+
+def load_macro(path):
+    g = load(path)
+    wo = {"method": g["method"]}
+    if bool(g["prob_precomputed"]):
+        wo["prob_precomputed"] = True
+    if g["integer"]:
+        wo.update(integer=True, multiplier=g["multiplier"])
+    g["weight_opts"] = wo
+    return g
 
 
 def load(path):
