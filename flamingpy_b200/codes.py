@@ -330,16 +330,18 @@ class SurfaceCode:
         return self.engine(1.0, 0.0, {"method": "uniform"}, device=device, lane="weighted")
 
     # ------------------------------------------------------------------ engine cache
-    def engine(self, delta, p_swap, weight_opts=None, device=0, mode="compat", lane=0, reserve_sms=0):
+    def engine(self, delta, p_swap, weight_opts=None, device=0, mode="compat", lane=0, reserve_sms=0,
+               lengths="float"):
         """The ``TrialEngine`` for these noise / weight options (created once).  ``lane`` > 0
         gives further engines with the same options (own stream and buffers) for pipelining."""
         from .engine import TrialEngine
 
         wo = dict(weight_opts or {})
-        key = (float(delta), float(p_swap or 0.0), tuple(sorted(wo.items())), device, mode, lane, reserve_sms)
+        key = (float(delta), float(p_swap or 0.0), tuple(sorted(wo.items())), device, mode, lane, reserve_sms, lengths)
         eng = self._engines.get(key)
         if eng is None:
-            eng = TrialEngine(self.lattice, delta, p_swap, wo, mode=mode, device=device, reserve_sms=reserve_sms)
+            eng = TrialEngine(self.lattice, delta, p_swap, wo, mode=mode, device=device, reserve_sms=reserve_sms,
+                              lengths=lengths)
             if lane and lane != "weighted" and self.engine(delta, p_swap, weight_opts, device, mode,
                                                            reserve_sms=reserve_sms).uses_table:
                 eng.build_table()

@@ -96,7 +96,7 @@ struct fpb_handle {
   int N = 0, Qtot = 0, bit_words = 0, ncx = 0;
   int S_max = 0, slots_max = 0;
   double delta = 0, p_swap = 0, weight_delta = 0, weight_multiplier = 1, step_factor = 1;
-  int weight_method = 0, weight_integer = 0, label_mode = 0, reserve_sms = 0;
+  int weight_method = 0, weight_integer = 0, label_mode = 0, reserve_sms = 0, length_mode = 0;
   long long chain_len = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -168,6 +168,14 @@ typedef void (*toggle_fn)(const PathsParams);
 // kernel variant by lattice size: NCH = 16-cube chunks each lane scans, NV = cubes relaxed per
 // lane per batch, MINB = CTAs per SM the register budget is sized for
 // (NV = 2 variants are compiled for at most 384 threads so that they get 170 registers)
+// FPB_LENGTH_RX_TRUNC: one warp per search, weights in global memory, int lengths carried along
+paths_fn pick_ilen_kernel(int S) {
+  if (S <= 1024) return k_paths<2, 1, 256, 1, true, true>;
+  if (S <= 2560) return k_paths<5, 1, 256, 1, true, true>;
+  if (S <= 4096) return k_paths<8, 1, 256, 1, true, true>;
+  if (S <= 8192) return k_paths<16, 1, 256, 1, true, true>;
+  return k_paths<32, 1, 256, 1, true, true>;
+}
 paths_fn pick_paths_kernel(int S, bool wg, int* max_warps) {
   if (wg) {  // weights and face tables in global memory: lattices that do not fit shared memory
     *max_warps = 8;
@@ -285,6 +293,27 @@ int configure_paths(fpb_handle* h) {
   h->ctas_per_sm = 0;
   if (h->S_max > 16 * 32 * MAX_CHUNKS || h->S_max > 65535)
     return fail(FPB_ERR_UNSUPPORTED, "lattice too large for the shortest-path kernel's bucket scan");
+  if (h->length_mode == FPB_LENGTH_RX_TRUNC) {
+    int max_optin = 0;
+    CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+    paths_fn fn = pick_ilen_kernel(h->S_max);
+    cudaFuncAttributes fattr;
+    CK(cudaFuncGetAttributes(&fattr, fn));
+    const size_t room = (size_t)max_optin - fattr.sharedSizeBytes;
+    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)room));
+    const size_t warp_b = paths_warp_bytes(h->S_max, false) + align16((size_t)h->S_max * 4);
+    int w = (int)(room / warp_b);
+    if (w > 8) w = 8;
+    if (w < 1) return fail(FPB_ERR_UNSUPPORTED, "lattice too large for the int-length shortest-path kernel");
+    h->warps = w;
+    h->ctas_per_sm = 1;
+    h->paths_wg = true;
+    h->paths_team = false;
+    h->team_w = 0;
+    h->paths_smem = (size_t)w * warp_b;
+    h->tasks_per_item = w * 4;
+    return FPB_OK;
+  }
   int rc = FPB_OK;
   if (h->S_max <= 16 * 32 * 16 && !getenv("FPB_FORCE_WG")) rc = configure_variant(h, false);
   if (rc) return rc;
@@ -410,7 +439,9 @@ int launch_paths(fpb_handle* h, long long T, int* launches) {
     pp.wscratch = h->wscratch.p;
   }
   int mw_unused = 0;
-  if (h->team_w)
+  if (h->length_mode == FPB_LENGTH_RX_TRUNC)
+    pick_ilen_kernel(h->S_max)<<<(unsigned)grid, h->warps * 32, h->paths_smem, st>>>(pp);
+  else if (h->team_w)
     pick_teamw_kernel(h->S_max, h->team_w)<<<(unsigned)grid, h->warps * h->team_w * 32, h->paths_smem, st>>>(pp);
   else if (h->paths_team)
     pick_team_kernel(h->S_max, h->paths_wg)<<<(unsigned)grid, h->warps * 64, h->paths_smem, st>>>(pp);
@@ -670,6 +701,11 @@ int fpb_create(const fpb_config* cfg, fpb_handle** out) {
   h->weight_multiplier = cfg->weight_multiplier != 0 ? cfg->weight_multiplier : 1.0;
   h->label_mode = cfg->label_mode;
   h->chain_len = cfg->chain_len;
+  h->length_mode = cfg->length_mode;
+  if (h->length_mode != FPB_LENGTH_FLOAT && h->length_mode != FPB_LENGTH_RX_TRUNC) {
+    fpb_destroy(h);
+    return fail(FPB_ERR_ARG, "unknown length_mode");
+  }
   h->reserve_sms = cfg->reserve_sms < 0 ? 0 : cfg->reserve_sms;
   if (h->reserve_sms >= h->sm_count) h->reserve_sms = h->sm_count - 1;
   h->step_factor = cfg->delta_step > 0 ? cfg->delta_step : 2.0;
@@ -1000,6 +1036,8 @@ int fpb_synchronize(fpb_handle* h) {
 int fpb_build_table(fpb_handle* h) {
   if (!h) return fail(FPB_ERR_ARG, "null handle");
   const bool uniform = h->weight_method == FPB_WEIGHT_UNIFORM;
+  if (h->length_mode != FPB_LENGTH_FLOAT && !uniform && !h->weight_integer)
+    return fail(FPB_ERR_UNSUPPORTED, "the static table holds float path sums; int-truncated lengths differ from them unless the weights are integers");
   if (!uniform && !(h->weight_method == FPB_WEIGHT_BLUEPRINT && h->p_swap >= 1.0))
     return fail(FPB_ERR_UNSUPPORTED, "weights are trial-dependent: the static table needs uniform weights or p_swap == 1");
   if (h->warps == 0) return fail(FPB_ERR_UNSUPPORTED, "shortest-path kernel not configured for this lattice");

@@ -446,6 +446,7 @@ struct WarpMem {
   uint8_t* bkt;     // [ceil16(S)] ring slot of the cube's pending entry, 0xFF none; 16-byte aligned
   uint16_t* stage;  // [STAGE_CAP]
   uint8_t* pred;    // [S] incoming direction (path-toggle kernel only)
+  int* ilen;        // [S] sum of int(weight) along the shortest path (FPB_LENGTH_RX_TRUNC only)
   int sb;           // 0: bkt[c] is cube c's byte; > 0: residue-major rows, byte (c & 15) * sb + (c >> 4)
 };
 
@@ -484,6 +485,7 @@ __device__ __forceinline__ WarpMem carve_warp(unsigned char* wp, int S_max, bool
   wm.sb = 0;
   wm.stage = (uint16_t*)wp; wp += align16((size_t)paths_stage_entries(S_max) * 2);
   wm.pred = pred ? (uint8_t*)wp : nullptr;
+  wm.ilen = nullptr;
   return wm;
 }
 
@@ -513,6 +515,7 @@ __device__ __forceinline__ void warp_clear(const WarpMem& wm, int S, int lane) {
 // Returns the lane's contribution to the `present` mask.
 __device__ __forceinline__ uint32_t seed_cube(const WarpMem& wm, int c, double d0, double inv, uint8_t pred_code) {
   wm.dist[c] = d0;
+  if (wm.ilen) wm.ilen[c] = (int)d0;  // int(weight) of the connector's boundary edge (0 for a source cube)
   int bi = bucket_of(d0, inv);
   bi = bi < NRING - 1 ? bi : NRING - 1;
   wm.bkt[wm.sb ? (c & 15) * wm.sb + (c >> 4) : c] = (uint8_t)bi;
@@ -559,6 +562,12 @@ __device__ __forceinline__ void sts_v4(uint32_t a, uint4 v) {
   asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
 }
 
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+
 // bytes of `word` equal to the byte replicated in r4: returns 0x80 in each matching byte
 // (exact: no carries cross a byte boundary)
 __device__ __forceinline__ uint32_t eq_bytes(uint32_t word, uint32_t r4) {
@@ -569,13 +578,18 @@ __device__ __forceinline__ uint32_t eq_bytes(uint32_t word, uint32_t r4) {
 // gather bits 7,15,23,31 into bits 0..3
 __device__ __forceinline__ uint32_t movemask4(uint32_t z) { return (z * 0x00204081u) >> 28; }
 
-template <bool PRED, int NCH, int NV, bool WG, bool LEAN = false>
+// ILEN (FPB_LENGTH_RX_TRUNC): next to the float distance every cube carries the sum of int(weight) along
+// the path that gave it that distance - what the reference's rustworkx backend reports as the path
+// weight (codes/graphs/stabilizer_graph.py:486-500: Dijkstra on the float weights, then
+// weight += int(edge weight) along the returned path).  The owner of a target's final distance writes it.
+template <bool PRED, int NCH, int NV, bool WG, bool LEAN = false, bool ILEN = false>
 __device__ __forceinline__ void warp_search(const CtaMem& cm, const WarpMem& wm, const DirTab& dt, int S,
                                             double step, uint32_t present, int lane, int stop_at) {
   const double inv = 1.0 / step;
   const int n16 = (S + 15) >> 4;
   const uint32_t dist_a = smem_addr(wm.dist), bkt_a = smem_addr(wm.bkt), stage_a = smem_addr(wm.stage);
   const uint32_t pred_a = PRED ? smem_addr(wm.pred) : 0u;
+  const uint32_t ilen_a = ILEN ? smem_addr(wm.ilen) : 0u;
   // WG: the trial's weights (and the face tables) live in global memory instead of shared memory
   const uint32_t wslot_a = WG ? 0u : smem_addr(cm.wslot);
   int cur = 0;
@@ -641,6 +655,7 @@ __device__ __forceinline__ void warp_search(const CtaMem& cm, const WarpMem& wm,
         uint32_t ua[NV][6];  // shared address of the neighbour's distance
         double nd[NV][6];
         bool imp[NV][6];
+        int il[NV][6];  // ILEN: int length of the candidate path
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
           const int idx = cb + k * 32 + lane;
@@ -648,6 +663,7 @@ __device__ __forceinline__ void warp_search(const CtaMem& cm, const WarpMem& wm,
           const int v = valid ? (int)lds_u16(stage_a + 2 * idx) : 0;
           const uint32_t va = dist_a + 8u * v;
           const double dv = lds_f64(va);
+          const int iv = ILEN ? (int)lds_u32(ilen_a + 4u * v) : 0;
           const int bt = bucket_of(dv, inv);
           if (valid && bt > cur) {  // a parked cube: move it towards its real bucket
             const int s2 = (bt < far ? bt : far) & (NRING - 1);
@@ -672,8 +688,10 @@ __device__ __forceinline__ void warp_search(const CtaMem& cm, const WarpMem& wm,
               nd[k][d] = cand ? dv + (WG ? cm.wslot[slot] : lds_f64(wslot_a + 8u * slot)) : 0.0;
               imp[k][d] = cand && nd[k][d] < old;
             } else {
-              nd[k][d] = dv + (WG ? cm.wslot[slot] : lds_f64(wslot_a + 8u * slot));
+              const double wgt = WG ? cm.wslot[slot] : lds_f64(wslot_a + 8u * slot);
+              nd[k][d] = dv + wgt;
               imp[k][d] = a && nd[k][d] < lds_f64(ua[k][d]);
+              if (ILEN) il[k][d] = iv + (a ? __double2int_rz(fmin(wgt, 2.0e9)) : 0);
             }
           }
         }
@@ -713,6 +731,9 @@ __device__ __forceinline__ void warp_search(const CtaMem& cm, const WarpMem& wm,
             if (PRED) {
               if (imp[k][d] && fin[k][d] == nd[k][d]) sts_u8(pred_a + ui, d);
             }
+            if (ILEN) {
+              if (imp[k][d] && fin[k][d] == nd[k][d]) asm volatile("st.shared.u32 [%0], %1;" ::"r"(ilen_a + 4u * ui), "r"(il[k][d]));
+            }
           }
         __syncwarp();
       }
@@ -741,7 +762,7 @@ __device__ __forceinline__ double bucket_step(double wmean, double factor) {
   return (wmean > 0.0 && wmean < FPB_INF) ? wmean * factor : 1.0;
 }
 
-template <int NCH, int NV, int MAXT, int MINB, bool WG>
+template <int NCH, int NV, int MAXT, int MINB, bool WG, bool ILEN = false>
 __global__ void __launch_bounds__(MAXT, MINB) k_paths(const __grid_constant__ PathsParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ int item_s;
@@ -764,7 +785,9 @@ __global__ void __launch_bounds__(MAXT, MINB) k_paths(const __grid_constant__ Pa
   }
   CtaMem cm;
   cm.wslot = wslot; cm.ninfo = ninfo_s; cm.sbase = sbase_s;
-  const WarpMem wm = carve_warp(ptr + (size_t)wid * paths_warp_bytes(p.S_max, false), p.S_max, false);
+  const size_t warp_b = paths_warp_bytes(p.S_max, false) + (ILEN ? align16((size_t)p.S_max * 4) : 0);
+  WarpMem wm = carve_warp(ptr + (size_t)wid * warp_b, p.S_max, false);
+  if (ILEN) wm.ilen = (int*)(ptr + (size_t)wid * warp_b + paths_warp_bytes(p.S_max, false));
 
   int staged_tc = -1, staged_c = -1;
   double step = 1.0;
@@ -848,16 +871,19 @@ __global__ void __launch_bounds__(MAXT, MINB) k_paths(const __grid_constant__ Pa
         } else {
           present = warp_seed_connector(cm, wm, c.n_high, c.high_cube, c.high_slot, inv, lane);
         }
-        warp_search<false, NCH, NV, WG, (MINB > 1)>(cm, wm, dt, S, step, present, lane, -1);
+        warp_search<false, NCH, NV, WG, (MINB > 1) && !ILEN, ILEN>(cm, wm, dt, S, step, present, lane, -1);
+        // ILEN: the reported length is the int sum; the nearer connector is chosen on the int sums, too
+        // (mwpm/matching.py:149-150 on the rustworkx lengths)
         if (pair_task) {
           const long long row = poff + (long long)task * K - (long long)task * (task + 1) / 2;
-          for (int b = task + 1 + lane; b < K; b += 32) c.pair_len[row + (b - task - 1)] = wm.dist[odd[b]];
+          for (int b = task + 1 + lane; b < K; b += 32)
+            c.pair_len[row + (b - task - 1)] = ILEN ? (double)wm.ilen[odd[b]] : wm.dist[odd[b]];
         } else if (ph == 0) {
-          for (int b = lane; b < K; b += 32) c.bnd_len[ooff + b] = wm.dist[odd[b]];
+          for (int b = lane; b < K; b += 32) c.bnd_len[ooff + b] = ILEN ? (double)wm.ilen[odd[b]] : wm.dist[odd[b]];
         } else {
           for (int b = lane; b < K; b += 32) {
             const double lo_d = c.bnd_len[ooff + b];
-            const double hi_d = wm.dist[odd[b]];
+            const double hi_d = ILEN ? (double)wm.ilen[odd[b]] : wm.dist[odd[b]];
             const bool high = hi_d < lo_d;
             c.bnd_len[ooff + b] = high ? hi_d : lo_d;
             c.bnd_side[ooff + b] = high ? 1 : 0;
@@ -896,12 +922,6 @@ struct TeamX {      // exchange words of one team (shared memory)
   int lp[2];        // slots filed by each half during a sub-round
   int redo[2][2];   // [round parity][half]
 };
-
-__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
-  uint32_t v;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
-  return v;
-}
 
 // cinfo_a: shared address of one 32-bit word per cube = face kinds (low 12 bits) | weight-slot
 // base << 16.  Each warp of the pair relaxes half of the staged cubes (all six directions).

@@ -23,7 +23,7 @@ def _require_trial(code):
     return code._trial
 
 
-def _run_trial(code, wo, stage):
+def _run_trial(code, wo, stage, lengths="float"):
     """Run the last noise realisation (one trial) through the device pipeline up to ``stage``.
     CVLayer realisations are (x, state, delta, p_swap); bit-level ones (IidNoise) are
     ("bits", bit values of all nodes) and need uniform weights."""
@@ -35,7 +35,7 @@ def _run_trial(code, wo, stage):
             raise ValueError("CVMacroLayer leaves no homodyne values on the reduced lattice: use weight_options "
                              "{'method': 'blueprint', 'prob_precomputed': True} (or 'uniform')")
         (state, mean, z), delta, p_swap = trial[1], trial[2], trial[3]
-        eng = code.engine(delta, p_swap, wo)
+        eng = code.engine(delta, p_swap, wo, lengths=lengths)
         eng.run_macro_injected(state[None, :], mean[None, :], z[None, :], stage=stage)
         return eng, eng.fetch(stage)
     if wo.get("prob_precomputed"):
@@ -43,11 +43,11 @@ def _run_trial(code, wo, stage):
     if isinstance(trial[0], str) and trial[0] == "bits":
         if wo.get("method", "uniform") != "uniform":
             raise ValueError("IidNoise has no homodyne outcomes: use weight_options {'method': 'uniform'}")
-        eng = code.engine(1.0, 0.0, wo)
+        eng = code.engine(1.0, 0.0, wo, lengths=lengths)
         qn = np.concatenate([code.lattice.complexes[e].qubits for e in code.ec])
         return eng, eng.run_bits(trial[1][qn][None, :], stage=stage)
     x, state, delta, p_swap = trial
-    eng = code.engine(delta, p_swap, wo)
+    eng = code.engine(delta, p_swap, wo, lengths=lengths)
     return eng, eng.run_injected(x[None, :], state[None, :], stage=stage)
 
 
@@ -155,7 +155,11 @@ def correct(code, decoder="MWPM", weight_options=None, sanity_check=False, decod
     ("native": exact C++ blossom matcher), like the reference's default is its compiled backend
     (``decoder.py:277``); the reference's "rustworkx" and "lemon" are not installable offline and
     map to it (same total weight, possibly another choice among tied matchings).  "networkx"
-    reproduces the reference's networkx verdicts trial by trial, ties included, and is slow."""
+    reproduces the reference's networkx verdicts trial by trial, ties included, and is slow.
+    ``decoder_opts["lengths"]``: "float" (default) - path lengths are the sums of the float weights, as
+    with the reference's networkx graphs; "rustworkx" - the sums of ``int(weight)`` along the
+    float-shortest paths, which is what the reference's default rustworkx graphs report
+    (``stabilizer_graph.py:486-500``) and therefore what its default ``correct`` matches on."""
     if decoder != "MWPM":
         raise NotImplementedError("only the MWPM decoder is on the accelerated path")
     if draw:
@@ -167,7 +171,7 @@ def correct(code, decoder="MWPM", weight_options=None, sanity_check=False, decod
         opts["backend"] = "native"
     wo = {"method": "uniform", "integer": False, "multiplier": 1}
     wo.update(weight_options)
-    eng, batch = _run_trial(code, wo, _lib.STAGE_GRAPH)
+    eng, batch = _run_trial(code, wo, _lib.STAGE_GRAPH, lengths=opts.get("lengths", "float"))
     is_cv = not isinstance(code._trial[0], str)  # CVLayer: homodyne values exist on the lattice
     g = code.graph
     g._ensure_arrays()

@@ -306,6 +306,46 @@ def matching_graph(ct, w_local: np.ndarray, parity: np.ndarray, want_paths: bool
     return MatchingData(odd, pair_len, bnd_len, bnd_side, pair_paths, bnd_paths)
 
 
+def _int_lengths(dist, pred, pred_q, w_local):
+    """``RxStabilizerGraph._path_weight`` (``codes/graphs/stabilizer_graph.py:486-500``): rustworkx runs
+    Dijkstra on the float weights, then the reference re-adds ``int(weight)`` of every edge along the
+    returned path.  Evaluated for every cube from the float shortest-path tree, in settle order."""
+    il = np.zeros(len(dist), np.int64)
+    for v in np.argsort(dist, kind="stable"):
+        if np.isfinite(dist[v]) and pred_q[v] >= 0:
+            il[v] = (il[pred[v]] if pred[v] >= 0 else 0) + int(w_local[pred_q[v]])
+    return il
+
+
+def matching_graph_rx(ct, w_local: np.ndarray, parity: np.ndarray) -> MatchingData:
+    """``matching_graph`` with the path weights of the reference's default rustworkx backend: the sum
+    of ``int(weight)`` along the float-shortest path (see ``_int_lengths``); the nearer connector is
+    chosen on these int lengths (``mwpm/matching.py:149-150``, ties -> low).  Restated from the code:
+    rustworkx is not installable here, so this is unpinned against a live run (with float weights the
+    shortest path is unique almost surely, so its Dijkstra's tie-breaking does not enter)."""
+    odd = np.nonzero(parity)[0].astype(np.int32)
+    K = len(odd)
+    pair_len = np.empty(K * (K - 1) // 2, np.float64)
+    pos = 0
+    for a in range(K - 1):
+        dist, pred, pred_q = _dijkstra(ct, w_local, [(int(odd[a]), 0.0, -1)], False)
+        il = _int_lengths(dist, pred, pred_q, w_local)
+        pair_len[pos : pos + K - 1 - a] = il[odd[a + 1 :]]
+        pos += K - 1 - a
+    bnd_len = np.empty(0, np.float64)
+    bnd_side = np.empty(0, np.uint8)
+    if ct.has_boundary and K > 0:
+        out = []
+        for cubes, slots in ((ct.low_seed_cube, ct.low_seed_slot), (ct.high_seed_cube, ct.high_seed_slot)):
+            seeds = [(int(c), float(w_local[ct.slot_qubit[s]]), int(ct.slot_qubit[s])) for c, s in zip(cubes, slots)]
+            dist, pred, pred_q = _dijkstra(ct, w_local, seeds, True)
+            out.append(_int_lengths(dist, pred, pred_q, w_local)[odd])
+        lo, hi = out
+        bnd_side = (hi < lo).astype(np.uint8)
+        bnd_len = np.where(bnd_side == 1, hi, lo).astype(np.float64)
+    return MatchingData(odd, pair_len, bnd_len, bnd_side)
+
+
 def _walk(pred, pred_q, target: int):
     """Qubits crossed on the tree path ending at ``target`` (any order)."""
     out = []

@@ -302,3 +302,36 @@ def test_device_tensors_are_zero_copy_views():
     assert np.array_equal(dv["primal"]["bnd_len"].cpu().numpy(), cb.bnd_len)
     # a device-side reduction without leaving the GPU
     assert float(dv["primal"]["pair_len"].min()) == float(cb.pair_len.min())
+
+
+@pytest.mark.parametrize("d,ec,b,delta,p_swap", [(5, "primal", "open", 0.1, 0.25), (6, "both", "periodic", 0.09, 0.0),
+                                                 (11, "primal", "open", 0.09, 0.0), (4, "dual", "toric", 0.12, 0.5)])
+def test_rustworkx_compat_int_lengths(d, ec, b, delta, p_swap):
+    """FPB_LENGTH_RX_TRUNC: the sum of int(weight) along the float-shortest path
+    (codes/graphs/stabilizer_graph.py:486-500), against the restatement; sides chosen on the int lengths."""
+    lat = build_lattice(d, ec, b)
+    wo = {"method": "blueprint", "delta": delta}
+    eng = _engine(lat, delta, p_swap, wo, mode="fresh", lengths="rustworkx")
+    flt = _engine(lat, delta, p_swap, wo, mode="fresh")
+    n = 3 if d > 6 else 6
+    batch = eng.run_rng(4, 0, n, want_draws=True)
+    ref = flt.run_rng(4, 0, n)
+    for t in range(n):
+        res = restate.trial_from_draws(lat, batch.state[t], batch.x[t], delta, wo, want_graph=False)
+        for e in lat.ec:
+            ct = lat.complexes[e]
+            m = res.per_complex[e]
+            g = restate.matching_graph_rx(ct, m["weights"], m["parity"])
+            cb = batch.complexes[e]
+            assert np.array_equal(cb.odd(t), g.odd)
+            assert np.array_equal(cb.pairs(t), g.pair_len)  # integers: exact
+            assert np.all(cb.pairs(t) <= ref.complexes[e].pairs(t) + 1e-9)  # truncation only lowers a path's weight
+            if ct.has_boundary:
+                bl, bs = cb.boundary(t)
+                assert np.array_equal(bl, g.bnd_len) and np.array_equal(bs, g.bnd_side)
+    # integer weights: both notions of length coincide
+    wi = {"method": "blueprint", "delta": delta, "integer": True, "multiplier": 10}
+    a = _engine(lat, delta, p_swap, wi, mode="fresh", lengths="rustworkx").run_rng(4, 0, 2)
+    c = _engine(lat, delta, p_swap, wi, mode="fresh").run_rng(4, 0, 2)
+    for e in lat.ec:
+        assert np.array_equal(a.complexes[e].pair_len, c.complexes[e].pair_len)
