@@ -77,6 +77,7 @@ struct ComplexHost {
   int d_off[12], s_off[12];
   DevBuf<uint32_t> parity;
   DevBuf<int> odd_count, odd_fixed, odd_ids;
+  DevBuf<uint16_t> word_rank;
   DevBuf<long long> odd_off, pair_off;
   DevBuf<double> pair_len, bnd_len;
   DevBuf<uint8_t> bnd_side;
@@ -156,7 +157,7 @@ ComplexDev make_dev(const ComplexHost& c) {
   d.low_cube = c.low_cube; d.low_slot = c.low_slot; d.high_cube = c.high_cube; d.high_slot = c.high_slot;
   memcpy(d.d_off, c.d_off, sizeof d.d_off);
   memcpy(d.s_off, c.s_off, sizeof d.s_off);
-  d.parity = c.parity.p; d.odd_count = c.odd_count.p; d.odd_fixed = c.odd_fixed.p;
+  d.parity = c.parity.p; d.odd_count = c.odd_count.p; d.odd_fixed = c.odd_fixed.p; d.word_rank = c.word_rank.p;
   d.odd_off = c.odd_off.p; d.pair_off = c.pair_off.p; d.odd_ids = c.odd_ids.p;
   d.pair_len = c.pair_len.p; d.bnd_len = c.bnd_len.p; d.bnd_side = c.bnd_side.p;
   return d;
@@ -409,6 +410,7 @@ int ensure_batch(fpb_handle* h, long long T) {
     if ((rc = cx.parity.ensure((size_t)T * cx.par_words))) return rc;
     if ((rc = cx.odd_count.ensure((size_t)T))) return rc;
     if ((rc = cx.odd_fixed.ensure((size_t)T * cx.S))) return rc;
+    if (h->use_table && getenv("FPB_GATHER_ROWS") && (rc = cx.word_rank.ensure((size_t)T * cx.par_words))) return rc;
     if ((rc = cx.odd_off.ensure((size_t)T + 1))) return rc;
     if ((rc = cx.pair_off.ensure((size_t)T + 1))) return rc;
   }
@@ -622,10 +624,28 @@ int run_pipeline(fpb_handle* h, long long T, int stage, int source, uint64_t see
       for (int c = 0; c < h->ncx; ++c) {
         ComplexHost& cx = h->cx[c];
         if (cx.total_odd == 0) continue;
-        // rows = odd cubes: no CTA beyond the largest odd count of the batch
-        dim3 grid((unsigned)T, (unsigned)((cx.max_odd + GATHER_ROWS - 1) / GATHER_ROWS));
-        k_gather<<<grid, GATHER_ROWS * 32, (size_t)cx.S * 2, st>>>(make_dev(cx), cx.tab_pair.p,
-                                                                  cx.n_low > 0 ? cx.tab_bnd.p : nullptr, cx.tab_side.p);
+        // FPB_GATHER_ROWS=1: the table-driven gather.  It reads the table once per batch (DRAM reads 2.5 GB ->
+        // 0.3 GB per 256 d=21 trials) but writes short unaligned segments: 2.76 TB/s against 3.4-3.7 TB/s of
+        // the trial-driven kernel below (profiles/r2_gather_experiment.md), so it stays opt-in.
+        static const bool by_rows = getenv("FPB_GATHER_ROWS") != nullptr;
+        if (by_rows && T >= 8) {
+          // table-driven: every table row is staged once per batch (k_gather_rows)
+          const size_t smem = (size_t)cx.S * sizeof(double);
+          CK(cudaFuncSetAttribute(k_gather_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          // one CTA per table row serves all trials (8 warps = 8 trials in flight), so that staging the row
+          // (<= 8 S bytes) is paid once per batch; FPB_GATHER_GROUPS splits the trials over more CTAs per row
+          static const int env_groups = getenv("FPB_GATHER_GROUPS") ? atoi(getenv("FPB_GATHER_GROUPS")) : 0;
+          int groups = env_groups > 0 ? env_groups : (int)(T / 512);
+          if (groups < 1) groups = 1;
+          if (groups > 16) groups = 16;
+          k_gather_rows<<<dim3((unsigned)cx.S, (unsigned)groups), 256, smem, st>>>(
+              make_dev(cx), cx.tab_pair.p, cx.n_low > 0 ? cx.tab_bnd.p : nullptr, cx.tab_side.p, (int)T);
+        } else {
+          // rows = odd cubes: no CTA beyond the largest odd count of the batch
+          dim3 grid((unsigned)T, (unsigned)((cx.max_odd + GATHER_ROWS - 1) / GATHER_ROWS));
+          k_gather<<<grid, GATHER_ROWS * 32, (size_t)cx.S * 2, st>>>(make_dev(cx), cx.tab_pair.p,
+                                                                    cx.n_low > 0 ? cx.tab_bnd.p : nullptr, cx.tab_side.p);
+        }
         ++launches;
       }
     } else {
@@ -783,7 +803,7 @@ int fpb_destroy(fpb_handle* h) {
   for (auto& cx : h->cx) {
     cudaFree(cx.cube_qubit); cudaFree(cx.ninfo); cudaFree(cx.sbase); cudaFree(cx.slot_qubit);
     cudaFree(cx.low_cube); cudaFree(cx.low_slot); cudaFree(cx.high_cube); cudaFree(cx.high_slot);
-    cx.parity.release(); cx.odd_count.release(); cx.odd_fixed.release(); cx.odd_ids.release();
+    cx.parity.release(); cx.odd_count.release(); cx.odd_fixed.release(); cx.word_rank.release(); cx.odd_ids.release();
     cx.odd_off.release(); cx.pair_off.release(); cx.pair_len.release(); cx.bnd_len.release();
     cx.bnd_side.release(); cx.knn.release(); cx.knn_len.release(); cx.tab_pair.release(); cx.tab_bnd.release(); cx.tab_side.release();
   }

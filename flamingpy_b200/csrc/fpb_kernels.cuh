@@ -40,6 +40,7 @@ struct ComplexDev {
   uint32_t* parity;      // [T][par_words]
   int* odd_count;        // [T]
   int* odd_fixed;        // [T][S]
+  uint16_t* word_rank;   // [T][par_words] odd cubes before each 32-cube parity word (static-weight gather), or nullptr
   long long* odd_off;    // [T+1]
   long long* pair_off;   // [T+1]
   int* odd_ids;          // [total_odd]
@@ -303,6 +304,8 @@ __global__ void __launch_bounds__(256) k_syndrome(SyndromeParams p) {
     int before = base_s;
     for (int w = 0; w < wid; ++w) before += warp_cnt[w];
     if (par) c.odd_fixed[(long long)t * c.S + before + __popc(m & ((1u << lane) - 1u))] = s;
+    if (c.word_rank && lane == 0 && s0 + wid * 32 < c.S)
+      c.word_rank[(long long)t * c.par_words + ((s0 + wid * 32) >> 5)] = (uint16_t)before;
     __syncthreads();
     if (threadIdx.x == 0) {
       int tot = 0;
@@ -2024,6 +2027,69 @@ __global__ void __launch_bounds__(GATHER_ROWS * 32) k_gather(ComplexDev c, const
     const long long o = c.odd_off[t] + a;
     c.bnd_len[o] = tab_bnd[src];
     c.bnd_side[o] = tab_side[src];
+  }
+}
+
+// k_gather_rows: the same gather, driven by the table instead of by the trials.  One CTA stages row `src`
+// of the all-pairs table in shared memory once and serves every trial of its group in which cube `src`
+// is odd, one warp per trial.  The warp walks the trial's parity words from `src` on: lane l of word w
+// stands for cube 32 w + l, and if that cube is odd its length row_s[cube - src - 1] goes to position
+// word_rank[w] + popc(word below l) of the trial's row - consecutive shared-memory reads, compacted
+// coalesced writes, and no index loads at all.  The 8-byte table entries are read from HBM once per
+// batch instead of once per trial (k_gather: one 32-byte sector per ~2 useful entries), so the DRAM
+// traffic is the written lengths alone.
+constexpr int GATHER_MAXK = 16;  // 32 parity words per register: S <= 16 * 32 * 32 = 16384 cubes
+
+__global__ void __launch_bounds__(256) k_gather_rows(ComplexDev c, const double* tab_pair, const double* tab_bnd,
+                                                     const uint8_t* tab_side, int T) {
+  extern __shared__ double row_s[];  // entries (src, src + 1 ..)
+  const int src = blockIdx.x;
+  const long long S = c.S;
+  const int n = (int)(S - src - 1);
+  const double* trow = tab_pair + ((long long)src * S - (long long)src * (src + 1) / 2);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) row_s[i] = trow[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int w0 = src >> 5, pwn = c.par_words;
+  const uint32_t below = (1u << (src & 31)) - 1u, lt = (1u << lane) - 1u;
+  const double* rs = row_s - src - 1;  // rs[cube] for cube > src
+  for (int t = blockIdx.y * nwarp + warp; t < T; t += gridDim.y * nwarp) {
+    const uint32_t* pw = c.parity + (long long)t * pwn;
+    const uint16_t* wr = c.word_rank + (long long)t * pwn;
+    const uint32_t word0 = pw[w0];
+    if (!((word0 >> (src & 31)) & 1u)) continue;  // cube `src` is even in this trial (uniform over the warp)
+    const long long a = wr[w0] + __popc(word0 & below);
+    const long long K = c.odd_count[t];
+    if (tab_bnd && lane == 0) {
+      const long long o = c.odd_off[t] + a;
+      c.bnd_len[o] = tab_bnd[src];
+      c.bnd_side[o] = tab_side[src];
+    }
+    double* orow = c.pair_len + c.pair_off[t] + (a * K - a * (a + 1) / 2 - a - 1);  // indexed by position b
+    // the trial's parity words and word ranks from w0 on, 32 words per register: one round trip to L2
+    uint32_t pwr[GATHER_MAXK];
+    uint32_t wrr[GATHER_MAXK];
+    const int k0 = w0 >> 5;
+#pragma unroll
+    for (int k = 0; k < GATHER_MAXK; ++k) {
+      const int idx = (k << 5) + lane;
+      const bool in = k >= k0 && idx < pwn;
+      pwr[k] = in ? pw[idx] : 0u;
+      wrr[k] = in ? (uint32_t)wr[idx] : 0u;
+    }
+    const uint32_t after = ~(below | (1u << (src & 31)));  // word w0: cubes after src only
+#pragma unroll
+    for (int k = 0; k < GATHER_MAXK; ++k) {
+      if (k < k0 || (k << 5) >= pwn) continue;  // uniform
+      const int i0 = k == k0 ? (w0 & 31) : 0;
+      const int i1 = min(32, pwn - (k << 5));
+      for (int i = i0; i < i1; ++i) {
+        const uint32_t word = __shfl_sync(0xffffffffu, pwr[k], i);
+        const uint32_t base = __shfl_sync(0xffffffffu, wrr[k], i);
+        const int w = (k << 5) + i;
+        if (((w == w0 ? word & after : word) >> lane) & 1u) orow[base + __popc(word & lt)] = rs[(w << 5) + lane];
+      }
+    }
   }
 }
 
