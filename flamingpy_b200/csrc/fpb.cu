@@ -12,12 +12,20 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX: named ranges per pipeline stage for nsys / ncu --nvtx
+
 #include "fpb_kernels.cuh"
 #include "fpb_macro.cuh"
 
 using namespace fpb;
 
 namespace {
+
+// one NVTX range per pipeline stage (the reference has no tracing at all)
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 thread_local std::string g_err;
 
@@ -504,7 +512,9 @@ int run_pipeline(fpb_handle* h, long long T, int stage, int source, uint64_t see
   for (int c = 0; c < h->ncx; ++c) h->cx[c].total_odd = h->cx[c].total_pairs = 0;
   int launches = 0;
 
+  NvtxRange nvtx_run("fpb:run_pipeline");
   CK(cudaEventRecord(h->ev[0], st));
+  nvtxRangePushA("fpb:gen");
   if (gen) {
     GenParams g;
     g.N = h->N;
@@ -557,7 +567,9 @@ int run_pipeline(fpb_handle* h, long long T, int stage, int source, uint64_t see
     k_macro_gen<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(g, T);
     ++launches;
   }
+  nvtxRangePop();
   CK(cudaEventRecord(h->ev[1], st));
+  nvtxRangePushA("fpb:noise+weights");
   if (macro) {
     MacroParams mp;
     mp.N = h->N; mp.partner = h->macro_partner; mp.sign = h->macro_sign;
@@ -601,8 +613,10 @@ int run_pipeline(fpb_handle* h, long long T, int stage, int source, uint64_t see
     k_noise<<<(unsigned)(bpt * T), 256, 0, st>>>(p);
     ++launches;
   }
+  nvtxRangePop();
   CK(cudaEventRecord(h->ev[2], st));
   if (stage >= FPB_STAGE_SYNDROME) {
+    NvtxRange nvtx_s("fpb:syndrome");
     SyndromeParams sp;
     sp.n_complex = h->ncx; sp.bit_words = h->bit_words; sp.bits = h->bits.p;
     for (int c = 0; c < h->ncx; ++c) sp.cx[c] = make_dev(h->cx[c]);
@@ -613,6 +627,7 @@ int run_pipeline(fpb_handle* h, long long T, int stage, int source, uint64_t see
   }
   CK(cudaEventRecord(h->ev[3], st));
   if (stage >= FPB_STAGE_GRAPH) {
+    NvtxRange nvtx_g("fpb:matching_graph");
     if (h->warps == 0) return fail(FPB_ERR_UNSUPPORTED, "shortest-path kernel not configured for this lattice");
     if (h->use_table) {
       // static weights: gather the matching graph from the all-pairs table

@@ -94,6 +94,20 @@ def test_both_complexes_full_size_against_c_oracle():
     assert batch.complexes["primal"].pair_len.size > 200000
 
 
+def test_headline_workload_compat_chain_full_size_against_c_oracle():
+    """The bench's default workload as it runs there: d=13 periodic, ec=both, compat chain (noisy / silent
+    trials alternate), device RNG - every output of four consecutive trials against the C oracle."""
+    lat = build_lattice(13, "both", "periodic")
+    delta = 0.09
+    wo = {"method": "blueprint", "delta": delta}
+    eng = _engine(lat, delta, 0, wo, mode="compat")
+    batch = eng.run_rng(20261019, 2048, 4, want_draws=True)
+    ref = c_oracle.run(lat, delta, 0, wo, batch.x, batch.state)
+    _same_as_oracle(lat, batch, ref)
+    k = batch.complexes["primal"].odd_count
+    assert k[0] > 400 and k[1] == 0 and k[2] > 400 and k[3] == 0
+
+
 def test_config4_lattice_d21_all_p():
     """d=21 open, p_swap=1 (configs[3]): too large for the shared-memory weight copy, so the
     graph stage runs the variant that keeps weights and face tables in global memory."""

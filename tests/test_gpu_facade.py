@@ -45,6 +45,23 @@ def test_apply_noise_and_correct_reproduce_reference_run(name):
         np.testing.assert_allclose(w, g[f"{e}_weights"][t], rtol=1e-9)
 
 
+def test_correct_with_rustworkx_compat_lengths():
+    """decoder_opts["lengths"] = "rustworkx": the matching runs on the int-truncated path weights of the
+    reference's default graphs (stabilizer_graph.py:486-500); with integer weights both notions coincide,
+    so the verdicts must be equal there."""
+    code = SurfaceCode(5, "primal", "open")
+    layer = CVLayer(code, delta=0.1, p_swap=0.2)
+    rng = np.random.default_rng(21)
+    wi = {"method": "blueprint", "delta": 0.1, "integer": True, "multiplier": 100}
+    for _ in range(4):
+        layer.apply_noise(rng)
+        a = correct(code, "MWPM", wi, decoder_opts={"lengths": "rustworkx"})
+        b = correct(code, "MWPM", wi)
+        assert a == b
+        assert isinstance(correct(code, "MWPM", {"method": "blueprint", "delta": 0.1},
+                                  decoder_opts={"backend": "rustworkx", "lengths": "rustworkx"}), bool)
+
+
 def test_weights_options_like_reference():
     """reference tests/decoders/test_decoder.py:75-95"""
     code = SurfaceCode(3, "primal", "open")
