@@ -197,7 +197,7 @@ def correct(code, decoder="MWPM", weight_options=None, sanity_check=False, decod
     return bool(np.all(result))
 
 
-def match_batch(code, eng, batch, backend="native", cands=None, handoff="full", stats=None):
+def match_batch(code, eng, batch, backend="native", cands=None, handoff="full", stats=None, threads=0):
     """Host matching of every trial of ``batch``: (trial, complex, src, dst) int32 arrays of the
     matched queries (dst = -1: to the connector).  ``backend="native"`` solves all trials with the
     C++ matcher (OpenMP over trials); ``cands`` = per-complex candidate lists (``candidates``).
@@ -214,7 +214,8 @@ def match_batch(code, eng, batch, backend="native", cands=None, handoff="full", 
 
             st = {} if stats is not None else None
             t_, s_, d_ = mwpm_native.solve_batch_sparse(eng, ci, cb.odd_count, cb.bnd_len if ct.has_boundary else None,
-                                                        stats=st, knn=cands[ci] if cands is not None else None)
+                                                        stats=st, knn=cands[ci] if cands is not None else None,
+                                                        threads=threads)
             if stats is not None:
                 for k, v in st.items():
                     stats[k] = stats.get(k, 0) + v
@@ -228,7 +229,7 @@ def match_batch(code, eng, batch, backend="native", cands=None, handoff="full", 
 
             cand = cands[ci] if cands is not None else candidates(eng, batch, ci, e)
             t_, s_, d_ = mwpm_native.solve_batch(cb.odd_count, cb.pair_len, cb.bnd_len if ct.has_boundary else None,
-                                                 cand=cand)
+                                                 threads=threads, cand=cand)
             trial.append(t_)
             cx.append(np.full(len(t_), ci, np.int32))
             src.append(s_)

@@ -58,7 +58,7 @@ def trial_range(trials: int, rank: int, size: int):
 
 def ec_monte_carlo(trials, code_instance, noise_instance, decoder, decoder_args, world_comm=None, mpi_rank=0,
                    mpi_size=1, *, seed=None, batch=1024, mode="compat", backend="native", device=None,
-                   return_stats=False, handoff=None):
+                   return_stats=False, handoff=None, match_workers=2):
     """Run ``trials`` Monte-Carlo trials of the complete error-correction procedure and
     return the number of logical errors.
 
@@ -134,7 +134,11 @@ def ec_monte_carlo(trials, code_instance, noise_instance, decoder, decoder_args,
     import threading
 
     starts = list(range(lo, hi, batch))
-    n_eng = min(3, max(1, len(starts)))
+    # `match_workers` host threads match different batches at the same time, each with its share of the
+    # host cores: the serial parts of one batch's matching (hand-over, late pricing rounds, stragglers)
+    # overlap the parallel part of the other's.  One lane (engine + buffers) per batch in flight.
+    match_workers = max(1, min(int(match_workers), len(starts))) if backend == "native" else 1
+    n_eng = min(2 + match_workers, max(1, len(starts)))
     engines = [eng] + [code.engine(n_delta, n_pswap, weight_opts, device=device, mode=mode, lane=i, reserve_sms=rsv)
                        for i in range(1, n_eng)]
     # pinned host buffers, one set per lane, kept on the code object: reused by every batch, every
@@ -188,26 +192,42 @@ def ec_monte_carlo(trials, code_instance, noise_instance, decoder, decoder_args,
                 state["error"] = exc
             free[lane].release()
 
+    from . import mwpm_native
+
+    threads_each = max(1, mwpm_native.default_threads() // match_workers)
+    stats_lock = threading.Lock()
+
+    def match():
+        while True:
+            item = q_graph.get()
+            if item is None:
+                q_graph.put(None)  # pass the end marker on to the other workers
+                return
+            lane, b, cands = item
+            queries = None
+            try:
+                if state["error"] is None:
+                    st = {}
+                    queries = match_batch(code, engines[lane], b, backend=backend, cands=cands, handoff=handoff,
+                                          stats=st, threads=threads_each)
+                    with stats_lock:
+                        for k, v in st.items():
+                            state["match"][k] = state["match"].get(k, 0) + v
+            except BaseException as exc:  # noqa: BLE001
+                state["error"] = exc
+            if queries is None:
+                free[lane].release()
+            else:
+                q_match.put((lane, b, queries))
+
     t_prod = threading.Thread(target=produce)
     t_fin = threading.Thread(target=finish)
-    t_prod.start()
-    t_fin.start()
-    while True:
-        item = q_graph.get()
-        if item is None:
-            break
-        lane, b, cands = item
-        queries = None
-        try:
-            if state["error"] is None:
-                queries = match_batch(code, engines[lane], b, backend=backend, cands=cands, handoff=handoff,
-                                      stats=state["match"])
-        except BaseException as exc:  # noqa: BLE001
-            state["error"] = exc
-        if queries is None:
-            free[lane].release()
-        else:
-            q_match.put((lane, b, queries))
+    t_match = [threading.Thread(target=match) for _ in range(match_workers - 1)]
+    for th in [t_prod, t_fin] + t_match:
+        th.start()
+    match()  # this thread is a matching worker, too
+    for th in t_match:
+        th.join()
     q_match.put(None)
     t_prod.join()
     t_fin.join()

@@ -81,8 +81,9 @@ def main(argv=None):
     a = ap.parse_args(argv)
     rows = sweep([int(v) for v in a.distances.split(",")], [float(v) for v in a.deltas.split(",")], a.trials,
                  a.p_swap, a.boundaries, a.ec, a.mode, a.fname, a.graph_only, batch=a.batch)
-    for r in rows:
-        print(",".join(str(v) for v in r))
+    if _dist_info()[1] == 0:
+        for r in rows:
+            print(",".join(str(v) for v in r))
 
 
 if __name__ == "__main__":

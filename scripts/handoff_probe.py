@@ -15,14 +15,17 @@ ap.add_argument("--delta", type=float, default=0.09)
 ap.add_argument("--trials", type=int, default=4096)
 ap.add_argument("--batch", type=int, default=512)
 ap.add_argument("--mode", default="fresh")
+ap.add_argument("--workers", type=int, nargs="*", default=[1, 2])
 a = ap.parse_args()
 code = SurfaceCode(a.d, a.ec, a.bound)
 noise = CVLayer(code, delta=a.delta, p_swap=0)
 args = {"weight_opts": {"method": "blueprint", "delta": a.delta}}
-for handoff in ("full", "sparse", "full", "sparse"):
-    mwpm_native.stats(reset=True)
-    t0 = time.perf_counter()
-    f, st = ec_monte_carlo(a.trials, code, noise, "MWPM", args, seed=5, batch=a.batch, mode=a.mode, handoff=handoff,
-                           return_stats=True)
-    dt = time.perf_counter() - t0
-    print(f"d={a.d} {a.ec} {a.bound} {handoff:6s}: {a.trials/dt:9.0f} trials/s  failures {f}  {st}  {mwpm_native.stats()}", flush=True)
+ec_monte_carlo(2048, code, noise, "MWPM", args, seed=5, batch=a.batch, mode=a.mode)  # warm-up
+for handoff in ("full", "sparse"):
+    for mw in a.workers:
+        mwpm_native.stats(reset=True)
+        t0 = time.perf_counter()
+        f, st = ec_monte_carlo(a.trials, code, noise, "MWPM", args, seed=5, batch=a.batch, mode=a.mode, handoff=handoff,
+                               return_stats=True, match_workers=mw)
+        dt = time.perf_counter() - t0
+        print(f"d={a.d} {a.ec} {a.bound} {handoff:6s} workers={mw}: {a.trials/dt:9.0f} trials/s  failures {f}  {st}", flush=True)
