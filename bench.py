@@ -444,7 +444,9 @@ def run_gpu_arm(args, cfg, lat):
         noise = CVLayer(code, delta=cfg["delta"], p_swap=cfg["p_swap"])
         dargs = {"weight_opts": cfg["weight_opts"]}
         n_full = args.full_trials * world  # ec_monte_carlo splits the global count over the ranks
-        ec_monte_carlo(min(n_full, 512 * world), code, noise, "MWPM", dargs, seed=SEED, batch=args.full_batch, mode=args.mode)
+        # warm-up: enough batches to create every lane's engine and pinned buffers and to fill the matcher's pools
+        ec_monte_carlo(8 * args.full_batch * world, code, noise, "MWPM", dargs, seed=SEED, batch=args.full_batch,
+                       mode=args.mode)
         barrier()
         t0 = time.perf_counter()
         fails, st_full = ec_monte_carlo(n_full, code, noise, "MWPM", dargs, seed=SEED + 1, batch=args.full_batch,
@@ -458,7 +460,7 @@ def run_gpu_arm(args, cfg, lat):
         e2e_full = {"value": n_full / float(f_t.item()), "unit": "trials/s", "trials": n_full, "failures": int(fails),
                     "api": "simulations.ec_monte_carlo(trials, SurfaceCode, CVLayer, 'MWPM', weight_opts): complete "
                            "error-correction trials incl. host MWPM, correction paths and logical check",
-                    "handoff": st_full["handoff"], "matcher_threads_per_rank": mwpm_native.default_threads(),
+                    "handoff": st_full["handoff"], "host_cores_per_rank": mwpm_native.default_threads(),
                     "batch": args.full_batch}
         code.release_engines()
 

@@ -58,17 +58,21 @@ def trial_range(trials: int, rank: int, size: int):
 
 def ec_monte_carlo(trials, code_instance, noise_instance, decoder, decoder_args, world_comm=None, mpi_rank=0,
                    mpi_size=1, *, seed=None, batch=1024, mode="compat", backend="native", device=None,
-                   return_stats=False, handoff=None, match_workers=2):
+                   return_stats=False, handoff=None, match_workers=None):
     """Run ``trials`` Monte-Carlo trials of the complete error-correction procedure and
     return the number of logical errors.
 
-    ``handoff``: how the matching graphs reach the host matcher.  "full" (default): every length is
-    copied to the host (the contract outputs of ``fpb_fetch``).  "sparse" (native matcher only): the
-    K(K-1)/2 lengths stay in HBM, the matcher receives candidate partners with lengths and prices the
-    complete graph on the device (``fpb_knn_len`` / ``fpb_pairs_at`` / ``fpb_price``) - the same exact
-    optimum for ~7 % of the bytes over the bus.  On one B200 with 16 host cores both are bound by the
-    matcher's stages (d=13 periodic: 8.6 k trials/s full, 7.1 k sparse, whose pricing rounds are
-    batch-synchronous); sparse is for hosts where the copy bandwidth is the scarce resource.
+    ``handoff``: how the matching graphs reach the host matcher.  "full": every length is copied to
+    the host (the contract outputs of ``fpb_fetch``).  "sparse" (native matcher only): the K(K-1)/2
+    lengths stay in HBM, the matcher receives candidate partners with lengths and prices the complete
+    graph on the device (``fpb_knn_len`` / ``fpb_pairs_at`` / ``fpb_price``) - the same exact optimum
+    for ~7 % of the bytes over the bus, and no host pass over the triangle.  Default: "sparse" on
+    lattices without boundary points, "full" otherwise (measured on one B200 + 16 cores, complete EC
+    trials per second: d=13 periodic 9.3 k sparse / 8.8 k full; d=13 open 7.3 k / 8.4 k - the boundary
+    chain and the tight connector pairs cost the sparse path more round trips).
+    ``match_workers``: host threads that match different batches at the same time, each with its
+    share of the cores (default 3 for the sparse hand-off, whose pricing rounds are batch-synchronous,
+    2 for the full one).
 
     Trial split: with ``torch.distributed`` initialised, over its ranks with one ``all_reduce`` of
     the counts (one process per GPU; NCCL).  Otherwise, if an mpi4py-style ``world_comm`` is given
@@ -115,7 +119,10 @@ def ec_monte_carlo(trials, code_instance, noise_instance, decoder, decoder_args,
             pass
     seed = int_time if seed is None else int(seed)
     if handoff is None:
-        handoff = "full"
+        periodic = not any(code_instance.lattice.complexes[e].has_boundary for e in code_instance.ec)
+        handoff = "sparse" if (backend == "native" and periodic) else "full"
+    if match_workers is None:
+        match_workers = 3 if handoff == "sparse" else 2
     if handoff not in ("sparse", "full") or (handoff == "sparse" and backend != "native"):
         raise ValueError("handoff must be 'sparse' (native matcher only) or 'full'")
     code = code_instance
