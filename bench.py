@@ -141,9 +141,9 @@ def paths_kernel_bytes(lat, n_trials, total_odd, total_pairs):
 
 def recorded_traffic(workload, mode, batch):
     """DRAM bytes per k_paths launch from the committed ncu capture, if it was taken on this
-    very configuration (profiles/r1_k_paths_traffic.json); None otherwise."""
+    very configuration (profiles/r2_k_paths_traffic.json); None otherwise."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_k_paths_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2_k_paths_traffic.json")) as f:
             t = json.load(f)
         if t["workload"] == workload and t["mode"] == mode and t["trials_per_gpu_per_step"] == batch:
             return t["traffic_bytes_per_launch"]
