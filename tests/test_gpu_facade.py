@@ -170,6 +170,35 @@ def test_failure_rate_consistent_with_reference(d, b, delta, ps, mode, ref_fail,
     assert abs(z) < 3.29, (errors, n, p1, p2, z)
 
 
+def _live_cases():
+    import json
+
+    path = os.path.join(gu.GOLDEN_DIR, "failure_rates_reference.json")
+    if not os.path.exists(path):
+        return []
+    with open(path) as f:
+        return [(r["noise"], r["distance"], r["boundaries"], r["delta"], r["p_swap"], r["weight_opts"], r["failures"],
+                 r["trials"], r["trials_per_chain"]) for r in json.load(f)]
+
+
+@pytest.mark.parametrize("noise,d,b,delta,ps,wo,ref_fail,ref_n,chain", _live_cases())
+def test_failure_rate_consistent_with_live_reference(noise, d, b, delta, ps, wo, ref_fail, ref_n, chain):
+    """Device-RNG failure rates (compat mode: one reused layer per chain, like each rank of the reference's
+    `ec_monte_carlo`) against rates measured on the live reference itself (oracle/gen_failure_rates_ref.py:
+    CVLayer and CVMacroLayer, networkx backend, 8 chains).  Two-sample binomial z test, gate as above."""
+    from flamingpy_b200.noise import CVMacroLayer
+
+    code = SurfaceCode(d, "primal", b)
+    layer = (CVMacroLayer if noise == "CVMacroLayer" else CVLayer)(code, delta=delta, p_swap=ps)
+    n = 40000 if d == 3 else 8000
+    errors = ec_monte_carlo(n, code, layer, "MWPM", {"weight_opts": wo}, seed=20261020, mode="compat", batch=4000)
+    p1, p2 = errors / n, ref_fail / ref_n
+    pooled = (errors + ref_fail) / (n + ref_n)
+    z = (p1 - p2) / np.sqrt(pooled * (1 - pooled) * (1 / n + 1 / ref_n))
+    print(f"{noise} d={d} ps={ps}: gpu {errors}/{n}={p1:.5f} live reference {ref_fail}/{ref_n}={p2:.5f} z={z:+.2f}")
+    assert abs(z) < 3.29, (errors, n, p1, p2, z)
+
+
 def test_native_matcher_end_to_end_agrees_with_networkx():
     """Same device trials decoded with the native blossom matcher and with networkx: equal
     matching weights imply equal corrections up to ties; with continuous weights (p_swap=0)
