@@ -1859,6 +1859,27 @@ __global__ void k_iota_odd(ComplexDev c) {  // the "every cube is odd" pseudo-tr
   if (blockIdx.x == 0 && threadIdx.x == 0) c.odd_count[0] = c.S;
 }
 
+constexpr int KNN_NONE = 0x7fffffff;
+
+// (length, index) order of the candidate lists: shorter first, ties by the lower index.
+__device__ __forceinline__ bool knn_less(double d, int b, double e, int f) { return d < e || (d == e && b < f); }
+
+// Keeps (d0,b0) <= (d1,b1) <= (d2,b2), the three smallest seen so far.
+__device__ __forceinline__ void knn_insert(double d, int b, double& d0, int& b0, double& d1, int& b1, double& d2,
+                                           int& b2) {
+  if (!knn_less(d, b, d2, b2)) return;
+  if (knn_less(d, b, d1, b1)) {
+    d2 = d1, b2 = b1;
+    if (knn_less(d, b, d0, b0)) {
+      d1 = d0, b1 = b0, d0 = d, b0 = b;
+    } else {
+      d1 = d, b1 = b;
+    }
+  } else {
+    d2 = d, b2 = b;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // k_knn: candidate partners for the host matcher.  One warp per odd cube a of trial t: its row of
 // the reduced complete graph, min(d_ab, b_a + b_b) (decoders/mwpm/matching.py:144-173 folded into
@@ -1881,50 +1902,58 @@ __global__ void k_knn(ComplexDev c, int kn, int row_cap, int* out /* [total_odd]
   const bool bnd = c.n_low > 0;
   const double ba = bnd ? c.bnd_len[ooff + a] : 0.0;
   double rmax = 2.0 * ba;
+  double d0 = FPB_INF, d1 = FPB_INF, d2 = FPB_INF;
+  int b0 = KNN_NONE, b1 = KNN_NONE, b2 = KNN_NONE, mine = 0;
   for (int b = lane; b < K; b += 32) {
     double d = FPB_INF;
     if (b < a) d = pl[(long long)b * K - (long long)b * (b + 1) / 2 + (a - b - 1)];
     else if (b > a) d = pl[(long long)a * K - (long long)a * (a + 1) / 2 + (b - a - 1)];
     if (bnd && b != a) d = fmin(d, ba + c.bnd_len[ooff + b]);
     row[b] = d;
-    if (b != a) rmax = fmax(rmax, d);
+    if (b != a) {
+      rmax = fmax(rmax, d);
+      ++mine;
+      knn_insert(d, b, d0, b0, d1, b1, d2, b2);
+    }
   }
   if (trial_wmax) {  // non-negative doubles order like their bit patterns
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) rmax = fmax(rmax, __shfl_xor_sync(0xffffffffu, rmax, off));
     if (lane == 0) atomicMax(&trial_wmax[t], (unsigned long long)__double_as_longlong(rmax));
   }
-  __syncwarp();
-  double pd = -1.0;
-  int pb = -1;
+  // Selection: every lane keeps the three smallest (length, index) of its own stride in registers;
+  // a round is then one warp argmin over the lane heads.  A lane whose three are used up rescans
+  // its stride for the next three (rare: twelve winners seldom sit in one residue class mod 32).
+  int used = 0;
   int* o = out + (ooff + a) * kn;
   for (int r = 0; r < kn; ++r) {
-    double bd = FPB_INF;
-    int bb = 0x7fffffff;
-    for (int b = lane; b < K; b += 32) {
-      const double d = row[b];
-      const bool after = d > pd || (d == pd && b > pb);
-      const bool better = d < bd || (d == bd && b < bb);
-      if (b != a && after && better) {
-        bd = d;
-        bb = b;
-      }
-    }
+    double bd = d0;
+    int bb = b0;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
       const double od = __shfl_xor_sync(0xffffffffu, bd, off);
       const int ob = __shfl_xor_sync(0xffffffffu, bb, off);
-      if (od < bd || (od == bd && ob < bb)) {
+      if (knn_less(od, ob, bd, bb)) {
         bd = od;
         bb = ob;
       }
     }
     if (lane == 0) {
-      o[r] = bb == 0x7fffffff ? -1 : bb;
+      o[r] = bb == KNN_NONE ? -1 : bb;
       if (out_len) out_len[(ooff + a) * kn + r] = bd;
     }
-    pd = bd;
-    pb = bb;
+    if (bb != KNN_NONE && bb == b0) {  // this lane's head was taken
+      ++used;
+      const double ld = d0;
+      const int lb = b0;
+      d0 = d1, b0 = b1, d1 = d2, b1 = b2, d2 = FPB_INF, b2 = KNN_NONE;
+      if (b0 == KNN_NONE && used < mine) {
+        for (int b = lane; b < K; b += 32) {
+          const double d = row[b];
+          if (b != a && knn_less(ld, lb, d, b)) knn_insert(d, b, d0, b0, d1, b1, d2, b2);
+        }
+      }
+    }
   }
 }
 
