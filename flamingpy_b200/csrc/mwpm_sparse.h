@@ -12,13 +12,19 @@
 // mwpm.cpp finds, only the choice among ties may differ.
 //
 // The solver is the classical primal-dual formulation with adjacency lists (labels S/T on
-// top-level blossoms, least-slack edge tracking per blossom, dual adjustment by the minimum of
-// the free-vertex / S-S / T-blossom slacks, blossom expansion during and at the end of a stage),
-// one augmentation per stage with every free vertex as a root, on weights -2*len so that vertex
-// duals stay integral and S-S slacks stay even.
+// top-level blossoms, dual adjustment by the minimum of the free-vertex / S-S / T-blossom slacks,
+// blossom expansion when a T-blossom's dual reaches zero), on weights -2*len so that vertex duals
+// stay integral and S-S slacks stay even - organised so that the work follows the part of the
+// forest that changes: every free vertex roots a tree once, an augmentation retires its two trees
+// and keeps the others, dual adjustments are lazy (one running sum), and the next adjustment
+// comes from three heaps instead of a pass over the forest (see SparseBlossom::solve).
 #pragma once
 #include <algorithm>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <functional>
+#include <utility>
 #include <vector>
 
 namespace fpb_sparse {
@@ -35,19 +41,21 @@ class SparseBlossom {
   std::vector<EdgeRec> E;
   std::vector<ll> dual;   // [0, n): vertices (2 x LP dual); [n, 2n): blossoms
   std::vector<int> mate;  // remote endpoint of the matched edge, -1 = free
-  long long n_stages = 0, n_deltas = 0;
+  long long n_stages = 0, n_deltas = 0, n_augmentations = 0;
 
   void reset(int n_) {
     n = n_;
     E.clear();
-    n_stages = n_deltas = 0;
+    n_stages = n_deltas = n_augmentations = 0;
   }
   int n_edges() const { return (int)E.size(); }
   void add_edge(int u, int v, ll w) { E.push_back(EdgeRec{u, v, w}); }
   int endpoint(int p) const { return (p & 1) ? E[p >> 1].v : E[p >> 1].u; }
+  // the dual of vertex x as of now (see solve(): adjustments are applied lazily)
+  ll act(int x) const { return dual[x] + voff[x] * Delta; }
   ll slack(int k) const {
     const EdgeRec& e = E[k];
-    return dual[e.u] + dual[e.v] - 2 * e.w;
+    return act(e.u) + act(e.v) - 2 * e.w;
   }
   int mate_vertex(int v) const { return mate[v] < 0 ? -1 : endpoint(mate[v]); }
 
@@ -124,140 +132,163 @@ class SparseBlossom {
     blossomparent.assign(m, -1);
     blossombase.assign(m, -1);
     for (int v = 0; v < n; ++v) blossombase[v] = v;
-    bestedge.assign(m, -1);
     if ((int)childs.size() < m) {
       childs.resize(m);
       endps.resize(m);
-      bestedges.resize(m);
     }
     for (int b = 0; b < m; ++b) {
       childs[b].clear();
       endps[b].clear();
-      bestedges[b].clear();
     }
-    has_bestedges.assign(m, 0);
     unused.clear();
     for (int b = m - 1; b >= n; --b) unused.push_back(b);
-    bestedgeto.assign(m, -1);
+    voff.assign(n, 0);
+    boff.assign(m, 0);
+    minkey.assign(n, KEY_NONE);
+    Delta = 0;
     stamp.assign(m, 0);
     stamp_t = 0;
+    treeroot.assign(m, -1);
+    dead.assign(n, 0);
+    dead_touched.clear();
   }
 
-  // Stages: label every free vertex S, grow the alternating forest along tight edges, adjust the
-  // duals when it is stuck, until one augmenting path is found; repeat until none exists.
-  // Labels, least-slack records and allowed-edge flags are tracked in lists, so that a dual
-  // adjustment and the clean-up of a stage cost the size of the forest, not of the graph.
+  // One search with persistent trees: every free vertex becomes the root of an alternating tree,
+  // the forest grows along tight edges and the duals are adjusted when it is stuck.  An augmenting
+  // path between two trees retires just those two trees (retire_trees): their vertices become
+  // unlabelled, the rest of the forest stays, so no tree is ever grown twice.
+  //
+  // Dual adjustments are lazy: only the running sum Delta of all adjustments is kept; a vertex under
+  // an S (T) top-level blossom has the dual  dual[x] - Delta  (+ Delta), an S (T) blossom the dual
+  // dual[b] + Delta  (- Delta), and the stored values are converted whenever a label changes
+  // (relabel).  The next adjustment is the smallest key of three heaps, each key being
+  // "value + Delta at insertion", which stays exact for as long as the labels at both ends stay:
+  // slack of an edge from an S-vertex to an unlabelled vertex, half the slack of an edge between two
+  // S-blossoms, dual of a T-blossom.  Entries are never removed when labels change; an entry is
+  // checked when it reaches the top, and whoever changes a label pushes the entries that are exact
+  // from then on (scan of a new S-vertex, retire_trees, expansion of a T-blossom).
   // Returns true when the matching is perfect.
   bool solve() {
     allow.assign(n_edges(), 0);
-    upd_stamp.assign(2 * (size_t)n, 0);
-    upd_t = 0;
     lab_touched.clear();
-    be_touched.clear();
     allow_touched.clear();
-    for (;;) {
-      queue.clear();
-      for (int v = 0; v < n; ++v)
-        if (mate[v] < 0 && label[inblossom[v]] == 0) assign_label(v, 1, -1);
-      if (queue.empty()) break;
-      ++n_stages;
-      bool augmented = false;
+    heap_free.clear();
+    heap_ss.clear();
+    heap_t.clear();
+    queue.clear();
+    Delta = 0;
+    std::fill(minkey.begin(), minkey.end(), KEY_NONE);
+    edge_queue.clear();
+    n_free = 0;
+    for (int v = 0; v < n; ++v)
+      if (mate[v] < 0 && label[inblossom[v]] == 0) {
+        assign_label(v, 1, -1);
+        ++n_free;
+      }
+    if (n_free) ++n_stages;
+    while (n_free > 0) {
       for (;;) {
-        while (!queue.empty() && !augmented) {
-          const int v = queue.back();
-          queue.pop_back();
-          for (int ai = adj_off[v]; ai < adj_off[v + 1]; ++ai) {
-            const AdjRec& ar = adj[ai];  // the neighbour and the weight travel with the adjacency entry
-            const int p = ar.p, k = p >> 1, w = ar.w;
-            if (inblossom[v] == inblossom[w]) continue;
-            ll kslack = 0;
-            if (!allow[k]) {
-              kslack = dual[v] + dual[w] - 2 * ar.wt;
-              if (kslack <= 0) set_allow(k);
-            }
-            if (allow[k]) {
-              if (label[inblossom[w]] == 0) {
-                assign_label(w, 2, p ^ 1);
-              } else if (label[inblossom[w]] == 1) {
-                const int base = scan_blossom(v, w);
-                if (base >= 0) {
-                  add_blossom(base, k);
-                } else {
-                  augment_matching(k);
-                  augmented = true;
-                  break;
-                }
-              } else if (label[w] == 0) {
-                set_label(w, 2);
-                labelend[w] = p ^ 1;
-              }
-            } else if (label[inblossom[w]] == 1) {
-              const int b = inblossom[v];
-              if (bestedge[b] < 0 || kslack < slack(bestedge[b])) set_bestedge(b, k);
-            } else if (label[w] == 0) {
-              if (bestedge[w] < 0 || kslack < slack(bestedge[w])) set_bestedge(w, k);
-            }
-          }
+        if (!edge_queue.empty()) {  // single edges that became tight
+          const int v = edge_queue.back().first, k = edge_queue.back().second;
+          edge_queue.pop_back();
+          if (label[inblossom[v]] == 1) scan_edge(v, E[k].u == v ? 2 * k + 1 : 2 * k, E[k].u == v ? E[k].v : E[k].u, E[k].w);
+#ifdef FPB_MWPM_CHECK
+          check_forest("after edge event");
+#endif
+          continue;
         }
-        if (augmented) break;
-        int deltatype = -1, deltaedge = -1, deltablossom = -1;
-        ll delta = 0;
-        for (size_t q = 0; q < be_touched.size(); ++q) {
-          const int i = be_touched[q], k = bestedge[i];
-          if (k < 0) continue;
-          if (i < n && label[inblossom[i]] == 0) {
-            const ll d = slack(k);
-            if (deltatype < 0 || d < delta) {
-              delta = d; deltatype = 2; deltaedge = k;
-            }
-          } else if (blossomparent[i] < 0 && label[i] == 1) {
-            const ll d = slack(k) / 2;
-            if (deltatype < 0 || d < delta) {
-              delta = d; deltatype = 3; deltaedge = k;
-            }
-          }
-        }
-        for (size_t q = 0; q < lab_touched.size(); ++q) {
-          const int b = lab_touched[q];
-          if (b >= n && blossombase[b] >= 0 && blossomparent[b] < 0 && label[b] == 2 && (deltatype < 0 || dual[b] < delta)) {
-            delta = dual[b]; deltatype = 4; deltablossom = b;
-          }
-        }
-        if (deltatype < 0) break;  // the candidate graph has no perfect matching
-        ++n_deltas;
-        ++upd_t;
-        for (size_t q = 0; q < lab_touched.size(); ++q) {
-          const int i = lab_touched[q];
-          if (blossomparent[i] >= 0 || (i >= n && blossombase[i] < 0)) continue;  // not top-level
-          const int l = label[i];
-          if ((l != 1 && l != 2) || upd_stamp[i] == upd_t) continue;
-          upd_stamp[i] = upd_t;
-          const ll dv = l == 1 ? -delta : delta;
-          leaves(i, [&](int x) { dual[x] += dv; });
-          if (i >= n) dual[i] -= dv;
-        }
-        if (deltatype == 2) {
-          set_allow(deltaedge);
-          int i = E[deltaedge].u;
-          if (label[inblossom[i]] == 0) i = E[deltaedge].v;
-          queue.push_back(i);
-        } else if (deltatype == 3) {
-          set_allow(deltaedge);
-          queue.push_back(E[deltaedge].u);
-        } else {
-          expand_blossom(deltablossom, false);
+        if (queue.empty()) break;
+        const int v = queue.back();  // a new S-vertex: all its edges
+        queue.pop_back();
+        if (label[inblossom[v]] != 1) continue;  // its tree was retired since it was queued
+        for (int ai = adj_off[v]; ai < adj_off[v + 1]; ++ai) {
+          const AdjRec& ar = adj[ai];  // the neighbour and the weight travel with the adjacency entry
+          const bool retired_v = scan_edge(v, ar.p, ar.w, ar.wt);
+#ifdef FPB_MWPM_CHECK
+          check_forest("after scan_edge");
+#endif
+          if (retired_v) break;  // v is unlabelled now
         }
       }
-      if (augmented) {
-        const size_t n_lab = lab_touched.size();  // expansions at the end of a stage add no labels
-        for (size_t q = 0; q < n_lab; ++q) {
-          const int b = lab_touched[q];
-          if (b >= n && blossomparent[b] < 0 && blossombase[b] >= 0 && label[b] == 1 && dual[b] == 0) expand_blossom(b, true);
-        }
+      if (n_free <= 0) break;
+      // the next event: the smallest exact key of the three heaps
+      int deltatype = -1;
+      ll key = 0;
+      while (!heap_free.empty()) {
+        const int k = heap_free.front().second;
+        const int lu = label[inblossom[E[k].u]], lv = label[inblossom[E[k].v]];
+        const ll kk = heap_free.front().first;
+        if (((lu == 1 && lv == 0) || (lu == 0 && lv == 1)) && slack(k) + Delta == kk) break;
+        heap_pop(heap_free);
+        // a stale entry may have kept better-looking edges of its unlabelled end out of the heap
+        if (lu == 0 && minkey[E[k].u] == kk) push_free_edges(E[k].u, false);
+        if (lv == 0 && minkey[E[k].v] == kk) push_free_edges(E[k].v, false);
       }
-      end_stage();
-      if (!augmented) break;
+      if (!edge_queue.empty()) continue;  // rebuilding a stale entry found edges that are tight already
+      if (!heap_free.empty()) {
+        deltatype = 2;
+        key = heap_free.front().first;
+      }
+      while (!heap_ss.empty()) {
+        const int k = heap_ss.front().second;
+        const int bu = inblossom[E[k].u], bv = inblossom[E[k].v];
+        if (bu != bv && label[bu] == 1 && label[bv] == 1 && slack(k) / 2 + Delta == heap_ss.front().first) break;
+        heap_pop(heap_ss);
+      }
+      if (!heap_ss.empty() && (deltatype < 0 || heap_ss.front().first < key)) {
+        deltatype = 3;
+        key = heap_ss.front().first;
+      }
+      while (!heap_t.empty()) {
+        const int b = heap_t.front().second;
+        if (blossomparent[b] < 0 && blossombase[b] >= 0 && label[b] == 2 && dual[b] == heap_t.front().first) break;
+        heap_pop(heap_t);
+      }
+      if (!heap_t.empty() && (deltatype < 0 || heap_t.front().first < key)) {
+        deltatype = 4;
+        key = heap_t.front().first;
+      }
+      if (deltatype < 0) break;  // the candidate graph has no perfect matching
+      ++n_deltas;
+#ifdef FPB_MWPM_CHECK
+      if (key < Delta) check_failed("event key below Delta", "adjustment", deltatype, 0, key);
+#endif
+      if (key > Delta) Delta = key;
+#ifdef FPB_MWPM_CHECK
+      check_duals("after adjustment");
+#endif
+      if (deltatype == 2) {
+        const int k = heap_free.front().second;
+        heap_pop(heap_free);
+        edge_queue.push_back(std::make_pair(label[inblossom[E[k].u]] == 1 ? E[k].u : E[k].v, k));
+      } else if (deltatype == 3) {
+        const int k = heap_ss.front().second;
+        heap_pop(heap_ss);
+        edge_queue.push_back(std::make_pair(E[k].u, k));
+      } else {
+        const int b = heap_t.front().second;
+        heap_pop(heap_t);
+        expand_blossom(b, false);
+      }
     }
+    // back to plain duals, then what the end of a stage does: S-blossoms with zero dual are expanded
+    for (int x = 0; x < n; ++x) {
+      dual[x] += voff[x] * Delta;
+      voff[x] = 0;
+    }
+    for (int b = n; b < 2 * n; ++b) {
+      dual[b] += boff[b] * Delta;
+      boff[b] = 0;
+    }
+    Delta = 0;
+    {
+      const size_t n_lab = lab_touched.size();  // expansions at the end add no labels
+      for (size_t q = 0; q < n_lab; ++q) {
+        const int b = lab_touched[q];
+        if (b >= n && blossomparent[b] < 0 && blossombase[b] >= 0 && label[b] == 1 && dual[b] == 0) expand_blossom(b, true);
+      }
+    }
+    end_stage();
     for (int v = 0; v < n; ++v)
       if (mate[v] < 0) return false;
     return true;
@@ -285,14 +316,34 @@ class SparseBlossom {
   };
   std::vector<int> adj_off, fill_tmp;
   std::vector<AdjRec> adj;
-  std::vector<int> label, labelend, inblossom, blossomparent, blossombase, bestedge;
-  std::vector<std::vector<int>> childs, endps, bestedges;
-  std::vector<char> has_bestedges, allow;
-  std::vector<int> unused, queue, bestedgeto, touched, stamp;
+  std::vector<int> label, labelend, inblossom, blossomparent, blossombase;
+  std::vector<std::vector<int>> childs, endps;
+  std::vector<char> allow;
+  std::vector<int> unused, queue, stamp;
+  std::vector<std::pair<int, int>> edge_queue;  // (S-vertex, edge) pairs to look at
+  int n_free = 0;
   int stamp_t = 0;
 
-  std::vector<int> lab_touched, be_touched, allow_touched, upd_stamp;
-  int upd_t = 0;
+  // lazy dual adjustments (see solve()): sign of Delta in the dual of a vertex / of a blossom
+  ll Delta = 0;
+  std::vector<signed char> voff, boff;
+  typedef std::pair<ll, int> HeapRec;  // (value + Delta at insertion, edge or blossom)
+  std::vector<HeapRec> heap_free, heap_ss, heap_t;
+  static constexpr ll KEY_NONE = INT64_MAX;
+  std::vector<ll> minkey;  // per unlabelled vertex: key of its entry in heap_free
+  static void heap_push(std::vector<HeapRec>& h, ll key, int id) {
+    h.push_back(HeapRec(key, id));
+    std::push_heap(h.begin(), h.end(), std::greater<HeapRec>());
+  }
+  static void heap_pop(std::vector<HeapRec>& h) {
+    std::pop_heap(h.begin(), h.end(), std::greater<HeapRec>());
+    h.pop_back();
+  }
+
+  std::vector<int> lab_touched, allow_touched;
+  std::vector<int> treeroot;  // per labelled top-level blossom: the root vertex of its tree
+  std::vector<char> dead;     // per root vertex: its tree was retired
+  std::vector<int> dead_touched, retired, to_expand;
 
   static int wrap(int j, int len) { return j < 0 ? j + len : j; }
 
@@ -301,10 +352,6 @@ class SparseBlossom {
     lab_touched.push_back(i);
     label[i] = t;
   }
-  void set_bestedge(int i, int k) {
-    if (bestedge[i] < 0) be_touched.push_back(i);
-    bestedge[i] = k;
-  }
   void set_allow(int k) {
     if (!allow[k]) {
       allow[k] = 1;
@@ -312,19 +359,130 @@ class SparseBlossom {
     }
   }
   void end_stage() {
+    for (size_t q = 0; q < lab_touched.size(); ++q) label[lab_touched[q]] = 0;
+    for (size_t q = 0; q < allow_touched.size(); ++q) allow[allow_touched[q]] = 0;
+    for (size_t q = 0; q < dead_touched.size(); ++q) dead[dead_touched[q]] = 0;
+    lab_touched.clear();
+    allow_touched.clear();
+    dead_touched.clear();
+  }
+
+  // The stored duals of top-level blossom b follow its label: t = 0 unlabelled, 1 = S, 2 = T.
+  void relabel(int b, int t) {
+    const int sv = t == 1 ? -1 : t == 2 ? 1 : 0;
+    leaves(b, [&](int x) {
+      dual[x] += (voff[x] - sv) * Delta;
+      voff[x] = (signed char)sv;
+    });
+    if (b >= n) {
+      dual[b] += (boff[b] + sv) * Delta;
+      boff[b] = (signed char)-sv;
+    }
+  }
+
+  // One edge (v, w) seen from the S-vertex v; p is the endpoint number at w.  Returns true when it
+  // closed an augmenting path (v's tree is retired then).
+  bool scan_edge(int v, int p, int w, ll wt) {
+    const int k = p >> 1;
+    if (inblossom[v] == inblossom[w]) return false;
+    ll kslack = 0;
+    if (!allow[k]) {
+      kslack = act(v) + act(w) - 2 * wt;
+      if (kslack <= 0) set_allow(k);
+    }
+    const int lw = label[inblossom[w]];
+    if (allow[k]) {
+      if (lw == 0) {
+        assign_label(w, 2, p ^ 1);
+      } else if (lw == 1) {
+        const int base = scan_blossom(v, w);
+        if (base >= 0) {
+          add_blossom(base, k);
+        } else {
+          const int r1 = treeroot[inblossom[v]], r2 = treeroot[inblossom[w]];
+          augment_matching(k);
+          retire_trees(r1, r2);
+          ++n_augmentations;
+          n_free -= 2;
+          return true;
+        }
+      } else if (label[w] == 0) {
+        set_label(w, 2);
+        labelend[w] = p ^ 1;
+      }
+    } else if (lw == 1) {
+      heap_push(heap_ss, kslack / 2 + Delta, k);
+    } else if (lw == 0 && kslack + Delta < minkey[w]) {  // only w's best edge needs an entry
+      minkey[w] = kslack + Delta;
+      heap_push(heap_free, kslack + Delta, k);
+    }
+    return false;
+  }
+
+  // The two trees rooted at the (just matched) vertices r1 and r2 leave the forest.  What the end
+  // of a stage does for the whole forest is done for their members only: labels are dropped, the
+  // duals become plain numbers again, S-blossoms with zero dual are expanded.  Then every edge from
+  // a retired vertex to a vertex that is still S is looked at again: a tight one re-queues the
+  // S-vertex (it will pull the retired vertex into its tree), the others enter the heap of
+  // S-to-unlabelled edges.  Allowed-edge flags of retired vertices are dropped, since such an edge
+  // may lose its tightness once one end is labelled again.  The list of labelled entries is
+  // compacted on the way.
+  void retire_trees(int r1, int r2) {
+    dead[r1] = dead[r2] = 1;
+    dead_touched.push_back(r1);
+    dead_touched.push_back(r2);
+    retired.clear();
+    to_expand.clear();
+    size_t keep = 0;
     for (size_t q = 0; q < lab_touched.size(); ++q) {
       const int i = lab_touched[q];
+      if (label[i] == 0) continue;
+      if (i >= n && blossombase[i] < 0) {  // a blossom number that was freed
+        label[i] = 0;
+        continue;
+      }
+      int top = i < n ? inblossom[i] : i;
+      while (blossomparent[top] >= 0) top = blossomparent[top];
+      if (top == i ? !dead[treeroot[i]] : (label[top] != 0 && !dead[treeroot[top]])) {
+        lab_touched[keep++] = i;
+        continue;
+      }
+      if (top == i) {
+        relabel(i, 0);
+        leaves(i, [&](int x) { retired.push_back(x); });
+        if (i >= n && label[i] == 1 && dual[i] == 0) to_expand.push_back(i);
+      }
       label[i] = 0;
-      if (i >= n) {
-        has_bestedges[i] = 0;
-        bestedges[i].clear();
+    }
+    lab_touched.resize(keep);
+    for (size_t q = 0; q < retired.size(); ++q) label[retired[q]] = 0;
+    for (size_t q = 0; q < to_expand.size(); ++q) expand_blossom(to_expand[q], true);
+    for (size_t q = 0; q < retired.size(); ++q) push_free_edges(retired[q], true);
+  }
+
+  // Edges from the unlabelled vertex w to S-vertices: a tight one is queued (its S-end will pull w
+  // into a tree), and the one with the least slack enters the heap of S-to-unlabelled edges as w's
+  // entry.  Called whenever w becomes unlabelled, and when w's entry turns out to be stale.
+  void push_free_edges(int w, bool drop_flags) {
+    ll best = KEY_NONE;
+    int bk = -1;
+    for (int ai = adj_off[w]; ai < adj_off[w + 1]; ++ai) {
+      const AdjRec& ar = adj[ai];
+      if (drop_flags) allow[ar.p >> 1] = 0;
+      const int lx = label[inblossom[ar.w]];
+      if (drop_flags && lx == 2 && inblossom[ar.w] != ar.w && label[ar.w] == 2 && endpoint(labelend[ar.w]) == w)
+        label[ar.w] = 0;  // a vertex inside a T-blossom was marked as reached from w
+      if (lx != 1) continue;
+      const ll sl = act(w) + act(ar.w) - 2 * ar.wt;
+      if (sl <= 0) {
+        edge_queue.push_back(std::make_pair(ar.w, ar.p >> 1));
+      } else if (sl + Delta < best) {
+        best = sl + Delta;
+        bk = ar.p >> 1;
       }
     }
-    for (size_t q = 0; q < be_touched.size(); ++q) bestedge[be_touched[q]] = -1;
-    for (size_t q = 0; q < allow_touched.size(); ++q) allow[allow_touched[q]] = 0;
-    lab_touched.clear();
-    be_touched.clear();
-    allow_touched.clear();
+    minkey[w] = best;
+    if (bk >= 0) heap_push(heap_free, best, bk);
   }
 
   template <class F>
@@ -336,15 +494,55 @@ class SparseBlossom {
     }
   }
 
+#ifdef FPB_MWPM_CHECK
+  // Invariant checks of the development build (g++ -DFPB_MWPM_CHECK, see tests/test_mwpm_native.py):
+  // dual feasibility on every edge between different top-level blossoms (S-S slacks even, blossom
+  // duals non-negative), and every labelled blossom hanging, through alternating labels of one
+  // tree, under the free vertex its treeroot names.
+  [[noreturn]] void check_failed(const char* what, const char* where, int a, int b, ll v) {
+    fprintf(stderr, "fpb_mwpm check failed (%s, %s): %d %d %lld, Delta %lld\n", what, where, a, b, v, Delta);
+    abort();
+  }
+  void check_duals(const char* where) {
+    for (int k = 0; k < n_edges(); ++k) {
+      const int bu = inblossom[E[k].u], bv = inblossom[E[k].v];
+      if (bu == bv) continue;
+      const ll sl = slack(k);
+      if (sl < 0 || (label[bu] == 1 && label[bv] == 1 && (sl & 1))) check_failed("edge slack", where, E[k].u, E[k].v, sl);
+    }
+    for (int b = n; b < 2 * n; ++b)
+      if (blossombase[b] >= 0 && dual[b] + boff[b] * Delta < 0) check_failed("blossom dual", where, b, 0, dual[b] + boff[b] * Delta);
+  }
+  void check_forest(const char* where) {
+    for (int v = 0; v < n; ++v) {
+      const int b = inblossom[v];
+      if (label[b] != 1 && label[b] != 2) continue;
+      int x = b, steps = 0;
+      bool bad = false;
+      while (labelend[x] >= 0 && steps++ < 2 * n) {
+        const int nx = inblossom[endpoint(labelend[x])];
+        bad = bad || label[nx] != 3 - label[x] || treeroot[nx] != treeroot[x];
+        x = nx;
+      }
+      int rootv = -1;
+      leaves(x, [&](int y) {
+        if (mate[y] < 0) rootv = y;
+      });
+      if (bad || rootv < 0 || rootv != treeroot[b]) check_failed("tree of a labelled blossom", where, b, rootv, treeroot[b]);
+    }
+  }
+#endif
   void assign_label(int w, int t, int p) {
     const int b = inblossom[w];
     set_label(w, t);
     set_label(b, t);
     labelend[w] = labelend[b] = p;
-    bestedge[w] = bestedge[b] = -1;
+    treeroot[b] = p < 0 ? w : treeroot[inblossom[endpoint(p)]];  // the free vertex this tree grows from
+    relabel(b, t);
     if (t == 1) {
       leaves(b, [&](int v) { queue.push_back(v); });
     } else {
+      if (b >= n) heap_push(heap_t, dual[b], b);  // a T-blossom's stored dual is its key
       const int base = blossombase[b];
       assign_label(endpoint(mate[base]), 1, mate[base] ^ 1);
     }
@@ -410,53 +608,29 @@ class SparseBlossom {
     }
     set_label(b, 1);
     labelend[b] = labelend[bb];
-    dual[b] = 0;
+    treeroot[b] = treeroot[bb];
+    for (size_t i = 0; i < pth.size(); ++i) {  // the children's duals stop moving
+      const int c = pth[i];
+      if (c >= n) {
+        dual[c] += boff[c] * Delta;
+        boff[c] = 0;
+      }
+    }
+    boff[b] = 1;
+    dual[b] = -Delta;  // zero as of now
     leaves(b, [&](int x) {
       if (label[inblossom[x]] == 2) queue.push_back(x);
+      if (voff[x] > 0) {  // was under a T-blossom
+        dual[x] += 2 * Delta;
+        voff[x] = -1;
+      }
       inblossom[x] = b;
     });
-    // least-slack edges from the new blossom to every neighbouring S-blossom
-    touched.clear();
-    auto consider = [&](int e) {
-      int j = E[e].v;
-      if (inblossom[j] == b) j = E[e].u;
-      const int bj = inblossom[j];
-      if (bj != b && label[bj] == 1) {
-        if (bestedgeto[bj] < 0) {
-          bestedgeto[bj] = e;
-          touched.push_back(bj);
-        } else if (slack(e) < slack(bestedgeto[bj])) {
-          bestedgeto[bj] = e;
-        }
-      }
-    };
-    for (size_t i = 0; i < pth.size(); ++i) {
-      const int c = pth[i];
-      if (c >= n && has_bestedges[c]) {
-        for (size_t q = 0; q < bestedges[c].size(); ++q) consider(bestedges[c][q]);
-      } else {
-        leaves(c, [&](int x) {
-          for (int ai = adj_off[x]; ai < adj_off[x + 1]; ++ai) consider(adj[ai].p >> 1);
-        });
-      }
-      if (c >= n) {
-        has_bestedges[c] = 0;
-        bestedges[c].clear();
-      }
-      bestedge[c] = -1;
-    }
-    bestedges[b].clear();
-    bestedge[b] = -1;
-    for (size_t i = 0; i < touched.size(); ++i) {
-      const int e = bestedgeto[touched[i]];
-      bestedgeto[touched[i]] = -1;
-      bestedges[b].push_back(e);
-      if (bestedge[b] < 0 || slack(e) < slack(bestedge[b])) set_bestedge(b, e);
-    }
-    has_bestedges[b] = 1;
   }
 
   void expand_blossom(int b, bool endstage) {
+    const bool t_node = !endstage && label[b] == 2;
+    if (t_node) relabel(b, 0);  // plain duals while the children are sorted out
     for (size_t i = 0; i < childs[b].size(); ++i) {
       const int s = childs[b][i];
       blossomparent[s] = -1;
@@ -468,7 +642,7 @@ class SparseBlossom {
         leaves(s, [&](int x) { inblossom[x] = s; });
       }
     }
-    if (!endstage && label[b] == 2) {
+    if (t_node) {
       // the blossom was a T-node of a tree: relabel the even-length half of its cycle that
       // leads from the entry child to the base, and re-examine the rest
       const int len = (int)childs[b].size();
@@ -495,7 +669,9 @@ class SparseBlossom {
       set_label(endpoint(p ^ 1), 2);
       set_label(bv, 2);
       labelend[endpoint(p ^ 1)] = labelend[bv] = p;
-      bestedge[bv] = -1;
+      treeroot[bv] = treeroot[b];
+      relabel(bv, 2);
+      if (bv >= n) heap_push(heap_t, dual[bv], bv);
       j += jstep;
       while (childs[b][wrap(j, len)] != entrychild) {
         bv = childs[b][wrap(j, len)];
@@ -514,15 +690,15 @@ class SparseBlossom {
         }
         j += jstep;
       }
+      // children that stay unlabelled: their edges to S-vertices count for the next adjustment
+      for (size_t i = 0; i < childs[b].size(); ++i)
+        if (label[childs[b][i]] == 0) leaves(childs[b][i], [&](int x) { push_free_edges(x, false); });
     }
     set_label(b, -1);
     labelend[b] = -1;
     childs[b].clear();
     endps[b].clear();
     blossombase[b] = -1;
-    has_bestedges[b] = 0;
-    bestedges[b].clear();
-    bestedge[b] = -1;
     unused.push_back(b);
   }
 

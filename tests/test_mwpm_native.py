@@ -194,3 +194,21 @@ def test_matcher_threads_are_shared_between_local_ranks(monkeypatch):
     assert mwpm_native.default_threads() == n
     monkeypatch.setenv("LOCAL_WORLD_SIZE", "8")
     assert mwpm_native.default_threads() == max(1, n // 8)
+
+
+def test_invariant_checking_build_survives_fuzz(tmp_path):
+    """The sparse solver compiled with -DFPB_MWPM_CHECK verifies, after every dual adjustment and every
+    scanned edge, dual feasibility on all edges and the tree of every labelled blossom (it aborts on a
+    violation); a short fuzz run against the dense solver goes through it in a subprocess."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = str(tmp_path / "libfpb_mwpm_check.so")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-fopenmp", "-fPIC", "-shared", "-DFPB_MWPM_CHECK",
+                           "-D_GLIBCXX_ASSERTIONS", "-o", lib, os.path.join(root, "flamingpy_b200", "csrc", "mwpm.cpp")])
+    env = dict(os.environ, FPB_MWPM_LIB=lib)
+    out = subprocess.run([sys.executable, os.path.join(root, "scripts", "mwpm_fuzz.py"), "8", "7"], cwd=root, env=env,
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.startswith("ok:"), out.stderr[-2000:]
