@@ -1,0 +1,263 @@
+// Host-side Union-Find + peeling decoder for a batch of trials (C ABI: include/fpb_uf.h).
+//
+// What it computes follows the reference's decoder (flamingpy/decoders/unionfind/algos.py and
+// uf_classes.py; Delfosse-Nickerson, arXiv:1709.06218, with erasures as in arXiv:1703.01517):
+//
+//  1. Clusters start as the connected components of the erased edges; every other node is a cluster
+//     of its own (algos.py:58-129).  A cluster's parity is the XOR of its cubes' parities; a cluster
+//     holding a boundary point counts as even (uf_classes.py:92-98, algos.py:186-191).
+//  2. While odd clusters remain, every node of every odd cluster grows each of its incident edges by
+//     half an edge (Support.grow, uf_classes.py:134-142: empty -> half-grown -> grown; an edge between
+//     two growing nodes gets both halves in one round); edges that became fully grown merge the
+//     clusters at their ends (algos.py:132-193).  The set of grown edges after each round does not
+//     depend on the order in which clusters, nodes and edges are visited, so it is reproduced exactly
+//     (tests/golden/uf_*.npz hold the reference's own Support tables).
+//  3. A spanning forest of the grown edges is peeled from the leaves (algos.py:196-311): an edge enters
+//     the recovery when the subtree it cuts off holds an odd number of unsatisfied cubes; in a tree
+//     with an odd number of them one boundary point absorbs the excess (algos.py:207-225).
+//     The reference takes rustworkx's minimum_spanning_tree and the boundary point its set iteration
+//     meets last; here the forest is a breadth-first one rooted at the lowest-numbered boundary point.
+//     Both choices give recoveries that clear the same syndrome and differ by cycles of grown edges.
+//
+// Written for this data layout: a CSR adjacency over cubes + boundary points shared by all trials,
+// per-trial state in flat arrays reused across trials (one workspace per OpenMP thread), cluster
+// node lists as intrusive singly linked lists so that a merge is O(1), pruning of fully grown nodes
+// done while a list is walked.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "../../include/fpb_uf.h"
+
+namespace {
+
+struct Graph {
+  int n_nodes = 0, n_cubes = 0, n_edges = 0;
+  std::vector<int> off, adj_edge, adj_node;
+  const int32_t *ea = nullptr, *eb = nullptr;
+};
+
+struct Workspace {
+  std::vector<int> parent, csize, head, tail, next, odd, odd_next, fusion, order, up_edge, up_node, stamp;
+  std::vector<uint8_t> cpar, cbnd, support, npar, seen;
+  int stamp_t = 0;
+
+  void resize(const Graph& g) {
+    parent.resize(g.n_nodes), csize.resize(g.n_nodes), head.resize(g.n_nodes), tail.resize(g.n_nodes);
+    next.resize(g.n_nodes), up_edge.resize(g.n_nodes), up_node.resize(g.n_nodes), stamp.assign(g.n_nodes, 0);
+    cpar.resize(g.n_nodes), cbnd.resize(g.n_nodes), npar.resize(g.n_nodes), seen.resize(g.n_nodes);
+    support.resize(g.n_edges);
+    stamp_t = 0;
+  }
+  int find(int u) {
+    int r = u;
+    while (parent[r] != r) r = parent[r];
+    while (parent[u] != r) {
+      const int nx = parent[u];
+      parent[u] = r;
+      u = nx;
+    }
+    return r;
+  }
+  void unite(int a, int b) {  // roots
+    if (csize[a] < csize[b]) {
+      const int t = a;
+      a = b;
+      b = t;
+    }
+    parent[b] = a;
+    csize[a] += csize[b];
+    cpar[a] ^= cpar[b];
+    cbnd[a] |= cbnd[b];
+    if (head[b] >= 0) {  // append b's node list
+      if (head[a] < 0) {
+        head[a] = head[b];
+      } else {
+        next[tail[a]] = head[b];
+      }
+      tail[a] = tail[b];
+    }
+  }
+};
+
+// Returns 0, or -1 when an odd cluster is stuck.
+int decode_one(const Graph& g, Workspace& w, const uint8_t* parity, const uint8_t* erased, uint8_t* flips, uint8_t* grown) {
+  const int n = g.n_nodes;
+  for (int u = 0; u < n; ++u) {
+    w.parent[u] = u;
+    w.csize[u] = 1;
+    w.head[u] = w.tail[u] = u;
+    w.next[u] = -1;
+    w.cpar[u] = u < g.n_cubes ? (parity[u] & 1) : 0;
+    w.cbnd[u] = u >= g.n_cubes;
+  }
+  for (int q = 0; q < g.n_edges; ++q) {
+    w.support[q] = 0;
+    if (g.ea[q] < 0) continue;
+    if (erased && erased[q]) {
+      w.support[q] = 2;
+      const int a = w.find(g.ea[q]), b = w.find(g.eb[q]);
+      if (a != b) w.unite(a, b);
+    }
+  }
+  // the first round grows every cluster of odd parity, also one that an erasure already ties to a
+  // boundary point (algos.py:124-126 fills the list by parity alone; the boundary test comes after
+  // the first growth, algos.py:186-191)
+  w.odd.clear();
+  for (int u = 0; u < n; ++u)
+    if (w.parent[u] == u && w.cpar[u]) w.odd.push_back(u);
+
+  while (!w.odd.empty()) {
+    w.fusion.clear();
+    long changed = 0;
+    for (size_t i = 0; i < w.odd.size(); ++i) {
+      const int r = w.odd[i];
+      int prev = -1, u = w.head[r];
+      while (u >= 0) {
+        bool open = false;  // does u keep an edge that is not fully grown?
+        for (int ai = g.off[u]; ai < g.off[u + 1]; ++ai) {
+          const int q = g.adj_edge[ai];
+          uint8_t& s = w.support[q];
+          if (s == 0) {
+            s = 1;
+            open = true;
+            ++changed;
+          } else if (s == 1) {
+            s = 2;
+            w.fusion.push_back(q);
+            ++changed;
+          }
+        }
+        const int nx = w.next[u];
+        if (!open) {  // prune: nothing left to grow from u
+          if (prev < 0) {
+            w.head[r] = nx;
+          } else {
+            w.next[prev] = nx;
+          }
+          if (w.tail[r] == u) w.tail[r] = prev;
+        } else {
+          prev = u;
+        }
+        u = nx;
+      }
+    }
+    if (!changed) return -1;
+    for (size_t i = 0; i < w.fusion.size(); ++i) {
+      const int q = w.fusion[i];
+      const int a = w.find(g.ea[q]), b = w.find(g.eb[q]);
+      if (a != b) w.unite(a, b);
+    }
+    ++w.stamp_t;
+    w.odd_next.clear();
+    for (size_t i = 0; i < w.odd.size(); ++i) {
+      const int r = w.find(w.odd[i]);
+      if (w.stamp[r] == w.stamp_t) continue;
+      w.stamp[r] = w.stamp_t;
+      if (w.cpar[r] && !w.cbnd[r]) w.odd_next.push_back(r);
+    }
+    w.odd.swap(w.odd_next);
+  }
+
+  if (grown)
+    for (int q = 0; q < g.n_edges; ++q) grown[q] = w.support[q] == 2;
+
+  // spanning forest of the grown edges, breadth first, boundary points first as roots; then peeling
+  std::memset(flips, 0, (size_t)g.n_edges);
+  std::memset(w.seen.data(), 0, (size_t)n);
+  for (int u = 0; u < n; ++u) w.npar[u] = u < g.n_cubes ? (parity[u] & 1) : 0;
+  w.order.clear();
+  int rc = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    const int lo = pass == 0 ? g.n_cubes : 0, hi = pass == 0 ? n : g.n_cubes;
+    for (int root = lo; root < hi; ++root) {
+      if (w.seen[root]) continue;
+      const size_t first = w.order.size();
+      w.seen[root] = 1;
+      w.up_edge[root] = -1;
+      w.order.push_back(root);
+      for (size_t i = first; i < w.order.size(); ++i) {
+        const int u = w.order[i];
+        for (int ai = g.off[u]; ai < g.off[u + 1]; ++ai) {
+          const int q = g.adj_edge[ai], v = g.adj_node[ai];
+          if (w.support[q] != 2 || w.seen[v]) continue;
+          w.seen[v] = 1;
+          w.up_edge[v] = q;
+          w.up_node[v] = u;
+          w.order.push_back(v);
+        }
+      }
+      for (size_t i = w.order.size(); i-- > first + 1;) {
+        const int u = w.order[i];
+        if (w.npar[u]) {
+          flips[w.up_edge[u]] ^= 1;
+          w.npar[w.up_node[u]] ^= 1;
+        }
+      }
+      if (root < g.n_cubes && w.npar[root]) rc = -1;  // an odd tree without a boundary point
+    }
+  }
+  return rc;
+}
+
+}  // namespace
+
+extern "C" int fpb_uf_max_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+extern "C" int fpb_uf_batch(int n_nodes, int n_cubes, int n_edges, const int32_t* edge_a, const int32_t* edge_b,
+                            int n_trials, const uint8_t* parity, const uint8_t* erased, uint8_t* flips, uint8_t* grown,
+                            int threads) {
+  Graph g;
+  g.n_nodes = n_nodes, g.n_cubes = n_cubes, g.n_edges = n_edges, g.ea = edge_a, g.eb = edge_b;
+  g.off.assign(n_nodes + 1, 0);
+  for (int q = 0; q < n_edges; ++q) {
+    if (edge_a[q] < 0) continue;
+    ++g.off[edge_a[q] + 1];
+    ++g.off[edge_b[q] + 1];
+  }
+  for (int u = 0; u < n_nodes; ++u) g.off[u + 1] += g.off[u];
+  g.adj_edge.resize(g.off[n_nodes]);
+  g.adj_node.resize(g.off[n_nodes]);
+  {
+    std::vector<int> fill(g.off.begin(), g.off.end() - 1);
+    for (int q = 0; q < n_edges; ++q) {
+      if (edge_a[q] < 0) continue;
+      g.adj_edge[fill[edge_a[q]]] = q, g.adj_node[fill[edge_a[q]]++] = edge_b[q];
+      g.adj_edge[fill[edge_b[q]]] = q, g.adj_node[fill[edge_b[q]]++] = edge_a[q];
+    }
+  }
+  int first_bad = -1;
+#ifdef _OPENMP
+  const int nt = threads > 0 ? threads : omp_get_max_threads();
+#pragma omp parallel num_threads(nt)
+#endif
+  {
+    Workspace w;
+    w.resize(g);
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 4)
+#endif
+    for (int t = 0; t < n_trials; ++t) {
+      const int rc = decode_one(g, w, parity + (size_t)t * n_cubes, erased ? erased + (size_t)t * n_edges : nullptr,
+                                flips + (size_t)t * n_edges, grown ? grown + (size_t)t * n_edges : nullptr);
+      if (rc) {
+#ifdef _OPENMP
+#pragma omp critical
+#endif
+        if (first_bad < 0 || t < first_bad) first_bad = t;
+      }
+    }
+  }
+  (void)threads;
+  return first_bad < 0 ? 0 : -(1 + first_bad);
+}

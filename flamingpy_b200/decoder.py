@@ -51,13 +51,108 @@ def _run_trial(code, wo, stage, lengths="float"):
     return eng, eng.run_injected(x[None, :], state[None, :], stage=stage)
 
 
+def _trial_state(code, eng=None):
+    """State labels (uint8[N], 2 = p-squeezed) of the last noise realisation, or None when the noise
+    model has none (IidNoise).  CVMacroLayer: the labels of the reduced lattice, computed by the
+    device pipeline (``eng`` must have run the trial)."""
+    trial = _require_trial(code)
+    if isinstance(trial[0], str):
+        if trial[0] == "macro":
+            if eng is None:
+                eng, _ = _run_trial(code, {"method": "uniform"}, _lib.STAGE_NOISE)
+            return eng.fetch_macro()["red_state"][0]
+        return None
+    return trial[1]
+
+
+def uf_erasures(code, state):
+    """Erased edges of the Union-Find decoder: syndrome qubits with two or more p-squeezed
+    neighbours (weight -1 of ``assign_weights(code, "UF")``, ``decoders/decoder.py:96-114``).
+    ``state`` uint8[T, N] (2 = p) -> uint8[T, Qtot]; None (no labels) -> None."""
+    if state is None:
+        return None
+    lat = code.lattice
+    nbr = code.__dict__.get("_uf_qubit_nbrs")
+    if nbr is None:
+        qn = np.concatenate([lat.complexes[e].qubits for e in code.ec])
+        deg = (lat.adj_indptr[qn + 1] - lat.adj_indptr[qn]).astype(np.int64)
+        nbr = np.full((len(qn), int(deg.max())), lat.N, np.int64)  # column N of the padded labels is 0
+        for j in range(nbr.shape[1]):
+            sel = deg > j
+            nbr[sel, j] = lat.adj_indices[lat.adj_indptr[qn[sel]] + j]
+        code.__dict__["_uf_qubit_nbrs"] = nbr
+    state = np.atleast_2d(state)
+    is_p = np.zeros((state.shape[0], lat.N + 1), np.uint8)
+    is_p[:, : lat.N] = state == 2
+    if not is_p.any():
+        return None
+    return (is_p[:, nbr].sum(axis=2) >= 2).astype(np.uint8)
+
+
+def uf_decode_batch(code, parity, erased=None, threads=0):
+    """Union-Find + peeling recovery of a batch: ``parity`` = per complex uint8[T, S], ``erased``
+    uint8[T, Qtot] or None -> bit flips uint8[T, Qtot] (host decoder, ``csrc/uf.cpp``)."""
+    from . import uf_native
+
+    out, off = [], 0
+    for i, e in enumerate(code.ec):
+        ct = code.lattice.complexes[e]
+        er = None if erased is None else erased[:, off : off + ct.Q]
+        out.append(uf_native.decode_batch(ct, parity[i], er, threads=threads))
+        off += ct.Q
+    return np.concatenate(out, axis=1)
+
+
+def uf_decoder(code, ec, draw=False, drawing_opts=None):
+    """``uf_decoder`` (``decoders/unionfind/algos.py:314-334``): Union-Find + peeling on the code's
+    current ``bit_val`` / ``weight`` attributes (weight -1 = erased edge); returns the set of qubits
+    (coordinates) whose bit values the recovery flips."""
+    if draw:
+        raise NotImplementedError("drawing is out of scope for the accelerated path")
+    from . import uf_native
+
+    g = code.graph
+    g._ensure_arrays()
+    ct = code.lattice.complexes[ec]
+    bits = g.bit_val[ct.qubits].astype(np.uint8)
+    parity = np.zeros(ct.S, np.uint8)
+    for f in range(6):
+        q = ct.cube_qubit[:, f]
+        parity[q >= 0] ^= bits[q[q >= 0]]
+    erased = (g.weight[ct.qubits] == -1).astype(np.uint8)
+    flips = uf_native.decode_batch(ct, parity[None, :], erased[None, :] if erased.any() else None)[0]
+    return {tuple(int(v) for v in code.lattice.coords[ct.qubits[q]]) for q in np.nonzero(flips)[0]}
+
+
+def _assign_weights_uf(code, wo):
+    """The ``decoder == "UF"`` branch of ``assign_weights`` (``decoders/decoder.py:94-114``)."""
+    if wo.get("method") == "blueprint":
+        raise Exception("Incompatible decoder & weight options combination.")  # noqa: TRY002 - the reference's
+    if wo.get("method") != "uniform":
+        raise ValueError(f"unknown weight method {wo.get('method')!r}")
+    er = uf_erasures(code, _trial_state(code))
+    g = code.graph
+    g._ensure_arrays()
+    off = 0
+    for e in code.ec:
+        ct = code.lattice.complexes[e]
+        w = np.full(ct.Q, 2.0)
+        if er is not None:
+            w[er[0, off : off + ct.Q] == 1] = -1.0
+        g.weight[ct.qubits] = w
+        off += ct.Q
+
+
 def assign_weights(code, decoder="MWPM", **kwargs):
-    """``assign_weights`` (``decoders/decoder.py:31-119``) for the MWPM decoder:
-    writes the ``weight`` attribute of every syndrome qubit."""
-    if decoder != "MWPM":
-        raise NotImplementedError("only the MWPM decoder is on the accelerated path")
+    """``assign_weights`` (``decoders/decoder.py:31-119``): writes the ``weight`` attribute of every
+    syndrome qubit - for the MWPM decoder on the device (uniform / blueprint), for the Union-Find
+    decoder (uniform only: 2 per edge, -1 for an erased one) on the host from the state labels."""
     wo = {"method": "uniform", "integer": False, "multiplier": 1}
     wo.update(kwargs)
+    if decoder == "UF":
+        return _assign_weights_uf(code, wo)
+    if decoder != "MWPM":
+        raise ValueError(f"unknown decoder {decoder!r}")
     eng, batch = _run_trial(code, wo, _lib.STAGE_NOISE)
     g = code.graph
     g._ensure_arrays()
@@ -160,11 +255,13 @@ def correct(code, decoder="MWPM", weight_options=None, sanity_check=False, decod
     with the reference's networkx graphs; "rustworkx" - the sums of ``int(weight)`` along the
     float-shortest paths, which is what the reference's default rustworkx graphs report
     (``stabilizer_graph.py:486-500``) and therefore what its default ``correct`` matches on."""
-    if decoder != "MWPM":
-        raise NotImplementedError("only the MWPM decoder is on the accelerated path")
+    if decoder not in ("MWPM", "UF"):
+        raise KeyError(decoder)  # the reference's decoder_dict lookup (decoder.py:279-286)
     if draw:
         raise NotImplementedError("drawing is out of scope for the accelerated path")
     weight_options = dict(weight_options or {})
+    if decoder == "UF":
+        return _correct_uf(code, weight_options, sanity_check)
     opts = {"backend": "native"}
     opts.update(decoder_opts or {})
     if opts["backend"] in ("rustworkx", "retworkx", "lemon"):
@@ -195,6 +292,38 @@ def correct(code, decoder="MWPM", weight_options=None, sanity_check=False, decod
     if sanity_check:
         return bool(np.all(result[0]))
     return bool(np.all(result))
+
+
+def _correct_uf(code, weight_options, sanity_check):
+    """``correct(code, "UF", ...)``: noise -> bits -> syndrome on the device, Union-Find + peeling on
+    the host, logical check."""
+    wo = {"method": "uniform", "integer": False, "multiplier": 1}
+    wo.update(weight_options)
+    if wo.get("method") == "blueprint":
+        raise Exception("Incompatible decoder & weight options combination.")  # noqa: TRY002 - the reference's
+    eng, batch = _run_trial(code, wo, _lib.STAGE_SYNDROME)
+    er = uf_erasures(code, _trial_state(code, eng))
+    g = code.graph
+    g._ensure_arrays()
+    off = 0
+    for e in code.ec:
+        ct = code.lattice.complexes[e]
+        w = np.full(ct.Q, 2.0)
+        if er is not None:
+            w[er[0, off : off + ct.Q] == 1] = -1.0
+        g.weight[ct.qubits] = w
+        g.bit_val[ct.qubits] = batch.bits[0, off : off + ct.Q]
+        off += ct.Q
+    flips = uf_decode_batch(code, [batch.complexes[e].parity for e in code.ec], er)
+    off = 0
+    for e in code.ec:
+        ct = code.lattice.complexes[e]
+        g.bit_val[ct.qubits] ^= flips[0, off : off + ct.Q].astype(np.int8)
+        off += ct.Q
+        if sanity_check:
+            recovery([], code, e, sanity_check=True)
+    result = check_correction(code, sanity_check=sanity_check)
+    return bool(np.all(result[0] if sanity_check else result))
 
 
 def match_batch(code, eng, batch, backend="native", cands=None, handoff="full", stats=None, threads=0):

@@ -250,6 +250,21 @@ class TrialEngine:
         self._h.run_macro_rng(seed & (2**64 - 1), first_trial, n_trials, stage)
         return self.fetch(stage) if fetch else TrialBatch(n_trials, stage, timings=self.timings())
 
+    def fetch_syndrome(self, want_state: bool = False):
+        """What the Union-Find decoder consumes from the last run (stage >= SYNDROME): the bit values
+        uint8[T, Qtot], per complex the cube parities uint8[T, S], and - on request - the state labels
+        uint8[T, N] (1 GKP, 2 p) that decide which edges are erased."""
+        s = self.sizes()
+        T = int(s.n_trials)
+        bufs = {"bits": np.empty((T, self.bit_words), np.uint32)}
+        if want_state:
+            bufs["state"] = np.empty((T, self.lat.N), np.uint8)
+        for i, ec in enumerate(self.ec):
+            bufs[f"parity{i}"] = np.empty((T, (self.lat.complexes[ec].S + 31) // 32), np.uint32)
+        self._h.fetch_into(bufs)
+        parity = [unpack_bits(bufs[f"parity{i}"], self.lat.complexes[ec].S) for i, ec in enumerate(self.ec)]
+        return unpack_bits(bufs["bits"], self.Qtot), parity, bufs.get("state")
+
     def fetch_macro(self) -> dict:
         """Reduced lattice of the last macronode run, each [T, N]: ``red_state`` (1 GKP, 2 p),
         ``bit_val``, ``p_phase_cond``, ``outcome`` (effective homodyne value)."""

@@ -26,6 +26,7 @@ import numpy as np
 from . import _lib
 from .codes import SurfaceCode
 from .decoder import candidates, correct, logical_failures, match_batch
+from .engine import TrialBatch
 from .noise import CVLayer, CVMacroLayer, IidNoise
 
 int_time = int(str(datetime.now().timestamp()).replace(".", ""))
@@ -80,13 +81,15 @@ def ec_monte_carlo(trials, code_instance, noise_instance, decoder, decoder_args,
     ``Reduce``, ``simulations.py:98-110``; every rank gets the total).  Without either, ``mpi_rank``
     / ``mpi_size`` are ignored and this process runs all ``trials``.
     """
-    if decoder != "MWPM":
-        raise NotImplementedError("only the MWPM decoder is on the accelerated path")
+    if decoder not in ("MWPM", "UF"):
+        raise KeyError(decoder)  # the reference's decoder_dict lookup (decoders/decoder.py:279-286)
     if not isinstance(noise_instance, (CVLayer, CVMacroLayer, IidNoise)):
         raise NotImplementedError("the batched driver accelerates CVLayer, CVMacroLayer and IidNoise")
     weight_opts = dict(decoder_args.get("weight_opts") or {})
     iid = isinstance(noise_instance, IidNoise)
     macro = isinstance(noise_instance, CVMacroLayer)
+    if decoder == "UF" and weight_opts.get("method", "uniform") == "blueprint":
+        raise Exception("Incompatible decoder & weight options combination.")  # noqa: TRY002 - decoder.py:94-95
     if macro and weight_opts.get("method", "uniform") == "blueprint" and not weight_opts.get("prob_precomputed"):
         raise ValueError("CVMacroLayer leaves no homodyne values on the reduced lattice: use weight_opts "
                          "{'method': 'blueprint', 'prob_precomputed': True} (or 'uniform')")
@@ -118,6 +121,32 @@ def ec_monte_carlo(trials, code_instance, noise_instance, decoder, decoder_args,
         except ImportError:  # pragma: no cover
             pass
     seed = int_time if seed is None else int(seed)
+    if decoder == "UF":
+        # Union-Find: the device pipeline stops after the syndrome (no matching graph); clusters are
+        # grown and peeled on the host cores (csrc/uf.cpp), one batch at a time
+        from .decoder import uf_decode_batch, uf_erasures
+
+        eng = code_instance.engine(n_delta, n_pswap, {"method": "uniform"}, device=device, mode=mode)
+        lo, hi = trial_range(trials, rank, size)
+        failures = done = 0
+        t_dev = 0.0
+        for first in range(lo, hi, batch):
+            n = min(batch, hi - first)
+            if iid:
+                eng.run_iid(seed, first, n, noise_instance.error_probability, stage=_lib.STAGE_SYNDROME, fetch=False)
+            elif macro:
+                eng.run_macro_rng(seed, first, n, stage=_lib.STAGE_SYNDROME, fetch=False)
+            else:
+                eng.run_rng(seed, first, n, stage=_lib.STAGE_SYNDROME, fetch=False)
+            bits, parity, st = eng.fetch_syndrome(want_state=not iid and not macro and bool(n_pswap))
+            if macro:
+                st = eng.fetch_macro()["red_state"]
+            flips = uf_decode_batch(code_instance, parity, uf_erasures(code_instance, st))
+            failures += int(logical_failures(code_instance, TrialBatch(n, _lib.STAGE_SYNDROME, bits=bits), flips).sum())
+            done += n
+            t_dev += eng.timings()["total_ms"]
+        return _reduce_counts(failures, done, trials, dist, rank, size, use_mpi, world_comm, device, return_stats,
+                              {"device_ms": t_dev, "handoff": "none"})
     if handoff is None:
         periodic = not any(code_instance.lattice.complexes[e].has_boundary for e in code_instance.ec)
         handoff = "sparse" if (backend == "native" and periodic) else "full"
@@ -240,7 +269,12 @@ def ec_monte_carlo(trials, code_instance, noise_instance, decoder, decoder_args,
     t_fin.join()
     if state["error"] is not None:
         raise state["error"]
-    failures, done, t_dev = state["failures"], state["done"], state["t_dev"]
+    return _reduce_counts(state["failures"], state["done"], trials, dist, rank, size, use_mpi, world_comm, device,
+                          return_stats, {"device_ms": state["t_dev"], "handoff": handoff, **state["match"]})
+
+
+def _reduce_counts(failures, done, trials, dist, rank, size, use_mpi, world_comm, device, return_stats, stats):
+    """Sum (failures, trials done) over the ranks and return the failure count (with ``stats``)."""
     counts = np.array([failures, done], np.int64)
     if dist is not None and size > 1:
         import torch
@@ -256,8 +290,7 @@ def ec_monte_carlo(trials, code_instance, noise_instance, decoder, decoder_args,
         raise RuntimeError(f"trial accounting: {int(counts[1])} trials completed, {trials} requested")
     errors = int(counts[0])
     if return_stats:
-        return errors, {"trials_done": int(counts[1]), "device_ms": t_dev, "rank": rank, "world_size": size,
-                        "handoff": handoff, **state["match"]}
+        return errors, {"trials_done": int(counts[1]), "rank": rank, "world_size": size, **stats}
     return errors
 
 
@@ -314,6 +347,8 @@ def main(argv=None):
     args = parser.parse_args(argv)
     if args.decoder.lower() in ["mwpm", "minimum weight perfect matching"]:
         dec = "MWPM"
+    elif args.decoder.lower() in ["unionfind", "uf", "union-find", "union find"]:
+        dec = "UF"
     else:
         raise ValueError(f"Decoder {args.decoder} is either invalid or not yet implemented.")
     classes = {"SurfaceCode": SurfaceCode, "CVLayer": CVLayer, "CVMacroLayer": CVMacroLayer, "IidNoise": IidNoise}

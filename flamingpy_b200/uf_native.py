@@ -1,0 +1,88 @@
+"""ctypes binding of the host-side Union-Find + peeling decoder (``csrc/uf.cpp`` -> ``libfpb_uf.so``,
+C ABI in ``include/fpb_uf.h``), the batch replacement of the reference's pure-Python
+``flamingpy/decoders/unionfind`` package, and the static graph it runs on."""
+
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional, Tuple
+
+import numpy as np
+
+LIB_PATH = os.environ.get("FPB_UF_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libfpb_uf.so")
+_lib = None
+_i32p = ctypes.POINTER(ctypes.c_int32)
+_u8p = ctypes.POINTER(ctypes.c_uint8)
+
+
+def load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} not built: run __graft_entry__.build()")
+        lib = ctypes.CDLL(LIB_PATH)
+        lib.fpb_uf_batch.restype = ctypes.c_int
+        lib.fpb_uf_batch.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, _i32p, _i32p, ctypes.c_int, _u8p, _u8p,
+                                     _u8p, _u8p, ctypes.c_int]
+        lib.fpb_uf_max_threads.restype = ctypes.c_int
+        _lib = lib
+    return _lib
+
+
+def uf_graph(ct) -> Tuple[int, np.ndarray, np.ndarray]:
+    """The stabilizer graph of one complex without its 'low' / 'high' connectors, as the decoder's
+    edge list: ``(n_nodes, edge_a, edge_b)`` with one entry per syndrome qubit (local id into
+    ``ct.qubits``).  Nodes ``[0, S)`` are the cubes; a qubit on a boundary face joins its cube to a
+    boundary point of its own (boundary points are leaves of the reference's graph,
+    ``surface_code.py:477-525``), numbered from ``S`` in qubit order.  A qubit with no edge (the
+    dropped half of a doubly shared face, ``stabilizer_graph.py:295-298``) has ``edge_a = -1``."""
+    cached = getattr(ct, "_uf_graph", None)
+    if cached is not None:
+        return cached
+    S, Q = ct.S, ct.Q
+    ea = np.full(Q, -1, np.int32)
+    eb = np.full(Q, -1, np.int32)
+    is_bnd = np.zeros(Q, bool)
+    for f in range(6):
+        q = ct.cube_qubit[:, f]
+        nb = ct.nbr[:, f]
+        for s in np.nonzero(q >= 0)[0]:
+            qq, o = int(q[s]), int(nb[s])
+            if o < 0:
+                continue
+            if o >= S:  # LOW / HIGH side: the qubit itself is the boundary point
+                ea[qq], is_bnd[qq] = s, True
+            elif ea[qq] < 0:
+                ea[qq], eb[qq] = min(s, o), max(s, o)
+    bq = np.nonzero(is_bnd)[0]
+    eb[bq] = S + np.arange(len(bq), dtype=np.int32)
+    out = (S + len(bq), ea, eb)
+    try:
+        ct._uf_graph = out
+    except AttributeError:  # pragma: no cover - frozen tables
+        pass
+    return out
+
+
+def decode_batch(ct, parity: np.ndarray, erased: Optional[np.ndarray] = None, threads: int = 0, want_grown: bool = False):
+    """Recovery of every trial: ``parity`` uint8[T, S] (1 = unsatisfied cube), ``erased`` uint8[T, Q] or
+    None; returns uint8[T, Q] bit flips (and the fully grown edges when ``want_grown``)."""
+    n_nodes, ea, eb = uf_graph(ct)
+    parity = np.ascontiguousarray(parity, np.uint8)
+    T = parity.shape[0]
+    if parity.shape != (T, ct.S):
+        raise ValueError("parity must be [trials, cubes]")
+    if erased is not None:
+        erased = np.ascontiguousarray(erased, np.uint8)
+        if erased.shape != (T, ct.Q):
+            raise ValueError("erased must be [trials, qubits]")
+    flips = np.zeros((T, ct.Q), np.uint8)
+    grown = np.zeros((T, ct.Q), np.uint8) if want_grown else None
+    rc = load().fpb_uf_batch(n_nodes, ct.S, ct.Q, ea.ctypes.data_as(_i32p), eb.ctypes.data_as(_i32p), T,
+                             parity.ctypes.data_as(_u8p), erased.ctypes.data_as(_u8p) if erased is not None else None,
+                             flips.ctypes.data_as(_u8p), grown.ctypes.data_as(_u8p) if want_grown else None, int(threads))
+    if rc:
+        raise ValueError(f"trial {-rc - 1}: an odd cluster can neither grow nor reach a boundary point "
+                         "(odd number of unsatisfied stabilizers on a complex without boundary)")
+    return (flips, grown) if want_grown else flips

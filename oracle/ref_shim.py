@@ -30,6 +30,14 @@ def load():
             mod = types.ModuleType(name)
             mod.__version__ = "0.0-stub"
             sys.modules[name] = mod
+    rx = sys.modules["rustworkx"]
+    if getattr(rx, "PyGraph", None) is None:
+        # rustworkx is not installed here.  The reference's Union-Find decoder (decoders/unionfind/)
+        # uses a small part of its public PyGraph API for the erasure graph and the spanning forest;
+        # a plain-Python stand-in of those calls lets the unmodified decoder run.
+        rx.PyGraph = _PyGraph
+        rx.connected_components = _connected_components
+        rx.minimum_spanning_tree = _minimum_spanning_tree
     sym = sys.modules["thewalrus.symplectic"]
     if getattr(sym, "expand", None) is None:
         # thewalrus is not installed here.  The reference uses two of its functions, for the fixed
@@ -48,6 +56,85 @@ def load():
         import flamingpy.noise  # noqa: F401
         import flamingpy.decoders.decoder  # noqa: F401
     return sys.modules["flamingpy"]
+
+
+class _PyGraph:
+    """The calls of rustworkx.PyGraph the reference's Union-Find decoder makes (undirected multigraph,
+    integer node indices in insertion order, arbitrary payloads)."""
+
+    def __init__(self):
+        self._nodes = []
+        self._adj = []  # per node: {neighbour: [payload, ...]}
+
+    def add_node(self, obj):
+        self._nodes.append(obj)
+        self._adj.append({})
+        return len(self._nodes) - 1
+
+    def add_edge(self, a, b, data):
+        self._adj[a].setdefault(b, []).append(data)
+        if a != b:
+            self._adj[b].setdefault(a, []).append(data)
+
+    def nodes(self):
+        return list(self._nodes)
+
+    def out_edges(self, node):
+        return [(node, nb, d) for nb, ds in self._adj[node].items() for d in ds]
+
+    def get_edge_data(self, a, b):
+        return self._adj[a][b][0]
+
+    def remove_edge(self, a, b):
+        self._adj[a][b].pop()
+        if not self._adj[a][b]:
+            del self._adj[a][b]
+        if a != b:
+            self._adj[b][a].pop()
+            if not self._adj[b][a]:
+                del self._adj[b][a]
+
+    def degree(self, node):
+        return sum(len(ds) for ds in self._adj[node].values())
+
+
+def _connected_components(graph):
+    seen, out = set(), []
+    for start in range(len(graph._nodes)):
+        if start in seen:
+            continue
+        comp, stack = {start}, [start]
+        seen.add(start)
+        while stack:
+            u = stack.pop()
+            for v in graph._adj[u]:
+                if v not in seen:
+                    seen.add(v)
+                    comp.add(v)
+                    stack.append(v)
+        out.append(comp)
+    return out
+
+
+def _minimum_spanning_tree(graph):
+    """All weights equal: any spanning forest (same node indices, payloads kept)."""
+    forest = _PyGraph()
+    for obj in graph._nodes:
+        forest.add_node(obj)
+    parent = list(range(len(graph._nodes)))
+
+    def find(u):
+        while parent[u] != u:
+            parent[u] = parent[parent[u]]
+            u = parent[u]
+        return u
+
+    for a in range(len(graph._nodes)):
+        for b, ds in graph._adj[a].items():
+            if a < b and find(a) != find(b):
+                parent[find(a)] = find(b)
+                forest.add_edge(a, b, ds[0])
+    return forest
 
 
 def _beam_splitter(theta, phi):
