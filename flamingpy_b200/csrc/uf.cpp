@@ -214,6 +214,29 @@ extern "C" int fpb_uf_max_threads(void) {
 #endif
 }
 
+extern "C" long long fpb_uf_erasures(int n_lattice_nodes, int n_edges, const int32_t* qubit_node, const int32_t* adj_indptr,
+                                     const int32_t* adj_indices, int n_trials, const uint8_t* state, uint8_t* erased,
+                                     int threads) {
+  long long total = 0;
+#ifdef _OPENMP
+  const int nt = threads > 0 ? threads : omp_get_max_threads();
+#pragma omp parallel for num_threads(nt) reduction(+ : total) schedule(static)
+#endif
+  for (int t = 0; t < n_trials; ++t) {
+    const uint8_t* st = state + (size_t)t * n_lattice_nodes;
+    uint8_t* er = erased + (size_t)t * n_edges;
+    for (int q = 0; q < n_edges; ++q) {
+      const int v = qubit_node[q];
+      int p_count = 0;
+      for (int i = adj_indptr[v]; i < adj_indptr[v + 1]; ++i) p_count += st[adj_indices[i]] == 2;
+      er[q] = p_count >= 2;
+      total += er[q];
+    }
+  }
+  (void)threads;
+  return total;
+}
+
 extern "C" int fpb_uf_batch(int n_nodes, int n_cubes, int n_edges, const int32_t* edge_a, const int32_t* edge_b,
                             int n_trials, const uint8_t* parity, const uint8_t* erased, uint8_t* flips, uint8_t* grown,
                             int threads) {

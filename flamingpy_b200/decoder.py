@@ -71,22 +71,13 @@ def uf_erasures(code, state):
     ``state`` uint8[T, N] (2 = p) -> uint8[T, Qtot]; None (no labels) -> None."""
     if state is None:
         return None
-    lat = code.lattice
-    nbr = code.__dict__.get("_uf_qubit_nbrs")
-    if nbr is None:
-        qn = np.concatenate([lat.complexes[e].qubits for e in code.ec])
-        deg = (lat.adj_indptr[qn + 1] - lat.adj_indptr[qn]).astype(np.int64)
-        nbr = np.full((len(qn), int(deg.max())), lat.N, np.int64)  # column N of the padded labels is 0
-        for j in range(nbr.shape[1]):
-            sel = deg > j
-            nbr[sel, j] = lat.adj_indices[lat.adj_indptr[qn[sel]] + j]
-        code.__dict__["_uf_qubit_nbrs"] = nbr
-    state = np.atleast_2d(state)
-    is_p = np.zeros((state.shape[0], lat.N + 1), np.uint8)
-    is_p[:, : lat.N] = state == 2
-    if not is_p.any():
-        return None
-    return (is_p[:, nbr].sum(axis=2) >= 2).astype(np.uint8)
+    from . import uf_native
+
+    qn = code.__dict__.get("_uf_qubit_nodes")
+    if qn is None:
+        qn = code.__dict__["_uf_qubit_nodes"] = np.ascontiguousarray(
+            np.concatenate([code.lattice.complexes[e].qubits for e in code.ec]), np.int32)
+    return uf_native.erasures(code.lattice, qn, state)
 
 
 def uf_decode_batch(code, parity, erased=None, threads=0):

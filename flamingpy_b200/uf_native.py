@@ -26,6 +26,9 @@ def load():
         lib.fpb_uf_batch.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, _i32p, _i32p, ctypes.c_int, _u8p, _u8p,
                                      _u8p, _u8p, ctypes.c_int]
         lib.fpb_uf_max_threads.restype = ctypes.c_int
+        lib.fpb_uf_erasures.restype = ctypes.c_longlong
+        lib.fpb_uf_erasures.argtypes = [ctypes.c_int, ctypes.c_int, _i32p, _i32p, _i32p, ctypes.c_int, _u8p, _u8p,
+                                        ctypes.c_int]
         _lib = lib
     return _lib
 
@@ -86,3 +89,17 @@ def decode_batch(ct, parity: np.ndarray, erased: Optional[np.ndarray] = None, th
         raise ValueError(f"trial {-rc - 1}: an odd cluster can neither grow nor reach a boundary point "
                          "(odd number of unsatisfied stabilizers on a complex without boundary)")
     return (flips, grown) if want_grown else flips
+
+
+def erasures(lat, qubit_nodes: np.ndarray, state: np.ndarray, threads: int = 0):
+    """Erased edges uint8[T, Q] (None when there is none) for the syndrome qubits ``qubit_nodes``
+    (lattice node indices) from the state labels uint8[T, N]: two or more p-squeezed neighbours."""
+    state = np.ascontiguousarray(np.atleast_2d(state), np.uint8)
+    qn = np.ascontiguousarray(qubit_nodes, np.int32)
+    indptr = np.ascontiguousarray(lat.adj_indptr, np.int32)
+    indices = np.ascontiguousarray(lat.adj_indices, np.int32)
+    out = np.empty((state.shape[0], len(qn)), np.uint8)
+    n = load().fpb_uf_erasures(lat.N, len(qn), qn.ctypes.data_as(_i32p), indptr.ctypes.data_as(_i32p),
+                               indices.ctypes.data_as(_i32p), state.shape[0], state.ctypes.data_as(_u8p),
+                               out.ctypes.data_as(_u8p), int(threads))
+    return out if n else None

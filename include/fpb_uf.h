@@ -39,6 +39,14 @@ extern "C" {
 int fpb_uf_batch(int n_nodes, int n_cubes, int n_edges, const int32_t* edge_a, const int32_t* edge_b, int n_trials,
                  const uint8_t* parity, const uint8_t* erased, uint8_t* flips, uint8_t* grown, int threads);
 
+/* Erased edges of a batch from the state labels: erased[t][q] = 1 when syndrome qubit q (lattice node
+ * qubit_node[q]) has two or more neighbours labelled p-squeezed (state == 2) - the weight -1 of
+ * `assign_weights(code, "UF")`, decoders/decoder.py:96-114.  adj_indptr / adj_indices: the lattice
+ * adjacency in CSR form (the same arrays fpb_config carries).  state [T][n_lattice_nodes], erased [T][n_edges].
+ * Returns the number of erased edges in the batch. */
+long long fpb_uf_erasures(int n_lattice_nodes, int n_edges, const int32_t* qubit_node, const int32_t* adj_indptr,
+                          const int32_t* adj_indices, int n_trials, const uint8_t* state, uint8_t* erased, int threads);
+
 int fpb_uf_max_threads(void);
 
 #ifdef __cplusplus

@@ -41,7 +41,7 @@ def _failures(ct, bits, flips):
 def test_library_exports_every_declared_symbol():
     header = open(os.path.join(ROOT, "include", "fpb_uf.h")).read()
     declared = set(re.findall(r"\b(fpb_uf[a-z_]*)\s*\(", header))
-    assert declared == {"fpb_uf_batch", "fpb_uf_max_threads"}
+    assert declared == {"fpb_uf_batch", "fpb_uf_erasures", "fpb_uf_max_threads"}
     lib = ctypes.CDLL(uf_native.LIB_PATH)
     for name in declared:
         assert hasattr(lib, name), name
