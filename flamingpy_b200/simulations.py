@@ -59,7 +59,7 @@ def trial_range(trials: int, rank: int, size: int):
 
 def ec_monte_carlo(trials, code_instance, noise_instance, decoder, decoder_args, world_comm=None, mpi_rank=0,
                    mpi_size=1, *, seed=None, batch=1024, mode="compat", backend="native", device=None,
-                   return_stats=False, handoff=None, match_workers=None):
+                   return_stats=False, handoff=None, match_workers=None, reserve_sms=None):
     """Run ``trials`` Monte-Carlo trials of the complete error-correction procedure and
     return the number of logical errors.
 
@@ -73,7 +73,8 @@ def ec_monte_carlo(trials, code_instance, noise_instance, decoder, decoder_args,
     chain and the tight connector pairs cost the sparse path more round trips).
     ``match_workers``: host threads that match different batches at the same time, each with its
     share of the cores (default 3 for the sparse hand-off, whose pricing rounds are batch-synchronous,
-    2 for the full one).
+    2 for the full one).  ``reserve_sms``: SMs the persistent shortest-path kernel leaves free for the
+    matcher's pricing kernels (default 4 with the sparse hand-off, else 0).
 
     Trial split: with ``torch.distributed`` initialised, over its ranks with one ``all_reduce`` of
     the counts (one process per GPU; NCCL).  Otherwise, if an mpi4py-style ``world_comm`` is given
@@ -157,7 +158,9 @@ def ec_monte_carlo(trials, code_instance, noise_instance, decoder, decoder_args,
     code = code_instance
     # sparse hand-off: the matcher's pricing kernels run while the next batch's persistent shortest-path
     # kernel holds the SMs; leaving it a few SMs short costs the graph stage ~3 % and the matcher no wait
-    rsv = 4 if handoff == "sparse" else 0
+    # (measured at 0 vs 4; with the faster matcher of the end of round 2 the waits for pricing rounds are as long as
+    # the solves, profiles/r2_final_checks.md - `reserve_sms` is the knob to sweep next)
+    rsv = (4 if handoff == "sparse" else 0) if reserve_sms is None else int(reserve_sms)
     eng = code.engine(n_delta, n_pswap, weight_opts, device=device, mode=mode, reserve_sms=rsv)
     if iid and not eng.uses_table:
         eng.build_table()  # uniform weights: every matching graph is a gather from one all-pairs table
