@@ -227,3 +227,36 @@ def test_monte_carlo_driver_with_uf_on_the_oracle_engine():
         ec_monte_carlo(10, code, layer, "UF", {"weight_opts": {"method": "blueprint", "delta": 0.09}})
     with pytest.raises(KeyError):
         ec_monte_carlo(10, code, layer, "BP", args)
+
+
+def test_restatement_is_pinned_to_the_reference_and_agrees_with_the_library_beyond_it():
+    """oracle/restate_uf.py (plain Python, the reference's data structures) reproduces the reference's Support
+    tables on the golden runs; then it is the oracle for csrc/uf.cpp on seeded syndromes and erasures at sizes the
+    golden files do not cover: identical Support tables, and recoveries with identical syndrome."""
+    from oracle import restate_uf
+
+    for path in gu.uf_files():
+        g = gu.load_uf(path)
+        lat = build_lattice(g["distance"], g["ec"], g["boundaries"])
+        for e in lat.ec:
+            ct = lat.complexes[e]
+            n_nodes, ea, eb = uf_native.uf_graph(ct)
+            for t in range(min(g["trials"], 6)):
+                flips, grown = restate_uf.decode(n_nodes, ct.S, ea, eb, g[f"{e}_parity"][t], g[f"{e}_weights"][t] == -1)
+                assert np.array_equal(grown, g[f"{e}_grown"][t])
+                assert np.array_equal(_syndrome_of(ct, flips[None])[0], g[f"{e}_parity"][t])
+    rng = np.random.default_rng(77)
+    for d, b, p_err, p_er in [(7, "open", 0.05, 0.08), (6, "periodic", 0.04, 0.0), (5, "toric", 0.08, 0.15), (9, "open", 0.03, 0.02)]:
+        ct = build_lattice(d, "primal", b).complexes["primal"]
+        n_nodes, ea, eb = uf_native.uf_graph(ct)
+        T = 10
+        err = (rng.random((T, ct.Q)) < p_err).astype(np.uint8)
+        err[:, ea < 0] = 0
+        parity = _syndrome_of(ct, err)
+        erased = (rng.random((T, ct.Q)) < p_er).astype(np.uint8)
+        flips, grown = uf_native.decode_batch(ct, parity, erased, want_grown=True)
+        for t in range(T):
+            f_o, g_o = restate_uf.decode(n_nodes, ct.S, ea, eb, parity[t], erased[t])
+            assert np.array_equal(grown[t], g_o), (d, b, t)
+            assert np.array_equal(_syndrome_of(ct, f_o[None])[0], parity[t])
+            assert np.array_equal(_syndrome_of(ct, flips[t][None])[0], parity[t])
