@@ -4,12 +4,12 @@
 // flamingpy/cpp/lemonpy.cpp:13-41 (and rx.max_weight_matching, decoders/mwpm/matching.py:286-292),
 // neither of which can be installed offline.  Host-side C++, C ABI, OpenMP over trials.
 //
-// Algorithm: Edmonds' blossom algorithm with dual variables for dense graphs, O(n^3), the
-// classical primal-dual formulation (Galil 1986): grow alternating trees from free vertices
-// along tight edges, shrink odd cycles into blossoms, adjust duals by the minimum slack,
-// expand blossoms whose dual reaches zero.  Lengths are scaled to 64-bit integers (2^-32
-// resolution) so that all dual arithmetic is exact; maximum-weight matching on C - w with C
-// large makes the optimum a minimum-weight perfect matching.
+// Algorithm: Edmonds' blossom algorithm in its primal-dual form on adjacency lists
+// (mwpm_sparse.h: persistent alternating trees, lazy dual adjustments, event heaps).  Lengths are
+// scaled to 64-bit integers (2^-32 resolution) and enter as weights -2 * length, so that all dual
+// arithmetic is exact.  Small graphs hand the solver every edge of the complete graph
+// (solve_one); from 48 cubes on it runs on a sparse candidate graph and the result is proved
+// optimal for the complete graph by pricing (solve_one_sparse, the fpb_mwpm_sparse_* batch form).
 //
 // Matching-graph structure used (decoders/mwpm/matching.py:97-173): K odd cubes, pairwise
 // lengths d_ab; with boundary points one private virtual partner per cube at length b_a and a
@@ -36,275 +36,66 @@ namespace {
 
 typedef long long ll;
 
-struct Edge {
-  int u, v;
-  ll w;
-};
-
 // non-negative scaled length -> integer, round half up (one cvttsd2si instead of a libm call)
 inline ll to_fixed(double v) { return (ll)(v + 0.5); }
 
-class Blossom {
- public:
-  explicit Blossom(int n) : n(n), nx(n), m(2 * n + 1) {
-    g.assign((size_t)m * m, Edge{0, 0, 0});
-    lab.assign(m, 0);
-    match.assign(m, 0);
-    slack.assign(m, 0);
-    st.assign(m, 0);
-    pa.assign(m, 0);
-    S.assign(m, 0);
-    vis.assign(m, 0);
-    flower.assign(m, std::vector<int>());
-    flower_from.assign((size_t)m * (n + 1), 0);
-    for (int u = 1; u <= n; ++u)
-      for (int v = 1; v <= n; ++v) G(u, v) = Edge{u, v, 0};
+// Greedy start of the primal-dual solver (all drivers below): feasible duals y_u = best incident
+// weight; then every free vertex lowers its dual until its first edge becomes tight and takes that
+// partner if it is still free; then augmenting paths of three tight edges (free - matched =
+// matched - free), which need no search.  All weights are even, so all duals stay even.  False
+// when some vertex has no edge at all.
+bool greedy_start(fpb_sparse::SparseBlossom& sb, int n, std::vector<ll>& y, std::vector<int>& vmate) {
+  y.assign(n, INT64_MIN);
+  vmate.assign(n, -1);
+  for (int k = 0; k < sb.n_edges(); ++k) {
+    y[sb.E[k].u] = std::max(y[sb.E[k].u], sb.E[k].w);
+    y[sb.E[k].v] = std::max(y[sb.E[k].v], sb.E[k].w);
   }
-  void set_weight(int u, int v, ll w) {  // 1-based, w > 0
-    G(u, v).w = w;
-    G(v, u).w = w;
-  }
-  // returns mate[1..n] (0 = unmatched)
-  const std::vector<int>& solve() {
-    std::fill(match.begin(), match.end(), 0);
-    nx = n;
-    for (int u = 0; u <= n; ++u) {
-      st[u] = u;
-      flower[u].clear();
-    }
-    // Jump start.  Duals only have to be feasible (lab[u] + lab[v] >= 2 w(u, v)); with
-    // lab[u] = max_v w(u, v) every vertex already has a tight edge to its best partner, and
-    // matching mutually unmatched best partners greedily leaves few free vertices for the
-    // O(n^2) augmentation phases.  Optimality follows from complementary slackness once the
-    // matching is perfect, whatever the starting duals were.
-    std::vector<int> best(n + 1, 0);
-    for (int u = 1; u <= n; ++u) {
-      ll mx = 0;
-      for (int v = 1; v <= n; ++v) {
-        FF(u, v) = (u == v ? u : 0);
-        if (v != u && G(u, v).w > mx) {
-          mx = G(u, v).w;
-          best[u] = v;
-        }
+  for (int u = 0; u < n; ++u)
+    if (y[u] == INT64_MIN) return false;
+  for (int u = 0; u < n; ++u) {
+    if (vmate[u] >= 0) continue;
+    ll smin = INT64_MAX;
+    int pick = -1;
+    sb.for_neighbours(u, [&](int v, ll w) {
+      const ll sl = y[u] + y[v] - 2 * w;
+      if (sl < smin || (sl == smin && pick >= 0 && vmate[pick] >= 0 && vmate[v] < 0)) {
+        smin = sl;
+        pick = v;
       }
-      lab[u] = mx;
+    });
+    y[u] -= smin;
+    if (vmate[pick] < 0) {
+      vmate[u] = pick;
+      vmate[pick] = u;
     }
-    for (int u = 1; u <= n; ++u) {
-      const int v = best[u];
-      if (v && !match[u] && !match[v] && lab[u] + lab[v] == 2 * G(u, v).w) {
-        match[u] = v;
-        match[v] = u;
-      }
-    }
-    while (matching()) {
-    }
-    return match;
   }
+  for (int u = 0; u < n; ++u) {
+    if (vmate[u] >= 0) continue;
+    bool found = false;
+    sb.for_neighbours(u, [&](int v, ll w) {
+      if (found || vmate[v] < 0 || y[u] + y[v] != 2 * w) return;
+      const int v2 = vmate[v];
+      int x = -1;
+      sb.for_neighbours(v2, [&](int c, ll w2) {
+        if (x < 0 && c != u && vmate[c] < 0 && y[v2] + y[c] == 2 * w2) x = c;
+      });
+      if (x >= 0) {
+        vmate[u] = v; vmate[v] = u;
+        vmate[v2] = x; vmate[x] = v2;
+        found = true;
+      }
+    });
+  }
+  sb.start(y, vmate);
+  return true;
+}
 
- private:
-  int n, nx, m;
-  std::vector<Edge> g;
-  std::vector<ll> lab;
-  std::vector<int> match, slack, st, pa, S, vis;
-  std::vector<std::vector<int>> flower;
-  std::vector<int> flower_from;
-  std::queue<int> q;
-  int vis_t = 0;
-
-  Edge& G(int u, int v) { return g[(size_t)u * m + v]; }
-  int& FF(int b, int x) { return flower_from[(size_t)b * (n + 1) + x]; }
-  ll e_delta(const Edge& e) { return lab[e.u] + lab[e.v] - G(e.u, e.v).w * 2; }
-  void update_slack(int u, int x) {
-    if (!slack[x] || e_delta(G(u, x)) < e_delta(G(slack[x], x))) slack[x] = u;
-  }
-  void set_slack(int x) {
-    slack[x] = 0;
-    for (int u = 1; u <= n; ++u)
-      if (G(u, x).w > 0 && st[u] != x && S[st[u]] == 0) update_slack(u, x);
-  }
-  void q_push(int x) {
-    if (x <= n) q.push(x);
-    else
-      for (size_t i = 0; i < flower[x].size(); ++i) q_push(flower[x][i]);
-  }
-  void set_st(int x, int b) {
-    st[x] = b;
-    if (x > n)
-      for (size_t i = 0; i < flower[x].size(); ++i) set_st(flower[x][i], b);
-  }
-  int get_pr(int b, int xr) {
-    int pr = (int)(std::find(flower[b].begin(), flower[b].end(), xr) - flower[b].begin());
-    if (pr % 2 == 1) {
-      std::reverse(flower[b].begin() + 1, flower[b].end());
-      return (int)flower[b].size() - pr;
-    }
-    return pr;
-  }
-  void set_match(int u, int v) {
-    match[u] = G(u, v).v;
-    if (u <= n) return;
-    Edge e = G(u, v);
-    int xr = FF(u, e.u), pr = get_pr(u, xr);
-    for (int i = 0; i < pr; ++i) set_match(flower[u][i], flower[u][i ^ 1]);
-    set_match(xr, v);
-    std::rotate(flower[u].begin(), flower[u].begin() + pr, flower[u].end());
-  }
-  void augment(int u, int v) {
-    for (;;) {
-      int xnv = st[match[u]];
-      set_match(u, v);
-      if (!xnv) return;
-      set_match(xnv, st[pa[xnv]]);
-      u = st[pa[xnv]];
-      v = xnv;
-    }
-  }
-  int get_lca(int u, int v) {
-    for (++vis_t; u || v; std::swap(u, v)) {
-      if (u == 0) continue;
-      if (vis[u] == vis_t) return u;
-      vis[u] = vis_t;
-      u = st[match[u]];
-      if (u) u = st[pa[u]];
-    }
-    return 0;
-  }
-  void add_blossom(int u, int lca, int v) {
-    int b = n + 1;
-    while (b <= nx && st[b]) ++b;
-    if (b > nx) ++nx;
-    lab[b] = 0;
-    S[b] = 0;
-    match[b] = match[lca];
-    flower[b].clear();
-    flower[b].push_back(lca);
-    for (int x = u, y; x != lca; x = st[pa[y]]) {
-      flower[b].push_back(x);
-      flower[b].push_back(y = st[match[x]]);
-      q_push(y);
-    }
-    std::reverse(flower[b].begin() + 1, flower[b].end());
-    for (int x = v, y; x != lca; x = st[pa[y]]) {
-      flower[b].push_back(x);
-      flower[b].push_back(y = st[match[x]]);
-      q_push(y);
-    }
-    set_st(b, b);
-    for (int x = 1; x <= nx; ++x) G(b, x).w = G(x, b).w = 0;
-    for (int x = 1; x <= n; ++x) FF(b, x) = 0;
-    for (size_t i = 0; i < flower[b].size(); ++i) {
-      int xs = flower[b][i];
-      for (int x = 1; x <= nx; ++x)
-        if (G(b, x).w == 0 || e_delta(G(xs, x)) < e_delta(G(b, x))) {
-          G(b, x) = G(xs, x);
-          G(x, b) = G(x, xs);
-        }
-      for (int x = 1; x <= n; ++x)
-        if (FF(xs, x)) FF(b, x) = xs;
-    }
-    set_slack(b);
-  }
-  void expand_blossom(int b) {
-    for (size_t i = 0; i < flower[b].size(); ++i) set_st(flower[b][i], flower[b][i]);
-    int xr = FF(b, G(b, pa[b]).u), pr = get_pr(b, xr);
-    for (int i = 0; i < pr; i += 2) {
-      int xs = flower[b][i], xns = flower[b][i + 1];
-      pa[xs] = G(xns, xs).u;
-      S[xs] = 1;
-      S[xns] = 0;
-      slack[xs] = 0;
-      set_slack(xns);
-      q_push(xns);
-    }
-    S[xr] = 1;
-    pa[xr] = pa[b];
-    for (size_t i = pr + 1; i < flower[b].size(); ++i) {
-      int xs = flower[b][i];
-      S[xs] = -1;
-      set_slack(xs);
-    }
-    st[b] = 0;
-  }
-  bool on_found_edge(const Edge& e) {
-    int u = st[e.u], v = st[e.v];
-    if (S[v] == -1) {
-      pa[v] = e.u;
-      S[v] = 1;
-      int nu = st[match[v]];
-      slack[v] = slack[nu] = 0;
-      S[nu] = 0;
-      q_push(nu);
-    } else if (S[v] == 0) {
-      int lca = get_lca(u, v);
-      if (!lca) {
-        augment(u, v);
-        augment(v, u);
-        return true;
-      }
-      add_blossom(u, lca, v);
-    }
-    return false;
-  }
-  bool matching() {
-    std::fill(S.begin() + 1, S.begin() + nx + 1, -1);
-    std::fill(slack.begin() + 1, slack.begin() + nx + 1, 0);
-    q = std::queue<int>();
-    for (int x = 1; x <= nx; ++x)
-      if (st[x] == x && !match[x]) {
-        pa[x] = 0;
-        S[x] = 0;
-        q_push(x);
-      }
-    if (q.empty()) return false;
-    for (;;) {
-      while (!q.empty()) {
-        int u = q.front();
-        q.pop();
-        if (S[st[u]] == 1) continue;
-        for (int v = 1; v <= n; ++v)
-          if (G(u, v).w > 0 && st[u] != st[v]) {
-            if (e_delta(G(u, v)) == 0) {
-              if (on_found_edge(G(u, v))) return true;
-            } else {
-              update_slack(u, st[v]);
-            }
-          }
-      }
-      ll d = INT64_MAX;
-      for (int b = n + 1; b <= nx; ++b)
-        if (st[b] == b && S[b] == 1) d = std::min(d, lab[b] / 2);
-      for (int x = 1; x <= nx; ++x)
-        if (st[x] == x && slack[x]) {
-          if (S[x] == -1) d = std::min(d, e_delta(G(slack[x], x)));
-          else if (S[x] == 0) d = std::min(d, e_delta(G(slack[x], x)) / 2);
-        }
-      for (int u = 1; u <= n; ++u) {
-        if (S[st[u]] == 0) {
-          if (lab[u] <= d) return false;
-          lab[u] -= d;
-        } else if (S[st[u]] == 1) {
-          lab[u] += d;
-        }
-      }
-      for (int b = n + 1; b <= nx; ++b)
-        if (st[b] == b) {
-          if (S[st[b]] == 0) lab[b] += d * 2;
-          else if (S[st[b]] == 1) lab[b] -= d * 2;
-        }
-      q = std::queue<int>();
-      for (int x = 1; x <= nx; ++x)
-        if (st[x] == x && slack[x] && st[slack[x]] != x && e_delta(G(slack[x], x)) == 0)
-          if (on_found_edge(G(slack[x], x))) return true;
-      for (int b = n + 1; b <= nx; ++b)
-        if (st[b] == b && S[b] == 1 && lab[b] == 0) expand_blossom(b);
-    }
-    return false;
-  }
-};
-
-// One matching graph.  pair_len: packed upper triangle (row-major, a < b); bnd_len: K lengths or
-// null.  Writes out_src / out_dst (dst = -1: matched to its connector); returns the number of
-// queries written (<= K) or a negative code.
+// One matching graph, every edge of the reduced complete graph handed to the solver (no candidate
+// selection, no pricing): the small-graph path and the last resort of the sparse drivers.
+// pair_len: packed upper triangle (row-major, a < b); bnd_len: K lengths or null.  Writes out_src /
+// out_dst (dst = -1: matched to its connector); returns the number of queries written (<= K) or a
+// negative code.
 int solve_one(int K, const double* pair_len, const double* bnd_len, int* out_src, int* out_dst) {
   if (K <= 0) return 0;
   if (!bnd_len && (K & 1)) return -1;  // no perfect matching
@@ -314,7 +105,7 @@ int solve_one(int K, const double* pair_len, const double* bnd_len, int* out_src
     return 1;
   }
   const int n = (bnd_len && (K & 1)) ? K + 1 : K;
-  // scale so that every weight is an even positive integer (duals halve) with ~2^-32 resolution
+  // scale to ~2^-32 resolution; the solver's weights are -2 * length, so S-S slacks stay even
   double wmax = 0;
   const long long npairs = (long long)K * (K - 1) / 2;
   for (long long i = 0; i < npairs; ++i) wmax = std::max(wmax, pair_len[i]);
@@ -324,35 +115,32 @@ int solve_one(int K, const double* pair_len, const double* bnd_len, int* out_src
   int shift = 32;
   while (shift > 0 && std::ldexp(wmax + 1.0, shift) * (double)(n + 2) > 1e17) --shift;
   const double scale = std::ldexp(1.0, shift);
-  const ll wmax_i = to_fixed(wmax * scale) + 1;
-  const ll C = wmax_i * (ll)(n + 1);  // C - w > 0 and large enough that cardinality dominates
-  Blossom bl(n);
-  std::vector<char> via_boundary((size_t)K * K, 0);
+  static thread_local fpb_sparse::SparseBlossom sb_tls;
+  static thread_local std::vector<ll> y_tls;
+  static thread_local std::vector<int> vmate_tls;
+  fpb_sparse::SparseBlossom& sb = sb_tls;
+  sb.reset(n);
   long long pos = 0;
   for (int a = 0; a < K - 1; ++a)
     for (int b = a + 1; b < K; ++b, ++pos) {
       double w = pair_len[pos];
-      if (bnd_len) {
-        const double wb = bnd_len[a] + bnd_len[b];
-        if (wb < w) {
-          w = wb;
-          via_boundary[(size_t)a * K + b] = 1;
-        }
-      }
-      bl.set_weight(a + 1, b + 1, 2 * (C - to_fixed(w * scale)));
+      if (bnd_len) w = std::min(w, bnd_len[a] + bnd_len[b]);
+      sb.add_edge(a, b, -(2 * to_fixed(w * scale)));
     }
   if (n > K)
-    for (int a = 0; a < K; ++a) bl.set_weight(a + 1, n, 2 * (C - to_fixed(bnd_len[a] * scale)));
-  const std::vector<int>& mate = bl.solve();
+    for (int a = 0; a < K; ++a) sb.add_edge(a, K, -(2 * to_fixed(bnd_len[a] * scale)));
+  sb.build_adjacency();
+  if (!greedy_start(sb, n, y_tls, vmate_tls) || !sb.solve()) return -3;
   int nq = 0;
   for (int a = 0; a < K; ++a) {
-    const int b = mate[a + 1] - 1;
+    const int b = sb.mate_vertex(a);
     if (b < 0) return -3;
     if (b >= K) {  // dummy
       out_src[nq] = a;
       out_dst[nq++] = -1;
     } else if (a < b) {
-      if (via_boundary[(size_t)a * K + b]) {
+      const long long at = (ll)a * K - (ll)a * (a + 1) / 2 + (b - a - 1);
+      if (bnd_len && bnd_len[a] + bnd_len[b] < pair_len[at]) {  // the pair weighs b_a + b_b: both end at their connector
         out_src[nq] = a; out_dst[nq++] = -1;
         out_src[nq] = b; out_dst[nq++] = -1;
       } else {
@@ -365,7 +153,7 @@ int solve_one(int K, const double* pair_len, const double* bnd_len, int* out_src
 }
 
 // Tuning / statistics of the sparse solver (process-wide).
-std::atomic<int> g_mode(0);   // 0: sparse from SPARSE_MIN_K cubes on, 1: always dense, 2: always sparse
+std::atomic<int> g_mode(0);   // 0: sparse from SPARSE_MIN_K cubes on, 1: always the complete graph, 2: always sparse
 std::atomic<int> g_knn(12);    // nearest partners per cube in the first candidate graph
 // sparse solves, retries with a denser candidate graph, pricing rounds, priced-in edges, then ns
 // spent in: candidate scan, graph build + jump start, solve stages, pricing (summed over threads)
@@ -377,7 +165,7 @@ const int SPARSE_MIN_K = 48;
 
 // Same problem as solve_one, solved on a sparse candidate graph and proved optimal for the
 // complete graph by pricing (mwpm_sparse.h).  Returns -100 when the caller should fall back to
-// the dense solver (candidate graph without a perfect matching, or too many pricing rounds).
+// the complete graph (candidate graph without a perfect matching, or too many pricing rounds).
 int solve_one_sparse(int K, const double* pair_len, const double* bnd_len, int* out_src, int* out_dst, int knn,
                      const int* cand = nullptr, int cand_k = 0) {
   using fpb_sparse::SparseBlossom;
@@ -579,56 +367,7 @@ int solve_one_sparse(int K, const double* pair_len, const double* bnd_len, int* 
   static thread_local std::vector<int> vmate_tls;
   std::vector<ll>& y = y_tls;
   std::vector<int>& vmate = vmate_tls;
-  // cold start (the usual greedy jump start of primal-dual matchers): feasible duals y_u = best
-  // incident weight; then every free vertex lowers its dual until its first edge becomes tight
-  // and takes that partner if it is still free.  All weights are even, so all duals stay even.
-  auto cold_start = [&]() -> bool {
-    y.assign(n, INT64_MIN);
-    vmate.assign(n, -1);
-    for (int k = 0; k < sb.n_edges(); ++k) {
-      y[sb.E[k].u] = std::max(y[sb.E[k].u], sb.E[k].w);
-      y[sb.E[k].v] = std::max(y[sb.E[k].v], sb.E[k].w);
-    }
-    for (int u = 0; u < n; ++u)
-      if (y[u] == INT64_MIN) return false;
-    for (int u = 0; u < n; ++u) {
-      if (vmate[u] >= 0) continue;
-      ll smin = INT64_MAX;
-      int pick = -1;
-      sb.for_neighbours(u, [&](int v, ll w) {
-        const ll sl = y[u] + y[v] - 2 * w;
-        if (sl < smin || (sl == smin && pick >= 0 && vmate[pick] >= 0 && vmate[v] < 0)) {
-          smin = sl;
-          pick = v;
-        }
-      });
-      y[u] -= smin;
-      if (vmate[pick] < 0) {
-        vmate[u] = pick;
-        vmate[pick] = u;
-      }
-    }
-    // augmenting paths of three tight edges (free - matched = matched - free) need no search
-    for (int u = 0; u < n; ++u) {
-      if (vmate[u] >= 0) continue;
-      bool found = false;
-      sb.for_neighbours(u, [&](int v, ll w) {
-        if (found || vmate[v] < 0 || y[u] + y[v] != 2 * w) return;
-        const int v2 = vmate[v];
-        int x = -1;
-        sb.for_neighbours(v2, [&](int c, ll w2) {
-          if (x < 0 && c != u && vmate[c] < 0 && y[v2] + y[c] == 2 * w2) x = c;
-        });
-        if (x >= 0) {
-          vmate[u] = v; vmate[v] = u;
-          vmate[v2] = x; vmate[x] = v2;
-          found = true;
-        }
-      });
-    }
-    sb.start(y, vmate);
-    return true;
-  };
+  auto cold_start = [&]() -> bool { return greedy_start(sb, n, y, vmate); };
   if (!cold_start()) return -100;
   g_stats[0].fetch_add(1);
   g_stats[5].fetch_add(now_ns() - t_scan);
@@ -827,7 +566,7 @@ struct SparseJob {
     if (!bnd && (K & 1)) { state = FAILED; error = -1; return; }
     n = (bnd && (K & 1)) ? K + 1 : K;
     if (bnd) blen.assign(bnd_len, bnd_len + K);
-    if (K < SPARSE_MIN_K || K < 4) {  // small graph: ask for every pair and solve it densely
+    if (K < SPARSE_MIN_K || K < 4) {  // small graph: ask for every pair and solve the complete graph
       for (int a = 0; a < K - 1; ++a)
         for (int b = a + 1; b < K; ++b) { req_a.push_back(a); req_b.push_back(b); }
       state = DENSE_WAIT;
@@ -915,52 +654,7 @@ struct SparseJob {
     if (state == FAILED) error = -100;
   }
 
-  bool cold_start() {  // as in solve_one_sparse
-    y.assign(n, INT64_MIN);
-    vmate.assign(n, -1);
-    for (int k = 0; k < sb.n_edges(); ++k) {
-      y[sb.E[k].u] = std::max(y[sb.E[k].u], sb.E[k].w);
-      y[sb.E[k].v] = std::max(y[sb.E[k].v], sb.E[k].w);
-    }
-    for (int u = 0; u < n; ++u)
-      if (y[u] == INT64_MIN) return false;
-    for (int u = 0; u < n; ++u) {
-      if (vmate[u] >= 0) continue;
-      ll smin = INT64_MAX;
-      int pick = -1;
-      sb.for_neighbours(u, [&](int v, ll w) {
-        const ll sl = y[u] + y[v] - 2 * w;
-        if (sl < smin || (sl == smin && pick >= 0 && vmate[pick] >= 0 && vmate[v] < 0)) {
-          smin = sl;
-          pick = v;
-        }
-      });
-      y[u] -= smin;
-      if (vmate[pick] < 0) {
-        vmate[u] = pick;
-        vmate[pick] = u;
-      }
-    }
-    for (int u = 0; u < n; ++u) {
-      if (vmate[u] >= 0) continue;
-      bool found = false;
-      sb.for_neighbours(u, [&](int v, ll w) {
-        if (found || vmate[v] < 0 || y[u] + y[v] != 2 * w) return;
-        const int v2 = vmate[v];
-        int x = -1;
-        sb.for_neighbours(v2, [&](int c, ll w2) {
-          if (x < 0 && c != u && vmate[c] < 0 && y[v2] + y[c] == 2 * w2) x = c;
-        });
-        if (x >= 0) {
-          vmate[u] = v; vmate[v] = u;
-          vmate[v2] = x; vmate[x] = v2;
-          found = true;
-        }
-      });
-    }
-    sb.start(y, vmate);
-    return true;
-  }
+  bool cold_start() { return greedy_start(sb, n, y, vmate); }
 
   // one solve; on success the duals for the device-side pricing pass: an edge of reduced length w is
   // violated iff y_u + y_v + ((4 * to_fixed(w * scale)) << wshift) + blossom duals < 0
@@ -1082,8 +776,8 @@ std::vector<SparseBatch*> g_pool;
 
 extern "C" {
 
-// mode 0: automatic (sparse + pricing for large graphs), 1: dense O(n^3) solver only, 2: sparse only
-// (dense fallback stays).  knn > 0 sets the nearest-partner count of the first candidate graph.
+// mode 0: automatic (sparse + pricing for large graphs), 1: complete graph only, 2: sparse only
+// (the complete-graph last resort stays).  knn > 0 sets the nearest-partner count of the first candidate graph.
 void fpb_mwpm_configure(int mode, int knn) {
   g_mode.store(mode);
   if (knn > 0) g_knn.store(knn);

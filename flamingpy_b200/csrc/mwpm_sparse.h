@@ -8,8 +8,8 @@
 // one of the K(K-1)/2 edges, edges with negative reduced cost are added, and the solver is
 // warm-started from the repaired duals until no edge is violated.  By LP duality (Edmonds'
 // perfect-matching polytope: vertex duals free, blossom duals >= 0) the final matching is a
-// minimum-weight perfect matching of the complete graph - the same optimum the dense solver in
-// mwpm.cpp finds, only the choice among ties may differ.
+// minimum-weight perfect matching of the complete graph - the same optimum as handing the solver
+// every edge (solve_one in mwpm.cpp), only the choice among ties may differ.
 //
 // The solver is the classical primal-dual formulation with adjacency lists (labels S/T on
 // top-level blossoms, dual adjustment by the minimum of the free-vertex / S-S / T-blossom slacks,

@@ -61,10 +61,11 @@ CAND_K = 12        # candidate partners per cube requested from the device (= th
 
 
 def configure(mode: str = "auto", knn: int = 0) -> None:
-    """Choose the solver: ``"auto"`` (sparse candidate graph + pricing from 48 cubes on, dense
-    O(n^3) below), ``"dense"`` or ``"sparse"``; ``knn`` = nearest partners per cube in the first
-    candidate graph (0 keeps the current value).  Both solvers return a minimum-weight perfect
-    matching of the same complete graph; only the choice among ties can differ."""
+    """Choose the driver: ``"auto"`` (sparse candidate graph + pricing from 48 cubes on, every edge
+    of the complete graph below), ``"dense"`` (the complete graph for every K) or ``"sparse"``;
+    ``knn`` = nearest partners per cube in the first candidate graph (0 keeps the current value).
+    Each returns a minimum-weight perfect matching of the same complete graph; only the choice among
+    ties can differ."""
     load().fpb_mwpm_configure(MODES[mode], int(knn))
 
 

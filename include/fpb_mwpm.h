@@ -70,10 +70,11 @@ void fpb_mwpm_sparse_free(void* ctx);
 
 int fpb_mwpm_max_threads(void);
 
-/* mode 0: sparse candidate graph + pricing from 48 cubes on, dense O(n^3) below (default);
- * 1: dense only; 2: sparse for every K >= 4.  knn > 0: nearest partners per cube in the first
- * candidate graph (default 12).  Both solvers return a minimum-weight perfect matching of the same
- * complete graph; only the choice among ties can differ. */
+/* mode 0: sparse candidate graph + pricing from 48 cubes on, every edge of the complete graph
+ * below (default); 1 ("dense"): the complete graph for every K; 2: sparse for every K >= 4.
+ * knn > 0: nearest partners per cube in the first candidate graph (default 12).  It is one
+ * primal-dual solver in all modes (csrc/mwpm_sparse.h); each mode returns a minimum-weight
+ * perfect matching of the same complete graph, only the choice among ties can differ. */
 void fpb_mwpm_configure(int mode, int knn);
 
 /* out[0..7]: sparse solves, retries with a denser candidate graph, pricing rounds, priced-in edges,

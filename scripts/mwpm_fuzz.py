@@ -1,17 +1,18 @@
-"""Fuzz the sparse matcher against the dense one on random matching graphs (no GPU needed): equal total
-weight on every graph.  Both paths are exercised: the triangle-based solver (``mwpm_native.solve``) and
+"""Fuzz the sparse-candidate + pricing driver against the complete-graph driver on random matching graphs (no GPU
+needed): equal total weight on every graph; every tenth graph of up to 70 cubes also against networkx.  Both paths are exercised: the triangle-based solver (``mwpm_native.solve``) and
 the sparse hand-off state machine against the NumPy device stand-in of tests/test_mwpm_sparse_handoff.py.
     python scripts/mwpm_fuzz.py [seconds] [seed]"""
 import sys, time; sys.path.insert(0, ".")
 import numpy as np
 from flamingpy_b200 import mwpm_native as mw
+from flamingpy_b200.matching import solve_matching
 from tests.test_mwpm_native import _random_graph, total_weight
 from tests.test_mwpm_sparse_handoff import DeviceStandIn
 
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
 seed = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 rng = np.random.default_rng(seed)
-t0, n_graphs, n_batches = time.time(), 0, 0
+t0, n_graphs, n_batches, n_nx = time.time(), 0, 0, 0
 try:
     while time.time() - t0 < budget:
         boundary = bool(rng.integers(0, 2))
@@ -30,6 +31,10 @@ try:
         wr, wg = total_weight(K, ref, pair, bnd), total_weight(K, got, pair, bnd)
         assert abs(wr - wg) <= 1e-9 + 1e-12 * abs(wr), ("solve", seed, n_graphs, K, kind, boundary, knn, wr, wg)
         n_graphs += 1
+        if n_graphs % 10 == 0 and K <= 70:  # an independent implementation
+            wn = total_weight(K, solve_matching(K, pair, b, backend="networkx"), pair, bnd)
+            assert abs(wr - wn) <= 1e-9 + 1e-9 * abs(wn), ("networkx", seed, n_graphs, K, kind, boundary, wr, wn)
+            n_nx += 1
         if n_graphs % 5 == 0:  # the hand-off path, a few graphs per batch
             Ks = [int(k) + (int(k) % 2 if not boundary else 0) for k in rng.choice([0, 3, 30, 50, 70, 110, 160], 4)]
             graphs = [_random_graph(rng, k, int(rng.integers(0, 4))) if k else (np.empty(0), np.empty(0)) for k in Ks]
@@ -48,4 +53,4 @@ try:
             n_batches += 1
 finally:
     mw.configure("auto", knn=12)
-print(f"ok: {n_graphs} graphs, {n_batches} hand-off batches in {time.time() - t0:.0f} s (seed {seed})")
+print(f"ok: {n_graphs} graphs ({n_nx} also against networkx), {n_batches} hand-off batches in {time.time() - t0:.0f} s (seed {seed})")
