@@ -543,6 +543,23 @@ __device__ __forceinline__ uint32_t seed_cube(const WarpMem& wm, int c, double d
 // ---- explicit shared-memory accessors (32-bit shared-window addresses; volatile keeps the
 // program order of the search's loads and stores, which the conflict resolution relies on) ----
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+#ifdef FPB_EMU  // host build of tests/emu (CPU SIMT emulation for the parity tests): plain volatile accesses
+__device__ __forceinline__ double lds_f64(uint32_t a) { return *fpb_emu::shared_ptr<volatile double>(a); }
+__device__ __forceinline__ void sts_f64(uint32_t a, double v) { *fpb_emu::shared_ptr<volatile double>(a) = v; }
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) { return *fpb_emu::shared_ptr<volatile uint16_t>(a); }
+__device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) { *fpb_emu::shared_ptr<volatile uint16_t>(a) = (uint16_t)v; }
+__device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) { *fpb_emu::shared_ptr<volatile uint8_t>(a) = (uint8_t)v; }
+__device__ __forceinline__ uint4 lds_v4(uint32_t a) {
+  volatile uint32_t* q = fpb_emu::shared_ptr<volatile uint32_t>(a);
+  return make_uint4(q[0], q[1], q[2], q[3]);
+}
+__device__ __forceinline__ void sts_v4(uint32_t a, uint4 v) {
+  volatile uint32_t* q = fpb_emu::shared_ptr<volatile uint32_t>(a);
+  q[0] = v.x; q[1] = v.y; q[2] = v.z; q[3] = v.w;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { return *fpb_emu::shared_ptr<volatile uint32_t>(a); }
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { *fpb_emu::shared_ptr<volatile uint32_t>(a) = v; }
+#else
 __device__ __forceinline__ double lds_f64(uint32_t a) {
   double v;
   asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
@@ -570,6 +587,8 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
   return v;
 }
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v)); }
+#endif
 
 // bytes of `word` equal to the byte replicated in r4: returns 0x80 in each matching byte
 // (exact: no carries cross a byte boundary)
@@ -698,6 +717,9 @@ __device__ __forceinline__ void warp_search(const CtaMem& cm, const WarpMem& wm,
             }
           }
         }
+        // ILEN: a staged cube's (distance, int length) pair must be read before any lane of this round stores,
+        // or a candidate could combine a neighbour's new distance with the old int length
+        if (ILEN) __syncwarp();
 #pragma unroll
         for (int d = 0; d < 6; ++d)
 #pragma unroll
@@ -735,7 +757,7 @@ __device__ __forceinline__ void warp_search(const CtaMem& cm, const WarpMem& wm,
               if (imp[k][d] && fin[k][d] == nd[k][d]) sts_u8(pred_a + ui, d);
             }
             if (ILEN) {
-              if (imp[k][d] && fin[k][d] == nd[k][d]) asm volatile("st.shared.u32 [%0], %1;" ::"r"(ilen_a + 4u * ui), "r"(il[k][d]));
+              if (imp[k][d] && fin[k][d] == nd[k][d]) sts_u32(ilen_a + 4u * ui, (uint32_t)il[k][d]);
             }
           }
         __syncwarp();
@@ -908,6 +930,10 @@ __global__ void __launch_bounds__(MAXT, MINB) k_paths(const __grid_constant__ Pa
 // all stores of a batch precede every verify load, and the redo flag, staging counts and filed
 // slots are exchanged through a few shared words.  Control flow is identical in both warps.
 // ------------------------------------------------------------------------------------------
+#ifdef FPB_EMU
+__device__ __forceinline__ void team_bar(int id) { fpb_emu::named_barrier(id, 64, 0); }
+__device__ __forceinline__ bool team_bar_or(int id, bool pred) { return fpb_emu::named_barrier(id, 64, pred) != 0; }
+#else
 __device__ __forceinline__ void team_bar(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 // the pair's barrier with an OR of one predicate per thread folded in (bar.red)
 __device__ __forceinline__ bool team_bar_or(int id, bool pred) {
@@ -919,6 +945,7 @@ __device__ __forceinline__ bool team_bar_or(int id, bool pred) {
       : "memory");
   return r != 0;
 }
+#endif
 
 struct TeamX {      // exchange words of one team (shared memory)
   int cnt[2];       // staged cubes per half
@@ -1427,6 +1454,12 @@ struct TeamXW {
   int lp[W];
   int redo[2][W];
 };
+#ifdef FPB_EMU
+template <int W>
+__device__ __forceinline__ void teamw_bar(int id) { fpb_emu::named_barrier(id, 32 * W, 0); }
+template <int W>
+__device__ __forceinline__ bool teamw_bar_or(int id, bool pred) { return fpb_emu::named_barrier(id, 32 * W, pred) != 0; }
+#else
 template <int W>
 __device__ __forceinline__ void teamw_bar(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(32 * W) : "memory"); }
 // barrier over the team that also ORs one predicate of every thread (one instruction instead of
@@ -1441,6 +1474,7 @@ __device__ __forceinline__ bool teamw_bar_or(int id, bool pred) {
       : "memory");
   return r != 0;
 }
+#endif
 
 template <int NCHW, int W>
 __device__ __forceinline__ void teamw_search(const CtaMem& cm, const WarpMem& wm, const DirTab& dt, int S, double step,
