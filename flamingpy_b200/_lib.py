@@ -155,6 +155,8 @@ EXPORTS = {
     "fpb_mark": (C.c_int, [C.c_void_p, C.c_int]),
     "fpb_elapsed_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "fpb_paths_toggle": (C.c_int, [C.c_void_p, C.c_int64, _i32p, _i32p, _i32p, _i32p, _u32p]),
+    "fpb_uf_set_graph": (C.c_int, [C.c_void_p, C.c_int, C.c_int32, _i32p, _i32p]),
+    "fpb_uf_decode": (C.c_int, [C.c_void_p, C.c_int, _u32p, _u32p, _i32p]),
 }
 
 _lib = None
@@ -479,6 +481,24 @@ class CtypesHandle:
         p = lambda a: a.ctypes.data_as(_i32p)  # noqa: E731
         check(self._lib.fpb_paths_list(self._h, n, p(trial), p(cx), p(src), p(dst), max_len, p(qubits), p(length)))
         return qubits, length
+
+
+# ---------------------------------------------------------------------------------------------
+# Device Union-Find decoder: plain C-ABI calls on the handle's address, the same for both bindings
+# ---------------------------------------------------------------------------------------------
+def uf_set_graph(handle, complex_index: int, n_nodes: int, edge_a, edge_b):
+    """``fpb_uf_set_graph`` on a handle of either binding (int32 arrays, one entry per syndrome qubit)."""
+    check(load().fpb_uf_set_graph(C.c_void_p(handle.address()), complex_index, int(n_nodes),
+                                  edge_a.ctypes.data_as(_i32p), edge_b.ctypes.data_as(_i32p)))
+
+
+def uf_decode(handle, use_erasures: bool, flips, grown=None) -> int:
+    """``fpb_uf_decode``: fills ``flips`` (and ``grown`` if given) uint32[T, bit_words]; returns the number of
+    stuck items."""
+    stuck = C.c_int32()
+    check(load().fpb_uf_decode(C.c_void_p(handle.address()), int(bool(use_erasures)), flips.ctypes.data_as(_u32p),
+                               grown.ctypes.data_as(_u32p) if grown is not None else None, C.byref(stuck)))
+    return int(stuck.value)
 
 
 _fpbpy = None

@@ -16,6 +16,7 @@
 
 #include "fpb_kernels.cuh"
 #include "fpb_macro.cuh"
+#include "fpb_uf.cuh"
 
 using namespace fpb;
 
@@ -125,6 +126,11 @@ struct fpb_handle {
   DevBuf<float> m_mean;
   DevBuf<double> m_z, m_val, m_p_phase, m_outcome;
   bool last_macro = false;
+  bool last_labels = false;  // the last run had state labels (injected, generated or macronode): erasures are defined
+  // device Union-Find decoder (fpb_uf_set_graph / fpb_uf_decode)
+  int* uf_edge_a[FPB_MAX_COMPLEX] = {nullptr, nullptr};
+  int* uf_edge_b[FPB_MAX_COMPLEX] = {nullptr, nullptr};
+  int uf_nodes[FPB_MAX_COMPLEX] = {0, 0};
   // sparse hand-off (fpb_knn_len / fpb_pairs_at / fpb_price)
   DevBuf<unsigned long long> trial_wmax, price_n;
   DevBuf<long long> price_y;
@@ -553,6 +559,7 @@ int run_pipeline(fpb_handle* h, long long T, int stage, int source, uint64_t see
   }
   const bool macro = source == SRC_MACRO || source == SRC_MACRO_GEN;
   h->last_macro = macro;
+  h->last_labels = macro || source == SRC_INJECTED || source == SRC_GEN;
   if (source == SRC_MACRO_GEN) {
     MacroGenParams g;
     g.M = 4 * h->N;
@@ -826,6 +833,7 @@ int fpb_destroy(fpb_handle* h) {
   h->flips.release(); h->item_off.release(); h->counter.release(); h->totals.release();
   h->path_qubits.release(); h->path_len.release();
   cudaFree(h->macro_partner); cudaFree(h->macro_sign);
+  for (int c = 0; c < FPB_MAX_COMPLEX; ++c) { cudaFree(h->uf_edge_a[c]); cudaFree(h->uf_edge_b[c]); }
   h->m_state.release(); h->m_body.release(); h->m_red_state.release(); h->m_bit_val.release(); h->m_mean.release();
   h->m_z.release(); h->m_val.release(); h->m_p_phase.release(); h->m_outcome.release();
   h->trial_wmax.release(); h->price_n.release(); h->price_y.release(); h->price_c.release(); h->price_ws.release(); h->price_top.release();
@@ -1391,6 +1399,83 @@ int fpb_paths_list(fpb_handle* h, int64_t n_queries, const int32_t* trial, const
   if (!h || !qubits || !length) return fail(FPB_ERR_ARG, "null argument");
   if (max_len < 1) return fail(FPB_ERR_ARG, "max_len must be positive");
   return run_path_queries(h, n_queries, trial, cx_id, src, dst, nullptr, max_len, qubits, length);
+}
+
+int fpb_uf_set_graph(fpb_handle* h, int complex_index, int32_t n_nodes, const int32_t* edge_a, const int32_t* edge_b) {
+  if (!h || !edge_a || !edge_b) return fail(FPB_ERR_ARG, "null argument");
+  if (complex_index < 0 || complex_index >= h->ncx) return fail(FPB_ERR_ARG, "complex index out of range");
+  const ComplexHost& cx = h->cx[complex_index];
+  if (n_nodes < cx.S || n_nodes > 65000) return fail(FPB_ERR_ARG, "n_nodes must be in [n_cubes, 65000]");
+  for (int q = 0; q < cx.Q; ++q) {
+    if (edge_a[q] < 0) continue;
+    if (edge_a[q] >= cx.S || edge_b[q] < 0 || edge_b[q] >= n_nodes || edge_b[q] == edge_a[q])
+      return fail(FPB_ERR_ARG, "edge end out of range (edge_a: a cube, edge_b: another cube or a boundary point)");
+  }
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  cudaFree(h->uf_edge_a[complex_index]);
+  cudaFree(h->uf_edge_b[complex_index]);
+  h->uf_edge_a[complex_index] = h->uf_edge_b[complex_index] = nullptr;
+  h->uf_nodes[complex_index] = 0;
+  int rc;
+  if ((rc = upload(edge_a, (size_t)cx.Q, &h->uf_edge_a[complex_index]))) return rc;
+  if ((rc = upload(edge_b, (size_t)cx.Q, &h->uf_edge_b[complex_index]))) return rc;
+  h->uf_nodes[complex_index] = n_nodes;
+  return FPB_OK;
+}
+
+int fpb_uf_decode(fpb_handle* h, int use_erasures, uint32_t* flips_host, uint32_t* grown_host, int32_t* n_stuck) {
+  if (!h || !flips_host || !n_stuck) return fail(FPB_ERR_ARG, "null argument");
+  if (h->T <= 0 || h->last_stage < FPB_STAGE_SYNDROME) return fail(FPB_ERR_STATE, "the Union-Find decoder needs a completed syndrome-stage run");
+  if (use_erasures && !h->last_labels) return fail(FPB_ERR_STATE, "the last run carried no state labels: no erasures to take");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  UfParams up;
+  memset(&up, 0, sizeof up);
+  up.n_complex = h->ncx; up.N = h->N; up.bit_words = h->bit_words;
+  size_t smem = 0;
+  for (int c = 0; c < h->ncx; ++c) {
+    if (!h->uf_edge_a[c]) return fail(FPB_ERR_STATE, "no decoder graph: call fpb_uf_set_graph for every complex first");
+    up.cx[c] = make_dev(h->cx[c]);
+    up.edge_a[c] = h->uf_edge_a[c];
+    up.edge_b[c] = h->uf_edge_b[c];
+    up.n_nodes[c] = h->uf_nodes[c];
+    const size_t b = uf_smem_bytes(h->uf_nodes[c], h->cx[c].Q);
+    if (b > smem) smem = b;
+  }
+  int max_optin = 0;
+  CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+  cudaFuncAttributes fattr;
+  CK(cudaFuncGetAttributes(&fattr, k_uf));
+  const size_t room = (size_t)max_optin - fattr.sharedSizeBytes;
+  if (smem > room) return fail(FPB_ERR_UNSUPPORTED, "lattice too large for the shared-memory Union-Find kernel");
+  CK(cudaFuncSetAttribute(k_uf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)room));
+  up.state = use_erasures ? (h->last_macro ? h->m_red_state.p : h->state.p) : nullptr;
+  up.adj_indptr = h->adj_indptr; up.adj_indices = h->adj_indices; up.qubit_node = h->qubit_node;
+  int rc;
+  const size_t nflip = (size_t)h->T * h->bit_words;
+  if ((rc = h->flips.ensure(nflip))) return rc;
+  if ((rc = h->counter.ensure(1))) return rc;
+  CK(cudaMemsetAsync(h->flips.p, 0, nflip * sizeof(uint32_t), st));
+  CK(cudaMemsetAsync(h->counter.p, 0, sizeof(int), st));
+  up.flips = h->flips.p;
+  up.stuck = h->counter.p;
+  if (grown_host) {  // second half of the flips buffer
+    if ((rc = h->flips.ensure(2 * nflip))) return rc;
+    up.flips = h->flips.p;
+    up.grown = h->flips.p + nflip;
+    CK(cudaMemsetAsync(h->flips.p, 0, 2 * nflip * sizeof(uint32_t), st));
+  }
+  NvtxRange nvtx_uf("fpb:union_find");
+  k_uf<<<dim3((unsigned)h->T, (unsigned)h->ncx), 256, smem, st>>>(up);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(flips_host, h->flips.p, nflip * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  if (grown_host) CK(cudaMemcpyAsync(grown_host, h->flips.p + nflip, nflip * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  int stuck = 0;
+  CK(cudaMemcpyAsync(&stuck, h->counter.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  *n_stuck = stuck;
+  return FPB_OK;
 }
 
 }  // extern "C"

@@ -265,6 +265,31 @@ class TrialEngine:
         parity = [unpack_bits(bufs[f"parity{i}"], self.lat.complexes[ec].S) for i, ec in enumerate(self.ec)]
         return unpack_bits(bufs["bits"], self.Qtot), parity, bufs.get("state")
 
+    def uf_decode(self, use_erasures: bool = True, want_grown: bool = False):
+        """Union-Find + peeling recovery of the last run (stage >= SYNDROME) computed on the device
+        (``fpb_uf_decode``, ``csrc/fpb_uf.cuh``): bit flips uint8[T, Qtot].  ``use_erasures``: start from the
+        erased edges the state labels of the run define (two or more p-squeezed neighbours); runs without
+        labels (bit-level, i.i.d.) have none.  ``want_grown``: also the fully grown edges uint8[T, Qtot] (the
+        reference's Support table when the growth stops).  Raises ``ValueError`` like the host decoder when
+        an odd cluster can neither grow nor reach a boundary point."""
+        from . import uf_native
+
+        if not getattr(self, "_uf_graph_set", False):
+            for i, ec in enumerate(self.ec):
+                n_nodes, ea, eb = uf_native.uf_graph(self.lat.complexes[ec])
+                _lib.uf_set_graph(self._h, i, n_nodes, np.ascontiguousarray(ea, np.int32), np.ascontiguousarray(eb, np.int32))
+            self._uf_graph_set = True
+        T = int(self.sizes().n_trials)
+        flips = np.zeros((T, self.bit_words), np.uint32)
+        grown = np.zeros((T, self.bit_words), np.uint32) if want_grown else None
+        stuck = _lib.uf_decode(self._h, use_erasures, flips, grown)
+        if stuck:
+            raise ValueError(f"{stuck} (trial, complex) item(s): an odd cluster can neither grow nor reach a boundary point "
+                             "(odd number of unsatisfied stabilizers on a complex without boundary)")
+        if want_grown:
+            return unpack_bits(flips, self.Qtot), unpack_bits(grown, self.Qtot)
+        return unpack_bits(flips, self.Qtot)
+
     def fetch_macro(self) -> dict:
         """Reduced lattice of the last macronode run, each [T, N]: ``red_state`` (1 GKP, 2 p),
         ``bit_val``, ``p_phase_cond``, ``outcome`` (effective homodyne value)."""

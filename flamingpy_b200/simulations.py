@@ -75,6 +75,9 @@ def ec_monte_carlo(trials, code_instance, noise_instance, decoder, decoder_args,
     share of the cores (default 3 for the sparse hand-off, whose pricing rounds are batch-synchronous,
     2 for the full one).  ``reserve_sms``: SMs the persistent shortest-path kernel leaves free for the
     matcher's pricing kernels (default 4 with the sparse hand-off, else 0).
+    ``decoder="UF"``: ``backend="native"`` (default) grows and peels the clusters on the host cores
+    (``csrc/uf.cpp``); ``backend="device"`` does it on the GPU (``fpb_uf_decode``, one CTA per trial
+    and complex), so that only bits and flips cross the bus.
 
     Trial split: with ``torch.distributed`` initialised, over its ranks with one ``all_reduce`` of
     the counts (one process per GPU; NCCL).  Otherwise, if an mpi4py-style ``world_comm`` is given
@@ -139,15 +142,19 @@ def ec_monte_carlo(trials, code_instance, noise_instance, decoder, decoder_args,
                 eng.run_macro_rng(seed, first, n, stage=_lib.STAGE_SYNDROME, fetch=False)
             else:
                 eng.run_rng(seed, first, n, stage=_lib.STAGE_SYNDROME, fetch=False)
-            bits, parity, st = eng.fetch_syndrome(want_state=not iid and not macro and bool(n_pswap))
-            if macro:
-                st = eng.fetch_macro()["red_state"]
-            flips = uf_decode_batch(code_instance, parity, uf_erasures(code_instance, st))
+            if backend == "device":
+                flips = eng.uf_decode(use_erasures=not iid and (macro or bool(n_pswap)))
+                bits = eng.fetch_syndrome()[0]
+            else:
+                bits, parity, st = eng.fetch_syndrome(want_state=not iid and not macro and bool(n_pswap))
+                if macro:
+                    st = eng.fetch_macro()["red_state"]
+                flips = uf_decode_batch(code_instance, parity, uf_erasures(code_instance, st))
             failures += int(logical_failures(code_instance, TrialBatch(n, _lib.STAGE_SYNDROME, bits=bits), flips).sum())
             done += n
             t_dev += eng.timings()["total_ms"]
         return _reduce_counts(failures, done, trials, dist, rank, size, use_mpi, world_comm, device, return_stats,
-                              {"device_ms": t_dev, "handoff": "none"})
+                              {"device_ms": t_dev, "handoff": "none", "uf_backend": "device" if backend == "device" else "host"})
     if handoff is None:
         periodic = not any(code_instance.lattice.complexes[e].has_boundary for e in code_instance.ec)
         handoff = "sparse" if (backend == "native" and periodic) else "full"

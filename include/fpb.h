@@ -299,6 +299,25 @@ int fpb_paths_toggle(fpb_handle* h, int64_t n_queries, const int32_t* trial, con
 int fpb_paths_list(fpb_handle* h, int64_t n_queries, const int32_t* trial, const int32_t* cx, const int32_t* src,
                    const int32_t* dst, int32_t max_len, int32_t* qubits, int32_t* length);
 
+/* Union-Find decoder on the device (csrc/fpb_uf.cuh), the alternative to the host decoder of
+ * include/fpb_uf.h: same cluster growth as uf_decode / union_find / peeling
+ * (flamingpy/decoders/unionfind/algos.py:58-334; Support.grow, uf_classes.py:134-142), one CTA per
+ * (trial, complex) on the syndromes the last run left in HBM.
+ *
+ * fpb_uf_set_graph: the decoder graph of one complex, once per handle - nodes [0, n_cubes) are the
+ * cubes, [n_cubes, n_nodes) one boundary point per boundary qubit; edge q (a syndrome qubit, local id)
+ * joins edge_a[q] (a cube, or -1: the qubit has no edge, stabilizer_graph.py:295-298) and edge_b[q].
+ * fpb_uf_decode: needs a run with stage >= FPB_STAGE_SYNDROME.  use_erasures != 0 starts from the
+ * erased edges of assign_weights(code, "UF") (two or more p-squeezed neighbours,
+ * decoders/decoder.py:96-114), taken from the state labels of the last run (the reduced labels after a
+ * macronode run).  Writes the recovery as flips [T][ceil(Qtot/32)] (bit-packed, layout of bits),
+ * optionally (grown_host != NULL, same layout) the fully grown edges when the growth stops - the
+ * reference's Support table, which does not depend on visiting order - and the number of
+ * (trial, complex) items left with an odd cluster that can neither grow nor reach a boundary point
+ * (their flips stay zero). */
+int fpb_uf_set_graph(fpb_handle* h, int complex_index, int32_t n_nodes, const int32_t* edge_a, const int32_t* edge_b);
+int fpb_uf_decode(fpb_handle* h, int use_erasures, uint32_t* flips_host, uint32_t* grown_host, int32_t* n_stuck);
+
 #ifdef __cplusplus
 }
 #endif

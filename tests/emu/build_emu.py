@@ -1,5 +1,5 @@
 """TEST INFRASTRUCTURE - builds ``tests/emu/_build/libfpb_emu.so``: the kernel sources of
-``flamingpy_b200/csrc`` (fpb.cu + fpb_kernels.cuh + fpb_macro.cuh + philox.cuh) compiled by g++ against the
+``flamingpy_b200/csrc`` (fpb.cu and every .cuh it includes) compiled by g++ against the
 stand-in ``tests/emu/include/cuda_runtime.h`` and the SIMT machine ``tests/emu/simt.cpp``, so that the parity
 tests can run the real kernel code on the CPU (no GPU in the build container).
 
@@ -25,7 +25,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "flamingpy_b200", "csrc")
 BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(BUILD, "libfpb_emu.so")
-SOURCES = ["fpb.cu", "fpb_kernels.cuh", "fpb_macro.cuh", "philox.cuh"]
+SOURCES = sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh")))
 
 
 def _match_back(s: str, i: int) -> int:

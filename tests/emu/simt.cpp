@@ -113,6 +113,20 @@ int named_barrier(int id, int n_threads, int pred) {
   return b.result;
 }
 
+// FPB_EMU_SHUFFLE=<seed>: visit warps and lanes in a pseudo-random order that changes from pass to pass, to run the
+// kernels under other interleavings than the fixed round-robin one
+static unsigned long long shuffle_state = 0;
+static bool shuffle_on = false;
+static unsigned next_random() {
+  shuffle_state = shuffle_state * 6364136223846793005ull + 1442695040888963407ull;
+  return (unsigned)(shuffle_state >> 33);
+}
+static void fill_order(int* order, int n) {
+  for (int i = 0; i < n; ++i) order[i] = i;
+  if (shuffle_on)
+    for (int i = n - 1; i > 0; --i) std::swap(order[i], order[next_random() % (unsigned)(i + 1)]);
+}
+
 static void run_cta() {
   const int n = M.n_threads;
   const int n_warps = (n + 31) / 32;
@@ -125,20 +139,26 @@ static void run_cta() {
   }
   for (int t = 0; t < n; ++t) prepare_fiber(t);
   M.live = n;
+  int warp_order[MAX_THREADS / 32], lane_order[32];
   while (M.live > 0) {
     const long long before_cta = M.progress;
-    for (int w = 0; w < n_warps && M.live > 0; ++w) {
+    fill_order(warp_order, n_warps);
+    for (int wi = 0; wi < n_warps && M.live > 0; ++wi) {
+      const int w = warp_order[wi];
       // lanes of one warp round-robin for as long as the warp gets anywhere on its own
+      // (shuffled runs: one pass per visit, so that warps interleave at every collective)
       for (;;) {
         const long long before = M.progress;
-        for (int l = 0; l < 32; ++l) {
+        fill_order(lane_order, 32);
+        for (int li = 0; li < 32; ++li) {
+          const int l = lane_order[li];
           const int t = 32 * w + l;
           if (t >= n || M.fiber[t].done) continue;
           M.cur = t;
           set_thread_index(t);
           fpb_emu_switch(&M.sched_sp, M.fiber[t].sp);
         }
-        if (M.progress == before) break;
+        if (M.progress == before || shuffle_on) break;
       }
     }
     if (M.progress == before_cta && M.live > 0) {
@@ -157,6 +177,10 @@ void run_grid(dim3 grid, dim3 block, size_t smem, const std::function<void()>& b
     abort();
   }
   if (!M.stacks) {
+    if (const char* sv = getenv("FPB_EMU_SHUFFLE")) {
+      shuffle_on = true;
+      shuffle_state = strtoull(sv, nullptr, 10) * 2654435761ull + 88172645463325252ull;
+    }
     M.stacks = (unsigned char*)mmap(nullptr, STACK_BYTES * MAX_THREADS, PROT_READ | PROT_WRITE,
                                     MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
     if (M.stacks == (unsigned char*)MAP_FAILED) abort();

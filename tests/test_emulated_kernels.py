@@ -35,8 +35,8 @@ def emulated_library():
     return build_emu.build()
 
 
-def _child_pytest(lib, args, timeout):
-    env = dict(os.environ, FPB_LIB=lib, FPB_BINDING="ctypes")
+def _child_pytest(lib, args, timeout, **extra_env):
+    env = dict(os.environ, FPB_LIB=lib, FPB_BINDING="ctypes", **extra_env)
     cmd = [sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-p", "no:cacheprovider", "--timeout=180"] + args
     r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=timeout)
     m = re.search(r"(\d+) passed", r.stdout)
@@ -68,6 +68,16 @@ def test_remaining_gpu_tests_pass_on_the_emulated_kernels(emulated_library):
     kernels, the i.i.d. arm and the Union-Find path - minus the cases listed in UNSUPPORTED / SLOW."""
     deselect = " and ".join(f"not ({k})" for k in UNSUPPORTED + SLOW)
     files = ["tests/test_gpu_edge_cases.py", "tests/test_gpu_facade.py", "tests/test_gpu_handoff.py",
-             "tests/test_gpu_uf.py", "tests/test_gpu_boundary.py", "tests/test_macro.py", "tests/test_iid.py"]
+             "tests/test_gpu_uf.py", "tests/test_zz_gpu_uf_device.py", "tests/test_gpu_boundary.py", "tests/test_macro.py",
+             "tests/test_iid.py"]
     r, passed = _child_pytest(emulated_library, files + ["-n", "4", "-k", deselect], 1500)
-    assert r.returncode == 0 and passed >= 80, r.stdout[-3000:] + r.stderr[-1000:]
+    assert r.returncode == 0 and passed >= 95, r.stdout[-3000:] + r.stderr[-1000:]
+
+
+def test_results_do_not_depend_on_the_interleaving_of_warps(emulated_library):
+    """``FPB_EMU_SHUFFLE``: warps and lanes are visited in a pseudo-random order that changes at every scheduling
+    pass.  The searches (one-warp and two-warp team kernels, store-then-verify protocol) and the device Union-Find
+    decoder (racing min-id hooks) must give the same results under any interleaving."""
+    r, passed = _child_pytest(emulated_library, ["tests/test_gpu_parity.py", "tests/test_zz_gpu_uf_device.py", "-n", "4"], 900,
+                              FPB_EMU_SHUFFLE="20261020")
+    assert r.returncode == 0 and passed >= 45, r.stdout[-3000:] + r.stderr[-1000:]

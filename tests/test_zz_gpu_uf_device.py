@@ -1,0 +1,134 @@
+"""The Union-Find decoder on the device (``fpb_uf_set_graph`` / ``fpb_uf_decode``, csrc/fpb_uf.cuh) against the
+reference's own Support tables (tests/golden/uf_*.npz: the fully grown edges when the reference's growth stops,
+which do not depend on visiting order), against the host decoder (csrc/uf.cpp) on seeded trials, and through
+``ec_monte_carlo(..., "UF", backend="device")``.
+
+Developed after the round's GPU budget was spent: these tests have run on the CPU SIMT emulation of the kernel only
+(tests/test_emulated_kernels.py, where they must pass), not yet on a B200 - see DESIGN.md section 7.  Until a
+hardware run has confirmed the kernel they are non-strict xfail on a real device (a pass shows as XPASS), and the
+file sorts last so that a fault in the new kernel cannot disturb any other test's CUDA context."""
+import os
+
+import numpy as np
+import pytest
+
+from flamingpy_b200 import _lib, uf_native
+from flamingpy_b200.codes import SurfaceCode
+from flamingpy_b200.decoder import logical_failures, uf_decode_batch, uf_erasures
+from flamingpy_b200.engine import TrialBatch
+from flamingpy_b200.noise import CVLayer, CVMacroLayer, IidNoise
+from flamingpy_b200.simulations import ec_monte_carlo
+from tests import golden_util as gu
+
+_EMULATED = "libfpb_emu" in os.environ.get("FPB_LIB", "")
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(condition=not _EMULATED, strict=False,
+                                reason="k_uf has only run under CPU emulation so far (no GPU budget left in the round it was written)")]
+
+
+def _cube_parity(ct, flips):
+    """Parity each cube sees of a set of flipped qubits: uint8[T, S]."""
+    par = np.zeros((flips.shape[0], ct.S), np.uint8)
+    for f in range(6):
+        q = ct.cube_qubit[:, f]
+        has = q >= 0
+        par[:, has] ^= flips[:, q[has]]
+    return par
+
+
+@pytest.mark.parametrize("path", gu.uf_files(), ids=lambda p: os.path.basename(p)[:-4])
+def test_device_growth_equals_the_reference_support_tables(path):
+    """Injected reference draws -> device syndrome -> device Union-Find: the grown edges equal the reference's
+    Support table edge for edge, the recovery lies inside them and leaves no unsatisfied stabilizer, and on open
+    boundaries the verdict is the reference's on every trial."""
+    g = gu.load_uf(path)
+    code = SurfaceCode(g["distance"], g["ec"], g["boundaries"])
+    eng = code.engine(g["delta"], g["p_swap"], {"method": "uniform"}, mode="fresh")
+    eng.run_injected(g["x"], g["state"], stage=_lib.STAGE_SYNDROME)
+    flips, grown = eng.uf_decode(use_erasures=bool(g["p_swap"]), want_grown=True)
+    bits, parity, _ = eng.fetch_syndrome()
+    off = 0
+    for i, e in enumerate(code.ec):
+        ct = code.lattice.complexes[e]
+        assert np.array_equal(parity[i], g[f"{e}_parity"])
+        assert np.array_equal(grown[:, off:off + ct.Q], g[f"{e}_grown"]), e
+        fl = flips[:, off:off + ct.Q]
+        assert not (fl & ~grown[:, off:off + ct.Q]).any()
+        assert np.array_equal(_cube_parity(ct, fl), parity[i])
+        off += ct.Q
+    if all(b == "open" for b in code.lattice.boundaries):
+        fails = logical_failures(code, TrialBatch(g["trials"], _lib.STAGE_SYNDROME, bits=bits), flips)
+        assert np.array_equal(~fails.astype(bool), g["success"].astype(bool))
+
+
+@pytest.mark.parametrize("d,ec,bnd,delta,ps", [(5, "primal", "open", 0.1, 0.2), (4, "dual", "toric", 0.09, 0.3),
+                                               (4, "both", "periodic", 0.1, 0.0), (7, "primal", "open", 0.11, 0.0),
+                                               ((2, 3, 4), "primal", "open", 0.1, 0.5)])
+def test_device_decoder_against_the_host_decoder(d, ec, bnd, delta, ps):
+    """Device-RNG trials decoded by both decoders: equal grown sets, both recoveries clear the syndrome; on open
+    boundaries equal verdicts unless a cluster touches both sides (then the two spanning forests may differ by a
+    boundary-to-boundary path) - allowed in at most 2 % of the trials."""
+    code = SurfaceCode(d, ec, bnd)
+    eng = code.engine(delta, ps, {"method": "uniform"}, mode="fresh")
+    T = 300
+    eng.run_rng(11, 0, T, stage=_lib.STAGE_SYNDROME, fetch=False)
+    flips, grown = eng.uf_decode(use_erasures=bool(ps), want_grown=True)
+    bits, parity, st = eng.fetch_syndrome(want_state=bool(ps))
+    er = uf_erasures(code, st)
+    off = 0
+    host = []
+    for i, e in enumerate(code.ec):
+        ct = code.lattice.complexes[e]
+        hf, hg = uf_native.decode_batch(ct, parity[i], None if er is None else er[:, off:off + ct.Q], want_grown=True)
+        host.append(hf)
+        assert np.array_equal(grown[:, off:off + ct.Q], hg), e
+        assert np.array_equal(_cube_parity(ct, flips[:, off:off + ct.Q]), parity[i])
+        off += ct.Q
+    assert np.array_equal(np.concatenate(host, axis=1), uf_decode_batch(code, parity, er))
+    batch = TrialBatch(T, _lib.STAGE_SYNDROME, bits=bits)
+    f_dev = logical_failures(code, batch, flips)
+    f_host = logical_failures(code, batch, np.concatenate(host, axis=1))
+    if bnd == "open":
+        assert (f_dev != f_host).sum() <= T // 50
+    assert abs(int(f_dev.sum()) - int(f_host.sum())) <= 3 * np.sqrt(T)
+
+
+def test_monte_carlo_with_the_device_decoder():
+    """``ec_monte_carlo(..., "UF", backend="device")``: batch-invariant, every noise model, zero errors at tiny delta,
+    and the same failure count as the host decoder on a lattice whose clusters stay small."""
+    code = SurfaceCode(5, "primal", "open")
+    args = {"weight_opts": {"method": "uniform"}}
+    layer = CVLayer(code, delta=0.09, p_swap=0.2)
+    a = ec_monte_carlo(600, code, layer, "UF", args, seed=5, batch=64, mode="fresh", backend="device")
+    b, st = ec_monte_carlo(600, code, layer, "UF", args, seed=5, batch=600, mode="fresh", backend="device", return_stats=True)
+    h = ec_monte_carlo(600, code, layer, "UF", args, seed=5, batch=600, mode="fresh")
+    assert a == b and st["uf_backend"] == "device" and 0 < a < 600
+    assert abs(a - h) <= 12
+    quiet = CVLayer(code, delta=0.06, p_swap=0)
+    assert (ec_monte_carlo(400, code, quiet, "UF", args, seed=9, mode="fresh", backend="device")
+            == ec_monte_carlo(400, code, quiet, "UF", args, seed=9, mode="fresh"))
+    periodic = SurfaceCode(4, "primal", "periodic")
+    e = ec_monte_carlo(400, periodic, IidNoise(periodic, 0.03), "UF", args, seed=6, batch=128, backend="device")
+    assert 0 <= e < 200
+    macro = ec_monte_carlo(300, code, CVMacroLayer(code, delta=0.08, p_swap=0.1), "UF", args, seed=7, batch=100, backend="device")
+    assert 0 <= macro < 300
+    assert ec_monte_carlo(200, code, CVLayer(code, delta=0.001, p_swap=0), "UF", args, seed=8, backend="device") == 0
+
+
+def test_device_decoder_error_paths():
+    code = SurfaceCode(3, "primal", "open")
+    eng = code.engine(0.09, 0.25, {"method": "uniform"}, mode="fresh")
+    eng.run_rng(3, 0, 4, stage=_lib.STAGE_NOISE, fetch=False)
+    with pytest.raises(_lib.FpbError, match="syndrome-stage"):
+        eng.uf_decode()
+    eng.run_iid(3, 0, 4, 0.05, stage=_lib.STAGE_SYNDROME, fetch=False)
+    with pytest.raises(_lib.FpbError, match="no state labels"):
+        eng.uf_decode(use_erasures=True)
+    assert eng.uf_decode(use_erasures=False).shape == (4, eng.Qtot)
+    # an odd number of unsatisfied cubes on a complex without boundary points cannot be resolved
+    per = SurfaceCode(3, "primal", "periodic")
+    pe = per.engine(0.1, 0, {"method": "uniform"}, mode="fresh")
+    bits = np.zeros((1, pe.Qtot), np.uint8)
+    bits[0, 0] = 1  # flips two cubes
+    pe.run_bits(bits, stage=_lib.STAGE_SYNDROME, fetch=False)
+    assert pe.uf_decode(use_erasures=False).sum() >= 1
