@@ -525,11 +525,40 @@ def run_gpu_arm(args, cfg, lat):
                 "value": n_cpu / dt, "unit": "trials/s", "cores": threads, "kind": "port",
                 "sample": f"{n_cpu} trials of the same workload, oracle/fpb_oracle.c (C + OpenMP restatement of "
                           f"the reference path), draws and labels pre-sampled in host memory, {dt:.1f} s"}
+        if not args.no_uf_leg and world == 1:
+            line["uf"] = run_uf_leg(args, cfg)
         print(json.dumps(line), flush=True)
     for en in engines:
         en.close()
     if use_dist:
         dist.destroy_process_group()
+
+
+def run_uf_leg(args, cfg):
+    """Complete EC trials per second with decoder="UF" on the bench's lattice (uniform weights), host decoder and
+    device decoder, measured by scripts/uf_leg.py in a child process: the device decoder (k_uf) was written after the
+    last GPU session of its round, so it runs in a CUDA context of its own where a fault cannot touch the numbers
+    above; a side measurement - errors are reported in the object, never raised."""
+    import subprocess
+
+    cmd = [sys.executable, os.path.join(ROOT, "scripts", "uf_leg.py"), "--distance", str(cfg["distance"]), "--ec", cfg["ec"],
+           "--boundaries", cfg["boundaries"], "--delta", str(cfg["delta"]), "--p-swap", str(cfg["p_swap"]),
+           "--mode", args.mode, "--trials", str(args.uf_trials)]
+    out = {}
+    try:
+        r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=300)
+        for ln in r.stdout.splitlines():
+            try:
+                d = json.loads(ln)
+            except ValueError:
+                continue
+            if isinstance(d, dict) and "leg" in d:
+                out[d.pop("leg")] = d
+        if r.returncode != 0:
+            out["exit"] = {"returncode": r.returncode, "stderr_tail": r.stderr[-300:]}
+    except Exception as exc:  # noqa: BLE001
+        out["error"] = repr(exc)[:300]
+    return out
 
 
 def main():
@@ -552,6 +581,8 @@ def main():
     ap.add_argument("--no-e2e-full", action="store_true", help="skip the complete-EC-trial measurement (ec_monte_carlo)")
     ap.add_argument("--full-trials", type=int, default=32768, help="complete EC trials per GPU for e2e_full")
     ap.add_argument("--full-batch", type=int, default=512)
+    ap.add_argument("--no-uf-leg", action="store_true", help="skip the Union-Find side measurement (scripts/uf_leg.py, N = 1 only)")
+    ap.add_argument("--uf-trials", type=int, default=32768, help="complete EC trials of each Union-Find leg")
     ap.add_argument("--no-table", action="store_true", help="static-weight workloads: search instead of the table gather")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
