@@ -157,6 +157,8 @@ EXPORTS = {
     "fpb_paths_toggle": (C.c_int, [C.c_void_p, C.c_int64, _i32p, _i32p, _i32p, _i32p, _u32p]),
     "fpb_uf_set_graph": (C.c_int, [C.c_void_p, C.c_int, C.c_int32, _i32p, _i32p]),
     "fpb_uf_decode": (C.c_int, [C.c_void_p, C.c_int, _u32p, _u32p, _i32p]),
+    "fpb_set_planes": (C.c_int, [C.c_void_p, C.c_int32, _i32p, _i32p]),
+    "fpb_logical_check": (C.c_int, [C.c_void_p, _u8p, C.POINTER(C.c_int64)]),
 }
 
 _lib = None
@@ -496,9 +498,24 @@ def uf_decode(handle, use_erasures: bool, flips, grown=None) -> int:
     """``fpb_uf_decode``: fills ``flips`` (and ``grown`` if given) uint32[T, bit_words]; returns the number of
     stuck items."""
     stuck = C.c_int32()
-    check(load().fpb_uf_decode(C.c_void_p(handle.address()), int(bool(use_erasures)), flips.ctypes.data_as(_u32p),
+    check(load().fpb_uf_decode(C.c_void_p(handle.address()), int(bool(use_erasures)),
+                               flips.ctypes.data_as(_u32p) if flips is not None else None,
                                grown.ctypes.data_as(_u32p) if grown is not None else None, C.byref(stuck)))
     return int(stuck.value)
+
+
+def set_planes(handle, plane_off, plane_qubits):
+    """``fpb_set_planes``: int32 offsets [n_planes + 1] and global qubit ids of the checked correlation surfaces."""
+    check(load().fpb_set_planes(C.c_void_p(handle.address()), len(plane_off) - 1, plane_off.ctypes.data_as(_i32p),
+                                plane_qubits.ctypes.data_as(_i32p)))
+
+
+def logical_check(handle, fail=None) -> int:
+    """``fpb_logical_check``: fills ``fail`` uint8[T] if given; returns the number of failed trials."""
+    n = C.c_int64()
+    check(load().fpb_logical_check(C.c_void_p(handle.address()), fail.ctypes.data_as(_u8p) if fail is not None else None,
+                                   C.byref(n)))
+    return int(n.value)
 
 
 _fpbpy = None

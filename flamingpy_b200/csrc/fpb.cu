@@ -131,6 +131,11 @@ struct fpb_handle {
   int* uf_edge_a[FPB_MAX_COMPLEX] = {nullptr, nullptr};
   int* uf_edge_b[FPB_MAX_COMPLEX] = {nullptr, nullptr};
   int uf_nodes[FPB_MAX_COMPLEX] = {0, 0};
+  // logical check on the device (fpb_set_planes / fpb_logical_check)
+  int n_planes = 0;
+  int *plane_off = nullptr, *plane_qubits = nullptr;
+  long long flips_T = 0;  // trials the flips buffer holds a recovery for (0: none)
+  DevBuf<uint8_t> fail;
   // sparse hand-off (fpb_knn_len / fpb_pairs_at / fpb_price)
   DevBuf<unsigned long long> trial_wmax, price_n;
   DevBuf<long long> price_y;
@@ -515,6 +520,7 @@ int run_pipeline(fpb_handle* h, long long T, int stage, int source, uint64_t see
   memset(&h->tm, 0, sizeof h->tm);
   h->T = 0;  // no valid result until every stage below has completed
   h->last_stage = 0;
+  h->flips_T = 0;
   for (int c = 0; c < h->ncx; ++c) h->cx[c].total_odd = h->cx[c].total_pairs = 0;
   int launches = 0;
 
@@ -834,6 +840,7 @@ int fpb_destroy(fpb_handle* h) {
   h->path_qubits.release(); h->path_len.release();
   cudaFree(h->macro_partner); cudaFree(h->macro_sign);
   for (int c = 0; c < FPB_MAX_COMPLEX; ++c) { cudaFree(h->uf_edge_a[c]); cudaFree(h->uf_edge_b[c]); }
+  cudaFree(h->plane_off); cudaFree(h->plane_qubits); h->fail.release();
   h->m_state.release(); h->m_body.release(); h->m_red_state.release(); h->m_bit_val.release(); h->m_mean.release();
   h->m_z.release(); h->m_val.release(); h->m_p_phase.release(); h->m_outcome.release();
   h->trial_wmax.release(); h->price_n.release(); h->price_y.release(); h->price_c.release(); h->price_ws.release(); h->price_top.release();
@@ -1385,6 +1392,7 @@ static int run_path_queries(fpb_handle* h, int64_t n_queries, const int32_t* tri
   }
   if (flips_host) CK(cudaMemcpyAsync(flips_host, h->flips.p, nflip * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  if (flips_host) h->flips_T = h->T;  // the recovery stays on the device for fpb_logical_check
   return FPB_OK;
 }
 
@@ -1425,7 +1433,7 @@ int fpb_uf_set_graph(fpb_handle* h, int complex_index, int32_t n_nodes, const in
 }
 
 int fpb_uf_decode(fpb_handle* h, int use_erasures, uint32_t* flips_host, uint32_t* grown_host, int32_t* n_stuck) {
-  if (!h || !flips_host || !n_stuck) return fail(FPB_ERR_ARG, "null argument");
+  if (!h || !n_stuck) return fail(FPB_ERR_ARG, "null argument");
   if (h->T <= 0 || h->last_stage < FPB_STAGE_SYNDROME) return fail(FPB_ERR_STATE, "the Union-Find decoder needs a completed syndrome-stage run");
   if (use_erasures && !h->last_labels) return fail(FPB_ERR_STATE, "the last run carried no state labels: no erasures to take");
   CK(cudaSetDevice(h->device));
@@ -1469,12 +1477,61 @@ int fpb_uf_decode(fpb_handle* h, int use_erasures, uint32_t* flips_host, uint32_
   NvtxRange nvtx_uf("fpb:union_find");
   k_uf<<<dim3((unsigned)h->T, (unsigned)h->ncx), 256, smem, st>>>(up);
   CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(flips_host, h->flips.p, nflip * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  if (flips_host) CK(cudaMemcpyAsync(flips_host, h->flips.p, nflip * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   if (grown_host) CK(cudaMemcpyAsync(grown_host, h->flips.p + nflip, nflip * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   int stuck = 0;
   CK(cudaMemcpyAsync(&stuck, h->counter.p, sizeof(int), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   *n_stuck = stuck;
+  h->flips_T = h->T;
+  return FPB_OK;
+}
+
+int fpb_set_planes(fpb_handle* h, int32_t n_planes, const int32_t* plane_off, const int32_t* plane_qubits) {
+  if (!h || !plane_off || (n_planes > 0 && !plane_qubits)) return fail(FPB_ERR_ARG, "null argument");
+  if (n_planes < 0 || plane_off[0] != 0) return fail(FPB_ERR_ARG, "plane offsets must start at 0");
+  for (int i = 0; i < n_planes; ++i)
+    if (plane_off[i + 1] < plane_off[i]) return fail(FPB_ERR_ARG, "plane offsets must not decrease");
+  const int total = plane_off[n_planes];
+  for (int i = 0; i < total; ++i)
+    if (plane_qubits[i] < 0 || plane_qubits[i] >= h->Qtot) return fail(FPB_ERR_ARG, "plane qubit out of range");
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  cudaFree(h->plane_off);
+  cudaFree(h->plane_qubits);
+  h->plane_off = h->plane_qubits = nullptr;
+  h->n_planes = 0;
+  int rc;
+  if ((rc = upload(plane_off, (size_t)n_planes + 1, &h->plane_off))) return rc;
+  if ((rc = upload(plane_qubits, (size_t)total, &h->plane_qubits))) return rc;
+  h->n_planes = n_planes;
+  return FPB_OK;
+}
+
+int fpb_logical_check(fpb_handle* h, uint8_t* fail_host, int64_t* n_fail) {
+  if (!h || !n_fail) return fail(FPB_ERR_ARG, "null argument");
+  if (!h->plane_off) return fail(FPB_ERR_STATE, "no correlation surfaces: call fpb_set_planes first");
+  if (h->T <= 0 || h->flips_T != h->T) return fail(FPB_ERR_STATE, "no recovery on the device for the last run (fpb_uf_decode / fpb_paths_toggle)");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  int rc;
+  if ((rc = h->fail.ensure((size_t)h->T))) return rc;
+  if ((rc = h->counter.ensure(1))) return rc;
+  CK(cudaMemsetAsync(h->counter.p, 0, sizeof(int), st));
+  CheckParams cp;
+  cp.T = (int)h->T; cp.bit_words = h->bit_words; cp.n_planes = h->n_planes;
+  cp.plane_off = h->plane_off; cp.plane_qubits = h->plane_qubits;
+  cp.bits = h->bits.p; cp.flips = h->flips.p; cp.fail = h->fail.p; cp.n_fail = h->counter.p;
+  long long blocks = (h->T + 7) / 8;
+  const long long cap = (long long)h->sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  k_logical_check<<<(unsigned)blocks, 256, 0, st>>>(cp);
+  CK(cudaGetLastError());
+  if (fail_host) CK(cudaMemcpyAsync(fail_host, h->fail.p, (size_t)h->T, cudaMemcpyDeviceToHost, st));
+  int nf = 0;
+  CK(cudaMemcpyAsync(&nf, h->counter.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  *n_fail = nf;
   return FPB_OK;
 }
 

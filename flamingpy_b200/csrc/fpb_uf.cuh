@@ -230,4 +230,42 @@ __global__ void __launch_bounds__(256) k_uf(const __grid_constant__ UfParams p) 
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// k_logical_check: the logical verdict of every trial after a recovery (check_correction,
+// decoders/decoder.py:151-224): a trial fails when any checked correlation surface - a plane of
+// syndrome qubits - has odd parity of bit_val XOR recovery.  One warp per trial; the planes are
+// index lists into the global qubit order (the layout of bits / flips).
+// ------------------------------------------------------------------------------------------
+struct CheckParams {
+  int T, bit_words, n_planes;
+  const int* plane_off;      // [n_planes + 1]
+  const int* plane_qubits;   // global qubit ids
+  const uint32_t* bits;      // [T][bit_words]
+  const uint32_t* flips;     // [T][bit_words]
+  uint8_t* fail;             // [T]
+  int* n_fail;
+};
+
+__global__ void __launch_bounds__(256) k_logical_check(CheckParams p) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < p.T; t += warps) {
+    const uint32_t* b = p.bits + (long long)t * p.bit_words;
+    const uint32_t* f = p.flips + (long long)t * p.bit_words;
+    int failed = 0;
+    for (int pl = 0; pl < p.n_planes; ++pl) {
+      int par = 0;
+      for (int i = p.plane_off[pl] + lane; i < p.plane_off[pl + 1]; i += 32) {
+        const int g = p.plane_qubits[i];
+        par ^= (int)(((b[g >> 5] ^ f[g >> 5]) >> (g & 31)) & 1u);
+      }
+      failed |= __popc(__ballot_sync(0xffffffffu, par)) & 1;
+    }
+    if (lane == 0) {
+      p.fail[t] = (uint8_t)failed;
+      if (failed) atomicAdd(p.n_fail, 1);
+    }
+  }
+}
+
 }  // namespace fpb

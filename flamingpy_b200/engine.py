@@ -265,13 +265,35 @@ class TrialEngine:
         parity = [unpack_bits(bufs[f"parity{i}"], self.lat.complexes[ec].S) for i, ec in enumerate(self.ec)]
         return unpack_bits(bufs["bits"], self.Qtot), parity, bufs.get("state")
 
-    def uf_decode(self, use_erasures: bool = True, want_grown: bool = False):
+    def logical_check(self, want_trials: bool = True):
+        """``check_correction`` of every trial of the last run on the device (``fpb_logical_check``): bit values
+        XOR the recovery the last ``uf_decode`` / ``paths_toggle`` left in HBM, over the lattice's correlation
+        surfaces.  Returns bool[T] (True = logical failure), or only their number with ``want_trials=False``."""
+        if not getattr(self, "_planes_set", False):
+            off, q, qoff = [0], [], 0
+            for ec in self.ec:
+                ct = self.lat.complexes[ec]
+                for plane in ct.planes:
+                    q.append(np.asarray(plane, np.int64) + qoff)
+                    off.append(off[-1] + len(plane))
+                qoff += ct.Q
+            _lib.set_planes(self._h, np.asarray(off, np.int32),
+                            np.ascontiguousarray(np.concatenate(q) if q else np.zeros(0), np.int32))
+            self._planes_set = True
+        if not want_trials:
+            return _lib.logical_check(self._h)
+        fail = np.zeros(int(self.sizes().n_trials), np.uint8)
+        _lib.logical_check(self._h, fail)
+        return fail.astype(bool)
+
+    def uf_decode(self, use_erasures: bool = True, want_grown: bool = False, fetch: bool = True):
         """Union-Find + peeling recovery of the last run (stage >= SYNDROME) computed on the device
         (``fpb_uf_decode``, ``csrc/fpb_uf.cuh``): bit flips uint8[T, Qtot].  ``use_erasures``: start from the
         erased edges the state labels of the run define (two or more p-squeezed neighbours); runs without
         labels (bit-level, i.i.d.) have none.  ``want_grown``: also the fully grown edges uint8[T, Qtot] (the
-        reference's Support table when the growth stops).  Raises ``ValueError`` like the host decoder when
-        an odd cluster can neither grow nor reach a boundary point."""
+        reference's Support table when the growth stops).  ``fetch=False``: the recovery stays on the device
+        (for ``logical_check``) and None is returned.  Raises ``ValueError`` like the host decoder when an odd
+        cluster can neither grow nor reach a boundary point."""
         from . import uf_native
 
         if not getattr(self, "_uf_graph_set", False):
@@ -280,7 +302,7 @@ class TrialEngine:
                 _lib.uf_set_graph(self._h, i, n_nodes, np.ascontiguousarray(ea, np.int32), np.ascontiguousarray(eb, np.int32))
             self._uf_graph_set = True
         T = int(self.sizes().n_trials)
-        flips = np.zeros((T, self.bit_words), np.uint32)
+        flips = np.zeros((T, self.bit_words), np.uint32) if fetch or want_grown else None
         grown = np.zeros((T, self.bit_words), np.uint32) if want_grown else None
         stuck = _lib.uf_decode(self._h, use_erasures, flips, grown)
         if stuck:
@@ -288,7 +310,7 @@ class TrialEngine:
                              "(odd number of unsatisfied stabilizers on a complex without boundary)")
         if want_grown:
             return unpack_bits(flips, self.Qtot), unpack_bits(grown, self.Qtot)
-        return unpack_bits(flips, self.Qtot)
+        return unpack_bits(flips, self.Qtot) if fetch else None
 
     def fetch_macro(self) -> dict:
         """Reduced lattice of the last macronode run, each [T, N]: ``red_state`` (1 GKP, 2 p),

@@ -142,9 +142,12 @@ def ec_monte_carlo(trials, code_instance, noise_instance, decoder, decoder_args,
                 eng.run_macro_rng(seed, first, n, stage=_lib.STAGE_SYNDROME, fetch=False)
             else:
                 eng.run_rng(seed, first, n, stage=_lib.STAGE_SYNDROME, fetch=False)
-            if backend == "device":
-                flips = eng.uf_decode(use_erasures=not iid and (macro or bool(n_pswap)))
-                bits = eng.fetch_syndrome()[0]
+            if backend == "device":  # growth, peeling and the logical check on the GPU: one count crosses the bus
+                eng.uf_decode(use_erasures=not iid and (macro or bool(n_pswap)), fetch=False)
+                failures += eng.logical_check(want_trials=False)
+                done += n
+                t_dev += eng.timings()["total_ms"]
+                continue
             else:
                 bits, parity, st = eng.fetch_syndrome(want_state=not iid and not macro and bool(n_pswap))
                 if macro:

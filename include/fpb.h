@@ -310,13 +310,25 @@ int fpb_paths_list(fpb_handle* h, int64_t n_queries, const int32_t* trial, const
  * fpb_uf_decode: needs a run with stage >= FPB_STAGE_SYNDROME.  use_erasures != 0 starts from the
  * erased edges of assign_weights(code, "UF") (two or more p-squeezed neighbours,
  * decoders/decoder.py:96-114), taken from the state labels of the last run (the reduced labels after a
- * macronode run).  Writes the recovery as flips [T][ceil(Qtot/32)] (bit-packed, layout of bits),
+ * macronode run).  Writes the recovery as flips [T][ceil(Qtot/32)] (bit-packed, layout of bits; NULL:
+ * it stays on the device for fpb_logical_check),
  * optionally (grown_host != NULL, same layout) the fully grown edges when the growth stops - the
  * reference's Support table, which does not depend on visiting order - and the number of
  * (trial, complex) items left with an odd cluster that can neither grow nor reach a boundary point
  * (their flips stay zero). */
 int fpb_uf_set_graph(fpb_handle* h, int complex_index, int32_t n_nodes, const int32_t* edge_a, const int32_t* edge_b);
 int fpb_uf_decode(fpb_handle* h, int use_erasures, uint32_t* flips_host, uint32_t* grown_host, int32_t* n_stuck);
+
+/* Logical verdict on the device: check_correction (flamingpy/decoders/decoder.py:151-224) for every
+ * trial of the last run, on the bit values in HBM XOR the recovery the last fpb_uf_decode or
+ * fpb_paths_toggle call left there (flips_host of fpb_uf_decode may be NULL: the recovery then never
+ * crosses the bus).  fpb_set_planes, once per handle: the checked correlation surfaces as index lists
+ * into the global qubit order (plane i = plane_qubits[plane_off[i] .. plane_off[i+1])) - for the
+ * reference's surface codes the syndrome qubits of plane 0 along x [open primal] / y [open dual] /
+ * x, y [toric] / x, y, z [periodic] of every complex (decoder.py:197-214).  fpb_logical_check:
+ * fail_host[t] = 1 where some plane has odd parity (NULL: only the count), *n_fail = their number. */
+int fpb_set_planes(fpb_handle* h, int32_t n_planes, const int32_t* plane_off, const int32_t* plane_qubits);
+int fpb_logical_check(fpb_handle* h, uint8_t* fail_host, int64_t* n_fail);
 
 #ifdef __cplusplus
 }

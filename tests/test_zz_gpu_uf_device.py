@@ -115,6 +115,34 @@ def test_monte_carlo_with_the_device_decoder():
     assert ec_monte_carlo(200, code, CVLayer(code, delta=0.001, p_swap=0), "UF", args, seed=8, backend="device") == 0
 
 
+@pytest.mark.parametrize("d,ec,bnd,ps", [(5, "primal", "open", 0.2), (4, "dual", "toric", 0.3), (4, "both", "periodic", 0.0),
+                                         (5, "dual", "open", 0.0)])
+def test_device_logical_check_equals_the_host_check(d, ec, bnd, ps):
+    """``fpb_logical_check`` (k_logical_check) against ``decoder.logical_failures`` (the vectorised check_correction)
+    on the same recovery: the Union-Find one left on the device, then one left by ``fpb_paths_toggle``."""
+    code = SurfaceCode(d, ec, bnd)
+    eng = code.engine(0.1, ps, {"method": "uniform"}, mode="fresh")
+    T = 200
+    eng.run_rng(17, 0, T, stage=_lib.STAGE_GRAPH, fetch=False)
+    with pytest.raises(_lib.FpbError, match="no recovery"):
+        eng.logical_check()
+    flips = eng.uf_decode(use_erasures=bool(ps))
+    bits = eng.fetch_syndrome()[0]
+    want = logical_failures(code, TrialBatch(T, _lib.STAGE_SYNDROME, bits=bits), flips)
+    got = eng.logical_check()
+    assert np.array_equal(got, want) and 0 < want.sum() < T
+    assert eng.logical_check(want_trials=False) == int(want.sum())
+    eng.uf_decode(use_erasures=bool(ps), fetch=False)  # the recovery never leaves the device
+    assert np.array_equal(eng.logical_check(), want)
+    # an arbitrary recovery through the path-toggle kernel: first odd cube of every trial to its connector / partner
+    cb = eng.fetch(_lib.STAGE_GRAPH).complexes[code.ec[0]]
+    has_bnd = code.lattice.complexes[code.ec[0]].has_boundary
+    trial = [t for t in range(T) if cb.odd_count[t] >= 2]
+    fl = eng.paths_toggle(trial, [0] * len(trial), [0] * len(trial), [-1 if has_bnd else 1] * len(trial))
+    want2 = logical_failures(code, TrialBatch(T, _lib.STAGE_SYNDROME, bits=bits), fl)
+    assert np.array_equal(eng.logical_check(), want2)
+
+
 def test_device_decoder_error_paths():
     code = SurfaceCode(3, "primal", "open")
     eng = code.engine(0.09, 0.25, {"method": "uniform"}, mode="fresh")
