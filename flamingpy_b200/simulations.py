@@ -87,6 +87,8 @@ def ec_monte_carlo(trials, code_instance, noise_instance, decoder, decoder_args,
     """
     if decoder not in ("MWPM", "UF"):
         raise KeyError(decoder)  # the reference's decoder_dict lookup (decoders/decoder.py:279-286)
+    if backend not in (("native", "device") if decoder == "UF" else ("native", "networkx")):
+        raise ValueError(f"unknown backend {backend!r} for decoder {decoder!r}")
     if not isinstance(noise_instance, (CVLayer, CVMacroLayer, IidNoise)):
         raise NotImplementedError("the batched driver accelerates CVLayer, CVMacroLayer and IidNoise")
     weight_opts = dict(decoder_args.get("weight_opts") or {})
@@ -127,7 +129,7 @@ def ec_monte_carlo(trials, code_instance, noise_instance, decoder, decoder_args,
     seed = int_time if seed is None else int(seed)
     if decoder == "UF":
         # Union-Find: the device pipeline stops after the syndrome (no matching graph); clusters are
-        # grown and peeled on the host cores (csrc/uf.cpp), one batch at a time
+        # grown and peeled on the host cores (csrc/uf.cpp) or by k_uf on the device, one batch at a time
         from .decoder import uf_decode_batch, uf_erasures
 
         eng = code_instance.engine(n_delta, n_pswap, {"method": "uniform"}, device=device, mode=mode)
