@@ -391,15 +391,28 @@ def decode_batch(code, eng, batch, backend="native"):
     return eng.paths_toggle(*match_batch(code, eng, batch, backend=backend))
 
 
+def check_planes(code):
+    """The checked correlation surfaces of all complexes as (int32 offsets [n_planes + 1], int32 global qubit ids)."""
+    cached = code.__dict__.get("_check_planes")
+    if cached is None:
+        off, q, qoff = [0], [], 0
+        for e in code.ec:
+            ct = code.lattice.complexes[e]
+            for plane in ct.planes:
+                q.append(np.asarray(plane, np.int64) + qoff)
+                off.append(off[-1] + len(plane))
+            qoff += ct.Q
+        cached = code.__dict__["_check_planes"] = (
+            np.asarray(off, np.int32), np.ascontiguousarray(np.concatenate(q) if q else np.zeros(0), np.int32))
+    return cached
+
+
 def logical_failures(code, batch, flips):
-    """Vectorised ``check_correction`` over a batch: bool[T], True where any checked
-    correlation surface of any complex has odd parity after the recovery."""
-    corrected = batch.bits ^ flips
-    fail = np.zeros(batch.n_trials, bool)
-    off = 0
-    for e in code.ec:
-        ct = code.lattice.complexes[e]
-        for plane in ct.planes:
-            fail |= (corrected[:, off + plane].sum(axis=1) % 2).astype(bool)
-        off += ct.Q
-    return fail
+    """``check_correction`` over a batch (``decoders/decoder.py:151-224``): bool[T], True where any checked
+    correlation surface of any complex has odd parity after the recovery.  ``batch.bits`` may be the
+    unpacked bit values uint8[T, Qtot] or the packed words uint32[T, ceil(Qtot/32)] as they come off the
+    device; only the planes' qubits are touched (``fpb_uf_check_correction``, host threads over trials)."""
+    from . import uf_native
+
+    off, q = check_planes(code)
+    return uf_native.check_correction(batch.bits, flips, off, q)

@@ -250,10 +250,11 @@ class TrialEngine:
         self._h.run_macro_rng(seed & (2**64 - 1), first_trial, n_trials, stage)
         return self.fetch(stage) if fetch else TrialBatch(n_trials, stage, timings=self.timings())
 
-    def fetch_syndrome(self, want_state: bool = False):
+    def fetch_syndrome(self, want_state: bool = False, packed_bits: bool = False):
         """What the Union-Find decoder consumes from the last run (stage >= SYNDROME): the bit values
-        uint8[T, Qtot], per complex the cube parities uint8[T, S], and - on request - the state labels
-        uint8[T, N] (1 GKP, 2 p) that decide which edges are erased."""
+        uint8[T, Qtot] (``packed_bits``: the device's uint32[T, ceil(Qtot/32)] words, LSB first, which
+        ``decoder.logical_failures`` reads directly), per complex the cube parities uint8[T, S], and - on
+        request - the state labels uint8[T, N] (1 GKP, 2 p) that decide which edges are erased."""
         s = self.sizes()
         T = int(s.n_trials)
         bufs = {"bits": np.empty((T, self.bit_words), np.uint32)}
@@ -263,7 +264,7 @@ class TrialEngine:
             bufs[f"parity{i}"] = np.empty((T, (self.lat.complexes[ec].S + 31) // 32), np.uint32)
         self._h.fetch_into(bufs)
         parity = [unpack_bits(bufs[f"parity{i}"], self.lat.complexes[ec].S) for i, ec in enumerate(self.ec)]
-        return unpack_bits(bufs["bits"], self.Qtot), parity, bufs.get("state")
+        return (bufs["bits"] if packed_bits else unpack_bits(bufs["bits"], self.Qtot)), parity, bufs.get("state")
 
     def logical_check(self, want_trials: bool = True):
         """``check_correction`` of every trial of the last run on the device (``fpb_logical_check``): bit values

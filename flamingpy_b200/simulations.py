@@ -151,7 +151,7 @@ def ec_monte_carlo(trials, code_instance, noise_instance, decoder, decoder_args,
                 t_dev += eng.timings()["total_ms"]
                 continue
             else:
-                bits, parity, st = eng.fetch_syndrome(want_state=not iid and not macro and bool(n_pswap))
+                bits, parity, st = eng.fetch_syndrome(want_state=not iid and not macro and bool(n_pswap), packed_bits=True)
                 if macro:
                     st = eng.fetch_macro()["red_state"]
                 flips = uf_decode_batch(code_instance, parity, uf_erasures(code_instance, st))

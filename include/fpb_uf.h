@@ -47,6 +47,15 @@ int fpb_uf_batch(int n_nodes, int n_cubes, int n_edges, const int32_t* edge_a, c
 long long fpb_uf_erasures(int n_lattice_nodes, int n_edges, const int32_t* qubit_node, const int32_t* adj_indptr,
                           const int32_t* adj_indices, int n_trials, const uint8_t* state, uint8_t* erased, int threads);
 
+/* check_correction (flamingpy/decoders/decoder.py:151-224) for a batch on the host: fail[t] = 1 when
+ * some checked correlation surface - plane i = global qubit ids plane_qubits[plane_off[i] ..
+ * plane_off[i+1]) - has odd parity of bit value XOR recovery.  Bit values either unpacked
+ * (bits [T][n_qubits], bit_words NULL) or as the device delivers them (bit_words
+ * [T][ceil(n_qubits/32)], LSB first, bits NULL); flips [T][n_qubits].  Returns the number of failures. */
+long long fpb_uf_check_correction(int n_trials, int n_qubits, const uint8_t* bits, const uint32_t* bit_words,
+                                  const uint8_t* flips, int n_planes, const int32_t* plane_off,
+                                  const int32_t* plane_qubits, uint8_t* fail, int threads);
+
 int fpb_uf_max_threads(void);
 
 #ifdef __cplusplus

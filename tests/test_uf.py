@@ -41,7 +41,7 @@ def _failures(ct, bits, flips):
 def test_library_exports_every_declared_symbol():
     header = open(os.path.join(ROOT, "include", "fpb_uf.h")).read()
     declared = set(re.findall(r"\b(fpb_uf[a-z_]*)\s*\(", header))
-    assert declared == {"fpb_uf_batch", "fpb_uf_erasures", "fpb_uf_max_threads"}
+    assert declared == {"fpb_uf_batch", "fpb_uf_erasures", "fpb_uf_check_correction", "fpb_uf_max_threads"}
     lib = ctypes.CDLL(uf_native.LIB_PATH)
     for name in declared:
         assert hasattr(lib, name), name
@@ -162,7 +162,7 @@ class OracleEngine:
         x, st = sample_batch(np.random.default_rng([seed, first]), self.lat.N, self.delta, self.p_swap, n, fresh=True)
         return self.run_injected(x, st, stage)
 
-    def fetch_syndrome(self, want_state=False):
+    def fetch_syndrome(self, want_state=False, packed_bits=False):  # unpacked bytes either way: both are accepted
         return (self._batch.bits, [self._batch.complexes[e].parity for e in self.lat.ec],
                 self._state if want_state else None)
 
@@ -260,3 +260,31 @@ def test_restatement_is_pinned_to_the_reference_and_agrees_with_the_library_beyo
             assert np.array_equal(grown[t], g_o), (d, b, t)
             assert np.array_equal(_syndrome_of(ct, f_o[None])[0], parity[t])
             assert np.array_equal(_syndrome_of(ct, flips[t][None])[0], parity[t])
+
+
+@pytest.mark.parametrize("d,ec,bnd", [(5, "primal", "open"), (4, "dual", "toric"), (3, "both", "periodic"), ((2, 3, 4), "dual", "open")])
+def test_check_correction_in_the_library_equals_the_numpy_restatement(d, ec, bnd):
+    """``decoder.logical_failures`` (``fpb_uf_check_correction``: plane parities of bit value XOR recovery,
+    decoders/decoder.py:197-214) on unpacked bytes and on the device's packed words against plain NumPy."""
+    from flamingpy_b200.decoder import logical_failures
+    from flamingpy_b200.engine import TrialBatch, unpack_bits
+
+    code = SurfaceCode(d, ec, bnd)
+    Q = sum(code.lattice.complexes[e].Q for e in code.ec)
+    rng = np.random.default_rng(Q)
+    T = 257
+    words = rng.integers(0, 2**32, (T, (Q + 31) // 32), dtype=np.uint32)
+    flips = rng.integers(0, 2, (T, Q), dtype=np.uint8)
+    bits = unpack_bits(words, Q)
+    corrected = bits ^ flips
+    want = np.zeros(T, bool)
+    off = 0
+    for e in code.ec:
+        ct = code.lattice.complexes[e]
+        for plane in ct.planes:
+            want |= (corrected[:, off + np.asarray(plane)].sum(axis=1) % 2).astype(bool)
+        off += ct.Q
+    assert 0 < want.sum() < T
+    assert np.array_equal(logical_failures(code, TrialBatch(T, 2, bits=bits), flips), want)
+    assert np.array_equal(logical_failures(code, TrialBatch(T, 2, bits=words), flips), want)
+    assert np.array_equal(logical_failures(code, TrialBatch(T, 2, bits=bits), flips[:, ::1].copy(order="F")), want)
