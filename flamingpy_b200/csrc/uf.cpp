@@ -22,7 +22,8 @@
 // Written for this data layout: a CSR adjacency over cubes + boundary points shared by all trials,
 // per-trial state in flat arrays reused across trials (one workspace per OpenMP thread), cluster
 // node lists as intrusive singly linked lists so that a merge is O(1), pruning of fully grown nodes
-// done while a list is walked.
+// done while a list is walked.  A trial touches only its own footprint (odd cubes, erased edges and
+// whatever the clusters grow over) and restores it afterwards, so a quiet trial costs next to nothing.
 #include <cstdint>
 #include <cstring>
 #include <vector>
@@ -43,14 +44,48 @@ struct Graph {
 
 struct Workspace {
   std::vector<int> parent, csize, head, tail, next, odd, odd_next, fusion, order, up_edge, up_node, stamp;
+  std::vector<int> touched_nodes, touched_edges;
   std::vector<uint8_t> cpar, cbnd, support, npar, seen;
+  std::vector<uint64_t> touched_bits;  // one bit per node: in touched_nodes
   int stamp_t = 0;
 
+  // The per-node / per-edge state is kept in its "nothing happened" form between trials (every node a
+  // cluster of its own, every edge empty); a trial records what it touches and puts exactly that back,
+  // so that its cost follows the size of its syndrome instead of the size of the lattice.
   void resize(const Graph& g) {
-    parent.resize(g.n_nodes), csize.resize(g.n_nodes), head.resize(g.n_nodes), tail.resize(g.n_nodes);
-    next.resize(g.n_nodes), up_edge.resize(g.n_nodes), up_node.resize(g.n_nodes), stamp.assign(g.n_nodes, 0);
-    cpar.resize(g.n_nodes), cbnd.resize(g.n_nodes), npar.resize(g.n_nodes), seen.resize(g.n_nodes);
-    support.resize(g.n_edges);
+    const int n = g.n_nodes;
+    parent.resize(n), csize.assign(n, 1), head.resize(n), tail.resize(n);
+    next.assign(n, -1), up_edge.resize(n), up_node.resize(n), stamp.assign(n, 0);
+    cpar.assign(n, 0), cbnd.resize(n), npar.assign(n, 0), seen.assign(n, 0), touched_bits.assign((n + 63) / 64, 0);
+    for (int u = 0; u < n; ++u) {
+      parent[u] = head[u] = tail[u] = u;
+      cbnd[u] = u >= g.n_cubes;
+    }
+    support.assign(g.n_edges, 0);
+    stamp_t = 0;
+  }
+  void touch(int u) {
+    uint64_t& wd = touched_bits[u >> 6];
+    const uint64_t bit = 1ull << (u & 63);
+    if (!(wd & bit)) {
+      wd |= bit;
+      touched_nodes.push_back(u);
+    }
+  }
+  void restore(const Graph& g) {
+    for (size_t i = 0; i < touched_nodes.size(); ++i) {
+      const int u = touched_nodes[i];
+      parent[u] = head[u] = tail[u] = u;
+      csize[u] = 1;
+      next[u] = -1;
+      cpar[u] = npar[u] = seen[u] = 0;
+      touched_bits[u >> 6] = 0;
+      cbnd[u] = u >= g.n_cubes;
+      stamp[u] = 0;
+    }
+    for (size_t i = 0; i < touched_edges.size(); ++i) support[touched_edges[i]] = 0;
+    touched_nodes.clear();
+    touched_edges.clear();
     stamp_t = 0;
   }
   int find(int u) {
@@ -86,31 +121,35 @@ struct Workspace {
 
 // Returns 0, or -1 when an odd cluster is stuck.
 int decode_one(const Graph& g, Workspace& w, const uint8_t* parity, const uint8_t* erased, uint8_t* flips, uint8_t* grown) {
-  const int n = g.n_nodes;
-  for (int u = 0; u < n; ++u) {
-    w.parent[u] = u;
-    w.csize[u] = 1;
-    w.head[u] = w.tail[u] = u;
-    w.next[u] = -1;
-    w.cpar[u] = u < g.n_cubes ? (parity[u] & 1) : 0;
-    w.cbnd[u] = u >= g.n_cubes;
-  }
-  for (int q = 0; q < g.n_edges; ++q) {
-    w.support[q] = 0;
-    if (g.ea[q] < 0) continue;
-    if (erased && erased[q]) {
+  std::memset(flips, 0, (size_t)g.n_edges);
+  if (grown) std::memset(grown, 0, (size_t)g.n_edges);
+  // The trial's footprint: every edge whose support leaves 0 (touched_edges), and as nodes the odd cubes
+  // and both ends of every fully grown edge - only those take part in merges, lists and the forest.
+  for (int u = 0; u < g.n_cubes; ++u)
+    if (parity[u] & 1) {
+      w.cpar[u] = 1;
+      w.touch(u);
+    }
+  if (erased)
+    for (int q = 0; q < g.n_edges; ++q) {
+      if (g.ea[q] < 0 || !erased[q]) continue;
       w.support[q] = 2;
+      w.touched_edges.push_back(q);
+      w.touch(g.ea[q]);
+      w.touch(g.eb[q]);
       const int a = w.find(g.ea[q]), b = w.find(g.eb[q]);
       if (a != b) w.unite(a, b);
     }
-  }
   // the first round grows every cluster of odd parity, also one that an erasure already ties to a
   // boundary point (algos.py:124-126 fills the list by parity alone; the boundary test comes after
   // the first growth, algos.py:186-191)
   w.odd.clear();
-  for (int u = 0; u < n; ++u)
+  for (size_t i = 0; i < w.touched_nodes.size(); ++i) {
+    const int u = w.touched_nodes[i];
     if (w.parent[u] == u && w.cpar[u]) w.odd.push_back(u);
+  }
 
+  int rc = 0;
   while (!w.odd.empty()) {
     w.fusion.clear();
     long changed = 0;
@@ -124,6 +163,7 @@ int decode_one(const Graph& g, Workspace& w, const uint8_t* parity, const uint8_
           uint8_t& s = w.support[q];
           if (s == 0) {
             s = 1;
+            w.touched_edges.push_back(q);
             open = true;
             ++changed;
           } else if (s == 1) {
@@ -146,9 +186,14 @@ int decode_one(const Graph& g, Workspace& w, const uint8_t* parity, const uint8_
         u = nx;
       }
     }
-    if (!changed) return -1;
+    if (!changed) {
+      rc = -1;
+      break;
+    }
     for (size_t i = 0; i < w.fusion.size(); ++i) {
       const int q = w.fusion[i];
+      w.touch(g.ea[q]);
+      w.touch(g.eb[q]);
       const int a = w.find(g.ea[q]), b = w.find(g.eb[q]);
       if (a != b) w.unite(a, b);
     }
@@ -162,45 +207,58 @@ int decode_one(const Graph& g, Workspace& w, const uint8_t* parity, const uint8_
     }
     w.odd.swap(w.odd_next);
   }
+  if (rc) {  // stuck: no recovery for this trial
+    w.restore(g);
+    return rc;
+  }
 
   if (grown)
-    for (int q = 0; q < g.n_edges; ++q) grown[q] = w.support[q] == 2;
+    for (size_t i = 0; i < w.touched_edges.size(); ++i) grown[w.touched_edges[i]] = w.support[w.touched_edges[i]] == 2;
 
-  // spanning forest of the grown edges, breadth first, boundary points first as roots; then peeling
-  std::memset(flips, 0, (size_t)g.n_edges);
-  std::memset(w.seen.data(), 0, (size_t)n);
-  for (int u = 0; u < n; ++u) w.npar[u] = u < g.n_cubes ? (parity[u] & 1) : 0;
-  w.order.clear();
-  int rc = 0;
-  for (int pass = 0; pass < 2; ++pass) {
-    const int lo = pass == 0 ? g.n_cubes : 0, hi = pass == 0 ? n : g.n_cubes;
-    for (int root = lo; root < hi; ++root) {
-      if (w.seen[root]) continue;
-      const size_t first = w.order.size();
-      w.seen[root] = 1;
-      w.up_edge[root] = -1;
-      w.order.push_back(root);
-      for (size_t i = first; i < w.order.size(); ++i) {
-        const int u = w.order[i];
-        for (int ai = g.off[u]; ai < g.off[u + 1]; ++ai) {
-          const int q = g.adj_edge[ai], v = g.adj_node[ai];
-          if (w.support[q] != 2 || w.seen[v]) continue;
-          w.seen[v] = 1;
-          w.up_edge[v] = q;
-          w.up_node[v] = u;
-          w.order.push_back(v);
-        }
-      }
-      for (size_t i = w.order.size(); i-- > first + 1;) {
-        const int u = w.order[i];
-        if (w.npar[u]) {
-          flips[w.up_edge[u]] ^= 1;
-          w.npar[w.up_node[u]] ^= 1;
-        }
-      }
-      if (root < g.n_cubes && w.npar[root]) rc = -1;  // an odd tree without a boundary point
-    }
+  // spanning forest of the grown edges, breadth first, boundary points first as roots (in ascending
+  // order, then the cubes in ascending order); then peeling.  Nodes outside the trial's footprint have
+  // no grown edge and even parity: trees of one node that contribute nothing.
+  for (size_t i = 0; i < w.touched_nodes.size(); ++i) {
+    const int u = w.touched_nodes[i];
+    w.npar[u] = u < g.n_cubes ? (parity[u] & 1) : 0;
   }
+  w.order.clear();
+  // one tree from `root`: breadth first over the grown edges, then peeled from the leaves
+  auto tree = [&](int root) {
+    const size_t first = w.order.size();
+    w.seen[root] = 1;
+    w.up_edge[root] = -1;
+    w.order.push_back(root);
+    for (size_t i = first; i < w.order.size(); ++i) {
+      const int u = w.order[i];
+      for (int ai = g.off[u]; ai < g.off[u + 1]; ++ai) {
+        const int q = g.adj_edge[ai], v = g.adj_node[ai];
+        if (w.support[q] != 2 || w.seen[v]) continue;
+        w.seen[v] = 1;
+        w.up_edge[v] = q;
+        w.up_node[v] = u;
+        w.order.push_back(v);
+      }
+    }
+    for (size_t i = w.order.size(); i-- > first + 1;) {
+      const int u = w.order[i];
+      if (w.npar[u]) {
+        flips[w.up_edge[u]] ^= 1;
+        w.npar[w.up_node[u]] ^= 1;
+      }
+    }
+    if (root < g.n_cubes && w.npar[root]) rc = -1;  // an odd tree without a boundary point
+  };
+  for (int pass = 0; pass < 2; ++pass) {
+    const int lo = pass == 0 ? g.n_cubes : 0, hi = pass == 0 ? g.n_nodes : g.n_cubes;
+    if (lo >= hi) continue;
+    for (int wi = lo >> 6; wi <= (hi - 1) >> 6; ++wi)
+      for (uint64_t m = w.touched_bits[wi]; m; m &= m - 1) {  // touched nodes in ascending order
+        const int root = (wi << 6) + __builtin_ctzll(m);
+        if (root >= lo && root < hi && !w.seen[root]) tree(root);
+      }
+  }
+  w.restore(g);
   return rc;
 }
 
