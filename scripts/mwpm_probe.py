@@ -1,5 +1,5 @@
 """Single-core timing of the native matcher on matching graphs of real trials (generated with the
-C oracle, so no GPU is needed): dense O(n^3) solver vs sparse candidate graph + pricing.
+C oracle, so no GPU is needed): the solver on the complete graph ("dense" mode) vs sparse candidate graph + pricing.
     python scripts/mwpm_probe.py [reps]"""
 import sys, time; sys.path.insert(0, ".")
 import numpy as np

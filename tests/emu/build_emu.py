@@ -110,8 +110,8 @@ def rewrite_dynamic_smem(src: str) -> str:
     return _DYN.sub(lambda m: f"{m.group(1)}* {m.group(2)} = ({m.group(1)}*)fpb_emu::dyn_smem();", src)
 
 
-def transform(name: str) -> str:
-    with open(os.path.join(CSRC, name)) as f:
+def transform(name: str, src_dir: str = CSRC) -> str:
+    with open(os.path.join(src_dir, name)) as f:
         src = f.read()
     src = rewrite_dynamic_smem(rewrite_launches(src))
     assert "<<<" not in src and "extern __shared__" not in src, name
@@ -135,6 +135,23 @@ def build(force: bool = False) -> str:
            os.path.join(BUILD, "fpb.cpp"), os.path.join(HERE, "simt.cpp"), "-o", LIB]
     subprocess.check_call(cmd, cwd=BUILD)
     return LIB
+
+
+def build_selftest(force: bool = False) -> str:
+    """``_build/libselftest_emu.so``: the kernels of tests/emu/selftest/selftest.cu on the SIMT machine."""
+    src_dir = os.path.join(HERE, "selftest")
+    lib = os.path.join(BUILD, "libselftest_emu.so")
+    deps = [os.path.join(src_dir, "selftest.cu"), os.path.join(HERE, "include", "cuda_runtime.h"),
+            os.path.join(HERE, "simt.cpp"), os.path.abspath(__file__)]
+    if not force and os.path.exists(lib) and all(os.path.getmtime(d) <= os.path.getmtime(lib) for d in deps):
+        return lib
+    os.makedirs(BUILD, exist_ok=True)
+    with open(os.path.join(BUILD, "selftest.cpp"), "w") as f:
+        f.write(transform("selftest.cu", src_dir))
+    subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-Wno-unknown-pragmas",
+                           "-Wno-attributes", "-I" + os.path.join(HERE, "include"), os.path.join(BUILD, "selftest.cpp"),
+                           os.path.join(HERE, "simt.cpp"), "-o", lib], cwd=BUILD)
+    return lib
 
 
 if __name__ == "__main__":

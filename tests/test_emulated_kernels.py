@@ -43,6 +43,46 @@ def _child_pytest(lib, args, timeout, **extra_env):
     return r, int(m.group(1)) if m else 0
 
 
+def test_simt_machine_semantics():
+    """The emulator itself: shuffles, votes, scans, __syncthreads with exited threads, atomics, named barriers with a
+    predicate OR, shared-window addresses and saturating conversions on small kernels with known answers
+    (tests/emu/selftest/selftest.cu), also under a shuffled schedule."""
+    import ctypes
+
+    import numpy as np
+
+    sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+    try:
+        import build_emu
+    finally:
+        sys.path.pop(0)
+    lib = ctypes.CDLL(build_emu.build_selftest())
+    out = np.zeros(1024, np.int32)
+    assert lib.selftest_run(out.ctypes.data_as(ctypes.POINTER(ctypes.c_int))) == 0
+    lane = np.arange(32)
+    v = lane * 3 + 1
+    assert np.array_equal(out[0:32], np.full(32, 16))
+    assert np.array_equal(out[32:64], np.where(lane >= 2, v[np.maximum(lane - 2, 0)], v))
+    assert np.array_equal(out[64:96], v[lane ^ 16])
+    ballot = sum(1 << i for i in range(32) if i % 3 == 0)
+    assert np.array_equal(out[96:128].view(np.uint32), np.full(32, ballot, np.uint32))
+    assert np.array_equal(out[128:160], np.full(32, 1 + 2 * 0xff))
+    assert np.array_equal(out[160:192], lane + 1)
+    tid = np.arange(128)
+    assert np.array_equal(out[192:320], 8128 + (127 - tid))
+    live = tid[40:]
+    assert np.array_equal(out[320 + 40:448], 7348 + (127 - (live - 40) % 88)) and not out[320:360].any()
+    team, r = tid >> 6, tid & 63
+    assert np.array_equal(out[448:576], ((team << 6) + (63 - r)) * 4 + (team == 1) * 2)
+    assert out[576:583].tolist() == [2**31 - 1, -2**31, -3, -2, 0, 0xc0000000 - 2**32, 5 + 800]
+    # the same answers when warps and lanes are visited in a shuffled order
+    code = ("import ctypes, numpy as np, sys; lib = ctypes.CDLL(sys.argv[1]); o = np.zeros(1024, np.int32); "
+            "lib.selftest_run(o.ctypes.data_as(ctypes.POINTER(ctypes.c_int))); sys.stdout.write(o.tobytes().hex())")
+    r2 = subprocess.run([sys.executable, "-c", code, build_emu.build_selftest()], capture_output=True, text=True,
+                        env=dict(os.environ, FPB_EMU_SHUFFLE="7"), timeout=120)
+    assert r2.returncode == 0 and bytes.fromhex(r2.stdout) == out.tobytes(), r2.stderr[-500:]
+
+
 def test_emulated_library_exports_the_whole_abi(emulated_library):
     """Same translation unit as libfpb.so, so the emulated build must export every entry point of include/fpb.h."""
     import ctypes
