@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(256) k_uf(const __grid_constant__ UfParams p) 
     }
     // parity and boundary contact of every cluster, kept at its root
     for (int u = tid; u < NN; u += nthr) cl[u] = 0;
-    if (tid == 0) flag_s[0] = flag_s[1] = 0;
+    if (tid == 0) flag_s[0] = flag_s[1] = flag_s[2] = 0;
     __syncthreads();
     for (int u = tid; u < NN; u += nthr) {
       const int r = par[u];
@@ -129,6 +129,7 @@ __global__ void __launch_bounds__(256) k_uf(const __grid_constant__ UfParams p) 
     for (int u = tid; u < NN; u += nthr) {
       const int f = cl[par[u]];
       if (round == 0 ? (f & 1) : (f == 1)) flag_s[1] = 1;
+      if (f == 1) flag_s[2] = 1;  // an odd cluster without a boundary point: it has to grow
     }
     for (int q = tid; q < Q; q += nthr) {
       const int a = ea[q];
@@ -143,11 +144,13 @@ __global__ void __launch_bounds__(256) k_uf(const __grid_constant__ UfParams p) 
       }
     }
     __syncthreads();
-    const int any_growing = flag_s[1], changed = flag_s[0];
+    const int any_growing = flag_s[1], changed = flag_s[0], must_grow = flag_s[2];
     __syncthreads();
     if (!any_growing) break;
-    if (!changed) {  // an odd cluster that can neither grow nor reach a boundary point
-      ok = false;
+    if (!changed) {
+      // nothing left to grow: fine if the odd clusters of the first round all hold a boundary point (every edge
+      // around them erased, p_swap = 1); an odd cluster without one can never be resolved
+      ok = !must_grow;
       break;
     }
     uf_merge(par, sup, ea, eb, Q, NN, &flag_s[0]);

@@ -186,10 +186,6 @@ int decode_one(const Graph& g, Workspace& w, const uint8_t* parity, const uint8_
         u = nx;
       }
     }
-    if (!changed) {
-      rc = -1;
-      break;
-    }
     for (size_t i = 0; i < w.fusion.size(); ++i) {
       const int q = w.fusion[i];
       w.touch(g.ea[q]);
@@ -206,6 +202,13 @@ int decode_one(const Graph& g, Workspace& w, const uint8_t* parity, const uint8_
       if (w.cpar[r] && !w.cbnd[r]) w.odd_next.push_back(r);
     }
     w.odd.swap(w.odd_next);
+    // nothing grew and an odd cluster without a boundary point remains: it never will (the reference loops
+    // forever here).  An odd cluster of the first round that already holds a boundary point just drops out,
+    // also when every edge around it is erased (p_swap = 1) and there is nothing to grow.
+    if (!changed && !w.odd.empty()) {
+      rc = -1;
+      break;
+    }
   }
   if (rc) {  // stuck: no recovery for this trial
     w.restore(g);

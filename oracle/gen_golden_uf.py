@@ -32,6 +32,9 @@ CASES = [
     ("uf_d2_periodic_both_ps0", 2, "both", "periodic", 0.12, 0, 8, 306),
     ("uf_d234_open_primal_ps01", (2, 3, 4), "primal", "open", 0.12, 0.1, 8, 307),
     ("uf_d4_open_dual_ps06", 4, "dual", "open", 0.09, 0.6, 10, 308),
+    # every node p-squeezed: every edge erased, nothing to grow; odd syndromes end at a boundary point
+    ("uf_d3_open_primal_ps1", 3, "primal", "open", 0.1, 1, 12, 309),
+    ("uf_d223_toric_dual_ps1", (2, 2, 3), "dual", "toric", 0.1, 1, 8, 310),
 ]
 
 

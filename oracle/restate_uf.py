@@ -70,12 +70,12 @@ def grow_clusters(n_nodes, n_cubes, edge_a, edge_b, parity, erased=None):
                         status[q] = 2
                         fusion.append(q)
                         changed = True
-        if not changed:
-            raise ValueError("an odd cluster can neither grow nor reach a boundary point")
         for q in fusion:
             union(edge_a[q], edge_b[q])
         odd = {find(r) for r in odd}
         odd = {r for r in odd if par[r] and not bnd[r]}  # algos.py:186-191
+        if odd and not changed:  # the reference would loop forever (algos.py:155); nothing can grow any more
+            raise ValueError("an odd cluster can neither grow nor reach a boundary point")
     return status
 
 
