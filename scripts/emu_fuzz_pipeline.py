@@ -1,6 +1,7 @@
 """Fuzz the whole trial pipeline against the NumPy oracle on random small lattices (sizes 2..7 per axis, every
 boundary / complex combination the code accepts, p_swap in {0, ..., 1}, blueprint / integer / uniform weights) and the
-correction-path and Union-Find stages with it.  Meant for the CPU SIMT emulation of the kernels (no GPU needed):
+correction-path and Union-Find stages with it; every fourth configuration also through the macronode kernels, every
+other fourth through the bit-level arm with and without the all-pairs table.  Meant for the CPU SIMT emulation of the kernels (no GPU needed):
     python tests/emu/build_emu.py
     FPB_LIB=tests/emu/_build/libfpb_emu.so FPB_BINDING=ctypes python scripts/emu_fuzz_pipeline.py [seconds] [seed]
 (on a GPU box it runs against the nvcc build the same way)."""
@@ -13,6 +14,33 @@ from flamingpy_b200.lattice import macro_tables
 from flamingpy_b200.noise import MacroSampler
 from oracle import restate
 from tests.test_gpu_parity import _compare_with_oracle
+
+
+def bits_case(rng, lat, tag):
+    """Bit-level trials (IidNoise arm): fpb_run_bits with the search and with the all-pairs table gather (also the
+    row-driven one if FPB_GATHER_ROWS is set) against restate.trial_from_bits, unit weights, bit-exact."""
+    T = int(rng.integers(1, 5))
+    p = float(rng.choice([0.01, 0.05, 0.15, 0.5]))
+    bit_val = (rng.random((T, lat.N)) < p).astype(np.uint8)
+    qn = np.concatenate([lat.complexes[e].qubits for e in lat.ec])
+    for table in (False, True):
+        eng = TrialEngine(lat, 1.0, 0.0, {"method": "uniform"}, mode="fresh", device=0)
+        try:
+            if table:
+                eng.build_table()
+            batch = eng.run_bits(bit_val[:, qn])
+            for t in range(T):
+                res = restate.trial_from_bits(lat, bit_val[t])
+                for e in lat.ec:
+                    m, cb = res.per_complex[e], batch.complexes[e]
+                    assert np.array_equal(cb.parity[t], m["parity"]) and np.array_equal(cb.odd(t), m["graph"].odd), ("bits", tag, table)
+                    assert np.array_equal(cb.pairs(t), m["graph"].pair_len), ("bits pairs", tag, table, e, t)
+                    if lat.complexes[e].has_boundary and cb.odd_count[t]:
+                        bl, bs = cb.boundary(t)
+                        assert np.array_equal(bl, m["graph"].bnd_len) and np.array_equal(bs, m["graph"].bnd_side), ("bits bnd", tag, table)
+        finally:
+            eng.close()
+    return 2 * T
 
 
 def macro_case(rng, lat, delta, ps, tag):
@@ -123,4 +151,6 @@ while time.time() - t0 < budget:
     n_trials += T
     if n_cfg % 4 == 0 and lat.N <= 600:
         n_trials += macro_case(rng, lat, delta, ps, tag)
+    if n_cfg % 4 == 2 and lat.N <= 900:
+        n_trials += bits_case(rng, lat, tag)
 print(f"ok: {n_cfg} configurations, {n_trials} trials in {time.time() - t0:.0f} s (seed {seed})")
