@@ -210,3 +210,31 @@ def test_trial_range_partitions_exactly():
             assert all(spans[i][1] == spans[i + 1][0] for i in range(size - 1))
             sizes = [b - a for a, b in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_bench_uf_leg_never_raises(monkeypatch):
+    """bench.run_uf_leg collects the JSON lines of scripts/uf_leg.py; a crashed, silent or hung child ends up as an
+    entry of the returned object, never as an exception in the bench line's path."""
+    import subprocess
+    import types
+
+    import bench
+
+    args = types.SimpleNamespace(mode="compat", uf_trials=64)
+    cfg = dict(distance=3, ec="primal", boundaries="open", delta=0.09, p_swap=0.0)
+
+    def fake(stdout="", returncode=0, stderr="", exc=None):
+        def run(cmd, **kw):
+            assert cmd[1].endswith("uf_leg.py") and "--trials" in cmd and kw["timeout"] > 0
+            if exc:
+                raise exc
+            return types.SimpleNamespace(stdout=stdout, stderr=stderr, returncode=returncode)
+        return run
+
+    monkeypatch.setattr(subprocess, "run", fake('noise\n{"leg": "host", "value": 5.0}\n{"leg": "device", "error": "x"}\n'))
+    assert bench.run_uf_leg(args, cfg) == {"host": {"value": 5.0}, "device": {"error": "x"}}
+    monkeypatch.setattr(subprocess, "run", fake('{"leg": "host", "value": 5.0}\n', returncode=-11, stderr="Segmentation fault"))
+    out = bench.run_uf_leg(args, cfg)
+    assert out["host"] == {"value": 5.0} and out["exit"]["returncode"] == -11
+    monkeypatch.setattr(subprocess, "run", fake(exc=subprocess.TimeoutExpired("uf_leg", 300)))
+    assert "TimeoutExpired" in bench.run_uf_leg(args, cfg)["error"]
