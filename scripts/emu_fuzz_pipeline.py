@@ -3,7 +3,8 @@ boundary / complex combination the code accepts, p_swap in {0, ..., 1}, blueprin
 correction-path and Union-Find stages with it; every fourth configuration also through the macronode kernels, every
 other fourth through the bit-level arm with and without the all-pairs table.  Meant for the CPU SIMT emulation of the kernels (no GPU needed):
     python tests/emu/build_emu.py
-    FPB_LIB=tests/emu/_build/libfpb_emu.so FPB_BINDING=ctypes python scripts/emu_fuzz_pipeline.py [seconds] [seed]
+    FPB_LIB=tests/emu/_build/libfpb_emu.so FPB_BINDING=ctypes python scripts/emu_fuzz_pipeline.py [seconds] [seed] [lo] [hi]
+(lo, hi: cubes per axis, default 2..7; 9..13 reaches the two-warp team kernels, S > 1024 cubes)
 (on a GPU box it runs against the nvcc build the same way)."""
 import sys, time; sys.path.insert(0, ".")
 import numpy as np
@@ -79,11 +80,13 @@ def macro_case(rng, lat, delta, ps, tag):
 
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 120.0
 seed = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+lo_dim = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+hi_dim = int(sys.argv[4]) if len(sys.argv) > 4 else 7
 rng = np.random.default_rng(seed)
 t0, n_cfg, n_trials = time.time(), 0, 0
 while time.time() - t0 < budget:
     bnd = str(rng.choice(["open", "toric", "periodic"]))
-    dims = tuple(int(v) for v in rng.integers(2, 8, 3))
+    dims = tuple(int(v) for v in rng.integers(lo_dim, hi_dim + 1, 3))
     if rng.random() < 0.4:
         dims = (dims[0],) * 3
     ec = str(rng.choice(["primal", "dual", "both"])) if bnd == "periodic" else str(rng.choice(["primal", "dual"]))
@@ -98,7 +101,7 @@ while time.time() - t0 < budget:
         lat = build_lattice(dims, ec, bnd)
     except ValueError:
         continue
-    T = int(rng.integers(1, 6))
+    T = int(rng.integers(1, 6)) if hi_dim <= 8 else 1
     chain = restate.LabelChain(lat.N, ps)
     states, xs = [], []
     for _ in range(T):
