@@ -10,6 +10,8 @@ Two interchangeable bindings with one interface (``open_handle``):
 Both are built in-tree by ``__graft_entry__.build()`` / ``python setup.py build_cmake``.  If
 ``libfpb.so`` is missing this module raises ``ImportError`` - there is deliberately no CPU
 fallback (the reference's own CPU path lives in the reference; ``oracle/`` is test infrastructure).
+``FPB_LIB`` names another build of the same ABI explicitly; the test suite uses it to run the GPU
+tests against the CPU emulation build of the kernel sources (``tests/emu``), nothing else sets it.
 """
 
 from __future__ import annotations
