@@ -245,14 +245,15 @@ def correct(code, decoder="MWPM", weight_options=None, sanity_check=False, decod
     ``decoder_opts["lengths"]``: "float" (default) - path lengths are the sums of the float weights, as
     with the reference's networkx graphs; "rustworkx" - the sums of ``int(weight)`` along the
     float-shortest paths, which is what the reference's default rustworkx graphs report
-    (``stabilizer_graph.py:486-500``) and therefore what its default ``correct`` matches on."""
+    (``stabilizer_graph.py:486-500``) and therefore what its default ``correct`` matches on.
+    With ``decoder="UF"``, ``decoder_opts["backend"]`` is "native" (host decoder, default) or "device"."""
     if decoder not in ("MWPM", "UF"):
         raise KeyError(decoder)  # the reference's decoder_dict lookup (decoder.py:279-286)
     if draw:
         raise NotImplementedError("drawing is out of scope for the accelerated path")
     weight_options = dict(weight_options or {})
     if decoder == "UF":
-        return _correct_uf(code, weight_options, sanity_check)
+        return _correct_uf(code, weight_options, sanity_check, (decoder_opts or {}).get("backend", "native"))
     opts = {"backend": "native"}
     opts.update(decoder_opts or {})
     if opts["backend"] in ("rustworkx", "retworkx", "lemon"):
@@ -285,9 +286,11 @@ def correct(code, decoder="MWPM", weight_options=None, sanity_check=False, decod
     return bool(np.all(result))
 
 
-def _correct_uf(code, weight_options, sanity_check):
+def _correct_uf(code, weight_options, sanity_check, backend="native"):
     """``correct(code, "UF", ...)``: noise -> bits -> syndrome on the device, Union-Find + peeling on
-    the host, logical check."""
+    the host (``decoder_opts["backend"] = "device"``: by ``k_uf`` on the GPU), logical check."""
+    if backend not in ("native", "device"):
+        raise ValueError(f"unknown Union-Find backend {backend!r}")
     wo = {"method": "uniform", "integer": False, "multiplier": 1}
     wo.update(weight_options)
     if wo.get("method") == "blueprint":
@@ -305,7 +308,10 @@ def _correct_uf(code, weight_options, sanity_check):
         g.weight[ct.qubits] = w
         g.bit_val[ct.qubits] = batch.bits[0, off : off + ct.Q]
         off += ct.Q
-    flips = uf_decode_batch(code, [batch.complexes[e].parity for e in code.ec], er)
+    if backend == "device":
+        flips = eng.uf_decode(use_erasures=er is not None)
+    else:
+        flips = uf_decode_batch(code, [batch.complexes[e].parity for e in code.ec], er)
     off = 0
     for e in code.ec:
         ct = code.lattice.complexes[e]

@@ -93,6 +93,20 @@ def test_device_decoder_against_the_host_decoder(d, ec, bnd, delta, ps):
     assert abs(int(f_dev.sum()) - int(f_host.sum())) <= 3 * np.sqrt(T)
 
 
+@pytest.mark.parametrize("name", ["uf_d3_open_primal_ps025", "uf_d4_open_dual_ps06", "uf_d3_open_primal_ps1"])
+def test_facade_correct_with_the_device_decoder(name):
+    """``correct(code, "UF", ..., decoder_opts={"backend": "device"})`` from the reference's seed: its verdicts."""
+    from flamingpy_b200.decoder import correct
+
+    g = gu.load_uf(os.path.join(gu.GOLDEN_DIR, name + ".npz"))
+    code = SurfaceCode(g["distance"], g["ec"], g["boundaries"])
+    layer = CVLayer(code, delta=g["delta"], p_swap=g["p_swap"])
+    rng = np.random.default_rng(int(g["seed"]))
+    for t in range(g["trials"]):
+        layer.apply_noise(rng)
+        assert correct(code, "UF", {"method": "uniform"}, decoder_opts={"backend": "device"}) == bool(g["success"][t]), t
+
+
 def test_monte_carlo_with_the_device_decoder():
     """``ec_monte_carlo(..., "UF", backend="device")``: batch-invariant, every noise model, zero errors at tiny delta,
     and the same failure count as the host decoder on a lattice whose clusters stay small."""
