@@ -299,8 +299,9 @@ extern "C" long long fpb_uf_erasures(int n_lattice_nodes, int n_edges, const int
 }
 
 extern "C" long long fpb_uf_check_correction(int n_trials, int n_qubits, const uint8_t* bits, const uint32_t* bit_words,
-                                             const uint8_t* flips, int n_planes, const int32_t* plane_off,
-                                             const int32_t* plane_qubits, uint8_t* fail, int threads) {
+                                             const uint8_t* flips, const uint32_t* flip_words, int n_planes,
+                                             const int32_t* plane_off, const int32_t* plane_qubits, uint8_t* fail,
+                                             int threads) {
   const int words = (n_qubits + 31) / 32;
   long long total = 0;
 #ifdef _OPENMP
@@ -308,15 +309,18 @@ extern "C" long long fpb_uf_check_correction(int n_trials, int n_qubits, const u
 #pragma omp parallel for num_threads(nt) reduction(+ : total) schedule(static)
 #endif
   for (int t = 0; t < n_trials; ++t) {
-    const uint8_t* fl = flips + (size_t)t * n_qubits;
     const uint8_t* b8 = bits ? bits + (size_t)t * n_qubits : nullptr;
     const uint32_t* bw = bit_words ? bit_words + (size_t)t * words : nullptr;
+    const uint8_t* f8 = flips ? flips + (size_t)t * n_qubits : nullptr;
+    const uint32_t* fw = flip_words ? flip_words + (size_t)t * words : nullptr;
     uint8_t failed = 0;
     for (int pl = 0; pl < n_planes; ++pl) {
       unsigned par = 0;
       for (int i = plane_off[pl]; i < plane_off[pl + 1]; ++i) {
         const int g = plane_qubits[i];
-        par ^= (b8 ? b8[g] : (uint8_t)((bw[g >> 5] >> (g & 31)) & 1u)) ^ fl[g];
+        const unsigned b = b8 ? b8[g] : (bw[g >> 5] >> (g & 31)) & 1u;
+        const unsigned f = f8 ? f8[g] : (fw[g >> 5] >> (g & 31)) & 1u;
+        par ^= b ^ f;
       }
       failed |= (uint8_t)(par & 1u);
     }

@@ -415,10 +415,11 @@ def check_planes(code):
 
 def logical_failures(code, batch, flips):
     """``check_correction`` over a batch (``decoders/decoder.py:151-224``): bool[T], True where any checked
-    correlation surface of any complex has odd parity after the recovery.  ``batch.bits`` may be the
-    unpacked bit values uint8[T, Qtot] or the packed words uint32[T, ceil(Qtot/32)] as they come off the
+    correlation surface of any complex has odd parity after the recovery.  ``batch.bits`` and ``flips`` may
+    each be unpacked uint8[T, Qtot] or the packed words uint32[T, ceil(Qtot/32)] as they come off the
     device; only the planes' qubits are touched (``fpb_uf_check_correction``, host threads over trials)."""
     from . import uf_native
 
     off, q = check_planes(code)
-    return uf_native.check_correction(batch.bits, flips, off, q)
+    Qtot = sum(code.lattice.complexes[e].Q for e in code.ec)
+    return uf_native.check_correction(batch.bits, flips, off, q, n_qubits=Qtot)

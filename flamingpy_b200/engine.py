@@ -442,11 +442,13 @@ class TrialEngine:
         self._h.fetch_into({k: v for k, v in bufs.items() if isinstance(v, np.ndarray)})
         return s
 
-    def fetch_decode(self, bufs: Optional[dict] = None, want_pairs: bool = True) -> "TrialBatch":
+    def fetch_decode(self, bufs: Optional[dict] = None, want_pairs: bool = True, packed_bits: bool = False) -> "TrialBatch":
         """What the host decoder needs of the last run - bits, odd counts, pair and boundary
         lengths - copied into reusable pinned buffers (``bufs``, grown on demand and owned by
         the caller; the returned arrays are views into them, valid until the next call).
-        ``want_pairs=False`` (sparse hand-off) leaves the K(K-1)/2 pair lengths on the device."""
+        ``want_pairs=False`` (sparse hand-off) leaves the K(K-1)/2 pair lengths on the device.
+        ``packed_bits``: ``batch.bits`` stays the device's uint32[T, ceil(Qtot/32)] words (a view;
+        ``decoder.logical_failures`` reads them as they are) instead of being unpacked to bytes."""
         import torch
 
         bufs = {} if bufs is None else bufs
@@ -472,7 +474,8 @@ class TrialEngine:
         self.fetch_into({k: v for k, v in bufs.items()
                          if not k.startswith("_keep_") and (want_pairs or not k.startswith("pair_len"))})
         batch = TrialBatch(T, _lib.STAGE_GRAPH)
-        batch.bits = unpack_bits(bufs["bits"][: T * self.bit_words].reshape(T, self.bit_words), self.Qtot)
+        words = bufs["bits"][: T * self.bit_words].reshape(T, self.bit_words)
+        batch.bits = words if packed_bits else unpack_bits(words, self.Qtot)
         batch.complexes = {}
         for i, ec in enumerate(self.ec):
             cb = ComplexBatch()
@@ -545,10 +548,10 @@ class TrialEngine:
             raise ValueError("a path is longer than max_len")
         return [qubits[i, : length[i]].copy() for i in range(len(trial))]
 
-    def paths_toggle(self, trial, cx, src, dst) -> np.ndarray:
+    def paths_toggle(self, trial, cx, src, dst, packed: bool = False) -> np.ndarray:
         """XOR-toggle the qubits on the shortest paths of the given (trial,
         complex, odd-index src, odd-index dst | -1) queries of the last run.
-        Returns uint8[T, Qtot] flips."""
+        Returns uint8[T, Qtot] flips (``packed``: the uint32[T, ceil(Qtot/32)] words as copied)."""
         s = self.sizes()
         T = int(s.n_trials)
         trial = np.ascontiguousarray(trial, np.int32)
@@ -557,7 +560,7 @@ class TrialEngine:
         dst = np.ascontiguousarray(dst, np.int32)
         flips = np.zeros((T, self.bit_words), np.uint32)
         self._h.paths_toggle(trial, cx, src, dst, flips)
-        return unpack_bits(flips, self.Qtot)
+        return flips if packed else unpack_bits(flips, self.Qtot)
 
 
 def unpack_bits(words: np.ndarray, n: int) -> np.ndarray:

@@ -213,7 +213,7 @@ def ec_monte_carlo(trials, code_instance, noise_instance, decoder, decoder_args,
                     en.run_macro_rng(seed, first, n, stage=_lib.STAGE_GRAPH, fetch=False)
                 else:
                     en.run_rng(seed, first, n, stage=_lib.STAGE_GRAPH, fetch=False)
-                b = en.fetch_decode(lane_bufs[lane], want_pairs=handoff == "full")
+                b = en.fetch_decode(lane_bufs[lane], want_pairs=handoff == "full", packed_bits=True)
                 if backend != "native":
                     cands = None
                 elif handoff == "full":
@@ -235,7 +235,7 @@ def ec_monte_carlo(trials, code_instance, noise_instance, decoder, decoder_args,
             lane, b, queries = item
             try:
                 if state["error"] is None:
-                    flips = engines[lane].paths_toggle(*queries)
+                    flips = engines[lane].paths_toggle(*queries, packed=True)  # words in, words out: nothing unpacked
                     state["failures"] += int(logical_failures(code, b, flips).sum())
                     state["done"] += b.n_trials
                     state["t_dev"] += b.timings["total_ms"]

@@ -30,26 +30,41 @@ def load():
         lib.fpb_uf_erasures.argtypes = [ctypes.c_int, ctypes.c_int, _i32p, _i32p, _i32p, ctypes.c_int, _u8p, _u8p,
                                         ctypes.c_int]
         lib.fpb_uf_check_correction.restype = ctypes.c_longlong
-        lib.fpb_uf_check_correction.argtypes = [ctypes.c_int, ctypes.c_int, _u8p, ctypes.POINTER(ctypes.c_uint32), _u8p,
-                                                ctypes.c_int, _i32p, _i32p, _u8p, ctypes.c_int]
+        u32p = ctypes.POINTER(ctypes.c_uint32)
+        lib.fpb_uf_check_correction.argtypes = [ctypes.c_int, ctypes.c_int, _u8p, u32p, _u8p, u32p, ctypes.c_int, _i32p, _i32p,
+                                                _u8p, ctypes.c_int]
         _lib = lib
     return _lib
 
 
 def check_correction(bits: np.ndarray, flips: np.ndarray, plane_off: np.ndarray, plane_qubits: np.ndarray,
-                     threads: int = 0) -> np.ndarray:
-    """bool[T]: some plane has odd parity of bit value XOR recovery.  ``bits`` uint8[T, Q] or the packed
-    uint32[T, ceil(Q/32)] words; ``flips`` uint8[T, Q]; planes as int32 offsets + global qubit ids."""
-    flips = np.ascontiguousarray(flips, np.uint8)
-    T, Q = flips.shape
-    packed = bits.dtype == np.uint32
-    bits = np.ascontiguousarray(bits, np.uint32 if packed else np.uint8)
-    if bits.shape != ((T, (Q + 31) // 32) if packed else (T, Q)):
-        raise ValueError("bits must be [trials, qubits] bytes or [trials, ceil(qubits / 32)] words")
-    fail = np.empty(T, np.uint8)
+                     n_qubits: Optional[int] = None, threads: int = 0) -> np.ndarray:
+    """bool[T]: some plane has odd parity of bit value XOR recovery.  ``bits`` and ``flips`` each uint8[T, Q] or the
+    packed uint32[T, ceil(Q/32)] words of the device; planes as int32 offsets + global qubit ids.  ``n_qubits`` is
+    needed when both come packed."""
     u32p = ctypes.POINTER(ctypes.c_uint32)
-    load().fpb_uf_check_correction(T, Q, None if packed else bits.ctypes.data_as(_u8p),
-                                   bits.ctypes.data_as(u32p) if packed else None, flips.ctypes.data_as(_u8p),
+
+    def split(a, name):
+        packed = a.dtype == np.uint32
+        a = np.ascontiguousarray(a, np.uint32 if packed else np.uint8)
+        if a.ndim != 2:
+            raise ValueError(f"{name} must be [trials, qubits] bytes or [trials, ceil(qubits / 32)] words")
+        return a, packed
+
+    bits, bp = split(bits, "bits")
+    flips, fp = split(flips, "flips")
+    T = flips.shape[0]
+    Q = int(n_qubits) if n_qubits is not None else (flips.shape[1] if not fp else (bits.shape[1] if not bp else -1))
+    if Q < 0:
+        raise ValueError("n_qubits is needed when bits and flips are both packed")
+    for a, packed, name in ((bits, bp, "bits"), (flips, fp, "flips")):
+        if a.shape != (T, (Q + 31) // 32 if packed else Q):
+            raise ValueError(f"{name} has shape {a.shape}, expected {T} trials of {Q} qubits")
+    if len(plane_qubits) and int(plane_qubits.max()) >= Q:
+        raise ValueError("plane qubit out of range")
+    fail = np.empty(T, np.uint8)
+    load().fpb_uf_check_correction(T, Q, None if bp else bits.ctypes.data_as(_u8p), bits.ctypes.data_as(u32p) if bp else None,
+                                   None if fp else flips.ctypes.data_as(_u8p), flips.ctypes.data_as(u32p) if fp else None,
                                    len(plane_off) - 1, plane_off.ctypes.data_as(_i32p), plane_qubits.ctypes.data_as(_i32p),
                                    fail.ctypes.data_as(_u8p), int(threads))
     return fail.astype(bool)

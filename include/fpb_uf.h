@@ -49,12 +49,12 @@ long long fpb_uf_erasures(int n_lattice_nodes, int n_edges, const int32_t* qubit
 
 /* check_correction (flamingpy/decoders/decoder.py:151-224) for a batch on the host: fail[t] = 1 when
  * some checked correlation surface - plane i = global qubit ids plane_qubits[plane_off[i] ..
- * plane_off[i+1]) - has odd parity of bit value XOR recovery.  Bit values either unpacked
- * (bits [T][n_qubits], bit_words NULL) or as the device delivers them (bit_words
- * [T][ceil(n_qubits/32)], LSB first, bits NULL); flips [T][n_qubits].  Returns the number of failures. */
+ * plane_off[i+1]) - has odd parity of bit value XOR recovery.  Bit values and recovery each either
+ * unpacked ([T][n_qubits] bytes; the word pointer NULL) or as the device delivers them
+ * ([T][ceil(n_qubits/32)] words, LSB first; the byte pointer NULL).  Returns the number of failures. */
 long long fpb_uf_check_correction(int n_trials, int n_qubits, const uint8_t* bits, const uint32_t* bit_words,
-                                  const uint8_t* flips, int n_planes, const int32_t* plane_off,
-                                  const int32_t* plane_qubits, uint8_t* fail, int threads);
+                                  const uint8_t* flips, const uint32_t* flip_words, int n_planes,
+                                  const int32_t* plane_off, const int32_t* plane_qubits, uint8_t* fail, int threads);
 
 int fpb_uf_max_threads(void);
 

@@ -288,3 +288,7 @@ def test_check_correction_in_the_library_equals_the_numpy_restatement(d, ec, bnd
     assert np.array_equal(logical_failures(code, TrialBatch(T, 2, bits=bits), flips), want)
     assert np.array_equal(logical_failures(code, TrialBatch(T, 2, bits=words), flips), want)
     assert np.array_equal(logical_failures(code, TrialBatch(T, 2, bits=bits), flips[:, ::1].copy(order="F")), want)
+    # the recovery as the device delivers it (fpb_paths_toggle / fpb_uf_decode): packed words, LSB first
+    fw = np.packbits(np.pad(flips, ((0, 0), (0, words.shape[1] * 32 - Q))), axis=1, bitorder="little").view(np.uint32)
+    assert np.array_equal(logical_failures(code, TrialBatch(T, 2, bits=words), fw), want)
+    assert np.array_equal(logical_failures(code, TrialBatch(T, 2, bits=bits), fw), want)
