@@ -195,6 +195,7 @@ def ec_monte_carlo(trials, code_instance, noise_instance, decoder, decoder_args,
     # pinned host buffers, one set per lane, kept on the code object: reused by every batch, every
     # later call and every other noise / weight setting of a sweep (pinning memory is slow)
     lane_bufs = [code.__dict__.setdefault("_decode_bufs", {}).setdefault((device, i), {}) for i in range(n_eng)]
+    knn_bufs = [code.__dict__.setdefault("_knn_bufs", {}).setdefault((device, i), {}) for i in range(n_eng)]
     free = [threading.Semaphore(1) for _ in engines]
     q_graph, q_match = queue.Queue(maxsize=2), queue.Queue(maxsize=2)
     state = {"failures": 0, "done": 0, "t_dev": 0.0, "error": None, "match": {}}
@@ -221,7 +222,7 @@ def ec_monte_carlo(trials, code_instance, noise_instance, decoder, decoder_args,
                 else:  # candidates with lengths: what the sparse hand-off starts from
                     from . import mwpm_native
 
-                    cands = [en.knn_len(ci, mwpm_native.CAND_K) for ci in range(len(code.ec))]
+                    cands = [en.knn_len_pinned(ci, mwpm_native.CAND_K, knn_bufs[lane]) for ci in range(len(code.ec))]
                 q_graph.put((lane, b, cands))
         except BaseException as exc:  # noqa: BLE001 - re-raised by the caller's thread
             state["error"] = exc
