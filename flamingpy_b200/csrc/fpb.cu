@@ -1448,7 +1448,7 @@ int fpb_uf_decode(fpb_handle* h, int use_erasures, uint32_t* flips_host, uint32_
     up.edge_a[c] = h->uf_edge_a[c];
     up.edge_b[c] = h->uf_edge_b[c];
     up.n_nodes[c] = h->uf_nodes[c];
-    const size_t b = uf_smem_bytes(h->uf_nodes[c], h->cx[c].Q);
+    const size_t b = uf_smem_bytes(h->uf_nodes[c], h->cx[c].S, h->cx[c].Q);
     if (b > smem) smem = b;
   }
   int max_optin = 0;

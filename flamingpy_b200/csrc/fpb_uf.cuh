@@ -11,7 +11,8 @@
 //      newly grown edges merge clusters.  The grown set after each round is independent of any visiting
 //      order, so it equals the reference's and the host decoder's;
 //   3. a breadth-first spanning forest of the grown edges, rooted at the lowest-numbered boundary point of
-//      each component (else its lowest cube), is peeled level by level from the leaves (algos.py:196-311).
+//      each component (else its lowest cube), is built one level per pass from a node-centric frontier and
+//      peeled level by level from the leaves (algos.py:196-311).
 //      Among the edges that can attach a node to the previous level the lowest-numbered one is its tree
 //      edge - a different forest than the host decoder's FIFO order, so the two recoveries may differ by
 //      cycles of grown edges; both clear the syndrome inside the same grown set.
@@ -40,8 +41,9 @@ struct UfParams {
   int* stuck;                 // number of (trial, complex) items whose odd cluster could not be resolved
 };
 
-__host__ __device__ inline size_t uf_smem_bytes(int n_nodes, int Q) {
-  return align16((size_t)Q) + 3 * align16((size_t)n_nodes * 4) + align16((size_t)n_nodes * 2);
+__host__ __device__ inline size_t uf_smem_bytes(int n_nodes, int n_cubes, int Q) {
+  return align16((size_t)Q) + 3 * align16((size_t)n_nodes * 4) + align16((size_t)n_nodes * 2) +
+         align16((size_t)(n_nodes - n_cubes) * 4);
 }
 
 __device__ __forceinline__ int uf_find(const volatile int* par, int u) {
@@ -90,7 +92,8 @@ __global__ void __launch_bounds__(256) k_uf(const __grid_constant__ UfParams p) 
   volatile int* par = (int*)ptr; ptr += align16((size_t)NN * 4);
   volatile int* cl = (int*)ptr; ptr += align16((size_t)NN * 4);   // growth: per root, bit 0 parity, bit 1 boundary; peeling: running parity
   volatile int* upe = (int*)ptr; ptr += align16((size_t)NN * 4);  // peeling: tree edge towards the root
-  volatile uint16_t* depth = (uint16_t*)ptr;
+  volatile uint16_t* depth = (uint16_t*)ptr; ptr += align16((size_t)NN * 2);
+  int* bedge = (int*)ptr;                                          // the one edge of every boundary point
   const uint32_t* parw = c.parity + (long long)t * c.par_words;
   auto cube_parity = [&](int u) -> int { return (int)((parw[u >> 5] >> (u & 31)) & 1u); };
 
@@ -105,6 +108,7 @@ __global__ void __launch_bounds__(256) k_uf(const __grid_constant__ UfParams p) 
       if (pc >= 2) s = 2;
     }
     sup[q] = s;
+    if (ea[q] >= 0 && eb[q] >= S) bedge[eb[q] - S] = q;
   }
   __syncthreads();
   if (st) uf_merge(par, sup, ea, eb, Q, NN, &flag_s[0]);
@@ -181,31 +185,40 @@ __global__ void __launch_bounds__(256) k_uf(const __grid_constant__ UfParams p) 
     if (par[u] == u) depth[cl[u] != 0x7fffffff ? cl[u] : u] = 0;
   __syncthreads();
   for (int u = tid; u < NN; u += nthr) cl[u] = u < S ? cube_parity(u) : 0;
+  // One level per pass over the nodes: a node of the current level offers each of its grown edges to the unreached
+  // node at the other end, which keeps the lowest-numbered offer as its tree edge (cubes have up to six edges,
+  // listed by cube_qubit; a boundary point has one).
   int levels = 0;
   for (; levels < NN; ++levels) {
     if (tid == 0) flag_s[2] = 0;
     __syncthreads();
-    for (int q = tid; q < Q; q += nthr) {
-      if (sup[q] < 2) continue;
-      const int a = ea[q], b = eb[q];
-      const int da = depth[a], db = depth[b];
-      if (da == levels && db == 0xffff) {
-        atomicMin((int*)&upe[b], q);
-        flag_s[2] = 1;
-      } else if (db == levels && da == 0xffff) {
-        atomicMin((int*)&upe[a], q);
-        flag_s[2] = 1;
+    for (int u = tid; u < NN; u += nthr) {
+      if (depth[u] != levels) continue;
+      if (u >= S) {
+        const int q = bedge[u - S];
+        if (sup[q] >= 2 && depth[ea[q]] == 0xffff) {
+          atomicMin((int*)&upe[ea[q]], q);
+          flag_s[2] = 1;
+        }
+        continue;
+      }
+#pragma unroll
+      for (int f = 0; f < 6; ++f) {
+        const int q = c.cube_qubit[u * 6 + f];
+        if (q < 0 || sup[q] < 2) continue;
+        const int a = ea[q];
+        if (a < 0) continue;
+        const int v = a == u ? eb[q] : a;
+        if (depth[v] == 0xffff) {
+          atomicMin((int*)&upe[v], q);
+          flag_s[2] = 1;
+        }
       }
     }
     __syncthreads();
     const int found = flag_s[2];
-    for (int q = tid; q < Q; q += nthr) {  // the winning edge of every newly reached node sets its depth
-      if (sup[q] < 2) continue;
-      const int a = ea[q], b = eb[q];
-      const int da = depth[a], db = depth[b];
-      if (da == levels && db == 0xffff && upe[b] == q) depth[b] = (uint16_t)(levels + 1);
-      else if (db == levels && da == 0xffff && upe[a] == q) depth[a] = (uint16_t)(levels + 1);
-    }
+    for (int u = tid; u < NN; u += nthr)
+      if (depth[u] == 0xffff && upe[u] != 0x7fffffff) depth[u] = (uint16_t)(levels + 1);
     __syncthreads();
     if (!found) break;
   }
