@@ -12,9 +12,16 @@ import re
 import subprocess
 import sys
 
+import platform
+import shutil
+
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+# the SIMT machine switches fibers with a few lines of x86-64 System V assembly (tests/emu/simt.cpp)
+pytestmark = pytest.mark.skipif(platform.machine() not in ("x86_64", "AMD64") or shutil.which("g++") is None,
+                                reason="the kernel emulation needs g++ on x86-64")
 
 # not runnable on the emulated library: the pybind11 module links the nvcc build; torch views need a CUDA context
 UNSUPPORTED = ["fpbpy", "device_tensors", "threshold_sweep"]
